@@ -1,0 +1,193 @@
+/*
+ * prtc.h -- C-ABI of the B200-native character-collision path ("prtc" = PRoTotype2 Collision).
+ *
+ * This is the drop-in boundary for the one hot path of ArneStenkrona/prototype2 that this repository
+ * accelerates: PhysicsSystem::updateCharacters and what it calls (broadphase AABB-tree query,
+ * capsule-vs-triangle narrowphase with push-out response, capsule-vs-capsule pass).  The reference has no
+ * FFI layer today -- the C++ class PhysicsSystem *is* the seam (reference
+ * src/game/system/physics/physics_system.h:24-77).  Every entry point below names the PhysicsSystem member
+ * it stands behind; the C++ drop-in class that keeps the reference's signatures and forwards to these
+ * functions lives in prototype2_b200/engine/physics_system.h, and INTEGRATION.md shows the binding.
+ *
+ * Conventions: extern "C", opaque context handle, int status (0 = PRTC_OK), no exceptions cross the
+ * boundary, caller-owned buffers, plain pointers and sizes.  All calls on one context must come from one
+ * host thread (the reference is single-threaded).  There is NO CPU fallback: every compute
+ * entry point fails with PRTC_ERR_CUDA when no sm_100 device is usable.
+ */
+#ifndef PRTC_H
+#define PRTC_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PRTC_VERSION 1
+
+enum prtc_status {
+    PRTC_OK = 0,
+    PRTC_ERR_INVALID = 1,   /* bad argument / call order */
+    PRTC_ERR_CUDA = 2,      /* CUDA runtime error or no usable device; see prtc_last_error() */
+    PRTC_ERR_CAPACITY = 3,  /* a caller-provided buffer was too small */
+    PRTC_ERR_ALLOC = 4
+};
+
+/* How the unqualified `abs(dist)` at reference collision_system.cpp:72 is resolved (it decides which
+ * triangles survive the range cull and therefore isGrounded):
+ *   PRTC_ABS_INT    libstdc++ builds: only `int abs(int)` is visible -> dist is truncated to int first
+ *                   (this is what the reference does when compiled on this image; default)
+ *   PRTC_ABS_FLOAT  libc++ / MSVC builds: the float overload is chosen */
+enum prtc_abs_mode { PRTC_ABS_INT = 0, PRTC_ABS_FLOAT = 1 };
+
+/* Candidate order (SURVEY.md findings 3, H3, H4):
+ *   PRTC_ORDER_CANONICAL  static-only tree built by the reference insertion algorithm, then frozen;
+ *                         capsule neighbours in ascending index order.  Scales to millions of capsules.
+ *   PRTC_ORDER_LITERAL    the reference's unified mesh+capsule tree is maintained on the host by the same
+ *                         algorithm every frame and re-flattened, and characters keep the reference's
+ *                         sequential visibility of one another; for engine-sized scenes. */
+enum prtc_order_mode { PRTC_ORDER_LITERAL = 0, PRTC_ORDER_CANONICAL = 1 };
+
+/* Dynamic-vs-dynamic (capsule-capsule) pass in CANONICAL order:
+ *   PRTC_DYN_OFF     capsules do not see one another (static pass only)
+ *   PRTC_DYN_JACOBI  every capsule collides against the start-of-frame pose of its neighbours */
+enum prtc_dyn_mode { PRTC_DYN_OFF = 0, PRTC_DYN_JACOBI = 2 };
+
+/* Compile-time constants of the reference turned into fields (defaults = reference values). */
+typedef struct prtc_config {
+    float gravity;         /* 1.0    physics_system.h:122 (m_gravity) */
+    float leaf_margin;     /* 0.05   aabb_tree.h:90 (buffer) */
+    float ground_dot;      /* 0.3    collision_system.cpp:245 */
+    float friction;        /* 10.0   physics_system.cpp:307 */
+    float stick;           /* 0.05   physics_system.cpp:280 */
+    uint32_t substeps;     /* 4      physics_system.cpp:346 (nTimeSteps) */
+    uint32_t abs_mode;     /* enum prtc_abs_mode */
+    uint32_t order_mode;   /* enum prtc_order_mode */
+    uint32_t dyn_mode;     /* enum prtc_dyn_mode */
+    int32_t device;        /* CUDA device ordinal */
+} prtc_config;
+
+/* Bit-compatible with the reference's `Transform` (src/game/component/component.h:14-17):
+ * glm::vec3 position; glm::quat rotation (glm 0.9.9 stores x,y,z,w); glm::vec3 scale.  40 bytes. */
+typedef struct prtc_transform {
+    float position[3];
+    float rotation[4];     /* x, y, z, w */
+    float scale[3];
+} prtc_transform;
+
+/* The fields of the reference's `CharacterPhysics` (src/game/system/character/character.h:19-27) that
+ * updateCharacters reads or writes, with the collider index widened to 32 bits.  44 bytes. */
+typedef struct prtc_char_physics {
+    float velocity[3];         /* in/out */
+    float movement[3];         /* in      movementVector */
+    float ground_normal[3];    /* in/out  groundNormal */
+    uint32_t collider;         /* in      colliderTag.index (capsule id from prtc_add_capsule) */
+    uint32_t grounded;         /* in/out  isGrounded (0/1) */
+} prtc_char_physics;
+
+/* Work counters accumulated on the device since the last reset. */
+typedef struct prtc_counters {
+    uint64_t substeps;     /* executed query-substeps (one broadphase query each) */
+    uint64_t tri_tests;    /* triangles entering the narrowphase loop (collision_system.cpp:29) */
+    uint64_t node_tests;   /* BVH nodes tested by the GPU traversal */
+    uint64_t contacts;     /* handleCollision calls (collision_system.cpp:236) */
+    uint64_t cc_tests;     /* capsule-capsule narrowphase tests */
+} prtc_counters;
+
+/* Parity trace of one traced step (prtc_step_characters_traced); same record layout as the oracles'.
+ * Arrays are caller-allocated; capacities in, counts out.  Queries are sorted by (character, substep). */
+typedef struct prtc_trace {
+    uint32_t cap_queries, cap_mesh_ids, cap_caps_ids, cap_hits;     /* in  */
+    uint32_t n_queries, n_mesh_ids, n_caps_ids, n_hits;              /* out */
+    uint32_t * q_char;        /* [cap_queries]      character index */
+    uint32_t * q_sub;         /* [cap_queries]      substep 0.. */
+    float * q_aabb;           /* [cap_queries*6]    query box lo.xyz hi.xyz */
+    uint32_t * q_mesh_off;    /* [cap_queries+1]    CSR offsets into mesh_ids */
+    uint32_t * q_caps_off;    /* [cap_queries+1]    CSR offsets into caps_ids */
+    uint32_t * mesh_ids;      /* [cap_mesh_ids]     candidate mesh colliders, in test order */
+    uint32_t * caps_ids;      /* [cap_caps_ids]     candidate capsules, in test order */
+    uint32_t * q_tri_tests;   /* [cap_queries] */
+    uint32_t * h_query;       /* [cap_hits]         index into q_* */
+    int32_t * h_poly;         /* [cap_hits]         triangle index within the query's candidate list, -1 = capsule */
+    float * h_impulse;        /* [cap_hits*3] */
+    float * h_normal;         /* [cap_hits*3] */
+    float * h_pos;            /* [cap_hits*3]       position right after the push */
+} prtc_trace;
+
+typedef struct prtc_ctx prtc_ctx;
+
+void prtc_default_config(prtc_config * cfg);
+const char * prtc_last_error(void);
+/* number of CUDA devices with compute capability 10.x; 0 when there is none (never an error) */
+int prtc_device_count(void);
+
+/* PhysicsSystem::PhysicsSystem()  physics_system.cpp:15-16 */
+int prtc_create(const prtc_config * cfg, prtc_ctx ** out);
+void prtc_destroy(prtc_ctx * ctx);
+
+/* PhysicsSystem::addModelCollider(Model const&, Transform const&)  physics_system.cpp:44-106.
+ * xyz: 3*n_vertices floats, index-expanded model-space positions (what the reference copies out of
+ * Model::vertexBuffer via indexBuffer, :85); mesh_first/mesh_count: one entry per Model::Mesh, in vertices
+ * (multiples of 3).  One mesh collider (= one BVH leaf) is created per mesh; ids are consecutive. */
+int prtc_add_model(prtc_ctx * ctx, const float * xyz, uint32_t n_vertices, const uint32_t * mesh_first,
+                   const uint32_t * mesh_count, uint32_t n_meshes, const prtc_transform * transform,
+                   uint32_t * out_model_id, uint32_t * out_first_mesh_id);
+
+/* PhysicsSystem::addCapsuleCollider(float h, float r, vec3 const& offset)  physics_system.cpp:22-42 */
+int prtc_add_capsule(prtc_ctx * ctx, float height, float radius, const float offset[3], uint32_t * out_id);
+/* PhysicsSystem::updateCapsuleCollider  physics_system.cpp:151-159 */
+int prtc_update_capsule(prtc_ctx * ctx, uint32_t id, float height, float radius, const float offset[3]);
+
+/* Makes registered colliders visible to the device: transforms vertices to world space, builds / extends
+ * the AABB tree with the reference's insertion algorithm (aabb_tree.cpp:134-180,243-339), flattens it in
+ * the reference's right-first DFS order and uploads.  Called implicitly by the step functions when needed. */
+int prtc_commit(prtc_ctx * ctx);
+
+/* PhysicsSystem::updateModelColliders(ColliderTag const*, Transform const*, size_t)  physics_system.cpp:161-202 */
+int prtc_update_models(prtc_ctx * ctx, const uint32_t * model_ids, const prtc_transform * transforms, uint32_t n);
+
+/* PhysicsSystem::updateCharacters(float dt, Scene&, Transform*)  physics_system.cpp:245-318.
+ * HOST buffers, updated in place; copies to and from the device are part of the call. */
+int prtc_step_characters(prtc_ctx * ctx, float dt, uint32_t n, prtc_transform * transforms,
+                         prtc_char_physics * physics);
+/* Same step on DEVICE-resident arrays (asynchronous on the context's stream). */
+int prtc_step_characters_device(prtc_ctx * ctx, float dt, uint32_t n, prtc_transform * d_transforms,
+                                prtc_char_physics * d_physics);
+/* Host-buffer step that also records the parity trace (slower; for tests). */
+int prtc_step_characters_traced(prtc_ctx * ctx, float dt, uint32_t n, prtc_transform * transforms,
+                                prtc_char_physics * physics, prtc_trace * trace);
+
+/* PhysicsSystem::raycast(origin, direction, maxDistance, hit&)  physics_system.cpp:205-242, batched:
+ * n rays; hit_xyz[3*i..] is written and hit_mask[i]=1 where ray i hits a mesh collider. */
+int prtc_raycast(prtc_ctx * ctx, uint32_t n, const float * origins, const float * directions,
+                 const float * max_distances, float * hit_xyz, uint8_t * hit_mask);
+
+/* stream control for callers that own device memory (bench / multi-GPU drivers) */
+int prtc_set_stream(prtc_ctx * ctx, void * cuda_stream);
+int prtc_synchronize(prtc_ctx * ctx);
+
+int prtc_get_counters(prtc_ctx * ctx, prtc_counters * out, int reset);
+
+/* Introspection for parity tests: the flattened tree.  leaf_mesh_ids receives the mesh-collider ids of all
+ * leaves in traversal (= reference DFS) order. */
+int prtc_get_tree_info(prtc_ctx * ctx, uint32_t * n_nodes, uint32_t * n_leaves, uint32_t * n_triangles);
+int prtc_get_leaf_order(prtc_ctx * ctx, uint32_t * leaf_mesh_ids, uint32_t capacity);
+/* world-space vertex cache as the device computed it (physics_system.cpp:86), 3 floats per vertex */
+int prtc_get_world_vertices(prtc_ctx * ctx, float * xyz, uint32_t capacity_vertices, uint32_t * n_vertices);
+/* candidate mesh colliders of one box, in test order (DynamicAABBTree::query, aabb_tree.cpp:34-68), on the device */
+int prtc_query_box(prtc_ctx * ctx, const float aabb6[6], uint32_t * mesh_ids, uint32_t capacity, uint32_t * n_found);
+
+
+/* Host-only utility (needs no device, performs no collision arithmetic): builds the reference's dynamic AABB
+ * tree over n boxes inserted in order (DynamicAABBTree::insert, aabb_tree.cpp:95-100) and returns it in the
+ * flattened device layout: nodes8 = 8 x 32-bit words per node {lo.xyz, link, hi.xyz, count} in right-first
+ * preorder (internal: link = skip index, count = -1; leaf: link = box index, count = 1), leaf_order = box
+ * indices in traversal order.  Lets the build / flatten logic be checked against the oracle without a GPU. */
+int prtc_host_build_tree(const float * aabbs6, uint32_t n, float margin, uint32_t * leaf_order, float * nodes8,
+                         uint32_t nodes_capacity, uint32_t * n_nodes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PRTC_H */

@@ -1,0 +1,209 @@
+// collide.cuh -- device-side narrowphase: one capsule against one triangle / one capsule, with the reference's
+// exact arithmetic, branch structure and quirks.
+//
+// Restates (for the GPU) reference src/game/system/physics/collision_system.cpp:19-156 (collideCapsuleMesh),
+// :158-234 (collideCapsuleCapsule), :236-252 (handleCollision, COLLIDE branch) and
+// src/util/physics_util.cpp:5-49 (closestPointOnTriangle), :125-139 (closestPointOnLineSegment).
+// What is hoisted out of the reference's per-triangle loop is hoisted only where the hoisted value is a pure
+// function of unchanged inputs, so every float that reaches a branch or an output is bit-identical:
+//   * the capsule segment (A, B, CapsuleNormal, pointA, segment direction and length) depends only on the
+//     capsule and the current position -> kept in `Pose`, recomputed after every non-zero push
+//   * the unit plane normal of a triangle depends only on the triangle -> precomputed once per commit by
+//     k_tri_setup with the same instruction sequence (stored in the .w lanes of the triangle record)
+#ifndef PRT_COLLIDE_CUH
+#define PRT_COLLIDE_CUH
+
+#include "prt_math.cuh"
+
+namespace prt {
+
+#define PRT_DEGENERATE_BITS 0x7FC0DEADu   /* NaN payload the FPU never produces: marks length(n)==0 triangles */
+
+struct CapsuleDev {          // CapsuleCollider (colliders.h:14-18), padded to 32 bytes
+    float height, radius;
+    float ox, oy, oz;
+    float pad0, pad1, pad2;
+};
+
+// Per-capsule constants of `tform * a` / `tform * b` (collision_system.cpp:37-43) with tform = [R | pos]:
+//   A = (R0*a.x + R1*a.y) + (R2*a.z + pos)      -> A = sa1 + (sa2 + pos)
+struct CapsuleFrame {
+    V3 sa1, sa2, sb1, sb2;
+    float radius;
+};
+PRT_HD CapsuleFrame capsule_frame(CapsuleDev const & c, Rot3 const & r) {
+    CapsuleFrame f;
+    V3 a = v3(c.ox, c.oy, c.oz);
+    V3 b = a + v3(0.0f, c.height, 0.0f);             // capsule.offset + vec3{0, height, 0}
+    f.sa1 = r.c0 * a.x + r.c1 * a.y; f.sa2 = r.c2 * a.z;
+    f.sb1 = r.c0 * b.x + r.c1 * b.y; f.sb2 = r.c2 * b.z;
+    f.radius = c.radius;
+    return f;
+}
+
+struct Pose {
+    V3 A, B;                 // segment end points in world space
+    V3 cn;                   // CapsuleNormal = normalize(A - B)                 :45
+    V3 pointA;               // A - cn * radius                                   :46-48
+    V3 segv; float segd;     // normalize(B - A), distance(A, B): closestPointOnLineSegment(A, B, .)   :67
+};
+PRT_HD void segment_ends(CapsuleFrame const & f, V3 pos, V3 & A, V3 & B) {
+    A = f.sa1 + (f.sa2 + pos);
+    B = f.sb1 + (f.sb2 + pos);
+}
+PRT_HD Pose make_pose(CapsuleFrame const & f, V3 pos) {
+    Pose p;
+    segment_ends(f, pos, p.A, p.B);
+    p.cn = normalize(p.A - p.B);
+    p.pointA = p.A - p.cn * f.radius;
+    V3 ba = p.B - p.A;
+    float dd = dot(ba, ba);
+    float s = fsqrt(dd);
+    p.segv = ba * fdiv(1.0f, s);
+    p.segd = s;
+    return p;
+}
+
+// physics_util.cpp:125-139 with v = normalize(b - a) and d = distance(a, b) supplied
+PRT_HD V3 closest_on_segment(V3 a, V3 b, V3 v, float d, V3 p) {
+    V3 c = p - a;
+    float t = dot(v, c);
+    if (t < 0) return a;
+    if (t > d) return b;
+    return a + v * t;
+}
+PRT_HD V3 closest_on_segment(V3 a, V3 b, V3 p) {
+    V3 ba = b - a;
+    float s = fsqrt(dot(ba, ba));
+    return closest_on_segment(a, b, ba * fdiv(1.0f, s), s, p);
+}
+
+// physics_util.cpp:5-49
+PRT_HD V3 closest_on_triangle(V3 a, V3 b, V3 c, V3 p) {
+    V3 ab = b - a;
+    V3 ac = c - a;
+    V3 bc = c - b;
+    float snom = dot(p - a, ab), sdenom = dot(p - b, a - b);
+    float tnom = dot(p - a, ac), tdenom = dot(p - c, a - c);
+    if (snom <= 0.0f && tnom <= 0.0f) return a;
+    float unom = dot(p - b, bc), udenom = dot(p - c, b - c);
+    if (sdenom <= 0.0f && unom <= 0.0f) return b;
+    if (tdenom <= 0.0f && udenom <= 0.0f) return c;
+    V3 n = cross(b - a, c - a);
+    float vc = dot(n, cross(a - p, b - p));
+    if (vc <= 0.0f && snom >= 0.0f && sdenom >= 0.0f) return a + fdiv(snom, snom + sdenom) * ab;
+    float va = dot(n, cross(b - p, c - p));
+    if (va <= 0.0f && unom >= 0.0f && udenom >= 0.0f) return b + fdiv(unom, unom + udenom) * bc;
+    float vb = dot(n, cross(c - p, a - p));
+    if (vb <= 0.0f && tnom >= 0.0f && tdenom >= 0.0f) return a + fdiv(tnom, tnom + tdenom) * ac;
+    float u = fdiv(va, (va + vb) + vc);
+    float v = fdiv(vb, (va + vb) + vc);
+    float w = (1.0f - u) - v;
+    return (u * a + v * b) + w * c;
+}
+
+// unit plane normal as collision_system.cpp:52-54 computes it; returns false for the degenerate skip
+PRT_HD bool triangle_normal(V3 pa, V3 pb, V3 pc, V3 & n) {
+    V3 nr = cross(pb - pa, pc - pa);
+    float dd = dot(nr, nr);
+    if (fsqrt(dd) == 0.0f) return false;
+    n = nr * fdiv(1.0f, fsqrt(dd));
+    return true;
+}
+
+struct Contact {
+    V3 impulse;
+    V3 normal;
+};
+
+// collision_system.cpp:56-142 for one triangle with unit normal n.  Returns true when the reference would call
+// handleCollision (`inside || intersects`), filling the contact.
+PRT_HD bool capsule_triangle(Pose const & ps, float radius, uint32_t abs_mode, V3 pa, V3 pb, V3 pc, V3 n, Contact & out) {
+    float nDotCn = dot(n, ps.cn);
+    V3 reference_point;
+    if (fabsf(nDotCn) > 0.0001f) {
+        float t = dot(n, (pa - ps.pointA) / fabsf(nDotCn));
+        V3 line_plane_intersection = ps.pointA + ps.cn * t;
+        reference_point = closest_on_triangle(pa, pb, pc, line_plane_intersection);
+    } else {
+        reference_point = pa;
+    }
+    V3 center = closest_on_segment(ps.A, ps.B, ps.segv, ps.segd, reference_point);
+
+    float dist = dot(center - pa, n);
+    if (dist < 0.0f) return false;                              // back-face cull                  :71
+    if (abs_dist(dist, abs_mode) > radius) return false;       // range cull (see prtc_abs_mode)  :72
+
+    V3 point0 = center - n * dist;
+    V3 c0 = cross(point0 - pa, pb - pa);
+    V3 c1 = cross(point0 - pb, pc - pb);
+    V3 c2 = cross(point0 - pc, pa - pc);
+    bool inside = dot(c0, n) <= 0 && dot(c1, n) <= 0 && dot(c2, n) <= 0;
+
+    float radiussq = radius * radius;
+    V3 point1 = closest_on_segment(pa, pb, center);
+    V3 v1 = center - point1;
+    float distsq1 = dot(v1, v1);
+    bool intersects = distsq1 < radiussq;
+    V3 point2 = closest_on_segment(pb, pc, center);
+    V3 v2 = center - point2;
+    float distsq2 = dot(v2, v2);
+    intersects |= distsq2 < radiussq;
+    V3 point3 = closest_on_segment(pc, pa, center);
+    V3 v3_ = center - point3;
+    float distsq3 = dot(v3_, v3_);
+    intersects |= distsq3 < radiussq;
+
+    if (!(inside || intersects)) return false;
+
+    V3 intersection_vec;
+    if (inside) {
+        intersection_vec = center - point0;
+    } else {
+        // :108-127 -- `distsq = best_distsq;` (sic, twice): best_distsq stays at edge 1's value, so edge 3
+        // wins over edge 2 whenever both beat edge 1
+        float best_distsq = distsq1;
+        intersection_vec = v1;
+        if (distsq2 < best_distsq) intersection_vec = v2;
+        if (distsq3 < best_distsq) intersection_vec = v3_;
+    }
+    float len = length(intersection_vec);
+    if (len > 0.0f && len < radius) {
+        float penetration_depth = radius - len;
+        V3 penetration_normal = intersection_vec / len;
+        out.impulse = penetration_depth * (penetration_normal + 0.0001f);   // scalar added to every component :136
+        out.normal = penetration_normal;
+    } else {
+        out.impulse = v3(0.0f);
+        out.normal = n;
+    }
+    return true;
+}
+
+// collision_system.cpp:164-221: capsule A (pose endpoints a_A, a_B) against capsule B (b_A, b_B).
+PRT_HD bool capsule_capsule(V3 a_A, V3 a_B, float radiusA, V3 b_A, V3 b_B, float radiusB, Contact & out) {
+    V3 v0 = b_A - a_A;
+    V3 v1 = b_B - a_A;
+    V3 v2 = b_A - a_B;
+    V3 v3_ = b_B - a_B;
+    float d0 = dot(v0, v0);
+    float d1 = dot(v1, v1);
+    float d2 = dot(v2, v2);
+    float d3 = dot(v3_, v3_);
+    V3 bestA;
+    if (d2 < d0 || d2 < d1 || d3 < d0 || d3 < d1) bestA = a_B;
+    else bestA = a_A;
+    V3 bestB = closest_on_segment(b_A, b_B, bestA);
+    bestA = closest_on_segment(a_A, a_B, bestB);
+    V3 penetration_normal = bestA - bestB;
+    float len = length(penetration_normal);
+    penetration_normal = penetration_normal / len;            // len == 0 -> NaN, unguarded in the reference
+    float penetration_depth = (radiusA + radiusB) - len;
+    if (!(penetration_depth > 0)) return false;
+    out.impulse = penetration_depth * (penetration_normal + 0.0001f);
+    out.normal = penetration_normal;
+    return true;
+}
+
+} // namespace prt
+#endif

@@ -1,0 +1,274 @@
+// kernels.cu -- sm_100a kernels of the character-collision path.
+//
+//   k_step             K1+K2+K3+K4+K6 fused: one thread per character runs the whole frame of
+//                      PhysicsSystem::updateCharacters for it (reference physics_system.cpp:245-318,330-438):
+//                      velocity pre-step, `substeps` x { advance, swept query box, stackless BVH traversal in the
+//                      reference's candidate order, Gauss-Seidel capsule-triangle push-out }, velocity finalize.
+//   k_transform_refit  K8: world-space vertex cache and per-mesh AABB (physics_system.cpp:68-93,161-202)
+//   k_tri_setup        leaf-ordered triangle records with precomputed unit normals
+//   k_query_box        one box against the flattened tree (introspection)
+//
+// Compile with -fmad=false: results must be bit-identical to the CPU reference (see prt_math.cuh).
+#include "kernels.cuh"
+
+namespace prt {
+
+namespace {
+
+__device__ __forceinline__ Box capsule_box(V3 tA, V3 tB, float radius) {     // CapsuleCollider::getAABB colliders.h:19-27
+    Box b;
+    b.lo = gmin(tA, tB) - v3(radius);
+    b.hi = gmax(tA, tB) + v3(radius);
+    return b;
+}
+
+__device__ __forceinline__ bool node_overlaps(float4 lo, float4 hi, Box const & q) {   // AABB::intersect aabb.cpp:3-10
+    return !(lo.x > q.hi.x || hi.x < q.lo.x || lo.y > q.hi.y || hi.y < q.lo.y || lo.z > q.hi.z || hi.z < q.lo.z);
+}
+
+template <bool TRACE>
+__global__ void __launch_bounds__(128) k_step(StepParams p) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t c_sub = 0, c_tri = 0, c_node = 0, c_contact = 0;
+
+    if (i < p.n) {
+        prtc_transform * tf = p.transforms + i;
+        prtc_char_physics * ph = p.physics + i;
+        V3 pos = v3(tf->position[0], tf->position[1], tf->position[2]);
+        Quat q; q.x = tf->rotation[0]; q.y = tf->rotation[1]; q.z = tf->rotation[2]; q.w = tf->rotation[3];
+        V3 vel = v3(ph->velocity[0], ph->velocity[1], ph->velocity[2]);
+        V3 gn = v3(ph->ground_normal[0], ph->ground_normal[1], ph->ground_normal[2]);
+        uint32_t grounded = ph->grounded;
+        const float mvx = ph->movement[0], mvz = ph->movement[2];
+        const CapsuleDev cap = p.capsules[ph->collider];
+        const Rot3 R = rotation_of(q);
+        const CapsuleFrame fr = capsule_frame(cap, R);
+        const float radius = cap.radius;
+
+        // ---- phase 1 (physics_system.cpp:277-285) ----
+        const V3 prevVel = vel;
+        if (grounded) vel = vel + ((-p.stick * p.gravity) * p.dt) * gn;
+        vel.x = vel.x + mvx;
+        vel.z = vel.z + mvz;
+        grounded = 0;
+
+        // ---- phase 2: collideCharacterWithWorld (physics_system.cpp:330-438) ----
+        const float fsub = float(p.substeps);
+        const V3 stepv = vel / fsub;
+        V3 prevA, prevB;
+        segment_ends(fr, pos, prevA, prevB);                      // prevTform                      :344
+        uint32_t stepsLeft = p.substeps;
+        while (stepsLeft != 0) {
+            --stepsLeft;
+            pos = pos + stepv;                                    //                                 :350
+            Pose ps = make_pose(fr, pos);
+            Box qb = box_union(capsule_box(prevA, prevB, radius), capsule_box(ps.A, ps.B, radius));   // :355-356
+            prevA = ps.A; prevB = ps.B;                           // prevTform = tform               :358
+            ++c_sub;
+
+            TraceQuery * tq = nullptr;
+            uint32_t slot = 0, t_mesh = 0, t_hits = 0, t_tris = 0;
+            if (TRACE) {
+                slot = i * p.substeps + (p.substeps - 1 - stepsLeft);
+                tq = p.trace.queries + slot;
+                tq->aabb[0] = qb.lo.x; tq->aabb[1] = qb.lo.y; tq->aabb[2] = qb.lo.z;
+                tq->aabb[3] = qb.hi.x; tq->aabb[4] = qb.hi.y; tq->aabb[5] = qb.hi.z;
+            }
+
+            // Stackless traversal in right-first preorder == DynamicAABBTree::query's emission order
+            // (aabb_tree.cpp:34-68).  The query box is fixed for the substep, so testing a leaf's triangles as
+            // soon as the leaf is reached is equivalent to the reference's "collect candidates, then
+            // collideCapsuleMesh" (physics_system.cpp:367,396-434).  "while-while": lanes leave the inner loop
+            // with a pending leaf and re-converge before the (expensive) triangle loop.
+            bool found = false;
+            uint32_t node = 0;
+            uint32_t poly = 0;
+            while (true) {
+                uint32_t triBeg = 0, triEnd = 0;
+                bool have = false;
+                while (node < p.n_nodes) {
+                    const float4 lo = __ldg(p.nodes + 2 * node);
+                    const float4 hi = __ldg(p.nodes + 2 * node + 1);
+                    const bool ov = node_overlaps(lo, hi, qb);
+                    const int link = __float_as_int(lo.w);
+                    const int cnt = __float_as_int(hi.w);
+                    ++c_node;
+                    if (cnt < 0) {
+                        node = ov ? node + 1 : uint32_t(link);
+                    } else {
+                        if (ov) {
+                            if (TRACE) {
+                                if (t_mesh < p.trace.cap_cand) p.trace.mesh_ids[size_t(slot) * p.trace.cap_cand + t_mesh] = p.node_leaf_id[node];
+                                ++t_mesh;
+                            }
+                            triBeg = uint32_t(link); triEnd = triBeg + uint32_t(cnt);
+                            have = true;
+                        }
+                        node = node + 1;
+                        if (have) break;
+                    }
+                }
+                if (!have) break;
+                found = true;
+                for (uint32_t t = triBeg; t < triEnd; ++t) {
+                    const float4 t0 = __ldg(p.tris + 3 * size_t(t));
+                    const float4 t1 = __ldg(p.tris + 3 * size_t(t) + 1);
+                    const float4 t2 = __ldg(p.tris + 3 * size_t(t) + 2);
+                    ++c_tri;
+                    if (TRACE) ++t_tris;
+                    const uint32_t my_poly = poly++;
+                    if (__float_as_uint(t0.w) == PRT_DEGENERATE_BITS) continue;       // length(n) == 0   :53
+                    Contact ct;
+                    if (!capsule_triangle(ps, radius, p.abs_mode, v3(t0.x, t0.y, t0.z), v3(t1.x, t1.y, t1.z),
+                                          v3(t2.x, t2.y, t2.z), v3(t0.w, t1.w, t2.w), ct))
+                        continue;
+                    // handleCollision (collision_system.cpp:242-252)
+                    pos = pos + ct.impulse;
+                    ++c_contact;
+                    if (dot(ct.normal, v3(0.0f, 1.0f, 0.0f)) > p.ground_dot) {
+                        grounded = 1;
+                        gn = ct.normal;
+                    }
+                    if (TRACE) {
+                        if (t_hits < p.trace.cap_hits) {
+                            TraceHit * h = p.trace.hits + size_t(slot) * p.trace.cap_hits + t_hits;
+                            h->poly = int32_t(my_poly);
+                            h->impulse[0] = ct.impulse.x; h->impulse[1] = ct.impulse.y; h->impulse[2] = ct.impulse.z;
+                            h->normal[0] = ct.normal.x; h->normal[1] = ct.normal.y; h->normal[2] = ct.normal.z;
+                            h->pos[0] = pos.x; h->pos[1] = pos.y; h->pos[2] = pos.z;
+                        }
+                        ++t_hits;
+                    }
+                    if (ct.impulse.x != 0.0f || ct.impulse.y != 0.0f || ct.impulse.z != 0.0f)
+                        ps = make_pose(fr, pos);                  // tform is rebuilt per triangle     :40
+                }
+            }
+            if (TRACE) {
+                tq->executed = 1; tq->n_mesh = t_mesh; tq->n_caps = 0; tq->n_hits = t_hits; tq->tri_tests = t_tris;
+            }
+            if (!found) break;                                    // `if (meshColIDs.empty()) break;`  :391-393
+        }
+        pos = pos + (float(stepsLeft) * vel) / fsub;              //                                   :437
+
+        // ---- phase 3 (physics_system.cpp:298-317) ----
+        vel = prevVel;
+        const float frictionRatio = fdiv(1.0f, 1.0f + (p.dt * p.friction));
+        vel.x = vel.x * frictionRatio;
+        vel.z = vel.z * frictionRatio;
+        if (grounded) vel.y = gmax((0.0f * p.gravity) * p.dt, vel.y);
+        else vel.y = vel.y + ((-1.0f * p.gravity) * p.dt);
+
+        tf->position[0] = pos.x; tf->position[1] = pos.y; tf->position[2] = pos.z;
+        ph->velocity[0] = vel.x; ph->velocity[1] = vel.y; ph->velocity[2] = vel.z;
+        ph->ground_normal[0] = gn.x; ph->ground_normal[1] = gn.y; ph->ground_normal[2] = gn.z;
+        ph->grounded = grounded;
+    }
+
+    // work counters: one atomic per warp per counter
+    c_sub = __reduce_add_sync(0xffffffffu, c_sub);
+    c_tri = __reduce_add_sync(0xffffffffu, c_tri);
+    c_node = __reduce_add_sync(0xffffffffu, c_node);
+    c_contact = __reduce_add_sync(0xffffffffu, c_contact);
+    if ((threadIdx.x & 31u) == 0 && p.counters) {
+        atomicAdd(p.counters + 0, (unsigned long long)c_sub);
+        atomicAdd(p.counters + 1, (unsigned long long)c_tri);
+        atomicAdd(p.counters + 2, (unsigned long long)c_node);
+        atomicAdd(p.counters + 3, (unsigned long long)c_contact);
+    }
+}
+
+// One thread per mesh collider: sequential left fold, exactly `min = glm::min(min, cache[i])`
+// (physics_system.cpp:80-91), so NaN vertices behave as in the reference.
+__global__ void k_transform_refit(const float * __restrict__ raw, float * __restrict__ world,
+                                  const MeshDev * __restrict__ meshes, uint32_t first_mesh, uint32_t n_meshes,
+                                  const ModelXform * __restrict__ xforms, float * __restrict__ aabbs) {
+    uint32_t m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= n_meshes) return;
+    m += first_mesh;
+    const MeshDev md = meshes[m];
+    const Affine xf = xforms[md.model].m;
+    V3 mn = v3(3.402823466e+38f);
+    V3 mx = v3(-3.402823466e+38f);
+    for (uint32_t k = 0; k < md.n_vertices; ++k) {
+        size_t o = 3 * size_t(md.first_vertex + k);
+        V3 w = affine_point(xf, v3(raw[o], raw[o + 1], raw[o + 2]));
+        world[o] = w.x; world[o + 1] = w.y; world[o + 2] = w.z;
+        mn = gmin(mn, w);
+        mx = gmax(mx, w);
+    }
+    float * a = aabbs + 6 * size_t(m);
+    a[0] = mn.x; a[1] = mn.y; a[2] = mn.z; a[3] = mx.x; a[4] = mx.y; a[5] = mx.z;
+}
+
+__global__ void k_tri_setup(const float * __restrict__ world, const uint32_t * __restrict__ tri_src_vertex,
+                            uint32_t n_tris, float4 * __restrict__ tris) {
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_tris) return;
+    size_t o = 3 * size_t(tri_src_vertex[t]);
+    V3 a = v3(world[o], world[o + 1], world[o + 2]);
+    V3 b = v3(world[o + 3], world[o + 4], world[o + 5]);
+    V3 c = v3(world[o + 6], world[o + 7], world[o + 8]);
+    V3 n = v3(0.0f);
+    bool ok = triangle_normal(a, b, c, n);
+    if (!ok) n = v3(__uint_as_float(PRT_DEGENERATE_BITS), 0.0f, 0.0f);
+    tris[3 * size_t(t)] = make_float4(a.x, a.y, a.z, n.x);
+    tris[3 * size_t(t) + 1] = make_float4(b.x, b.y, b.z, n.y);
+    tris[3 * size_t(t) + 2] = make_float4(c.x, c.y, c.z, n.z);
+}
+
+__global__ void k_query_box(const float4 * __restrict__ nodes, uint32_t n_nodes, const uint32_t * __restrict__ node_leaf_id,
+                            const float * __restrict__ aabb6, uint32_t * out_ids, uint32_t capacity, uint32_t * out_count) {
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    Box q;
+    q.lo = v3(aabb6[0], aabb6[1], aabb6[2]);
+    q.hi = v3(aabb6[3], aabb6[4], aabb6[5]);
+    uint32_t node = 0, found = 0;
+    while (node < n_nodes) {
+        const float4 lo = nodes[2 * node];
+        const float4 hi = nodes[2 * node + 1];
+        const bool ov = node_overlaps(lo, hi, q);
+        const int cnt = __float_as_int(hi.w);
+        if (cnt < 0) {
+            node = ov ? node + 1 : uint32_t(__float_as_int(lo.w));
+        } else {
+            if (ov) {
+                if (found < capacity) out_ids[found] = node_leaf_id[node];
+                ++found;
+            }
+            ++node;
+        }
+    }
+    *out_count = found;
+}
+
+} // namespace
+
+void launch_step(StepParams const & p, bool traced, cudaStream_t stream) {
+    if (p.n == 0) return;
+    const uint32_t block = 128;
+    const uint32_t grid = (p.n + block - 1) / block;
+    if (traced) k_step<true><<<grid, block, 0, stream>>>(p);
+    else k_step<false><<<grid, block, 0, stream>>>(p);
+}
+
+void launch_transform_refit(const float * raw_xyz, float * world_xyz, const MeshDev * meshes, uint32_t first_mesh,
+                            uint32_t n_meshes, const ModelXform * xforms, float * mesh_aabbs, cudaStream_t stream) {
+    if (n_meshes == 0) return;
+    const uint32_t block = 128;
+    k_transform_refit<<<(n_meshes + block - 1) / block, block, 0, stream>>>(raw_xyz, world_xyz, meshes, first_mesh,
+                                                                           n_meshes, xforms, mesh_aabbs);
+}
+
+void launch_tri_setup(const float * world_xyz, const uint32_t * tri_src_vertex, uint32_t n_tris, float4 * tris,
+                      cudaStream_t stream) {
+    if (n_tris == 0) return;
+    const uint32_t block = 256;
+    k_tri_setup<<<(n_tris + block - 1) / block, block, 0, stream>>>(world_xyz, tri_src_vertex, n_tris, tris);
+}
+
+void launch_query_box(const float4 * nodes, uint32_t n_nodes, const uint32_t * node_leaf_id, const float * aabb6,
+                      uint32_t * out_ids, uint32_t capacity, uint32_t * out_count, cudaStream_t stream) {
+    k_query_box<<<1, 32, 0, stream>>>(nodes, n_nodes, node_leaf_id, aabb6, out_ids, capacity, out_count);
+}
+
+} // namespace prt

@@ -1,0 +1,78 @@
+// kernels.cuh -- launch parameter blocks shared by kernels.cu (device) and prtc.cu (host side of the C-ABI).
+#ifndef PRT_KERNELS_CUH
+#define PRT_KERNELS_CUH
+
+#include <cuda_runtime.h>
+#include <cstdint>
+
+#include "../../include/prtc.h"
+#include "collide.cuh"
+
+namespace prt {
+
+// per-(character, substep) trace slot written by the traced kernel variant
+struct TraceQuery {
+    float aabb[6];
+    uint32_t executed;      // 1 when the substep ran
+    uint32_t n_mesh;        // candidate mesh colliders found (may exceed the slot capacity)
+    uint32_t n_caps;
+    uint32_t n_hits;
+    uint32_t tri_tests;
+    uint32_t pad;
+};
+struct TraceHit {
+    int32_t poly;
+    float impulse[3];
+    float normal[3];
+    float pos[3];
+};
+
+struct TraceBuffers {
+    TraceQuery * queries;   // [n * substeps]
+    uint32_t * mesh_ids;    // [n * substeps * cap_cand]
+    uint32_t * caps_ids;    // [n * substeps * cap_cand]
+    TraceHit * hits;        // [n * substeps * cap_hits]
+    uint32_t cap_cand, cap_hits;
+};
+
+struct StepParams {
+    // static geometry (replicated on every GPU)
+    const float4 * nodes;           // 2 float4 per node, right-first preorder (bvh_builder.h FlatNode)
+    uint32_t n_nodes;
+    const float4 * tris;            // 3 float4 per triangle, leaf order: (a, n.x) (b, n.y) (c, n.z)
+    const uint32_t * node_leaf_id;  // mesh-collider id per node (trace only)
+    const CapsuleDev * capsules;
+    uint32_t n_capsules;
+    // characters (in/out)
+    prtc_transform * transforms;
+    prtc_char_physics * physics;
+    uint32_t n;
+    // dynamic pass (CANONICAL / JACOBI): start-of-frame capsule segments and stored fat boxes of ALL capsules
+    const float4 * dyn_boxes;       // 2 float4 per capsule: stored fat AABB lo/hi
+    const float4 * dyn_segs;        // 2 float4 per capsule: (A.xyz, radius) (B.xyz, unused) at the snapshot pose
+    uint32_t dyn_count;             // 0 => pass disabled
+    uint32_t dyn_self_base;         // global index of this launch's character 0 within the dyn arrays
+    // constants (prtc_config)
+    float dt, gravity, ground_dot, friction, stick;
+    uint32_t substeps, abs_mode;
+    unsigned long long * counters;  // prtc_counters layout
+    TraceBuffers trace;
+};
+
+void launch_step(StepParams const & p, bool traced, cudaStream_t stream);
+
+// K8: world-space vertex cache + per-mesh AABB (physics_system.cpp:68-93 / :161-202)
+struct MeshDev { uint32_t first_vertex, n_vertices, model; uint32_t pad; };
+struct ModelXform { Affine m; };
+void launch_transform_refit(const float * raw_xyz, float * world_xyz, const MeshDev * meshes, uint32_t first_mesh,
+                            uint32_t n_meshes, const ModelXform * xforms, float * mesh_aabbs /*6 per mesh*/,
+                            cudaStream_t stream);
+// leaf-ordered triangle records with precomputed unit normals
+void launch_tri_setup(const float * world_xyz, const uint32_t * tri_src_vertex, uint32_t n_tris, float4 * tris,
+                      cudaStream_t stream);
+// single box query (introspection / tests)
+void launch_query_box(const float4 * nodes, uint32_t n_nodes, const uint32_t * node_leaf_id, const float * aabb6,
+                      uint32_t * out_ids, uint32_t capacity, uint32_t * out_count, cudaStream_t stream);
+
+} // namespace prt
+#endif

@@ -1,0 +1,589 @@
+// prtc.cu -- host side of the C-ABI declared in include/prtc.h: collider registry, commit (vertex transform on
+// the device, reference-algorithm tree build on the host, flatten, upload) and the per-frame step launches.
+// There is no CPU implementation of the compute path in this library: without a compute-capability-10 device
+// prtc_create fails and nothing else can be called.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/prtc.h"
+#include "bvh_builder.h"
+#include "kernels.cuh"
+
+using namespace prt;
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(int code, const std::string & msg) {
+    g_last_error = msg;
+    return code;
+}
+
+#define PRTC_CUDA(expr)                                                                                   \
+    do {                                                                                                  \
+        cudaError_t _e = (expr);                                                                          \
+        if (_e != cudaSuccess)                                                                            \
+            return fail(PRTC_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));               \
+    } while (0)
+
+template <class T>
+struct DevBuf {
+    T * ptr = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t n) {
+        if (n <= cap) return cudaSuccess;
+        if (ptr) cudaFree(ptr);
+        ptr = nullptr; cap = 0;
+        size_t want = std::max<size_t>(n, 16);
+        cudaError_t e = cudaMalloc(reinterpret_cast<void **>(&ptr), want * sizeof(T));
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (ptr) cudaFree(ptr); ptr = nullptr; cap = 0; }
+};
+
+struct MeshHost { uint32_t first_vertex, n_vertices, model; int32_t tree_index; };
+struct ModelHost { uint32_t first_mesh, n_meshes; prtc_transform transform; };
+
+Affine affine_from(prtc_transform const & t) {
+    Quat q; q.x = t.rotation[0]; q.y = t.rotation[1]; q.z = t.rotation[2]; q.w = t.rotation[3];
+    return affine_of(v3(t.position[0], t.position[1], t.position[2]), q, v3(t.scale[0], t.scale[1], t.scale[2]));
+}
+
+} // namespace
+
+struct prtc_ctx {
+    prtc_config cfg;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+
+    // host registry
+    std::vector<float> raw;                 // model-space xyz of every registered model, back to back
+    std::vector<MeshHost> meshes;
+    std::vector<ModelHost> models;
+    std::vector<CapsuleDev> capsules;
+    RefTree tree;
+    FlatTree flat;
+    std::vector<uint32_t> tri_src;          // per leaf-ordered triangle: index of its first vertex in `raw`/`world`
+    uint32_t meshes_in_tree = 0;
+    bool geometry_dirty = false;            // raw / meshes / xforms changed since the last upload
+    bool tree_dirty = false;                // tree changed since the last flatten
+    bool capsules_dirty = false;
+    std::vector<uint32_t> moved_models;     // models whose transform changed (prtc_update_models)
+
+    // device
+    DevBuf<float> d_raw, d_world, d_aabbs;
+    DevBuf<MeshDev> d_meshes;
+    DevBuf<ModelXform> d_xforms;
+    DevBuf<float4> d_nodes, d_tris;
+    DevBuf<uint32_t> d_node_leaf_id, d_tri_src;
+    DevBuf<CapsuleDev> d_capsules;
+    DevBuf<unsigned long long> d_counters;
+    DevBuf<prtc_transform> d_tf;
+    DevBuf<prtc_char_physics> d_ph;
+    // trace scratch
+    DevBuf<TraceQuery> d_tq;
+    DevBuf<uint32_t> d_tmesh, d_tcaps;
+    DevBuf<TraceHit> d_thits;
+    DevBuf<float> d_scratch_f;
+    DevBuf<uint32_t> d_scratch_u;
+};
+
+namespace {
+
+int commit_impl(prtc_ctx * c) {
+    cudaStream_t s = c->stream;
+    const uint32_t n_meshes = uint32_t(c->meshes.size());
+    const uint32_t n_vertices = uint32_t(c->raw.size() / 3);
+
+    if (c->capsules_dirty) {
+        PRTC_CUDA(c->d_capsules.reserve(c->capsules.size()));
+        if (!c->capsules.empty())
+            PRTC_CUDA(cudaMemcpyAsync(c->d_capsules.ptr, c->capsules.data(), c->capsules.size() * sizeof(CapsuleDev),
+                                      cudaMemcpyHostToDevice, s));
+        c->capsules_dirty = false;
+    }
+
+    if (c->geometry_dirty) {
+        // (re)upload the registry.  The world cache and AABBs of meshes that are already in the tree stay valid
+        // unless a device buffer has to grow, in which case everything is re-derived (simple and rare).
+        PRTC_CUDA(c->d_raw.reserve(c->raw.size()));
+        bool world_realloc = c->d_world.cap < c->raw.size() || c->d_aabbs.cap < size_t(n_meshes) * 6;
+        PRTC_CUDA(c->d_world.reserve(c->raw.size()));
+        PRTC_CUDA(c->d_aabbs.reserve(size_t(n_meshes) * 6));
+        PRTC_CUDA(c->d_meshes.reserve(n_meshes));
+        PRTC_CUDA(c->d_xforms.reserve(c->models.size()));
+        if (n_vertices) PRTC_CUDA(cudaMemcpyAsync(c->d_raw.ptr, c->raw.data(), c->raw.size() * sizeof(float), cudaMemcpyHostToDevice, s));
+        std::vector<MeshDev> md(n_meshes);
+        for (uint32_t m = 0; m < n_meshes; ++m) md[m] = MeshDev{c->meshes[m].first_vertex, c->meshes[m].n_vertices, c->meshes[m].model, 0u};
+        std::vector<ModelXform> xf(c->models.size());
+        for (size_t m = 0; m < c->models.size(); ++m) xf[m].m = affine_from(c->models[m].transform);
+        if (n_meshes) PRTC_CUDA(cudaMemcpyAsync(c->d_meshes.ptr, md.data(), md.size() * sizeof(MeshDev), cudaMemcpyHostToDevice, s));
+        if (!xf.empty()) PRTC_CUDA(cudaMemcpyAsync(c->d_xforms.ptr, xf.data(), xf.size() * sizeof(ModelXform), cudaMemcpyHostToDevice, s));
+        PRTC_CUDA(cudaStreamSynchronize(s));     // md / xf are stack-owned
+
+        // K8 over every mesh that is new, moved, or whose cache was lost to a reallocation
+        std::vector<float> aabbs(size_t(n_meshes) * 6);
+        uint32_t first_new = world_realloc ? 0u : c->meshes_in_tree;
+        if (n_meshes > first_new) {
+            launch_transform_refit(c->d_raw.ptr, c->d_world.ptr, c->d_meshes.ptr, first_new, n_meshes - first_new,
+                                   c->d_xforms.ptr, c->d_aabbs.ptr, s);
+        }
+        for (uint32_t model : c->moved_models) {
+            ModelHost const & mh = c->models[model];
+            if (mh.first_mesh >= first_new) continue;     // already covered
+            launch_transform_refit(c->d_raw.ptr, c->d_world.ptr, c->d_meshes.ptr, mh.first_mesh,
+                                   std::min(mh.n_meshes, first_new - mh.first_mesh), c->d_xforms.ptr, c->d_aabbs.ptr, s);
+        }
+        PRTC_CUDA(cudaGetLastError());
+        if (n_meshes) PRTC_CUDA(cudaMemcpyAsync(aabbs.data(), c->d_aabbs.ptr, aabbs.size() * sizeof(float), cudaMemcpyDeviceToHost, s));
+        PRTC_CUDA(cudaStreamSynchronize(s));
+
+        auto box_of = [&](uint32_t m) {
+            Box b;
+            b.lo = v3(aabbs[6 * size_t(m)], aabbs[6 * size_t(m) + 1], aabbs[6 * size_t(m) + 2]);
+            b.hi = v3(aabbs[6 * size_t(m) + 3], aabbs[6 * size_t(m) + 4], aabbs[6 * size_t(m) + 5]);
+            return b;
+        };
+        // moved models first (they were registered earlier): DynamicAABBTree::update per model, physics_system.cpp:199-200
+        for (uint32_t model : c->moved_models) {
+            ModelHost const & mh = c->models[model];
+            for (uint32_t m = mh.first_mesh; m < mh.first_mesh + mh.n_meshes && m < c->meshes_in_tree; ++m) {
+                Box b = box_of(m);
+                c->tree.update(&c->meshes[m].tree_index, &b, 1);
+            }
+        }
+        c->moved_models.clear();
+        // new meshes: DynamicAABBTree::insert in registration order, physics_system.cpp:102
+        for (uint32_t m = c->meshes_in_tree; m < n_meshes; ++m)
+            c->meshes[m].tree_index = c->tree.insert_leaf(m, LEAF_MESH, box_of(m));
+        c->meshes_in_tree = n_meshes;
+        c->geometry_dirty = false;
+        c->tree_dirty = true;
+    }
+
+    if (c->tree_dirty) {
+        c->tri_src.clear();
+        c->tri_src.reserve(n_vertices / 3);
+        c->tree.flatten(c->flat, [&](uint32_t mesh_id, uint32_t & first, uint32_t & count) {
+            MeshHost const & mh = c->meshes[mesh_id];
+            first = uint32_t(c->tri_src.size());
+            count = mh.n_vertices / 3;
+            for (uint32_t k = 0; k < count; ++k) c->tri_src.push_back(mh.first_vertex + 3 * k);
+        });
+        const size_t nn = c->flat.nodes.size();
+        const size_t nt = c->tri_src.size();
+        PRTC_CUDA(c->d_nodes.reserve(nn * 2));
+        PRTC_CUDA(c->d_node_leaf_id.reserve(nn));
+        PRTC_CUDA(c->d_tri_src.reserve(nt));
+        PRTC_CUDA(c->d_tris.reserve(nt * 3));
+        static_assert(sizeof(FlatNode) == 32, "FlatNode must be two float4");
+        if (nn) {
+            PRTC_CUDA(cudaMemcpyAsync(c->d_nodes.ptr, c->flat.nodes.data(), nn * sizeof(FlatNode), cudaMemcpyHostToDevice, s));
+            PRTC_CUDA(cudaMemcpyAsync(c->d_node_leaf_id.ptr, c->flat.node_leaf_id.data(), nn * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+        }
+        if (nt) {
+            PRTC_CUDA(cudaMemcpyAsync(c->d_tri_src.ptr, c->tri_src.data(), nt * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+            launch_tri_setup(c->d_world.ptr, c->d_tri_src.ptr, uint32_t(nt), c->d_tris.ptr, s);
+            PRTC_CUDA(cudaGetLastError());
+        }
+        PRTC_CUDA(cudaStreamSynchronize(s));
+        c->tree_dirty = false;
+    }
+    return PRTC_OK;
+}
+
+int fill_params(prtc_ctx * c, float dt, uint32_t n, prtc_transform * d_tf, prtc_char_physics * d_ph, StepParams & p) {
+    std::memset(&p, 0, sizeof(p));
+    p.nodes = c->d_nodes.ptr;
+    p.n_nodes = uint32_t(c->flat.nodes.size());
+    p.tris = c->d_tris.ptr;
+    p.node_leaf_id = c->d_node_leaf_id.ptr;
+    p.capsules = c->d_capsules.ptr;
+    p.n_capsules = uint32_t(c->capsules.size());
+    p.transforms = d_tf;
+    p.physics = d_ph;
+    p.n = n;
+    p.dt = dt;
+    p.gravity = c->cfg.gravity;
+    p.ground_dot = c->cfg.ground_dot;
+    p.friction = c->cfg.friction;
+    p.stick = c->cfg.stick;
+    p.substeps = c->cfg.substeps;
+    p.abs_mode = c->cfg.abs_mode;
+    p.counters = c->d_counters.ptr;
+    return PRTC_OK;
+}
+
+int check_mode(prtc_ctx * c) {
+    if (c->cfg.order_mode != PRTC_ORDER_CANONICAL)
+        return fail(PRTC_ERR_INVALID, "order_mode PRTC_ORDER_LITERAL is not available in this build; use PRTC_ORDER_CANONICAL");
+    if (c->cfg.dyn_mode != PRTC_DYN_OFF)
+        return fail(PRTC_ERR_INVALID, "dyn_mode PRTC_DYN_JACOBI is not available in this build; use PRTC_DYN_OFF");
+    return PRTC_OK;
+}
+
+} // namespace
+
+extern "C" {
+
+void prtc_default_config(prtc_config * cfg) {
+    if (!cfg) return;
+    cfg->gravity = 1.0f;
+    cfg->leaf_margin = 0.05f;
+    cfg->ground_dot = 0.3f;
+    cfg->friction = 10.0f;
+    cfg->stick = 0.05f;
+    cfg->substeps = 4;
+    cfg->abs_mode = PRTC_ABS_INT;
+    cfg->order_mode = PRTC_ORDER_CANONICAL;
+    cfg->dyn_mode = PRTC_DYN_OFF;
+    cfg->device = 0;
+}
+
+const char * prtc_last_error(void) { return g_last_error.c_str(); }
+
+int prtc_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    int ok = 0;
+    for (int d = 0; d < n; ++d) {
+        cudaDeviceProp prop;
+        if (cudaGetDeviceProperties(&prop, d) == cudaSuccess && prop.major == 10) ++ok;
+    }
+    return ok;
+}
+
+int prtc_create(const prtc_config * cfg, prtc_ctx ** out) {
+    if (!out) return fail(PRTC_ERR_INVALID, "prtc_create: out is null");
+    *out = nullptr;
+    prtc_config c;
+    if (cfg) c = *cfg; else prtc_default_config(&c);
+    if (c.substeps == 0) return fail(PRTC_ERR_INVALID, "prtc_create: substeps must be > 0");
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        return fail(PRTC_ERR_CUDA, std::string("prtc_create: no CUDA device (") + (e != cudaSuccess ? cudaGetErrorString(e) : "count 0") +
+                                   "); this library has no CPU path");
+    }
+    if (c.device < 0 || c.device >= n) return fail(PRTC_ERR_INVALID, "prtc_create: device ordinal out of range");
+    cudaDeviceProp prop;
+    PRTC_CUDA(cudaGetDeviceProperties(&prop, c.device));
+    if (prop.major != 10)
+        return fail(PRTC_ERR_CUDA, std::string("prtc_create: device '") + prop.name + "' is not compute capability 10.x; kernels are built for sm_100a only");
+    PRTC_CUDA(cudaSetDevice(c.device));
+    prtc_ctx * ctx = new (std::nothrow) prtc_ctx();
+    if (!ctx) return fail(PRTC_ERR_ALLOC, "prtc_create: out of host memory");
+    ctx->cfg = c;
+    ctx->tree.set_margin(c.leaf_margin);
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        delete ctx;
+        return fail(PRTC_ERR_CUDA, "prtc_create: cudaStreamCreate failed");
+    }
+    ctx->own_stream = true;
+    if (ctx->d_counters.reserve(8) != cudaSuccess || cudaMemsetAsync(ctx->d_counters.ptr, 0, 8 * sizeof(unsigned long long), ctx->stream) != cudaSuccess) {
+        prtc_destroy(ctx);
+        return fail(PRTC_ERR_CUDA, "prtc_create: counter allocation failed");
+    }
+    *out = ctx;
+    return PRTC_OK;
+}
+
+void prtc_destroy(prtc_ctx * c) {
+    if (!c) return;
+    cudaSetDevice(c->cfg.device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    c->d_raw.release(); c->d_world.release(); c->d_aabbs.release(); c->d_meshes.release(); c->d_xforms.release();
+    c->d_nodes.release(); c->d_tris.release(); c->d_node_leaf_id.release(); c->d_tri_src.release();
+    c->d_capsules.release(); c->d_counters.release(); c->d_tf.release(); c->d_ph.release();
+    c->d_tq.release(); c->d_tmesh.release(); c->d_tcaps.release(); c->d_thits.release();
+    c->d_scratch_f.release(); c->d_scratch_u.release();
+    if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+int prtc_add_model(prtc_ctx * c, const float * xyz, uint32_t n_vertices, const uint32_t * mesh_first,
+                   const uint32_t * mesh_count, uint32_t n_meshes, const prtc_transform * transform,
+                   uint32_t * out_model_id, uint32_t * out_first_mesh_id) {
+    if (!c || (!xyz && n_vertices) || (n_meshes && (!mesh_first || !mesh_count)) || !transform)
+        return fail(PRTC_ERR_INVALID, "prtc_add_model: null argument");
+    for (uint32_t m = 0; m < n_meshes; ++m) {
+        if (mesh_count[m] % 3 != 0 || uint64_t(mesh_first[m]) + mesh_count[m] > n_vertices)
+            return fail(PRTC_ERR_INVALID, "prtc_add_model: mesh range must be a multiple of 3 vertices inside the model");
+    }
+    // physics_system.cpp:66-91: vertices are copied mesh by mesh in mesh order (geometry.raw[i], i running)
+    uint32_t model_id = uint32_t(c->models.size());
+    ModelHost mh;
+    mh.first_mesh = uint32_t(c->meshes.size());
+    mh.n_meshes = n_meshes;
+    mh.transform = *transform;
+    for (uint32_t m = 0; m < n_meshes; ++m) {
+        MeshHost me;
+        me.first_vertex = uint32_t(c->raw.size() / 3);
+        me.n_vertices = mesh_count[m];
+        me.model = model_id;
+        me.tree_index = -1;
+        c->raw.insert(c->raw.end(), xyz + 3 * size_t(mesh_first[m]), xyz + 3 * (size_t(mesh_first[m]) + mesh_count[m]));
+        c->meshes.push_back(me);
+    }
+    c->models.push_back(mh);
+    c->geometry_dirty = true;
+    if (out_model_id) *out_model_id = model_id;
+    if (out_first_mesh_id) *out_first_mesh_id = mh.first_mesh;
+    return PRTC_OK;
+}
+
+int prtc_add_capsule(prtc_ctx * c, float height, float radius, const float offset[3], uint32_t * out_id) {
+    if (!c || !offset) return fail(PRTC_ERR_INVALID, "prtc_add_capsule: null argument");
+    CapsuleDev d;
+    d.height = height; d.radius = radius; d.ox = offset[0]; d.oy = offset[1]; d.oz = offset[2];
+    d.pad0 = d.pad1 = d.pad2 = 0.0f;
+    if (out_id) *out_id = uint32_t(c->capsules.size());
+    c->capsules.push_back(d);
+    c->capsules_dirty = true;
+    return PRTC_OK;
+}
+
+int prtc_update_capsule(prtc_ctx * c, uint32_t id, float height, float radius, const float offset[3]) {
+    if (!c || !offset || id >= c->capsules.size()) return fail(PRTC_ERR_INVALID, "prtc_update_capsule: bad capsule id");
+    CapsuleDev & d = c->capsules[id];
+    d.height = height; d.radius = radius; d.ox = offset[0]; d.oy = offset[1]; d.oz = offset[2];
+    c->capsules_dirty = true;
+    return PRTC_OK;
+}
+
+int prtc_commit(prtc_ctx * c) {
+    if (!c) return fail(PRTC_ERR_INVALID, "prtc_commit: null context");
+    PRTC_CUDA(cudaSetDevice(c->cfg.device));
+    return commit_impl(c);
+}
+
+int prtc_update_models(prtc_ctx * c, const uint32_t * model_ids, const prtc_transform * transforms, uint32_t n) {
+    if (!c || (n && (!model_ids || !transforms))) return fail(PRTC_ERR_INVALID, "prtc_update_models: null argument");
+    for (uint32_t i = 0; i < n; ++i) {
+        if (model_ids[i] >= c->models.size()) return fail(PRTC_ERR_INVALID, "prtc_update_models: bad model id");
+        c->models[model_ids[i]].transform = transforms[i];
+        c->moved_models.push_back(model_ids[i]);
+    }
+    if (n) c->geometry_dirty = true;
+    return PRTC_OK;
+}
+
+int prtc_set_stream(prtc_ctx * c, void * cuda_stream) {
+    if (!c) return fail(PRTC_ERR_INVALID, "prtc_set_stream: null context");
+    if (c->own_stream && c->stream) { cudaStreamSynchronize(c->stream); cudaStreamDestroy(c->stream); }
+    c->stream = static_cast<cudaStream_t>(cuda_stream);
+    c->own_stream = false;
+    return PRTC_OK;
+}
+
+int prtc_synchronize(prtc_ctx * c) {
+    if (!c) return fail(PRTC_ERR_INVALID, "prtc_synchronize: null context");
+    PRTC_CUDA(cudaStreamSynchronize(c->stream));
+    return PRTC_OK;
+}
+
+int prtc_step_characters_device(prtc_ctx * c, float dt, uint32_t n, prtc_transform * d_tf, prtc_char_physics * d_ph) {
+    if (!c || (n && (!d_tf || !d_ph))) return fail(PRTC_ERR_INVALID, "prtc_step_characters_device: null argument");
+    int rc = check_mode(c);
+    if (rc) return rc;
+    PRTC_CUDA(cudaSetDevice(c->cfg.device));
+    if (c->geometry_dirty || c->tree_dirty || c->capsules_dirty) { rc = commit_impl(c); if (rc) return rc; }
+    if (c->capsules.empty() && n) return fail(PRTC_ERR_INVALID, "prtc_step_characters: no capsule collider registered");
+    StepParams p;
+    fill_params(c, dt, n, d_tf, d_ph, p);
+    launch_step(p, false, c->stream);
+    PRTC_CUDA(cudaGetLastError());
+    return PRTC_OK;
+}
+
+int prtc_step_characters(prtc_ctx * c, float dt, uint32_t n, prtc_transform * tf, prtc_char_physics * ph) {
+    if (!c || (n && (!tf || !ph))) return fail(PRTC_ERR_INVALID, "prtc_step_characters: null argument");
+    PRTC_CUDA(cudaSetDevice(c->cfg.device));
+    PRTC_CUDA(c->d_tf.reserve(n));
+    PRTC_CUDA(c->d_ph.reserve(n));
+    if (n) {
+        PRTC_CUDA(cudaMemcpyAsync(c->d_tf.ptr, tf, size_t(n) * sizeof(prtc_transform), cudaMemcpyHostToDevice, c->stream));
+        PRTC_CUDA(cudaMemcpyAsync(c->d_ph.ptr, ph, size_t(n) * sizeof(prtc_char_physics), cudaMemcpyHostToDevice, c->stream));
+    }
+    int rc = prtc_step_characters_device(c, dt, n, c->d_tf.ptr, c->d_ph.ptr);
+    if (rc) return rc;
+    if (n) {
+        PRTC_CUDA(cudaMemcpyAsync(tf, c->d_tf.ptr, size_t(n) * sizeof(prtc_transform), cudaMemcpyDeviceToHost, c->stream));
+        PRTC_CUDA(cudaMemcpyAsync(ph, c->d_ph.ptr, size_t(n) * sizeof(prtc_char_physics), cudaMemcpyDeviceToHost, c->stream));
+    }
+    PRTC_CUDA(cudaStreamSynchronize(c->stream));
+    return PRTC_OK;
+}
+
+int prtc_step_characters_traced(prtc_ctx * c, float dt, uint32_t n, prtc_transform * tf, prtc_char_physics * ph, prtc_trace * tr) {
+    if (!c || !tr || (n && (!tf || !ph))) return fail(PRTC_ERR_INVALID, "prtc_step_characters_traced: null argument");
+    int rc = check_mode(c);
+    if (rc) return rc;
+    PRTC_CUDA(cudaSetDevice(c->cfg.device));
+    if (c->geometry_dirty || c->tree_dirty || c->capsules_dirty) { rc = commit_impl(c); if (rc) return rc; }
+    if (c->capsules.empty() && n) return fail(PRTC_ERR_INVALID, "prtc_step_characters: no capsule collider registered");
+    const uint32_t nsub = c->cfg.substeps;
+    const size_t slots = size_t(n) * nsub;
+    const uint32_t cap_cand = 64, cap_hits = 96;
+    cudaStream_t s = c->stream;
+    PRTC_CUDA(c->d_tf.reserve(n));
+    PRTC_CUDA(c->d_ph.reserve(n));
+    PRTC_CUDA(c->d_tq.reserve(slots));
+    PRTC_CUDA(c->d_tmesh.reserve(slots * cap_cand));
+    PRTC_CUDA(c->d_tcaps.reserve(slots * cap_cand));
+    PRTC_CUDA(c->d_thits.reserve(slots * cap_hits));
+    tr->n_queries = tr->n_mesh_ids = tr->n_caps_ids = tr->n_hits = 0;
+    if (n == 0) { if (tr->q_mesh_off && tr->cap_queries + 1 > 0) tr->q_mesh_off[0] = 0; if (tr->q_caps_off) tr->q_caps_off[0] = 0; return PRTC_OK; }
+    PRTC_CUDA(cudaMemsetAsync(c->d_tq.ptr, 0, slots * sizeof(TraceQuery), s));
+    PRTC_CUDA(cudaMemcpyAsync(c->d_tf.ptr, tf, size_t(n) * sizeof(prtc_transform), cudaMemcpyHostToDevice, s));
+    PRTC_CUDA(cudaMemcpyAsync(c->d_ph.ptr, ph, size_t(n) * sizeof(prtc_char_physics), cudaMemcpyHostToDevice, s));
+    StepParams p;
+    fill_params(c, dt, n, c->d_tf.ptr, c->d_ph.ptr, p);
+    p.trace.queries = c->d_tq.ptr; p.trace.mesh_ids = c->d_tmesh.ptr; p.trace.caps_ids = c->d_tcaps.ptr; p.trace.hits = c->d_thits.ptr;
+    p.trace.cap_cand = cap_cand; p.trace.cap_hits = cap_hits;
+    launch_step(p, true, s);
+    PRTC_CUDA(cudaGetLastError());
+    std::vector<TraceQuery> tq(slots);
+    std::vector<uint32_t> tmesh(slots * cap_cand);
+    std::vector<TraceHit> thits(slots * cap_hits);
+    PRTC_CUDA(cudaMemcpyAsync(tf, c->d_tf.ptr, size_t(n) * sizeof(prtc_transform), cudaMemcpyDeviceToHost, s));
+    PRTC_CUDA(cudaMemcpyAsync(ph, c->d_ph.ptr, size_t(n) * sizeof(prtc_char_physics), cudaMemcpyDeviceToHost, s));
+    PRTC_CUDA(cudaMemcpyAsync(tq.data(), c->d_tq.ptr, slots * sizeof(TraceQuery), cudaMemcpyDeviceToHost, s));
+    PRTC_CUDA(cudaMemcpyAsync(tmesh.data(), c->d_tmesh.ptr, tmesh.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    PRTC_CUDA(cudaMemcpyAsync(thits.data(), c->d_thits.ptr, thits.size() * sizeof(TraceHit), cudaMemcpyDeviceToHost, s));
+    PRTC_CUDA(cudaStreamSynchronize(s));
+
+    uint32_t nq = 0, nm = 0, nc = 0, nh = 0;
+    bool overflow = false;
+    if (tr->q_mesh_off && tr->cap_queries) tr->q_mesh_off[0] = 0;
+    if (tr->q_caps_off && tr->cap_queries) tr->q_caps_off[0] = 0;
+    for (uint32_t i = 0; i < n; ++i) {
+        for (uint32_t sub = 0; sub < nsub; ++sub) {
+            size_t slot = size_t(i) * nsub + sub;
+            TraceQuery const & q = tq[slot];
+            if (!q.executed) continue;
+            if (q.n_mesh > cap_cand || q.n_hits > cap_hits) overflow = true;
+            if (nq >= tr->cap_queries) { overflow = true; continue; }
+            tr->q_char[nq] = i;
+            tr->q_sub[nq] = sub;
+            for (int k = 0; k < 6; ++k) tr->q_aabb[6 * size_t(nq) + k] = q.aabb[k];
+            tr->q_tri_tests[nq] = q.tri_tests;
+            for (uint32_t k = 0; k < std::min(q.n_mesh, cap_cand); ++k) {
+                if (nm < tr->cap_mesh_ids) tr->mesh_ids[nm++] = tmesh[slot * cap_cand + k]; else overflow = true;
+            }
+            for (uint32_t k = 0; k < std::min(q.n_hits, cap_hits); ++k) {
+                if (nh >= tr->cap_hits) { overflow = true; break; }
+                TraceHit const & h = thits[slot * cap_hits + k];
+                tr->h_query[nh] = nq;
+                tr->h_poly[nh] = h.poly;
+                for (int d = 0; d < 3; ++d) {
+                    tr->h_impulse[3 * size_t(nh) + d] = h.impulse[d];
+                    tr->h_normal[3 * size_t(nh) + d] = h.normal[d];
+                    tr->h_pos[3 * size_t(nh) + d] = h.pos[d];
+                }
+                ++nh;
+            }
+            ++nq;
+            tr->q_mesh_off[nq] = nm;
+            tr->q_caps_off[nq] = nc;
+        }
+    }
+    tr->n_queries = nq; tr->n_mesh_ids = nm; tr->n_caps_ids = nc; tr->n_hits = nh;
+    if (overflow) return fail(PRTC_ERR_CAPACITY, "prtc_step_characters_traced: trace capacity exceeded (state is valid, trace is truncated)");
+    return PRTC_OK;
+}
+
+int prtc_raycast(prtc_ctx * c, uint32_t, const float *, const float *, const float *, float *, uint8_t *) {
+    if (!c) return fail(PRTC_ERR_INVALID, "prtc_raycast: null context");
+    return fail(PRTC_ERR_INVALID, "prtc_raycast: not available in this build");
+}
+
+int prtc_get_counters(prtc_ctx * c, prtc_counters * out, int reset) {
+    if (!c || !out) return fail(PRTC_ERR_INVALID, "prtc_get_counters: null argument");
+    PRTC_CUDA(cudaSetDevice(c->cfg.device));
+    unsigned long long h[8];
+    PRTC_CUDA(cudaMemcpyAsync(h, c->d_counters.ptr, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+    if (reset) PRTC_CUDA(cudaMemsetAsync(c->d_counters.ptr, 0, sizeof(h), c->stream));
+    PRTC_CUDA(cudaStreamSynchronize(c->stream));
+    out->substeps = h[0]; out->tri_tests = h[1]; out->node_tests = h[2]; out->contacts = h[3]; out->cc_tests = h[4];
+    return PRTC_OK;
+}
+
+int prtc_get_tree_info(prtc_ctx * c, uint32_t * n_nodes, uint32_t * n_leaves, uint32_t * n_triangles) {
+    if (!c) return fail(PRTC_ERR_INVALID, "prtc_get_tree_info: null context");
+    if (n_nodes) *n_nodes = uint32_t(c->flat.nodes.size());
+    if (n_leaves) *n_leaves = uint32_t(c->flat.leaf_order.size());
+    if (n_triangles) *n_triangles = uint32_t(c->tri_src.size());
+    return PRTC_OK;
+}
+
+int prtc_host_build_tree(const float * aabbs6, uint32_t n, float margin, uint32_t * leaf_order, float * nodes8,
+                         uint32_t nodes_capacity, uint32_t * n_nodes) {
+    if ((n && !aabbs6) || !n_nodes) return fail(PRTC_ERR_INVALID, "prtc_host_build_tree: null argument");
+    RefTree tree(margin);
+    for (uint32_t i = 0; i < n; ++i) {
+        Box b;
+        b.lo = v3(aabbs6[6 * size_t(i)], aabbs6[6 * size_t(i) + 1], aabbs6[6 * size_t(i) + 2]);
+        b.hi = v3(aabbs6[6 * size_t(i) + 3], aabbs6[6 * size_t(i) + 4], aabbs6[6 * size_t(i) + 5]);
+        tree.insert_leaf(i, LEAF_MESH, b);
+    }
+    FlatTree flat;
+    tree.flatten(flat, [&](uint32_t id, uint32_t & first, uint32_t & count) { first = id; count = 1; });
+    *n_nodes = uint32_t(flat.nodes.size());
+    if (leaf_order) std::copy(flat.leaf_order.begin(), flat.leaf_order.end(), leaf_order);
+    if (nodes8) {
+        if (nodes_capacity < flat.nodes.size()) return fail(PRTC_ERR_CAPACITY, "prtc_host_build_tree: node buffer too small");
+        std::memcpy(nodes8, flat.nodes.data(), flat.nodes.size() * sizeof(FlatNode));
+    }
+    return PRTC_OK;
+}
+
+int prtc_get_leaf_order(prtc_ctx * c, uint32_t * leaf_mesh_ids, uint32_t capacity) {
+    if (!c || !leaf_mesh_ids) return fail(PRTC_ERR_INVALID, "prtc_get_leaf_order: null argument");
+    if (capacity < c->flat.leaf_order.size()) return fail(PRTC_ERR_CAPACITY, "prtc_get_leaf_order: buffer too small");
+    std::copy(c->flat.leaf_order.begin(), c->flat.leaf_order.end(), leaf_mesh_ids);
+    return PRTC_OK;
+}
+
+int prtc_get_world_vertices(prtc_ctx * c, float * xyz, uint32_t capacity_vertices, uint32_t * n_vertices) {
+    if (!c) return fail(PRTC_ERR_INVALID, "prtc_get_world_vertices: null context");
+    uint32_t nv = uint32_t(c->raw.size() / 3);
+    if (n_vertices) *n_vertices = nv;
+    if (!xyz) return PRTC_OK;
+    if (capacity_vertices < nv) return fail(PRTC_ERR_CAPACITY, "prtc_get_world_vertices: buffer too small");
+    PRTC_CUDA(cudaSetDevice(c->cfg.device));
+    if (nv) PRTC_CUDA(cudaMemcpyAsync(xyz, c->d_world.ptr, size_t(nv) * 3 * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    PRTC_CUDA(cudaStreamSynchronize(c->stream));
+    return PRTC_OK;
+}
+
+int prtc_query_box(prtc_ctx * c, const float aabb6[6], uint32_t * mesh_ids, uint32_t capacity, uint32_t * n_found) {
+    if (!c || !aabb6 || !n_found || (capacity && !mesh_ids)) return fail(PRTC_ERR_INVALID, "prtc_query_box: null argument");
+    PRTC_CUDA(cudaSetDevice(c->cfg.device));
+    if (c->geometry_dirty || c->tree_dirty || c->capsules_dirty) { int rc = commit_impl(c); if (rc) return rc; }
+    PRTC_CUDA(c->d_scratch_f.reserve(6));
+    PRTC_CUDA(c->d_scratch_u.reserve(size_t(capacity) + 1));
+    PRTC_CUDA(cudaMemcpyAsync(c->d_scratch_f.ptr, aabb6, 6 * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    launch_query_box(c->d_nodes.ptr, uint32_t(c->flat.nodes.size()), c->d_node_leaf_id.ptr, c->d_scratch_f.ptr,
+                     c->d_scratch_u.ptr + 1, capacity, c->d_scratch_u.ptr, c->stream);
+    PRTC_CUDA(cudaGetLastError());
+    uint32_t found = 0;
+    PRTC_CUDA(cudaMemcpyAsync(&found, c->d_scratch_u.ptr, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+    PRTC_CUDA(cudaStreamSynchronize(c->stream));
+    *n_found = found;
+    uint32_t ncopy = std::min(found, capacity);
+    if (ncopy) PRTC_CUDA(cudaMemcpy(mesh_ids, c->d_scratch_u.ptr + 1, ncopy * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    if (found > capacity) return fail(PRTC_ERR_CAPACITY, "prtc_query_box: more candidates than capacity");
+    return PRTC_OK;
+}
+
+} // extern "C"
