@@ -95,7 +95,7 @@ typedef struct prtc_counters {
     uint64_t cc_tests;     /* capsule-capsule narrowphase tests */
 } prtc_counters;
 
-/* Parity trace of one traced step (prtc_step_characters_traced); same record layout as the oracles'.
+/* Parity trace of one traced step (prtc_step_characters_traced); same record layout the CPU checkers under tests/ use.
  * Arrays are caller-allocated; capacities in, counts out.  Queries are sorted by (character, substep). */
 typedef struct prtc_trace {
     uint32_t cap_queries, cap_mesh_ids, cap_caps_ids, cap_hits;     /* in  */
@@ -183,7 +183,7 @@ int prtc_query_box(prtc_ctx * ctx, const float aabb6[6], uint32_t * mesh_ids, ui
  * tree over n boxes inserted in order (DynamicAABBTree::insert, aabb_tree.cpp:95-100) and returns it in the
  * flattened device layout: nodes8 = 8 x 32-bit words per node {lo.xyz, link, hi.xyz, count} in right-first
  * preorder (internal: link = skip index, count = -1; leaf: link = box index, count = 1), leaf_order = box
- * indices in traversal order.  Lets the build / flatten logic be checked against the oracle without a GPU. */
+ * indices in traversal order.  Lets the build / flatten logic be checked on a CPU-only box by the tests. */
 int prtc_host_build_tree(const float * aabbs6, uint32_t n, float margin, uint32_t * leaf_order, float * nodes8,
                          uint32_t nodes_capacity, uint32_t * n_nodes);
 
