@@ -26,128 +26,155 @@ __device__ __forceinline__ bool node_overlaps(float4 lo, float4 hi, Box const & 
     return !(lo.x > q.hi.x || hi.x < q.lo.x || lo.y > q.hi.y || hi.y < q.lo.y || lo.z > q.hi.z || hi.z < q.lo.z);
 }
 
+// One thread per character, but every loop is WARP-UNIFORM: trip counts come from votes, so the 32 lanes of a
+// warp walk "advance -> traverse -> test triangles" in lock step and only the bodies are predicated.  (The first
+// version let each lane run its own loops; ncu showed 2.55 of 32 lanes active per instruction -- lanes ended up
+// testing their triangles one after another.  profiles/r01_a_kstep_v1_ncu_summary.json)
 template <bool TRACE>
 __global__ void __launch_bounds__(128) k_step(StepParams p) {
+    constexpr unsigned FULL = 0xffffffffu;
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = i < p.n;
     uint32_t c_sub = 0, c_tri = 0, c_node = 0, c_contact = 0;
 
-    if (i < p.n) {
-        prtc_transform * tf = p.transforms + i;
-        prtc_char_physics * ph = p.physics + i;
-        V3 pos = v3(tf->position[0], tf->position[1], tf->position[2]);
+    prtc_transform * tf = p.transforms + (valid ? i : 0);
+    prtc_char_physics * ph = p.physics + (valid ? i : 0);
+    V3 pos = v3(0.0f), vel = v3(0.0f), gn = v3(0.0f), prevVel = v3(0.0f);
+    uint32_t grounded = 0;
+    CapsuleFrame fr;
+    fr.sa1 = fr.sa2 = fr.sb1 = fr.sb2 = v3(0.0f);
+    fr.radius = 0.0f;
+    float radius = 0.0f;
+    if (valid) {
+        pos = v3(tf->position[0], tf->position[1], tf->position[2]);
         Quat q; q.x = tf->rotation[0]; q.y = tf->rotation[1]; q.z = tf->rotation[2]; q.w = tf->rotation[3];
-        V3 vel = v3(ph->velocity[0], ph->velocity[1], ph->velocity[2]);
-        V3 gn = v3(ph->ground_normal[0], ph->ground_normal[1], ph->ground_normal[2]);
-        uint32_t grounded = ph->grounded;
+        vel = v3(ph->velocity[0], ph->velocity[1], ph->velocity[2]);
+        gn = v3(ph->ground_normal[0], ph->ground_normal[1], ph->ground_normal[2]);
+        grounded = ph->grounded;
         const float mvx = ph->movement[0], mvz = ph->movement[2];
         const CapsuleDev cap = p.capsules[ph->collider];
-        const Rot3 R = rotation_of(q);
-        const CapsuleFrame fr = capsule_frame(cap, R);
-        const float radius = cap.radius;
-
+        fr = capsule_frame(cap, rotation_of(q));
+        radius = cap.radius;
         // ---- phase 1 (physics_system.cpp:277-285) ----
-        const V3 prevVel = vel;
+        prevVel = vel;
         if (grounded) vel = vel + ((-p.stick * p.gravity) * p.dt) * gn;
         vel.x = vel.x + mvx;
         vel.z = vel.z + mvz;
         grounded = 0;
+    }
 
-        // ---- phase 2: collideCharacterWithWorld (physics_system.cpp:330-438) ----
-        const float fsub = float(p.substeps);
-        const V3 stepv = vel / fsub;
-        V3 prevA, prevB;
-        segment_ends(fr, pos, prevA, prevB);                      // prevTform                      :344
-        uint32_t stepsLeft = p.substeps;
-        while (stepsLeft != 0) {
+    // ---- phase 2: collideCharacterWithWorld (physics_system.cpp:330-438) ----
+    const float fsub = float(p.substeps);
+    const V3 stepv = vel / fsub;
+    V3 prevA, prevB;
+    segment_ends(fr, pos, prevA, prevB);                          // prevTform                      :344
+    uint32_t stepsLeft = valid ? p.substeps : 0u;
+    bool alive = stepsLeft != 0;                                  // this lane is still inside the substep loop
+    while (__any_sync(FULL, alive)) {
+        Pose ps;
+        Box qb;
+        uint32_t slot = 0, t_mesh = 0, t_hits = 0, t_tris = 0;
+        if (alive) {
             --stepsLeft;
             pos = pos + stepv;                                    //                                 :350
-            Pose ps = make_pose(fr, pos);
-            Box qb = box_union(capsule_box(prevA, prevB, radius), capsule_box(ps.A, ps.B, radius));   // :355-356
+            ps = make_pose(fr, pos);
+            qb = box_union(capsule_box(prevA, prevB, radius), capsule_box(ps.A, ps.B, radius));   // :355-356
             prevA = ps.A; prevB = ps.B;                           // prevTform = tform               :358
             ++c_sub;
-
-            TraceQuery * tq = nullptr;
-            uint32_t slot = 0, t_mesh = 0, t_hits = 0, t_tris = 0;
             if (TRACE) {
                 slot = i * p.substeps + (p.substeps - 1 - stepsLeft);
-                tq = p.trace.queries + slot;
+                TraceQuery * tq = p.trace.queries + slot;
                 tq->aabb[0] = qb.lo.x; tq->aabb[1] = qb.lo.y; tq->aabb[2] = qb.lo.z;
                 tq->aabb[3] = qb.hi.x; tq->aabb[4] = qb.hi.y; tq->aabb[5] = qb.hi.z;
             }
+        } else {
+            ps = make_pose(fr, pos);
+            qb.lo = v3(0.0f); qb.hi = v3(0.0f);
+        }
 
-            // Stackless traversal in right-first preorder == DynamicAABBTree::query's emission order
-            // (aabb_tree.cpp:34-68).  The query box is fixed for the substep, so testing a leaf's triangles as
-            // soon as the leaf is reached is equivalent to the reference's "collect candidates, then
-            // collideCapsuleMesh" (physics_system.cpp:367,396-434).  "while-while": lanes leave the inner loop
-            // with a pending leaf and re-converge before the (expensive) triangle loop.
-            bool found = false;
-            uint32_t node = 0;
-            uint32_t poly = 0;
-            while (true) {
-                uint32_t triBeg = 0, triEnd = 0;
-                bool have = false;
-                while (node < p.n_nodes) {
-                    const float4 lo = __ldg(p.nodes + 2 * node);
-                    const float4 hi = __ldg(p.nodes + 2 * node + 1);
-                    const bool ov = node_overlaps(lo, hi, qb);
-                    const int link = __float_as_int(lo.w);
-                    const int cnt = __float_as_int(hi.w);
-                    ++c_node;
-                    if (cnt < 0) {
-                        node = ov ? node + 1 : uint32_t(link);
-                    } else {
-                        if (ov) {
-                            if (TRACE) {
-                                if (t_mesh < p.trace.cap_cand) p.trace.mesh_ids[size_t(slot) * p.trace.cap_cand + t_mesh] = p.node_leaf_id[node];
-                                ++t_mesh;
-                            }
-                            triBeg = uint32_t(link); triEnd = triBeg + uint32_t(cnt);
-                            have = true;
+        // Stackless traversal in right-first preorder == DynamicAABBTree::query's emission order
+        // (aabb_tree.cpp:34-68).  The query box is fixed for the substep, so testing a leaf's triangles as soon as
+        // the leaf is reached is equivalent to the reference's "collect candidates, then collideCapsuleMesh"
+        // (physics_system.cpp:367,396-434).  While-while: each lane walks to its next overlapping leaf, the warp
+        // re-converges on a vote, then all pending leaves are tested together.
+        bool found = false;
+        uint32_t node = alive ? 0u : p.n_nodes;
+        uint32_t poly = 0;
+        while (true) {
+            uint32_t triBeg = 0, triCnt = 0;
+            bool have = false;
+            while (node < p.n_nodes) {
+                const float4 lo = __ldg(p.nodes + 2 * node);
+                const float4 hi = __ldg(p.nodes + 2 * node + 1);
+                const bool ov = node_overlaps(lo, hi, qb);
+                const int link = __float_as_int(lo.w);
+                const int cnt = __float_as_int(hi.w);
+                ++c_node;
+                if (cnt < 0) {
+                    node = ov ? node + 1 : uint32_t(link);
+                } else {
+                    if (ov) {
+                        if (TRACE) {
+                            if (t_mesh < p.trace.cap_cand) p.trace.mesh_ids[size_t(slot) * p.trace.cap_cand + t_mesh] = p.node_leaf_id[node];
+                            ++t_mesh;
                         }
-                        node = node + 1;
-                        if (have) break;
+                        triBeg = uint32_t(link); triCnt = uint32_t(cnt);
+                        have = true;
                     }
+                    node = node + 1;
+                    if (have) break;
                 }
-                if (!have) break;
-                found = true;
-                for (uint32_t t = triBeg; t < triEnd; ++t) {
-                    const float4 t0 = __ldg(p.tris + 3 * size_t(t));
-                    const float4 t1 = __ldg(p.tris + 3 * size_t(t) + 1);
-                    const float4 t2 = __ldg(p.tris + 3 * size_t(t) + 2);
+            }
+            if (!__any_sync(FULL, have)) break;                   // every lane has exhausted its traversal
+            if (have) found = true;
+            const uint32_t rounds = __reduce_max_sync(FULL, triCnt);
+            for (uint32_t k = 0; k < rounds; ++k) {
+                if (k < triCnt) {
+                    const size_t t = size_t(triBeg) + k;
+                    const float4 t0 = __ldg(p.tris + 3 * t);
+                    const float4 t1 = __ldg(p.tris + 3 * t + 1);
+                    const float4 t2 = __ldg(p.tris + 3 * t + 2);
                     ++c_tri;
                     if (TRACE) ++t_tris;
                     const uint32_t my_poly = poly++;
-                    if (__float_as_uint(t0.w) == PRT_DEGENERATE_BITS) continue;       // length(n) == 0   :53
                     Contact ct;
-                    if (!capsule_triangle(ps, radius, p.abs_mode, v3(t0.x, t0.y, t0.z), v3(t1.x, t1.y, t1.z),
-                                          v3(t2.x, t2.y, t2.z), v3(t0.w, t1.w, t2.w), ct))
-                        continue;
-                    // handleCollision (collision_system.cpp:242-252)
-                    pos = pos + ct.impulse;
-                    ++c_contact;
-                    if (dot(ct.normal, v3(0.0f, 1.0f, 0.0f)) > p.ground_dot) {
-                        grounded = 1;
-                        gn = ct.normal;
-                    }
-                    if (TRACE) {
-                        if (t_hits < p.trace.cap_hits) {
-                            TraceHit * h = p.trace.hits + size_t(slot) * p.trace.cap_hits + t_hits;
-                            h->poly = int32_t(my_poly);
-                            h->impulse[0] = ct.impulse.x; h->impulse[1] = ct.impulse.y; h->impulse[2] = ct.impulse.z;
-                            h->normal[0] = ct.normal.x; h->normal[1] = ct.normal.y; h->normal[2] = ct.normal.z;
-                            h->pos[0] = pos.x; h->pos[1] = pos.y; h->pos[2] = pos.z;
+                    if (__float_as_uint(t0.w) != PRT_DEGENERATE_BITS &&               // length(n) == 0   :53
+                        capsule_triangle(ps, radius, p.abs_mode, v3(t0.x, t0.y, t0.z), v3(t1.x, t1.y, t1.z),
+                                         v3(t2.x, t2.y, t2.z), v3(t0.w, t1.w, t2.w), ct)) {
+                        // handleCollision (collision_system.cpp:242-252)
+                        pos = pos + ct.impulse;
+                        ++c_contact;
+                        if (dot(ct.normal, v3(0.0f, 1.0f, 0.0f)) > p.ground_dot) {
+                            grounded = 1;
+                            gn = ct.normal;
                         }
-                        ++t_hits;
+                        if (TRACE) {
+                            if (t_hits < p.trace.cap_hits) {
+                                TraceHit * h = p.trace.hits + size_t(slot) * p.trace.cap_hits + t_hits;
+                                h->poly = int32_t(my_poly);
+                                h->impulse[0] = ct.impulse.x; h->impulse[1] = ct.impulse.y; h->impulse[2] = ct.impulse.z;
+                                h->normal[0] = ct.normal.x; h->normal[1] = ct.normal.y; h->normal[2] = ct.normal.z;
+                                h->pos[0] = pos.x; h->pos[1] = pos.y; h->pos[2] = pos.z;
+                            }
+                            ++t_hits;
+                        }
+                        if (ct.impulse.x != 0.0f || ct.impulse.y != 0.0f || ct.impulse.z != 0.0f)
+                            ps = make_pose(fr, pos);              // tform is rebuilt per triangle     :40
                     }
-                    if (ct.impulse.x != 0.0f || ct.impulse.y != 0.0f || ct.impulse.z != 0.0f)
-                        ps = make_pose(fr, pos);                  // tform is rebuilt per triangle     :40
                 }
+                __syncwarp(FULL);                                 // keep the lanes in step round by round
             }
+        }
+        if (alive) {
             if (TRACE) {
+                TraceQuery * tq = p.trace.queries + slot;
                 tq->executed = 1; tq->n_mesh = t_mesh; tq->n_caps = 0; tq->n_hits = t_hits; tq->tri_tests = t_tris;
             }
-            if (!found) break;                                    // `if (meshColIDs.empty()) break;`  :391-393
+            if (!found || stepsLeft == 0) alive = false;          // `if (meshColIDs.empty()) break;`  :391-393
         }
+    }
+
+    if (valid) {
         pos = pos + (float(stepsLeft) * vel) / fsub;              //                                   :437
 
         // ---- phase 3 (physics_system.cpp:298-317) ----
@@ -165,10 +192,10 @@ __global__ void __launch_bounds__(128) k_step(StepParams p) {
     }
 
     // work counters: one atomic per warp per counter
-    c_sub = __reduce_add_sync(0xffffffffu, c_sub);
-    c_tri = __reduce_add_sync(0xffffffffu, c_tri);
-    c_node = __reduce_add_sync(0xffffffffu, c_node);
-    c_contact = __reduce_add_sync(0xffffffffu, c_contact);
+    c_sub = __reduce_add_sync(FULL, c_sub);
+    c_tri = __reduce_add_sync(FULL, c_tri);
+    c_node = __reduce_add_sync(FULL, c_node);
+    c_contact = __reduce_add_sync(FULL, c_contact);
     if ((threadIdx.x & 31u) == 0 && p.counters) {
         atomicAdd(p.counters + 0, (unsigned long long)c_sub);
         atomicAdd(p.counters + 1, (unsigned long long)c_tri);
