@@ -26,14 +26,42 @@ __device__ __forceinline__ bool node_overlaps(float4 lo, float4 hi, Box const & 
     return !(lo.x > q.hi.x || hi.x < q.lo.x || lo.y > q.hi.y || hi.y < q.lo.y || lo.z > q.hi.z || hi.z < q.lo.z);
 }
 
-// One thread per character, but every loop is WARP-UNIFORM: trip counts come from votes, so the 32 lanes of a
-// warp walk "advance -> traverse -> test triangles" in lock step and only the bodies are predicated.  (The first
-// version let each lane run its own loops; ncu showed 2.55 of 32 lanes active per instruction -- lanes ended up
-// testing their triangles one after another.  profiles/r01_a_kstep_v1_ncu_summary.json)
+// Conservative per-triangle pre-cull.  A contact needs `inside || intersects` (collision_system.cpp:101):
+//   intersects -> a point of the triangle lies within `radius` of `center`, and `center` lies on the segment AB;
+//   inside     -> point0 = center - n*dist lies in the triangle with 0 <= dist < dmax (the range cull :71-72), so
+//                 center lies within dmax*|n_axis| of the triangle's extent along every axis.
+// Hence if the triangle's AABB, grown per axis by max(radius, dmax*|n_axis|) + eps, misses the AABB of AB, the exact
+// test cannot report a contact at this pose and skipping it changes nothing.  eps (StepParams::qr_eps, >= 64 ulp of
+// the largest world coordinate) absorbs the rounding of the exact test's intermediate points.  Any NaN makes every
+// compare false => "not rejected", i.e. the exact path decides.
+__device__ __forceinline__ bool quick_reject(V3 smin, V3 smax, float radius, float dmax, float eps,
+                                             float4 t0, float4 t1, float4 t2) {
+    const float ex = fmaxf(radius, dmax * fabsf(t0.w)) + eps;
+    const float ey = fmaxf(radius, dmax * fabsf(t1.w)) + eps;
+    const float ez = fmaxf(radius, dmax * fabsf(t2.w)) + eps;
+    const float lox = fminf(fminf(t0.x, t1.x), t2.x), hix = fmaxf(fmaxf(t0.x, t1.x), t2.x);
+    const float loy = fminf(fminf(t0.y, t1.y), t2.y), hiy = fmaxf(fmaxf(t0.y, t1.y), t2.y);
+    const float loz = fminf(fminf(t0.z, t1.z), t2.z), hiz = fmaxf(fmaxf(t0.z, t1.z), t2.z);
+    return (lox - ex > smax.x) || (hix + ex < smin.x) || (loy - ey > smax.y) || (hiy + ey < smin.y) ||
+           (loz - ez > smax.z) || (hiz + ez < smin.z);
+}
+
+constexpr int STEP_BLOCK = 128;
+constexpr int LEAF_CAP = 8;      // candidate leaves buffered per lane and pass (more => another pass)
+
+// One thread per character; every loop is WARP-UNIFORM (trip counts come from votes), bodies are predicated.
+//   phase A  each lane walks the flattened tree for its query box and buffers the overlapping leaves, in the
+//            reference's emission order, in shared memory;
+//   phase B  each lane runs a cheap filter loop over its buffered triangles (load, degenerate skip, conservative
+//            pre-cull) until one needs the exact test; the warp votes and all pending exact tests run together.
+// History (profiles/): v1 let each lane run its own loops -> 2.55 of 32 lanes active per instruction; v2 made the
+// loops vote-driven (13.5 lanes) but interleaved traversal and testing leaf by leaf.
 template <bool TRACE>
-__global__ void __launch_bounds__(128) k_step(StepParams p) {
+__global__ void __launch_bounds__(STEP_BLOCK) k_step(StepParams p) {
     constexpr unsigned FULL = 0xffffffffu;
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    __shared__ uint2 s_leaf[LEAF_CAP][STEP_BLOCK];
+    const uint32_t tid = threadIdx.x;
+    const uint32_t i = blockIdx.x * blockDim.x + tid;
     const bool valid = i < p.n;
     uint32_t c_sub = 0, c_tri = 0, c_node = 0, c_contact = 0;
 
@@ -44,7 +72,7 @@ __global__ void __launch_bounds__(128) k_step(StepParams p) {
     CapsuleFrame fr;
     fr.sa1 = fr.sa2 = fr.sb1 = fr.sb2 = v3(0.0f);
     fr.radius = 0.0f;
-    float radius = 0.0f;
+    float radius = 0.0f, qr_eps = 0.0f;
     if (valid) {
         pos = v3(tf->position[0], tf->position[1], tf->position[2]);
         Quat q; q.x = tf->rotation[0]; q.y = tf->rotation[1]; q.z = tf->rotation[2]; q.w = tf->rotation[3];
@@ -55,6 +83,7 @@ __global__ void __launch_bounds__(128) k_step(StepParams p) {
         const CapsuleDev cap = p.capsules[ph->collider];
         fr = capsule_frame(cap, rotation_of(q));
         radius = cap.radius;
+        qr_eps = p.qr_eps + 1e-5f * (fabsf(cap.radius) + fabsf(cap.height) + fabsf(cap.ox) + fabsf(cap.oy) + fabsf(cap.oz));
         // ---- phase 1 (physics_system.cpp:277-285) ----
         prevVel = vel;
         if (grounded) vel = vel + ((-p.stick * p.gravity) * p.dt) * gn;
@@ -62,6 +91,9 @@ __global__ void __launch_bounds__(128) k_step(StepParams p) {
         vel.z = vel.z + mvz;
         grounded = 0;
     }
+    // largest plane distance that survives the range cull (collision_system.cpp:72, see prtc_abs_mode)
+    const float dmax = (p.abs_mode == 1u) ? radius : floorf(radius) + 1.0f;
+    const bool use_qr = p.qr_enable != 0u;
 
     // ---- phase 2: collideCharacterWithWorld (physics_system.cpp:330-438) ----
     const float fsub = float(p.substeps);
@@ -92,18 +124,15 @@ __global__ void __launch_bounds__(128) k_step(StepParams p) {
             qb.lo = v3(0.0f); qb.hi = v3(0.0f);
         }
 
-        // Stackless traversal in right-first preorder == DynamicAABBTree::query's emission order
-        // (aabb_tree.cpp:34-68).  The query box is fixed for the substep, so testing a leaf's triangles as soon as
-        // the leaf is reached is equivalent to the reference's "collect candidates, then collideCapsuleMesh"
-        // (physics_system.cpp:367,396-434).  While-while: each lane walks to its next overlapping leaf, the warp
-        // re-converges on a vote, then all pending leaves are tested together.
         bool found = false;
         uint32_t node = alive ? 0u : p.n_nodes;
         uint32_t poly = 0;
         while (true) {
-            uint32_t triBeg = 0, triCnt = 0;
-            bool have = false;
-            while (node < p.n_nodes) {
+            // ---- phase A: stackless traversal in right-first preorder == DynamicAABBTree::query's emission order
+            // (aabb_tree.cpp:34-68).  The query box is fixed for the substep, so buffering candidates and testing
+            // them afterwards is exactly the reference's "query, then collideCapsuleMesh" (physics_system.cpp:367,431).
+            uint32_t nleaf = 0;
+            while (node < p.n_nodes && nleaf < LEAF_CAP) {
                 const float4 lo = __ldg(p.nodes + 2 * node);
                 const float4 hi = __ldg(p.nodes + 2 * node + 1);
                 const bool ov = node_overlaps(lo, hi, qb);
@@ -118,28 +147,46 @@ __global__ void __launch_bounds__(128) k_step(StepParams p) {
                             if (t_mesh < p.trace.cap_cand) p.trace.mesh_ids[size_t(slot) * p.trace.cap_cand + t_mesh] = p.node_leaf_id[node];
                             ++t_mesh;
                         }
-                        triBeg = uint32_t(link); triCnt = uint32_t(cnt);
-                        have = true;
+                        s_leaf[nleaf][tid] = make_uint2(uint32_t(link), uint32_t(cnt));
+                        ++nleaf;
                     }
                     node = node + 1;
-                    if (have) break;
                 }
             }
-            if (!__any_sync(FULL, have)) break;                   // every lane has exhausted its traversal
-            if (have) found = true;
-            const uint32_t rounds = __reduce_max_sync(FULL, triCnt);
-            for (uint32_t k = 0; k < rounds; ++k) {
-                if (k < triCnt) {
-                    const size_t t = size_t(triBeg) + k;
-                    const float4 t0 = __ldg(p.tris + 3 * t);
-                    const float4 t1 = __ldg(p.tris + 3 * t + 1);
-                    const float4 t2 = __ldg(p.tris + 3 * t + 2);
+            if (!__any_sync(FULL, nleaf != 0)) break;             // every lane has exhausted its traversal
+            if (nleaf) found = true;
+
+            // ---- phase B: Gauss-Seidel push-out over the buffered triangles, in order (collision_system.cpp:29-155)
+            uint32_t lj = 0, tcur = 0, tend = 0;
+            while (true) {
+                bool pending = false;
+                float4 t0, t1, t2;
+                uint32_t my_poly = 0;
+                V3 smin = gmin(ps.A, ps.B), smax = gmax(ps.A, ps.B);
+                while (true) {                                    // filter loop: cheap, per lane
+                    if (tcur == tend) {
+                        if (lj == nleaf) break;
+                        const uint2 e = s_leaf[lj][tid];
+                        ++lj;
+                        tcur = e.x; tend = e.x + e.y;
+                        continue;
+                    }
+                    t0 = __ldg(p.tris + 3 * size_t(tcur));
+                    t1 = __ldg(p.tris + 3 * size_t(tcur) + 1);
+                    t2 = __ldg(p.tris + 3 * size_t(tcur) + 2);
+                    ++tcur;
                     ++c_tri;
                     if (TRACE) ++t_tris;
-                    const uint32_t my_poly = poly++;
+                    my_poly = poly++;
+                    if (__float_as_uint(t0.w) == PRT_DEGENERATE_BITS) continue;       // length(n) == 0   :53
+                    if (use_qr && quick_reject(smin, smax, radius, dmax, qr_eps, t0, t1, t2)) continue;
+                    pending = true;
+                    break;
+                }
+                if (!__any_sync(FULL, pending)) break;
+                if (pending) {
                     Contact ct;
-                    if (__float_as_uint(t0.w) != PRT_DEGENERATE_BITS &&               // length(n) == 0   :53
-                        capsule_triangle(ps, radius, p.abs_mode, v3(t0.x, t0.y, t0.z), v3(t1.x, t1.y, t1.z),
+                    if (capsule_triangle(ps, radius, p.abs_mode, v3(t0.x, t0.y, t0.z), v3(t1.x, t1.y, t1.z),
                                          v3(t2.x, t2.y, t2.z), v3(t0.w, t1.w, t2.w), ct)) {
                         // handleCollision (collision_system.cpp:242-252)
                         pos = pos + ct.impulse;
@@ -196,7 +243,7 @@ __global__ void __launch_bounds__(128) k_step(StepParams p) {
     c_tri = __reduce_add_sync(FULL, c_tri);
     c_node = __reduce_add_sync(FULL, c_node);
     c_contact = __reduce_add_sync(FULL, c_contact);
-    if ((threadIdx.x & 31u) == 0 && p.counters) {
+    if ((tid & 31u) == 0 && p.counters) {
         atomicAdd(p.counters + 0, (unsigned long long)c_sub);
         atomicAdd(p.counters + 1, (unsigned long long)c_tri);
         atomicAdd(p.counters + 2, (unsigned long long)c_node);
@@ -272,7 +319,7 @@ __global__ void k_query_box(const float4 * __restrict__ nodes, uint32_t n_nodes,
 
 void launch_step(StepParams const & p, bool traced, cudaStream_t stream) {
     if (p.n == 0) return;
-    const uint32_t block = 128;
+    const uint32_t block = STEP_BLOCK;
     const uint32_t grid = (p.n + block - 1) / block;
     if (traced) k_step<true><<<grid, block, 0, stream>>>(p);
     else k_step<false><<<grid, block, 0, stream>>>(p);

@@ -55,6 +55,9 @@ struct StepParams {
     // constants (prtc_config)
     float dt, gravity, ground_dot, friction, stick;
     uint32_t substeps, abs_mode;
+    // conservative pre-cull (kernels.cu quick_reject): margin and enable, derived from the scene extent at commit
+    float qr_eps;
+    uint32_t qr_enable;
     unsigned long long * counters;  // prtc_counters layout
     TraceBuffers trace;
 };

@@ -6,6 +6,8 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -76,6 +78,8 @@ struct prtc_ctx {
     bool geometry_dirty = false;            // raw / meshes / xforms changed since the last upload
     bool tree_dirty = false;                // tree changed since the last flatten
     bool capsules_dirty = false;
+    float world_max_abs = 0.0f;             // largest |coordinate| of any mesh AABB (margin of the pre-cull)
+    int quick_reject = 1;                   // PRTC_QUICK_REJECT=0 in the environment disables the pre-cull (A/B runs)
     std::vector<uint32_t> moved_models;     // models whose transform changed (prtc_update_models)
 
     // device
@@ -161,6 +165,8 @@ int commit_impl(prtc_ctx * c) {
             }
         }
         c->moved_models.clear();
+        c->world_max_abs = 0.0f;
+        for (float v : aabbs) { float a = std::fabs(v); if (a > c->world_max_abs) c->world_max_abs = a; }   // NaN never wins
         // new meshes: DynamicAABBTree::insert in registration order, physics_system.cpp:102
         for (uint32_t m = c->meshes_in_tree; m < n_meshes; ++m)
             c->meshes[m].tree_index = c->tree.insert_leaf(m, LEAF_MESH, box_of(m));
@@ -219,6 +225,13 @@ int fill_params(prtc_ctx * c, float dt, uint32_t n, prtc_transform * d_tf, prtc_
     p.substeps = c->cfg.substeps;
     p.abs_mode = c->cfg.abs_mode;
     p.counters = c->d_counters.ptr;
+    // pre-cull margin: 64 ulp of the largest world coordinate, at least 1e-3; switched off for absurd extents
+    {
+        float m = c->world_max_abs;
+        float ulp = std::nextafter(m, INFINITY) - m;
+        p.qr_eps = std::max(1e-3f, 64.0f * ulp);
+        p.qr_enable = (c->quick_reject && m < 1.0e6f) ? 1u : 0u;
+    }
     return PRTC_OK;
 }
 
@@ -283,6 +296,7 @@ int prtc_create(const prtc_config * cfg, prtc_ctx ** out) {
     prtc_ctx * ctx = new (std::nothrow) prtc_ctx();
     if (!ctx) return fail(PRTC_ERR_ALLOC, "prtc_create: out of host memory");
     ctx->cfg = c;
+    if (const char * e = std::getenv("PRTC_QUICK_REJECT")) ctx->quick_reject = std::atoi(e);
     ctx->tree.set_margin(c.leaf_margin);
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
         delete ctx;
