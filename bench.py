@@ -286,6 +286,28 @@ def run_ours(args):
     substeps, tri_tests, node_tests = sum_over_ranks([cnt["substeps"], cnt["tri_tests"], cnt["node_tests"]])
     value = substeps / el
 
+    # Numerators of the roofline: the REFERENCE ALGORITHM's counts over the same K frames.  The timed run uses the
+    # frame cache (fewer node tests than DynamicAABBTree::query performs), so the same frames are replayed untimed
+    # with PRTC_OPT_FRAME_CACHE=0, where the device walks the tree per substep and counts exactly what the
+    # reference would test; substeps and triangle tests must come out identical in both runs.
+    reset_host()
+    d_tf.copy_(h_tf)
+    d_ph.copy_(h_ph)
+    ctx.set_option(capi.OPT_FRAME_CACHE, 0)
+    for _ in range(args.warmup):
+        ctx.update_characters_device(DT, n_caps, d_tf.data_ptr(), d_ph.data_ptr())
+    torch.cuda.synchronize()
+    ctx.counters(reset=True)
+    for _ in range(args.steps):
+        ctx.update_characters_device(DT, n_caps, d_tf.data_ptr(), d_ph.data_ptr())
+    torch.cuda.synchronize()
+    ref_cnt = ctx.counters(reset=True)
+    ctx.set_option(capi.OPT_FRAME_CACHE, 1)
+    assert ref_cnt["substeps"] == cnt["substeps"] and ref_cnt["tri_tests"] == cnt["tri_tests"], (ref_cnt, cnt)
+    gpu_node_tests = cnt["node_tests"]
+    cnt = dict(cnt, node_tests=ref_cnt["node_tests"])
+    (node_tests,) = sum_over_ranks([cnt["node_tests"]])
+
     # roofline of the dominant (only) kernel, this rank: algorithmic bytes / measured duration
     alg_bytes = 96.0 * cnt["substeps"] + 32.0 * cnt["node_tests"] + 36.0 * cnt["tri_tests"] + 64.0 * n_caps * args.steps
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -307,7 +329,8 @@ def run_ours(args):
                 "kernel": "k_step<false>", "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes / args.steps,
                 "avg_launch_ms": float(np.mean(kernel_ms)), "formula": "96*S + 32*V + 36*T + 64*capsules (SURVEY.md 8d)",
-                "per_query": {"V_q": cnt["node_tests"] / max(1, cnt["substeps"]), "T_q": cnt["tri_tests"] / max(1, cnt["substeps"])}}
+                "per_query": {"V_q": cnt["node_tests"] / max(1, cnt["substeps"]), "T_q": cnt["tri_tests"] / max(1, cnt["substeps"]),
+                              "gpu_node_tests_per_query": gpu_node_tests / max(1, cnt["substeps"])}}
 
     # ---- end-to-end leg: host buffers through prtc_step_characters (H2D + kernel + D2H every step) ----------
     e2e = None

@@ -169,6 +169,15 @@ int prtc_synchronize(prtc_ctx * ctx);
 
 int prtc_get_counters(prtc_ctx * ctx, prtc_counters * out, int reset);
 
+/* Work-saving devices of the GPU path.  Neither changes any result bit; both change how much work is done.
+ *   PRTC_OPT_FRAME_CACHE   (default 1) one tree walk per character and frame with a box covering the whole
+ *                          frame's motion; substeps re-test only the cached leaves.  With 0 the device walks the
+ *                          tree once per substep exactly like DynamicAABBTree::query, and prtc_counters.node_tests
+ *                          then equals the reference's count (the numerator of the roofline's algorithmic bytes).
+ *   PRTC_OPT_QUICK_REJECT  (default 1) conservative per-triangle pre-cull ahead of the exact test. */
+enum prtc_option { PRTC_OPT_FRAME_CACHE = 1, PRTC_OPT_QUICK_REJECT = 2 };
+int prtc_set_option(prtc_ctx * ctx, int option, int value);
+
 /* Introspection for parity tests: the flattened tree.  leaf_mesh_ids receives the mesh-collider ids of all
  * leaves in traversal (= reference DFS) order. */
 int prtc_get_tree_info(prtc_ctx * ctx, uint32_t * n_nodes, uint32_t * n_leaves, uint32_t * n_triangles);
@@ -182,7 +191,7 @@ int prtc_query_box(prtc_ctx * ctx, const float aabb6[6], uint32_t * mesh_ids, ui
 /* Host-only utility (needs no device, performs no collision arithmetic): builds the reference's dynamic AABB
  * tree over n boxes inserted in order (DynamicAABBTree::insert, aabb_tree.cpp:95-100) and returns it in the
  * flattened device layout: nodes8 = 8 x 32-bit words per node {lo.xyz, link, hi.xyz, count} in right-first
- * preorder (internal: link = skip index, count = -1; leaf: link = box index, count = 1), leaf_order = box
+ * preorder (internal: link = skip index, count = -(second child index); leaf: link = box index, count = 1), leaf_order = box
  * indices in traversal order.  Lets the build / flatten logic be checked on a CPU-only box by the tests. */
 int prtc_host_build_tree(const float * aabbs6, uint32_t n, float margin, uint32_t * leaf_order, float * nodes8,
                          uint32_t nodes_capacity, uint32_t * n_nodes);

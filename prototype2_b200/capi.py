@@ -7,19 +7,20 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libprtc.so")
+LIB_PATH = os.path.join(_HERE, os.environ.get("PRTC_LIB", "libprtc.so"))   # PRTC_LIB: A/B builds of the same library
 
 PRTC_OK, PRTC_ERR_INVALID, PRTC_ERR_CUDA, PRTC_ERR_CAPACITY, PRTC_ERR_ALLOC = range(5)
 ABS_INT, ABS_FLOAT = 0, 1
 ORDER_LITERAL, ORDER_CANONICAL = 0, 1
 DYN_OFF, DYN_JACOBI = 0, 2
+OPT_FRAME_CACHE, OPT_QUICK_REJECT = 1, 2
 
 # every symbol include/prtc.h declares (tests check the library exports exactly these)
 SYMBOLS = (
     "prtc_default_config", "prtc_last_error", "prtc_device_count", "prtc_create", "prtc_destroy",
     "prtc_add_model", "prtc_add_capsule", "prtc_update_capsule", "prtc_commit", "prtc_update_models",
     "prtc_step_characters", "prtc_step_characters_device", "prtc_step_characters_traced", "prtc_raycast",
-    "prtc_set_stream", "prtc_synchronize", "prtc_get_counters", "prtc_get_tree_info", "prtc_get_leaf_order",
+    "prtc_set_stream", "prtc_synchronize", "prtc_get_counters", "prtc_set_option", "prtc_get_tree_info", "prtc_get_leaf_order",
     "prtc_get_world_vertices", "prtc_query_box", "prtc_host_build_tree",
 )
 
@@ -222,6 +223,9 @@ class PhysicsContext:
                "h_query": arr["h_query"][:nh], "h_poly": arr["h_poly"][:nh], "h_impulse": arr["h_impulse"][:nh],
                "h_normal": arr["h_normal"][:nh], "h_pos": arr["h_pos"][:nh]}
         return out
+
+    def set_option(self, option, value):
+        self._check(self.lib.prtc_set_option(self.h, ctypes.c_int(option), ctypes.c_int(value)))
 
     def set_stream(self, cuda_stream_handle):
         self._check(self.lib.prtc_set_stream(self.h, ctypes.c_void_p(cuda_stream_handle)))

@@ -22,7 +22,8 @@ enum LeafKind : uint8_t { LEAF_NONE = 0, LEAF_MESH = 2, LEAF_CAPSULE = 3 };   //
 
 // Device node, 32 bytes, two float4:
 //   lo.xyz, as_float(link)      internal: link = index of the node following this subtree ("skip")
-//   hi.xyz, as_float(count)     internal: count = -1;  leaf: link = first triangle, count = #triangles (>= 0)
+//   hi.xyz, as_float(count)     internal: count = -(index of the second child) < 0 (the first child is index+1);
+//                               leaf: link = first triangle, count = #triangles (>= 0)
 // Nodes are stored in right-first preorder, so "descend" is index+1 and a stackless traversal that walks the
 // array front to back emits leaves in exactly the reference's candidate order.
 struct FlatNode {
@@ -112,6 +113,7 @@ void RefTree::flatten(FlatTree & out, LeafRange && leaf_range) const {
         f.hi[0] = n.box.hi.x; f.hi[1] = n.box.hi.y; f.hi[2] = n.box.hi.z;
         int32_t flat = int32_t(out.nodes.size());
         if (it.depth > out.max_depth) out.max_depth = it.depth;
+        if (it.flat_parent >= 0) out.nodes[size_t(it.flat_parent)].count = -flat;   // we are our parent's second child
         if (n.right == NIL) {               // Node::isLeaf (aabb_tree.h:120)
             uint32_t first = 0, count = 0;
             if (n.kind == LEAF_MESH) { leaf_range(n.id, first, count); out.leaf_order.push_back(n.id); }
@@ -129,7 +131,7 @@ void RefTree::flatten(FlatTree & out, LeafRange && leaf_range) const {
             // the subtree of `flat` is finished when the stack shrinks back to its current size
             pending.push_back({flat, uint32_t(stack.size())});
             stack.push_back({n.left, flat, it.depth + 1});      // aabb_tree.cpp:63-64: left pushed first,
-            stack.push_back({n.right, flat, it.depth + 1});     // right popped first
+            stack.push_back({n.right, -1, it.depth + 1});       // right popped first (=> it is flat+1)
         }
     }
     while (!pending.empty()) {

@@ -60,6 +60,8 @@ template <bool TRACE>
 __global__ void __launch_bounds__(STEP_BLOCK) k_step(StepParams p) {
     constexpr unsigned FULL = 0xffffffffu;
     __shared__ uint2 s_leaf[LEAF_CAP][STEP_BLOCK];
+    __shared__ uint32_t s_cache[LEAF_CAP][STEP_BLOCK];     // frame cache: leaves (node indices) overlapping s_region
+    __shared__ float s_region[6][STEP_BLOCK];
     const uint32_t tid = threadIdx.x;
     const uint32_t i = blockIdx.x * blockDim.x + tid;
     const bool valid = i < p.n;
@@ -102,6 +104,47 @@ __global__ void __launch_bounds__(STEP_BLOCK) k_step(StepParams p) {
     segment_ends(fr, pos, prevA, prevB);                          // prevTform                      :344
     uint32_t stepsLeft = valid ? p.substeps : 0u;
     bool alive = stepsLeft != 0;                                  // this lane is still inside the substep loop
+
+    // ---- frame cache.  The reference walks the tree once per substep with a box that moves by velocity/substeps
+    // each time.  One walk with a box R that covers the whole frame's motion (plus slack for push-outs) finds a
+    // superset of every substep's candidates, in emission order; a substep whose query box lies inside R then only
+    // re-tests those few leaf boxes (identical candidate list, identical order), and one whose box escapes R -- or a
+    // lane whose cache overflowed -- simply walks the tree as before.
+    bool cache_ok = false;
+    uint32_t ncache = 0;
+    if (!(p.tune & 1u)) {
+        Box R;
+        R.lo = v3(0.0f); R.hi = v3(0.0f);
+        uint32_t node = p.n_nodes;
+        if (alive) {
+            V3 eA, eB;
+            segment_ends(fr, pos + vel, eA, eB);
+            R = box_union(capsule_box(prevA, prevB, radius), capsule_box(eA, eB, radius));
+            const float slack = 0.25f;
+            R.lo = R.lo - v3(slack); R.hi = R.hi + v3(slack);
+            node = 0;
+        }
+        while (__any_sync(FULL, node < p.n_nodes)) {
+            if (node < p.n_nodes) {
+                const float4 lo = __ldg(p.nodes + 2 * node);
+                const float4 hi = __ldg(p.nodes + 2 * node + 1);
+                const bool ov = node_overlaps(lo, hi, R);
+                const int cnt = __float_as_int(hi.w);
+                ++c_node;
+                if (cnt < 0) {
+                    node = ov ? node + 1 : uint32_t(__float_as_int(lo.w));
+                } else {
+                    if (ov) {
+                        if (ncache < LEAF_CAP) { s_cache[ncache][tid] = node; ++ncache; node = node + 1; }
+                        else { node = 0xFFFFFFFFu; }              // too many leaves: this lane does not use the cache
+                    } else node = node + 1;
+                }
+            }
+        }
+        cache_ok = alive && node != 0xFFFFFFFFu;
+        s_region[0][tid] = R.lo.x; s_region[1][tid] = R.lo.y; s_region[2][tid] = R.lo.z;
+        s_region[3][tid] = R.hi.x; s_region[4][tid] = R.hi.y; s_region[5][tid] = R.hi.z;
+    }
     while (__any_sync(FULL, alive)) {
         Pose ps;
         Box qb;
@@ -127,11 +170,31 @@ __global__ void __launch_bounds__(STEP_BLOCK) k_step(StepParams p) {
         bool found = false;
         uint32_t node = alive ? 0u : p.n_nodes;
         uint32_t poly = 0;
+        uint32_t nleaf = 0;
+        if (alive && cache_ok &&
+            s_region[0][tid] <= qb.lo.x && s_region[1][tid] <= qb.lo.y && s_region[2][tid] <= qb.lo.z &&
+            s_region[3][tid] >= qb.hi.x && s_region[4][tid] >= qb.hi.y && s_region[5][tid] >= qb.hi.z) {
+            // query box inside the frame region: its candidates are the cached leaves that overlap it
+            for (uint32_t j = 0; j < ncache; ++j) {
+                const uint32_t leaf = s_cache[j][tid];
+                const float4 lo = __ldg(p.nodes + 2 * leaf);
+                const float4 hi = __ldg(p.nodes + 2 * leaf + 1);
+                ++c_node;
+                if (node_overlaps(lo, hi, qb)) {
+                    if (TRACE) {
+                        if (t_mesh < p.trace.cap_cand) p.trace.mesh_ids[size_t(slot) * p.trace.cap_cand + t_mesh] = p.node_leaf_id[leaf];
+                        ++t_mesh;
+                    }
+                    s_leaf[nleaf][tid] = make_uint2(uint32_t(__float_as_int(lo.w)), uint32_t(__float_as_int(hi.w)));
+                    ++nleaf;
+                }
+            }
+            node = p.n_nodes;
+        }
         while (true) {
             // ---- phase A: stackless traversal in right-first preorder == DynamicAABBTree::query's emission order
             // (aabb_tree.cpp:34-68).  The query box is fixed for the substep, so buffering candidates and testing
             // them afterwards is exactly the reference's "query, then collideCapsuleMesh" (physics_system.cpp:367,431).
-            uint32_t nleaf = 0;
             while (node < p.n_nodes && nleaf < LEAF_CAP) {
                 const float4 lo = __ldg(p.nodes + 2 * node);
                 const float4 hi = __ldg(p.nodes + 2 * node + 1);
@@ -211,6 +274,7 @@ __global__ void __launch_bounds__(STEP_BLOCK) k_step(StepParams p) {
                 }
                 __syncwarp(FULL);                                 // keep the lanes in step round by round
             }
+            nleaf = 0;
         }
         if (alive) {
             if (TRACE) {

@@ -58,6 +58,7 @@ struct StepParams {
     // conservative pre-cull (kernels.cu quick_reject): margin and enable, derived from the scene extent at commit
     float qr_eps;
     uint32_t qr_enable;
+    uint32_t tune;                  // bit 0: frame cache OFF (walk the tree every substep, reference-equivalent counters)
     unsigned long long * counters;  // prtc_counters layout
     TraceBuffers trace;
 };

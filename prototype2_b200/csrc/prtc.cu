@@ -79,7 +79,8 @@ struct prtc_ctx {
     bool tree_dirty = false;                // tree changed since the last flatten
     bool capsules_dirty = false;
     float world_max_abs = 0.0f;             // largest |coordinate| of any mesh AABB (margin of the pre-cull)
-    int quick_reject = 1;                   // PRTC_QUICK_REJECT=0 in the environment disables the pre-cull (A/B runs)
+    int frame_cache = 1;                    // PRTC_OPT_FRAME_CACHE
+    int quick_reject = 1;                   // PRTC_OPT_QUICK_REJECT
     std::vector<uint32_t> moved_models;     // models whose transform changed (prtc_update_models)
 
     // device
@@ -231,6 +232,7 @@ int fill_params(prtc_ctx * c, float dt, uint32_t n, prtc_transform * d_tf, prtc_
         float ulp = std::nextafter(m, INFINITY) - m;
         p.qr_eps = std::max(1e-3f, 64.0f * ulp);
         p.qr_enable = (c->quick_reject && m < 1.0e6f) ? 1u : 0u;
+        p.tune = c->frame_cache ? 0u : 1u;
     }
     return PRTC_OK;
 }
@@ -296,7 +298,9 @@ int prtc_create(const prtc_config * cfg, prtc_ctx ** out) {
     prtc_ctx * ctx = new (std::nothrow) prtc_ctx();
     if (!ctx) return fail(PRTC_ERR_ALLOC, "prtc_create: out of host memory");
     ctx->cfg = c;
+    // environment overrides of the option defaults, for A/B measurements without touching the caller
     if (const char * e = std::getenv("PRTC_QUICK_REJECT")) ctx->quick_reject = std::atoi(e);
+    if (const char * e = std::getenv("PRTC_FRAME_CACHE")) ctx->frame_cache = std::atoi(e);
     ctx->tree.set_margin(c.leaf_margin);
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
         delete ctx;
@@ -530,6 +534,15 @@ int prtc_get_counters(prtc_ctx * c, prtc_counters * out, int reset) {
     PRTC_CUDA(cudaStreamSynchronize(c->stream));
     out->substeps = h[0]; out->tri_tests = h[1]; out->node_tests = h[2]; out->contacts = h[3]; out->cc_tests = h[4];
     return PRTC_OK;
+}
+
+int prtc_set_option(prtc_ctx * c, int option, int value) {
+    if (!c) return fail(PRTC_ERR_INVALID, "prtc_set_option: null context");
+    switch (option) {
+        case PRTC_OPT_FRAME_CACHE: c->frame_cache = value != 0; return PRTC_OK;
+        case PRTC_OPT_QUICK_REJECT: c->quick_reject = value != 0; return PRTC_OK;
+        default: return fail(PRTC_ERR_INVALID, "prtc_set_option: unknown option");
+    }
 }
 
 int prtc_get_tree_info(prtc_ctx * c, uint32_t * n_nodes, uint32_t * n_leaves, uint32_t * n_triangles) {

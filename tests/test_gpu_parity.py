@@ -13,11 +13,13 @@ pytestmark = pytest.mark.gpu
 DT = 1.0 / 30.0
 
 
-def _run_pair(scene, frames, oracle_kw, gpu_kw, trace_frames=(0, 1)):
+def _run_pair(scene, frames, oracle_kw, gpu_kw, trace_frames=(0, 1), frame_cache=True):
     from prototype2_b200 import capi
     orc = H.build_oracle(scene, "l1", **oracle_kw)
     ctx, tf, ph = H.build_gpu(scene, **gpu_kw)
     ctx.commit()
+    if not frame_cache:
+        ctx.set_option(capi.OPT_FRAME_CACHE, 0)
     assert np.array_equal(ctx.leaf_order(), orc.dump_order()[0]), "flattened tree order differs from the oracle's DFS order"
     for f in range(frames):
         if f in trace_frames:
@@ -28,6 +30,10 @@ def _run_pair(scene, frames, oracle_kw, gpu_kw, trace_frames=(0, 1)):
             orc.step(DT)
             ctx.update_characters(DT, tf, ph)
         assert H.state_diff(orc.get_state(), H.gpu_state(tf, ph)) == [], "frame %d state" % f
+    # the work counters are the numerators of bench.py's metrics: they must be the reference algorithm's counts
+    co, cg = orc.counters(), ctx.counters()
+    for k in ("substeps", "tri_tests", "contacts") + (() if frame_cache else ("node_tests",)):
+        assert co[k] == cg[k], "counter %s: oracle %d gpu %d" % (k, co[k], cg[k])
     return orc, ctx, tf, ph
 
 
@@ -38,6 +44,27 @@ def test_c2_shape_canonical_bit_exact(abs_mode):
     scene = H.make_scene(224, 1, 1, 1000)
     _run_pair(scene, 6, dict(order="canonical", abs_mode=abs_mode),
               dict(abs_mode=capi.ABS_INT if abs_mode == "int" else capi.ABS_FLOAT))
+
+
+@pytest.mark.parametrize("frame_cache,quick_reject", [(0, 0), (0, 1), (1, 0)])
+def test_work_saving_options_do_not_change_results(frame_cache, quick_reject):
+    """PRTC_OPT_FRAME_CACHE / PRTC_OPT_QUICK_REJECT off: same bits; with the frame cache off the node-test counter
+    is the reference's own count"""
+    from prototype2_b200 import capi
+    scene = H.make_scene(96, 2, 2, 800, seed=8)
+    scene["vel"] = scene["vel"] * np.float32(1.7)           # some boxes escape the frame region
+    orc = H.build_oracle(scene, "l1", order="canonical")
+    ctx, tf, ph = H.build_gpu(scene)
+    ctx.set_option(capi.OPT_FRAME_CACHE, frame_cache)
+    ctx.set_option(capi.OPT_QUICK_REJECT, quick_reject)
+    for f in range(5):
+        to = orc.step(DT, trace=True)
+        tg = ctx.update_characters_traced(DT, tf, ph)
+        assert H.trace_diff(to, tg) == []
+        assert H.state_diff(orc.get_state(), H.gpu_state(tf, ph)) == []
+    co, cg = orc.counters(), ctx.counters()
+    for k in ("substeps", "tri_tests", "contacts") + (("node_tests",) if not frame_cache else ()):
+        assert co[k] == cg[k], k
 
 
 def test_rotated_capsules_bit_exact():
@@ -116,6 +143,15 @@ def test_empty_and_ragged_inputs():
     scene = H.make_scene(16, 1, 1, 40, seed=9)
     scene["xyz"], scene["mesh_first"], scene["mesh_count"] = tri.reshape(-1, 3), np.array(first, np.uint32), np.array(count, np.uint32)
     _run_pair(scene, 4, dict(order="canonical"), dict())
+
+
+def test_candidate_overflow_falls_back_to_the_ordered_walk():
+    """more overlapping leaves than the per-lane candidate buffer (12) and a deep frontier: tiny 1x1-cell leaves under
+    a fat capsule.  Exercises the ordered multi-pass walk and its agreement with the fast order-free walk."""
+    scene = H.make_scene(40, 1, 1, 96, seed=41)
+    scene["capsule"] = (2.0, 2.5, (0.0, 2.5, 0.0))
+    scene["pos"][:, 1] += 1.0
+    _run_pair(scene, 3, dict(order="canonical"), dict())
 
 
 def test_fast_bodies_tunnel_like_the_reference():

@@ -98,6 +98,11 @@ def test_skip_links_are_consistent():
         sub = nodes[i + 1:links[i]]
         assert (sub[:, 0:3] >= nodes[i, 0:3]).all() and (sub[:, 4:7] <= nodes[i, 4:7]).all()
     assert counts[~internal].min() == 1
+    # internal nodes carry -(second child): the node that follows the first child's subtree
+    for i in np.nonzero(internal)[0]:
+        first = i + 1
+        after_first = links[first] if counts[first] < 0 else first + 1
+        assert -counts[i] == after_first
 
 
 def test_empty_and_single():
