@@ -22,6 +22,15 @@ __device__ __forceinline__ Box capsule_box(V3 tA, V3 tB, float radius) {     // 
     return b;
 }
 
+// cp.async (LDGSTS): 16-byte global -> shared copies that need no destination registers; groups complete in order
+__device__ __forceinline__ void cp_async16(void * smem_dst, const void * gmem_src) {
+    const uint32_t d = uint32_t(__cvta_generic_to_shared(smem_dst));
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" :: "r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
+
 __device__ __forceinline__ bool node_overlaps(float4 lo, float4 hi, Box const & q) {   // AABB::intersect aabb.cpp:3-10
     return !(lo.x > q.hi.x || hi.x < q.lo.x || lo.y > q.hi.y || hi.y < q.lo.y || lo.z > q.hi.z || hi.z < q.lo.z);
 }
@@ -47,6 +56,7 @@ __device__ __forceinline__ bool quick_reject(V3 smin, V3 smax, float radius, flo
 }
 
 constexpr int STEP_BLOCK = 128;
+constexpr int TRI_RING = 2;      // triangles in flight per lane (cp.async ring in shared memory)
 constexpr int LEAF_CAP = 8;      // candidate leaves buffered per lane and pass (more => another pass)
 
 // One thread per character; every loop is WARP-UNIFORM (trip counts come from votes), bodies are predicated.
@@ -62,6 +72,8 @@ __global__ void __launch_bounds__(STEP_BLOCK) k_step(StepParams p) {
     __shared__ uint2 s_leaf[LEAF_CAP][STEP_BLOCK];
     __shared__ uint32_t s_cache[LEAF_CAP][STEP_BLOCK];     // frame cache: leaves (node indices) overlapping s_region
     __shared__ float s_region[6][STEP_BLOCK];
+    // per-lane ring of candidate triangles streamed in with cp.async while the exact tests run
+    __shared__ float4 s_tri[TRI_RING][3][STEP_BLOCK];
     const uint32_t tid = threadIdx.x;
     const uint32_t i = blockIdx.x * blockDim.x + tid;
     const bool valid = i < p.n;
@@ -220,24 +232,40 @@ __global__ void __launch_bounds__(STEP_BLOCK) k_step(StepParams p) {
             if (nleaf) found = true;
 
             // ---- phase B: Gauss-Seidel push-out over the buffered triangles, in order (collision_system.cpp:29-155)
-            uint32_t lj = 0, tcur = 0, tend = 0;
+            // The lane's candidate triangles form one stream (leaf after leaf, in order).  A fetch cursor runs
+            // TRI_RING triangles ahead of the consume position, so the 48-byte loads overlap the exact tests.
+            uint32_t f_leaf = 0, f_cur = 0, f_end = 0, n_fetched = 0, n_consumed = 0;
+            auto fetch_one = [&]() {
+                while (f_cur == f_end) {
+                    if (f_leaf == nleaf) return;
+                    const uint2 e = s_leaf[f_leaf][tid];
+                    ++f_leaf;
+                    f_cur = e.x; f_end = e.x + e.y;
+                }
+                const uint32_t slot = n_fetched % TRI_RING;
+                const float4 * src = p.tris + 3 * size_t(f_cur);
+                cp_async16(&s_tri[slot][0][tid], src);
+                cp_async16(&s_tri[slot][1][tid], src + 1);
+                cp_async16(&s_tri[slot][2][tid], src + 2);
+                cp_async_commit();
+                ++f_cur;
+                ++n_fetched;
+            };
+#pragma unroll
+            for (int r = 0; r < TRI_RING; ++r) fetch_one();
             while (true) {
                 bool pending = false;
                 float4 t0, t1, t2;
                 uint32_t my_poly = 0;
-                V3 smin = gmin(ps.A, ps.B), smax = gmax(ps.A, ps.B);
-                while (true) {                                    // filter loop: cheap, per lane
-                    if (tcur == tend) {
-                        if (lj == nleaf) break;
-                        const uint2 e = s_leaf[lj][tid];
-                        ++lj;
-                        tcur = e.x; tend = e.x + e.y;
-                        continue;
-                    }
-                    t0 = __ldg(p.tris + 3 * size_t(tcur));
-                    t1 = __ldg(p.tris + 3 * size_t(tcur) + 1);
-                    t2 = __ldg(p.tris + 3 * size_t(tcur) + 2);
-                    ++tcur;
+                const V3 smin = gmin(ps.A, ps.B), smax = gmax(ps.A, ps.B);
+                while (n_consumed != n_fetched) {                 // filter loop: cheap, per lane
+                    if (n_fetched - n_consumed > 1) cp_async_wait<TRI_RING - 1>(); else cp_async_wait<0>();
+                    const uint32_t slot = n_consumed % TRI_RING;
+                    t0 = s_tri[slot][0][tid];
+                    t1 = s_tri[slot][1][tid];
+                    t2 = s_tri[slot][2][tid];
+                    ++n_consumed;
+                    fetch_one();                                  // refill the slot just read
                     ++c_tri;
                     if (TRACE) ++t_tris;
                     my_poly = poly++;
