@@ -23,7 +23,8 @@ enum LeafKind : uint8_t { LEAF_NONE = 0, LEAF_MESH = 2, LEAF_CAPSULE = 3 };   //
 // Device node, 32 bytes, two float4:
 //   lo.xyz, as_float(link)      internal: link = index of the node following this subtree ("skip")
 //   hi.xyz, as_float(count)     internal: count = -(index of the second child) < 0 (the first child is index+1);
-//                               leaf: link = first triangle, count = #triangles (>= 0)
+//                               mesh leaf: link = first triangle, count = #triangles (>= 0);
+//                               capsule leaf (unified LITERAL tree only): link = capsule id, count = 0x40000000
 // Nodes are stored in right-first preorder, so "descend" is index+1 and a stackless traversal that walks the
 // array front to back emits leaves in exactly the reference's candidate order.
 struct FlatNode {
@@ -36,6 +37,7 @@ struct FlatTree {
     std::vector<uint32_t> node_leaf_id;     // per node: collider id of the leaf, 0xFFFFFFFF for internal nodes
     std::vector<uint8_t> node_leaf_kind;    // per node: LeafKind
     std::vector<uint32_t> leaf_order;       // collider ids of MESH leaves in traversal order
+    std::vector<uint32_t> capsule_order;    // collider ids of CAPSULE leaves in traversal order (unified LITERAL tree)
     uint32_t max_depth = 0;
 };
 
@@ -89,7 +91,7 @@ private:
 
 template <class LeafRange>
 void RefTree::flatten(FlatTree & out, LeafRange && leaf_range) const {
-    out.nodes.clear(); out.node_leaf_id.clear(); out.node_leaf_kind.clear(); out.leaf_order.clear();
+    out.nodes.clear(); out.node_leaf_id.clear(); out.node_leaf_kind.clear(); out.leaf_order.clear(); out.capsule_order.clear();
     out.max_depth = 0;
     if (root_ == NIL) return;
     out.nodes.reserve(size_t(size_));
@@ -117,6 +119,7 @@ void RefTree::flatten(FlatTree & out, LeafRange && leaf_range) const {
         if (n.right == NIL) {               // Node::isLeaf (aabb_tree.h:120)
             uint32_t first = 0, count = 0;
             if (n.kind == LEAF_MESH) { leaf_range(n.id, first, count); out.leaf_order.push_back(n.id); }
+            else if (n.kind == LEAF_CAPSULE) { first = n.id; count = 0x40000000u; out.capsule_order.push_back(n.id); }   // PRT_CAPSULE_LEAF
             f.link = int32_t(first);
             f.count = int32_t(count);
             out.nodes.push_back(f);

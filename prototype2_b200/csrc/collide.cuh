@@ -17,6 +17,7 @@
 
 namespace prt {
 
+#define PRT_CAPSULE_LEAF 0x40000000      /* leaf `count` flag: the leaf is a capsule of the unified (LITERAL) tree, link = capsule id */
 #define PRT_DEGENERATE_BITS 0x7FC0DEADu   /* NaN payload the FPU never produces: marks length(n)==0 triangles */
 
 struct CapsuleDev {          // CapsuleCollider (colliders.h:14-18), padded to 32 bytes
@@ -39,6 +40,14 @@ PRT_HD CapsuleFrame capsule_frame(CapsuleDev const & c, Rot3 const & r) {
     f.sb1 = r.c0 * b.x + r.c1 * b.y; f.sb2 = r.c2 * b.z;
     f.radius = c.radius;
     return f;
+}
+
+// CapsuleCollider::getAABB (colliders.h:19-27) for already transformed segment ends
+PRT_HD Box capsule_box(V3 tA, V3 tB, float radius) {
+    Box b;
+    b.lo = gmin(tA, tB) - v3(radius);
+    b.hi = gmax(tA, tB) + v3(radius);
+    return b;
 }
 
 struct Pose {

@@ -15,13 +15,6 @@ namespace prt {
 
 namespace {
 
-__device__ __forceinline__ Box capsule_box(V3 tA, V3 tB, float radius) {     // CapsuleCollider::getAABB colliders.h:19-27
-    Box b;
-    b.lo = gmin(tA, tB) - v3(radius);
-    b.hi = gmax(tA, tB) + v3(radius);
-    return b;
-}
-
 // cp.async (LDGSTS): 16-byte global -> shared copies that need no destination registers; groups complete in order
 __device__ __forceinline__ void cp_async16(void * smem_dst, const void * gmem_src) {
     const uint32_t d = uint32_t(__cvta_generic_to_shared(smem_dst));
@@ -66,7 +59,7 @@ constexpr int LEAF_CAP = 8;      // candidate leaves buffered per lane and pass 
 //            pre-cull) until one needs the exact test; the warp votes and all pending exact tests run together.
 // History (profiles/): v1 let each lane run its own loops -> 2.55 of 32 lanes active per instruction; v2 made the
 // loops vote-driven (13.5 lanes) but interleaved traversal and testing leaf by leaf.
-template <bool TRACE>
+template <bool TRACE, bool LITERAL>
 __global__ void __launch_bounds__(STEP_BLOCK) k_step(StepParams p) {
     constexpr unsigned FULL = 0xffffffffu;
     __shared__ uint2 s_leaf[LEAF_CAP][STEP_BLOCK];
@@ -87,6 +80,7 @@ __global__ void __launch_bounds__(STEP_BLOCK) k_step(StepParams p) {
     fr.sa1 = fr.sa2 = fr.sb1 = fr.sb2 = v3(0.0f);
     fr.radius = 0.0f;
     float radius = 0.0f, qr_eps = 0.0f;
+    uint32_t my_capsule = 0xFFFFFFFFu, c_cc = 0;
     if (valid) {
         pos = v3(tf->position[0], tf->position[1], tf->position[2]);
         Quat q; q.x = tf->rotation[0]; q.y = tf->rotation[1]; q.z = tf->rotation[2]; q.w = tf->rotation[3];
@@ -95,6 +89,7 @@ __global__ void __launch_bounds__(STEP_BLOCK) k_step(StepParams p) {
         grounded = ph->grounded;
         const float mvx = ph->movement[0], mvz = ph->movement[2];
         const CapsuleDev cap = p.capsules[ph->collider];
+        my_capsule = ph->collider;
         fr = capsule_frame(cap, rotation_of(q));
         radius = cap.radius;
         qr_eps = p.qr_eps + 1e-5f * (fabsf(cap.radius) + fabsf(cap.height) + fabsf(cap.ox) + fabsf(cap.oy) + fabsf(cap.oz));
@@ -124,7 +119,7 @@ __global__ void __launch_bounds__(STEP_BLOCK) k_step(StepParams p) {
     // lane whose cache overflowed -- simply walks the tree as before.
     bool cache_ok = false;
     uint32_t ncache = 0;
-    if (!(p.tune & 1u)) {
+    if (!LITERAL && !(p.tune & 1u)) {
         Box R;
         R.lo = v3(0.0f); R.hi = v3(0.0f);
         uint32_t node = p.n_nodes;
@@ -179,6 +174,68 @@ __global__ void __launch_bounds__(STEP_BLOCK) k_step(StepParams p) {
             qb.lo = v3(0.0f); qb.hi = v3(0.0f);
         }
 
+        if (LITERAL) {
+            // ---- capsule-capsule pass (physics_system.cpp:369-389): every capsule leaf of the unified tree that the
+            // query box overlaps, in emission order, BEFORE any triangle.  Character j is seen at its end-of-frame
+            // pose of the previous fixpoint round when j < i and at its start-of-frame pose when j > i -- at the
+            // fixpoint that is exactly the reference's sequential visibility (T18).
+            uint32_t cnode = alive ? 0u : p.n_nodes;
+            uint32_t t_caps = 0;
+            while (true) {
+                uint32_t other = 0xFFFFFFFFu;
+                while (cnode < p.n_nodes) {
+                    const float4 lo = __ldg(p.nodes + 2 * cnode);
+                    const float4 hi = __ldg(p.nodes + 2 * cnode + 1);
+                    const bool ov = node_overlaps(lo, hi, qb);
+                    const int link = __float_as_int(lo.w);
+                    const int cnt = __float_as_int(hi.w);
+                    if (cnt < 0) {
+                        cnode = ov ? cnode + 1 : uint32_t(link);
+                    } else {
+                        cnode = cnode + 1;
+                        if (ov && (cnt & PRT_CAPSULE_LEAF) && uint32_t(link) != my_capsule) { other = uint32_t(link); break; }
+                    }
+                }
+                if (!__any_sync(FULL, other != 0xFFFFFFFFu)) break;
+                if (other != 0xFFFFFFFFu) {
+                    if (TRACE) {
+                        if (t_caps < p.trace.cap_cand) p.trace.caps_ids[size_t(slot) * p.trace.cap_cand + t_caps] = other;
+                        ++t_caps;
+                    }
+                    const uint32_t j = p.cap2char[other];
+                    const float4 * seg = (j < i ? p.seg_prev : p.seg_start) + 2 * size_t(j);
+                    const float4 sA = __ldg(seg), sB = __ldg(seg + 1);
+                    V3 aA, aB;
+                    segment_ends(fr, pos, aA, aB);
+                    Contact ct;
+                    ++c_cc;
+                    if (capsule_capsule(aA, aB, radius, v3(sA.x, sA.y, sA.z), v3(sB.x, sB.y, sB.z), sA.w, ct)) {
+                        pos = pos + ct.impulse;                   // handleCollision (collision_system.cpp:242-252)
+                        ++c_contact;
+                        if (dot(ct.normal, v3(0.0f, 1.0f, 0.0f)) > p.ground_dot) {
+                            grounded = 1;
+                            gn = ct.normal;
+                        }
+                        if (TRACE) {
+                            if (t_hits < p.trace.cap_hits) {
+                                TraceHit * h = p.trace.hits + size_t(slot) * p.trace.cap_hits + t_hits;
+                                h->poly = -1;
+                                h->impulse[0] = ct.impulse.x; h->impulse[1] = ct.impulse.y; h->impulse[2] = ct.impulse.z;
+                                h->normal[0] = ct.normal.x; h->normal[1] = ct.normal.y; h->normal[2] = ct.normal.z;
+                                h->pos[0] = pos.x; h->pos[1] = pos.y; h->pos[2] = pos.z;
+                            }
+                            ++t_hits;
+                        }
+                    }
+                }
+            }
+            if (TRACE && alive) p.trace.queries[slot].n_caps = t_caps;
+            ps = make_pose(fr, pos);
+            if (alive && p.last_box) {
+                float * lb = p.last_box + 6 * size_t(i);
+                lb[0] = qb.lo.x; lb[1] = qb.lo.y; lb[2] = qb.lo.z; lb[3] = qb.hi.x; lb[4] = qb.hi.y; lb[5] = qb.hi.z;
+            }
+        }
         bool found = false;
         uint32_t node = alive ? 0u : p.n_nodes;
         uint32_t poly = 0;
@@ -217,7 +274,7 @@ __global__ void __launch_bounds__(STEP_BLOCK) k_step(StepParams p) {
                 if (cnt < 0) {
                     node = ov ? node + 1 : uint32_t(link);
                 } else {
-                    if (ov) {
+                    if (ov && !(LITERAL && (cnt & PRT_CAPSULE_LEAF))) {
                         if (TRACE) {
                             if (t_mesh < p.trace.cap_cand) p.trace.mesh_ids[size_t(slot) * p.trace.cap_cand + t_mesh] = p.node_leaf_id[node];
                             ++t_mesh;
@@ -307,7 +364,7 @@ __global__ void __launch_bounds__(STEP_BLOCK) k_step(StepParams p) {
         if (alive) {
             if (TRACE) {
                 TraceQuery * tq = p.trace.queries + slot;
-                tq->executed = 1; tq->n_mesh = t_mesh; tq->n_caps = 0; tq->n_hits = t_hits; tq->tri_tests = t_tris;
+                tq->executed = 1; tq->n_mesh = t_mesh; if (!LITERAL) tq->n_caps = 0; tq->n_hits = t_hits; tq->tri_tests = t_tris;
             }
             if (!found || stepsLeft == 0) alive = false;          // `if (meshColIDs.empty()) break;`  :391-393
         }
@@ -335,7 +392,9 @@ __global__ void __launch_bounds__(STEP_BLOCK) k_step(StepParams p) {
     c_tri = __reduce_add_sync(FULL, c_tri);
     c_node = __reduce_add_sync(FULL, c_node);
     c_contact = __reduce_add_sync(FULL, c_contact);
+    if (LITERAL) c_cc = __reduce_add_sync(FULL, c_cc);
     if ((tid & 31u) == 0 && p.counters) {
+        if (LITERAL) atomicAdd(p.counters + 4, (unsigned long long)c_cc);
         atomicAdd(p.counters + 0, (unsigned long long)c_sub);
         atomicAdd(p.counters + 1, (unsigned long long)c_tri);
         atomicAdd(p.counters + 2, (unsigned long long)c_node);
@@ -409,12 +468,17 @@ __global__ void k_query_box(const float4 * __restrict__ nodes, uint32_t n_nodes,
 
 } // namespace
 
-void launch_step(StepParams const & p, bool traced, cudaStream_t stream) {
+void launch_step(StepParams const & p, bool traced, bool literal, cudaStream_t stream) {
     if (p.n == 0) return;
     const uint32_t block = STEP_BLOCK;
     const uint32_t grid = (p.n + block - 1) / block;
-    if (traced) k_step<true><<<grid, block, 0, stream>>>(p);
-    else k_step<false><<<grid, block, 0, stream>>>(p);
+    if (literal) {
+        if (traced) k_step<true, true><<<grid, block, 0, stream>>>(p);
+        else k_step<false, true><<<grid, block, 0, stream>>>(p);
+    } else {
+        if (traced) k_step<true, false><<<grid, block, 0, stream>>>(p);
+        else k_step<false, false><<<grid, block, 0, stream>>>(p);
+    }
 }
 
 void launch_transform_refit(const float * raw_xyz, float * world_xyz, const MeshDev * meshes, uint32_t first_mesh,

@@ -47,11 +47,11 @@ struct StepParams {
     prtc_transform * transforms;
     prtc_char_physics * physics;
     uint32_t n;
-    // dynamic pass (CANONICAL / JACOBI): start-of-frame capsule segments and stored fat boxes of ALL capsules
-    const float4 * dyn_boxes;       // 2 float4 per capsule: stored fat AABB lo/hi
-    const float4 * dyn_segs;        // 2 float4 per capsule: (A.xyz, radius) (B.xyz, unused) at the snapshot pose
-    uint32_t dyn_count;             // 0 => pass disabled
-    uint32_t dyn_self_base;         // global index of this launch's character 0 within the dyn arrays
+    // LITERAL order: capsule-capsule pass against the other characters' capsule segments
+    const uint32_t * cap2char;      // capsule id -> character index (tagToCharacter, physics_system.cpp:275)
+    const float4 * seg_start;       // 2 float4 per character: (A.xyz, radius) (B.xyz, 0) at the start-of-frame pose
+    const float4 * seg_prev;        // same at the end-of-frame pose of the previous fixpoint round
+    float * last_box;               // out, 6 floats per character: the last executed substep's query box
     // constants (prtc_config)
     float dt, gravity, ground_dot, friction, stick;
     uint32_t substeps, abs_mode;
@@ -63,7 +63,7 @@ struct StepParams {
     TraceBuffers trace;
 };
 
-void launch_step(StepParams const & p, bool traced, cudaStream_t stream);
+void launch_step(StepParams const & p, bool traced, bool literal, cudaStream_t stream);
 
 // K8: world-space vertex cache + per-mesh AABB (physics_system.cpp:68-93 / :161-202)
 struct MeshDev { uint32_t first_vertex, n_vertices, model; uint32_t pad; };

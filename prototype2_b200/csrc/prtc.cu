@@ -74,7 +74,11 @@ struct prtc_ctx {
     RefTree tree;
     FlatTree flat;
     std::vector<uint32_t> tri_src;          // per leaf-ordered triangle: index of its first vertex in `raw`/`world`
-    uint32_t meshes_in_tree = 0;
+    uint32_t meshes_in_tree = 0;            // meshes that have a leaf in `tree`
+    uint32_t meshes_on_device = 0;          // meshes whose world cache / AABB the device has computed
+    // LITERAL order: the reference's unified tree also holds one leaf per capsule (physics_system.cpp:36-39)
+    std::vector<int32_t> capsule_tree_index;
+    std::vector<Box> capsule_aabbs;         // m_aabbData.capsuleAABBs
     bool geometry_dirty = false;            // raw / meshes / xforms changed since the last upload
     bool tree_dirty = false;                // tree changed since the last flatten
     bool capsules_dirty = false;
@@ -99,6 +103,11 @@ struct prtc_ctx {
     DevBuf<TraceHit> d_thits;
     DevBuf<float> d_scratch_f;
     DevBuf<uint32_t> d_scratch_u;
+    // LITERAL order
+    DevBuf<uint32_t> d_cap2char;
+    DevBuf<float4> d_seg_start, d_seg_prev;
+    DevBuf<float> d_last_box;
+    bool literal() const { return cfg.order_mode == PRTC_ORDER_LITERAL; }
 };
 
 namespace {
@@ -136,7 +145,7 @@ int commit_impl(prtc_ctx * c) {
 
         // K8 over every mesh that is new, moved, or whose cache was lost to a reallocation
         std::vector<float> aabbs(size_t(n_meshes) * 6);
-        uint32_t first_new = world_realloc ? 0u : c->meshes_in_tree;
+        uint32_t first_new = world_realloc ? 0u : c->meshes_on_device;
         if (n_meshes > first_new) {
             launch_transform_refit(c->d_raw.ptr, c->d_world.ptr, c->d_meshes.ptr, first_new, n_meshes - first_new,
                                    c->d_xforms.ptr, c->d_aabbs.ptr, s);
@@ -172,6 +181,7 @@ int commit_impl(prtc_ctx * c) {
         for (uint32_t m = c->meshes_in_tree; m < n_meshes; ++m)
             c->meshes[m].tree_index = c->tree.insert_leaf(m, LEAF_MESH, box_of(m));
         c->meshes_in_tree = n_meshes;
+        c->meshes_on_device = n_meshes;
         c->geometry_dirty = false;
         c->tree_dirty = true;
     }
@@ -237,11 +247,188 @@ int fill_params(prtc_ctx * c, float dt, uint32_t n, prtc_transform * d_tf, prtc_
     return PRTC_OK;
 }
 
-int check_mode(prtc_ctx * c) {
-    if (c->cfg.order_mode != PRTC_ORDER_CANONICAL)
-        return fail(PRTC_ERR_INVALID, "order_mode PRTC_ORDER_LITERAL is not available in this build; use PRTC_ORDER_CANONICAL");
-    if (c->cfg.dyn_mode != PRTC_DYN_OFF)
-        return fail(PRTC_ERR_INVALID, "dyn_mode PRTC_DYN_JACOBI is not available in this build; use PRTC_DYN_OFF");
+int check_mode(prtc_ctx * c, bool device_pointers) {
+    if (c->cfg.order_mode != PRTC_ORDER_CANONICAL && c->cfg.order_mode != PRTC_ORDER_LITERAL)
+        return fail(PRTC_ERR_INVALID, "unknown order_mode");
+    if (c->literal() && device_pointers)
+        return fail(PRTC_ERR_INVALID, "PRTC_ORDER_LITERAL maintains the unified tree on the host every frame and needs the "
+                                      "host-buffer entry points (prtc_step_characters / _traced)");
+    if (c->cfg.dyn_mode != PRTC_DYN_OFF && !c->literal())
+        return fail(PRTC_ERR_INVALID, "dyn_mode PRTC_DYN_JACOBI is not available in this build; use PRTC_DYN_OFF "
+                                      "(PRTC_ORDER_LITERAL always runs the reference's capsule-capsule pass)");
+    return PRTC_OK;
+}
+
+// copies the device-side trace slots of one traced launch into the caller's prtc_trace
+int gather_trace(prtc_ctx * c, uint32_t n, uint32_t cap_cand, uint32_t cap_hits, prtc_trace * tr) {
+    cudaStream_t s = c->stream;
+    const uint32_t nsub = c->cfg.substeps;
+    const size_t slots = size_t(n) * nsub;
+    std::vector<TraceQuery> tq(slots);
+    std::vector<uint32_t> tmesh(slots * cap_cand), tcaps(slots * cap_cand);
+    std::vector<TraceHit> thits(slots * cap_hits);
+    PRTC_CUDA(cudaMemcpyAsync(tq.data(), c->d_tq.ptr, slots * sizeof(TraceQuery), cudaMemcpyDeviceToHost, s));
+    PRTC_CUDA(cudaMemcpyAsync(tmesh.data(), c->d_tmesh.ptr, tmesh.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    PRTC_CUDA(cudaMemcpyAsync(tcaps.data(), c->d_tcaps.ptr, tcaps.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    PRTC_CUDA(cudaMemcpyAsync(thits.data(), c->d_thits.ptr, thits.size() * sizeof(TraceHit), cudaMemcpyDeviceToHost, s));
+    PRTC_CUDA(cudaStreamSynchronize(s));
+    uint32_t nq = 0, nm = 0, nc = 0, nh = 0;
+    bool overflow = false;
+    if (tr->q_mesh_off && tr->cap_queries) tr->q_mesh_off[0] = 0;
+    if (tr->q_caps_off && tr->cap_queries) tr->q_caps_off[0] = 0;
+    for (uint32_t i = 0; i < n; ++i) {
+        for (uint32_t sub = 0; sub < nsub; ++sub) {
+            size_t slot = size_t(i) * nsub + sub;
+            TraceQuery const & q = tq[slot];
+            if (!q.executed) continue;
+            if (q.n_mesh > cap_cand || q.n_caps > cap_cand || q.n_hits > cap_hits) overflow = true;
+            if (nq >= tr->cap_queries) { overflow = true; continue; }
+            tr->q_char[nq] = i;
+            tr->q_sub[nq] = sub;
+            for (int k = 0; k < 6; ++k) tr->q_aabb[6 * size_t(nq) + k] = q.aabb[k];
+            tr->q_tri_tests[nq] = q.tri_tests;
+            for (uint32_t k = 0; k < std::min(q.n_mesh, cap_cand); ++k) {
+                if (nm < tr->cap_mesh_ids) tr->mesh_ids[nm++] = tmesh[slot * cap_cand + k]; else overflow = true;
+            }
+            for (uint32_t k = 0; k < std::min(q.n_caps, cap_cand); ++k) {
+                if (nc < tr->cap_caps_ids) tr->caps_ids[nc++] = tcaps[slot * cap_cand + k]; else overflow = true;
+            }
+            for (uint32_t k = 0; k < std::min(q.n_hits, cap_hits); ++k) {
+                if (nh >= tr->cap_hits) { overflow = true; break; }
+                TraceHit const & h = thits[slot * cap_hits + k];
+                tr->h_query[nh] = nq;
+                tr->h_poly[nh] = h.poly;
+                for (int d = 0; d < 3; ++d) {
+                    tr->h_impulse[3 * size_t(nh) + d] = h.impulse[d];
+                    tr->h_normal[3 * size_t(nh) + d] = h.normal[d];
+                    tr->h_pos[3 * size_t(nh) + d] = h.pos[d];
+                }
+                ++nh;
+            }
+            ++nq;
+            tr->q_mesh_off[nq] = nm;
+            tr->q_caps_off[nq] = nc;
+        }
+    }
+    tr->n_queries = nq; tr->n_mesh_ids = nm; tr->n_caps_ids = nc; tr->n_hits = nh;
+    if (overflow) return fail(PRTC_ERR_CAPACITY, "prtc_step_characters_traced: trace capacity exceeded (state is valid, trace is truncated)");
+    return PRTC_OK;
+}
+
+constexpr uint32_t TRACE_CAP_CAND = 64, TRACE_CAP_HITS = 96;
+
+int prepare_trace(prtc_ctx * c, uint32_t n, StepParams & p) {
+    const size_t slots = size_t(n) * c->cfg.substeps;
+    PRTC_CUDA(c->d_tq.reserve(slots));
+    PRTC_CUDA(c->d_tmesh.reserve(slots * TRACE_CAP_CAND));
+    PRTC_CUDA(c->d_tcaps.reserve(slots * TRACE_CAP_CAND));
+    PRTC_CUDA(c->d_thits.reserve(slots * TRACE_CAP_HITS));
+    PRTC_CUDA(cudaMemsetAsync(c->d_tq.ptr, 0, slots * sizeof(TraceQuery), c->stream));
+    p.trace.queries = c->d_tq.ptr; p.trace.mesh_ids = c->d_tmesh.ptr; p.trace.caps_ids = c->d_tcaps.ptr; p.trace.hits = c->d_thits.ptr;
+    p.trace.cap_cand = TRACE_CAP_CAND; p.trace.cap_hits = TRACE_CAP_HITS;
+    return PRTC_OK;
+}
+
+// One frame in LITERAL order (host buffers).  Everything the reference does to its unified tree per frame is
+// replayed on the host with the same algorithm; the device runs the collide phase; the reference's sequential
+// visibility between characters (T18) is reached as the fixpoint of repeated whole-batch launches.
+int literal_step(prtc_ctx * c, float dt, uint32_t n, prtc_transform * tf, prtc_char_physics * ph, prtc_trace * tr) {
+    cudaStream_t s = c->stream;
+    for (uint32_t i = 0; i < n; ++i)
+        if (ph[i].collider >= c->capsules.size()) return fail(PRTC_ERR_INVALID, "prtc_step_characters: collider id out of range");
+
+    // phase 1 AABBs (physics_system.cpp:263-273): pose box united with the box after `velocity + gravity*dt`,
+    // the displacement being applied in the capsule's rotated frame (glm::translate(tform, v), trap T3)
+    std::vector<float4> seg_start(2 * size_t(n));
+    std::vector<uint32_t> cap2char(c->capsules.size(), 0u);
+    for (uint32_t i = 0; i < n; ++i) {
+        CapsuleDev const & cap = c->capsules[ph[i].collider];
+        Quat q; q.x = tf[i].rotation[0]; q.y = tf[i].rotation[1]; q.z = tf[i].rotation[2]; q.w = tf[i].rotation[3];
+        const Rot3 R = rotation_of(q);
+        const CapsuleFrame fr = capsule_frame(cap, R);
+        const V3 pos = v3(tf[i].position[0], tf[i].position[1], tf[i].position[2]);
+        V3 A, B;
+        segment_ends(fr, pos, A, B);
+        Box e = capsule_box(A, B, cap.radius);
+        const V3 vel = v3(ph[i].velocity[0], ph[i].velocity[1], ph[i].velocity[2]);
+        const V3 d = vel + (v3(0.0f, -1.0f, 0.0f) * c->cfg.gravity) * dt;
+        const V3 pos2 = ((R.c0 * d.x + R.c1 * d.y) + R.c2 * d.z) + pos;       // translate(): m[0]*v.x + m[1]*v.y + m[2]*v.z + m[3]
+        V3 A2, B2;
+        segment_ends(fr, pos2, A2, B2);
+        e = box_union(e, capsule_box(A2, B2, cap.radius));
+        c->capsule_aabbs[ph[i].collider] = e;
+        cap2char[ph[i].collider] = i;                                          // tagToCharacter, :275
+        seg_start[2 * size_t(i)] = make_float4(A.x, A.y, A.z, cap.radius);
+        seg_start[2 * size_t(i) + 1] = make_float4(B.x, B.y, B.z, 0.0f);
+    }
+    // m_aabbData.tree.update(all capsule leaves) (physics_system.cpp:289)
+    if (!c->capsule_tree_index.empty())
+        c->tree.update(c->capsule_tree_index.data(), c->capsule_aabbs.data(), c->capsule_tree_index.size());
+    c->tree_dirty = true;
+    int rc = commit_impl(c);                                                    // re-flatten + upload (+ triangles in the new leaf order)
+    if (rc) return rc;
+
+    PRTC_CUDA(c->d_tf.reserve(n));
+    PRTC_CUDA(c->d_ph.reserve(n));
+    PRTC_CUDA(c->d_cap2char.reserve(cap2char.size()));
+    PRTC_CUDA(c->d_seg_start.reserve(seg_start.size()));
+    PRTC_CUDA(c->d_seg_prev.reserve(seg_start.size()));
+    PRTC_CUDA(c->d_last_box.reserve(6 * size_t(n)));
+    if (n == 0) { if (tr) { tr->n_queries = tr->n_mesh_ids = tr->n_caps_ids = tr->n_hits = 0; if (tr->q_mesh_off) tr->q_mesh_off[0] = 0; if (tr->q_caps_off) tr->q_caps_off[0] = 0; } return PRTC_OK; }
+    PRTC_CUDA(cudaMemcpyAsync(c->d_cap2char.ptr, cap2char.data(), cap2char.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+    PRTC_CUDA(cudaMemcpyAsync(c->d_seg_start.ptr, seg_start.data(), seg_start.size() * sizeof(float4), cudaMemcpyHostToDevice, s));
+
+    unsigned long long base[8];
+    PRTC_CUDA(cudaMemcpyAsync(base, c->d_counters.ptr, sizeof(base), cudaMemcpyDeviceToHost, s));
+    PRTC_CUDA(cudaStreamSynchronize(s));
+
+    std::vector<prtc_transform> out_tf(n), prev_tf;
+    std::vector<prtc_char_physics> out_ph(n);
+    std::vector<float4> seg_prev(seg_start);
+    const uint32_t max_rounds = n + 2;
+    for (uint32_t round = 0; round < max_rounds; ++round) {
+        PRTC_CUDA(cudaMemcpyAsync(c->d_counters.ptr, base, sizeof(base), cudaMemcpyHostToDevice, s));   // only the last round counts
+        PRTC_CUDA(cudaMemcpyAsync(c->d_tf.ptr, tf, size_t(n) * sizeof(prtc_transform), cudaMemcpyHostToDevice, s));
+        PRTC_CUDA(cudaMemcpyAsync(c->d_ph.ptr, ph, size_t(n) * sizeof(prtc_char_physics), cudaMemcpyHostToDevice, s));
+        PRTC_CUDA(cudaMemcpyAsync(c->d_seg_prev.ptr, seg_prev.data(), seg_prev.size() * sizeof(float4), cudaMemcpyHostToDevice, s));
+        StepParams p;
+        fill_params(c, dt, n, c->d_tf.ptr, c->d_ph.ptr, p);
+        p.cap2char = c->d_cap2char.ptr; p.seg_start = c->d_seg_start.ptr; p.seg_prev = c->d_seg_prev.ptr; p.last_box = c->d_last_box.ptr;
+        if (tr) { rc = prepare_trace(c, n, p); if (rc) return rc; }
+        launch_step(p, tr != nullptr, true, s);
+        PRTC_CUDA(cudaGetLastError());
+        PRTC_CUDA(cudaMemcpyAsync(out_tf.data(), c->d_tf.ptr, size_t(n) * sizeof(prtc_transform), cudaMemcpyDeviceToHost, s));
+        PRTC_CUDA(cudaMemcpyAsync(out_ph.data(), c->d_ph.ptr, size_t(n) * sizeof(prtc_char_physics), cudaMemcpyDeviceToHost, s));
+        unsigned long long now[8];
+        PRTC_CUDA(cudaMemcpyAsync(now, c->d_counters.ptr, sizeof(now), cudaMemcpyDeviceToHost, s));
+        PRTC_CUDA(cudaStreamSynchronize(s));
+        const bool any_capsule_test = now[4] != base[4];
+        const bool settled = !prev_tf.empty() && std::memcmp(prev_tf.data(), out_tf.data(), size_t(n) * sizeof(prtc_transform)) == 0;
+        if (!any_capsule_test || settled) break;
+        // next round: characters j < i are seen where this round left them
+        for (uint32_t i = 0; i < n; ++i) {
+            CapsuleDev const & cap = c->capsules[ph[i].collider];
+            Quat q; q.x = tf[i].rotation[0]; q.y = tf[i].rotation[1]; q.z = tf[i].rotation[2]; q.w = tf[i].rotation[3];
+            V3 A, B;
+            segment_ends(capsule_frame(cap, rotation_of(q)), v3(out_tf[i].position[0], out_tf[i].position[1], out_tf[i].position[2]), A, B);
+            seg_prev[2 * size_t(i)] = make_float4(A.x, A.y, A.z, cap.radius);
+            seg_prev[2 * size_t(i) + 1] = make_float4(B.x, B.y, B.z, 0.0f);
+        }
+        prev_tf = out_tf;
+    }
+    // m_aabbData.capsuleAABBs[tag.index] is left at the last executed substep's query box (physics_system.cpp:355-356)
+    std::vector<float> last_box(6 * size_t(n));
+    PRTC_CUDA(cudaMemcpyAsync(last_box.data(), c->d_last_box.ptr, last_box.size() * sizeof(float), cudaMemcpyDeviceToHost, s));
+    PRTC_CUDA(cudaStreamSynchronize(s));
+    for (uint32_t i = 0; i < n; ++i) {
+        Box b;
+        b.lo = v3(last_box[6 * size_t(i)], last_box[6 * size_t(i) + 1], last_box[6 * size_t(i) + 2]);
+        b.hi = v3(last_box[6 * size_t(i) + 3], last_box[6 * size_t(i) + 4], last_box[6 * size_t(i) + 5]);
+        c->capsule_aabbs[ph[i].collider] = b;
+    }
+    std::memcpy(tf, out_tf.data(), size_t(n) * sizeof(prtc_transform));
+    std::memcpy(ph, out_ph.data(), size_t(n) * sizeof(prtc_char_physics));
+    if (tr) return gather_trace(c, n, TRACE_CAP_CAND, TRACE_CAP_HITS, tr);
     return PRTC_OK;
 }
 
@@ -324,6 +511,7 @@ void prtc_destroy(prtc_ctx * c) {
     c->d_capsules.release(); c->d_counters.release(); c->d_tf.release(); c->d_ph.release();
     c->d_tq.release(); c->d_tmesh.release(); c->d_tcaps.release(); c->d_thits.release();
     c->d_scratch_f.release(); c->d_scratch_u.release();
+    c->d_cap2char.release(); c->d_seg_start.release(); c->d_seg_prev.release(); c->d_last_box.release();
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -354,6 +542,26 @@ int prtc_add_model(prtc_ctx * c, const float * xyz, uint32_t n_vertices, const u
     }
     c->models.push_back(mh);
     c->geometry_dirty = true;
+    if (c->literal()) {
+        // the reference inserts the mesh leaves right here (physics_system.cpp:102), interleaved with capsule leaves
+        // in call order, and the tree's shape depends on that order: derive the AABBs on the host with the same
+        // arithmetic as k_transform_refit (physics_system.cpp:80-91) instead of waiting for the commit
+        const Affine xf = affine_from(mh.transform);
+        for (uint32_t m = mh.first_mesh; m < mh.first_mesh + n_meshes; ++m) {
+            MeshHost & me = c->meshes[m];
+            V3 mn = v3(3.402823466e+38f), mx = v3(-3.402823466e+38f);
+            for (uint32_t k = 0; k < me.n_vertices; ++k) {
+                const float * r = &c->raw[3 * size_t(me.first_vertex + k)];
+                V3 w = affine_point(xf, v3(r[0], r[1], r[2]));
+                mn = gmin(mn, w);
+                mx = gmax(mx, w);
+            }
+            Box b; b.lo = mn; b.hi = mx;
+            me.tree_index = c->tree.insert_leaf(m, LEAF_MESH, b);
+        }
+        c->meshes_in_tree = uint32_t(c->meshes.size());
+        c->tree_dirty = true;
+    }
     if (out_model_id) *out_model_id = model_id;
     if (out_first_mesh_id) *out_first_mesh_id = mh.first_mesh;
     return PRTC_OK;
@@ -367,6 +575,16 @@ int prtc_add_capsule(prtc_ctx * c, float height, float radius, const float offse
     if (out_id) *out_id = uint32_t(c->capsules.size());
     c->capsules.push_back(d);
     c->capsules_dirty = true;
+    if (c->literal()) {
+        // physics_system.cpp:36-39: the capsule's leaf is created at the IDENTITY pose
+        Quat qi; qi.x = qi.y = qi.z = 0.0f; qi.w = 1.0f;
+        V3 A, B;
+        segment_ends(capsule_frame(d, rotation_of(qi)), v3(0.0f), A, B);
+        Box b = capsule_box(A, B, d.radius);
+        c->capsule_aabbs.push_back(b);
+        c->capsule_tree_index.push_back(c->tree.insert_leaf(uint32_t(c->capsules.size() - 1), LEAF_CAPSULE, b));
+        c->tree_dirty = true;
+    }
     return PRTC_OK;
 }
 
@@ -411,28 +629,32 @@ int prtc_synchronize(prtc_ctx * c) {
 
 int prtc_step_characters_device(prtc_ctx * c, float dt, uint32_t n, prtc_transform * d_tf, prtc_char_physics * d_ph) {
     if (!c || (n && (!d_tf || !d_ph))) return fail(PRTC_ERR_INVALID, "prtc_step_characters_device: null argument");
-    int rc = check_mode(c);
+    int rc = check_mode(c, true);
     if (rc) return rc;
     PRTC_CUDA(cudaSetDevice(c->cfg.device));
     if (c->geometry_dirty || c->tree_dirty || c->capsules_dirty) { rc = commit_impl(c); if (rc) return rc; }
     if (c->capsules.empty() && n) return fail(PRTC_ERR_INVALID, "prtc_step_characters: no capsule collider registered");
     StepParams p;
     fill_params(c, dt, n, d_tf, d_ph, p);
-    launch_step(p, false, c->stream);
+    launch_step(p, false, false, c->stream);
     PRTC_CUDA(cudaGetLastError());
     return PRTC_OK;
 }
 
 int prtc_step_characters(prtc_ctx * c, float dt, uint32_t n, prtc_transform * tf, prtc_char_physics * ph) {
     if (!c || (n && (!tf || !ph))) return fail(PRTC_ERR_INVALID, "prtc_step_characters: null argument");
+    int rc = check_mode(c, false);
+    if (rc) return rc;
     PRTC_CUDA(cudaSetDevice(c->cfg.device));
+    if (c->capsules.empty() && n) return fail(PRTC_ERR_INVALID, "prtc_step_characters: no capsule collider registered");
+    if (c->literal()) return literal_step(c, dt, n, tf, ph, nullptr);
     PRTC_CUDA(c->d_tf.reserve(n));
     PRTC_CUDA(c->d_ph.reserve(n));
     if (n) {
         PRTC_CUDA(cudaMemcpyAsync(c->d_tf.ptr, tf, size_t(n) * sizeof(prtc_transform), cudaMemcpyHostToDevice, c->stream));
         PRTC_CUDA(cudaMemcpyAsync(c->d_ph.ptr, ph, size_t(n) * sizeof(prtc_char_physics), cudaMemcpyHostToDevice, c->stream));
     }
-    int rc = prtc_step_characters_device(c, dt, n, c->d_tf.ptr, c->d_ph.ptr);
+    rc = prtc_step_characters_device(c, dt, n, c->d_tf.ptr, c->d_ph.ptr);
     if (rc) return rc;
     if (n) {
         PRTC_CUDA(cudaMemcpyAsync(tf, c->d_tf.ptr, size_t(n) * sizeof(prtc_transform), cudaMemcpyDeviceToHost, c->stream));
@@ -444,80 +666,28 @@ int prtc_step_characters(prtc_ctx * c, float dt, uint32_t n, prtc_transform * tf
 
 int prtc_step_characters_traced(prtc_ctx * c, float dt, uint32_t n, prtc_transform * tf, prtc_char_physics * ph, prtc_trace * tr) {
     if (!c || !tr || (n && (!tf || !ph))) return fail(PRTC_ERR_INVALID, "prtc_step_characters_traced: null argument");
-    int rc = check_mode(c);
+    int rc = check_mode(c, false);
     if (rc) return rc;
     PRTC_CUDA(cudaSetDevice(c->cfg.device));
-    if (c->geometry_dirty || c->tree_dirty || c->capsules_dirty) { rc = commit_impl(c); if (rc) return rc; }
     if (c->capsules.empty() && n) return fail(PRTC_ERR_INVALID, "prtc_step_characters: no capsule collider registered");
-    const uint32_t nsub = c->cfg.substeps;
-    const size_t slots = size_t(n) * nsub;
-    const uint32_t cap_cand = 64, cap_hits = 96;
+    if (c->literal()) return literal_step(c, dt, n, tf, ph, tr);
+    if (c->geometry_dirty || c->tree_dirty || c->capsules_dirty) { rc = commit_impl(c); if (rc) return rc; }
     cudaStream_t s = c->stream;
     PRTC_CUDA(c->d_tf.reserve(n));
     PRTC_CUDA(c->d_ph.reserve(n));
-    PRTC_CUDA(c->d_tq.reserve(slots));
-    PRTC_CUDA(c->d_tmesh.reserve(slots * cap_cand));
-    PRTC_CUDA(c->d_tcaps.reserve(slots * cap_cand));
-    PRTC_CUDA(c->d_thits.reserve(slots * cap_hits));
     tr->n_queries = tr->n_mesh_ids = tr->n_caps_ids = tr->n_hits = 0;
-    if (n == 0) { if (tr->q_mesh_off && tr->cap_queries + 1 > 0) tr->q_mesh_off[0] = 0; if (tr->q_caps_off) tr->q_caps_off[0] = 0; return PRTC_OK; }
-    PRTC_CUDA(cudaMemsetAsync(c->d_tq.ptr, 0, slots * sizeof(TraceQuery), s));
+    if (n == 0) { if (tr->q_mesh_off) tr->q_mesh_off[0] = 0; if (tr->q_caps_off) tr->q_caps_off[0] = 0; return PRTC_OK; }
     PRTC_CUDA(cudaMemcpyAsync(c->d_tf.ptr, tf, size_t(n) * sizeof(prtc_transform), cudaMemcpyHostToDevice, s));
     PRTC_CUDA(cudaMemcpyAsync(c->d_ph.ptr, ph, size_t(n) * sizeof(prtc_char_physics), cudaMemcpyHostToDevice, s));
     StepParams p;
     fill_params(c, dt, n, c->d_tf.ptr, c->d_ph.ptr, p);
-    p.trace.queries = c->d_tq.ptr; p.trace.mesh_ids = c->d_tmesh.ptr; p.trace.caps_ids = c->d_tcaps.ptr; p.trace.hits = c->d_thits.ptr;
-    p.trace.cap_cand = cap_cand; p.trace.cap_hits = cap_hits;
-    launch_step(p, true, s);
+    rc = prepare_trace(c, n, p);
+    if (rc) return rc;
+    launch_step(p, true, false, s);
     PRTC_CUDA(cudaGetLastError());
-    std::vector<TraceQuery> tq(slots);
-    std::vector<uint32_t> tmesh(slots * cap_cand);
-    std::vector<TraceHit> thits(slots * cap_hits);
     PRTC_CUDA(cudaMemcpyAsync(tf, c->d_tf.ptr, size_t(n) * sizeof(prtc_transform), cudaMemcpyDeviceToHost, s));
     PRTC_CUDA(cudaMemcpyAsync(ph, c->d_ph.ptr, size_t(n) * sizeof(prtc_char_physics), cudaMemcpyDeviceToHost, s));
-    PRTC_CUDA(cudaMemcpyAsync(tq.data(), c->d_tq.ptr, slots * sizeof(TraceQuery), cudaMemcpyDeviceToHost, s));
-    PRTC_CUDA(cudaMemcpyAsync(tmesh.data(), c->d_tmesh.ptr, tmesh.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
-    PRTC_CUDA(cudaMemcpyAsync(thits.data(), c->d_thits.ptr, thits.size() * sizeof(TraceHit), cudaMemcpyDeviceToHost, s));
-    PRTC_CUDA(cudaStreamSynchronize(s));
-
-    uint32_t nq = 0, nm = 0, nc = 0, nh = 0;
-    bool overflow = false;
-    if (tr->q_mesh_off && tr->cap_queries) tr->q_mesh_off[0] = 0;
-    if (tr->q_caps_off && tr->cap_queries) tr->q_caps_off[0] = 0;
-    for (uint32_t i = 0; i < n; ++i) {
-        for (uint32_t sub = 0; sub < nsub; ++sub) {
-            size_t slot = size_t(i) * nsub + sub;
-            TraceQuery const & q = tq[slot];
-            if (!q.executed) continue;
-            if (q.n_mesh > cap_cand || q.n_hits > cap_hits) overflow = true;
-            if (nq >= tr->cap_queries) { overflow = true; continue; }
-            tr->q_char[nq] = i;
-            tr->q_sub[nq] = sub;
-            for (int k = 0; k < 6; ++k) tr->q_aabb[6 * size_t(nq) + k] = q.aabb[k];
-            tr->q_tri_tests[nq] = q.tri_tests;
-            for (uint32_t k = 0; k < std::min(q.n_mesh, cap_cand); ++k) {
-                if (nm < tr->cap_mesh_ids) tr->mesh_ids[nm++] = tmesh[slot * cap_cand + k]; else overflow = true;
-            }
-            for (uint32_t k = 0; k < std::min(q.n_hits, cap_hits); ++k) {
-                if (nh >= tr->cap_hits) { overflow = true; break; }
-                TraceHit const & h = thits[slot * cap_hits + k];
-                tr->h_query[nh] = nq;
-                tr->h_poly[nh] = h.poly;
-                for (int d = 0; d < 3; ++d) {
-                    tr->h_impulse[3 * size_t(nh) + d] = h.impulse[d];
-                    tr->h_normal[3 * size_t(nh) + d] = h.normal[d];
-                    tr->h_pos[3 * size_t(nh) + d] = h.pos[d];
-                }
-                ++nh;
-            }
-            ++nq;
-            tr->q_mesh_off[nq] = nm;
-            tr->q_caps_off[nq] = nc;
-        }
-    }
-    tr->n_queries = nq; tr->n_mesh_ids = nm; tr->n_caps_ids = nc; tr->n_hits = nh;
-    if (overflow) return fail(PRTC_ERR_CAPACITY, "prtc_step_characters_traced: trace capacity exceeded (state is valid, trace is truncated)");
-    return PRTC_OK;
+    return gather_trace(c, n, TRACE_CAP_CAND, TRACE_CAP_HITS, tr);
 }
 
 int prtc_raycast(prtc_ctx * c, uint32_t, const float *, const float *, const float *, float *, uint8_t *) {

@@ -168,3 +168,93 @@ def test_movement_and_grounded_inputs():
     scene["move"] = (rs.uniform(-0.2, 0.2, (256, 3))).astype(np.float32)
     orc, ctx, tf, ph = _run_pair(scene, 12, dict(order="canonical"), dict(), trace_frames=(0, 5, 11))
     assert ph["grounded"].sum() > 0
+
+
+# ------------------------------------------------------------------------------------------------------------
+# LITERAL order: the reference's unified mesh+capsule tree is maintained on the host every frame with the
+# reference's own algorithm and characters keep their sequential visibility of one another -> the result must be
+# bit-identical to L0, the reference's own code, end to end (parity level P4), capsule-capsule included.
+# ------------------------------------------------------------------------------------------------------------
+LITERAL_KEYS = H.TRACE_KEYS + ("q_caps_off", "caps_ids")
+
+
+def _run_literal_vs_l0(scene, frames, variant="traced", abs_mode=0, trace_frames=(0, 1, 2)):
+    from prototype2_b200 import capi
+    l0 = H.build_oracle(scene, "l0", variant=variant)
+    ctx, tf, ph = H.build_gpu(scene, order_mode=capi.ORDER_LITERAL, abs_mode=abs_mode)
+    cc = 0
+    for f in range(frames):
+        if variant == "traced" and f in trace_frames:
+            t0 = l0.step(DT, trace=True)
+            tg = ctx.update_characters_traced(DT, tf, ph)
+            assert H.trace_diff(t0, tg, LITERAL_KEYS) == [], "frame %d trace" % f
+            cc += int((t0.h_poly < 0).sum())
+        else:
+            l0.step(DT)
+            ctx.update_characters(DT, tf, ph)
+        assert H.state_diff(l0.get_state(), H.gpu_state(tf, ph)) == [], "frame %d state" % f
+    return cc
+
+
+@pytest.mark.skipif(not L0World.available("traced"), reason="oracle/_ref not built")
+def test_literal_mode_equals_reference_crowded():
+    scene = H.make_scene(40, 2, 1, 80, seed=101)             # random placement: capsules overlap and push each other
+    cc = _run_literal_vs_l0(scene, 25, trace_frames=(0, 1, 2, 3, 10, 24))
+    assert cc > 0, "scene was meant to exercise the capsule-capsule pass"
+
+
+@pytest.mark.skipif(not L0World.available("traced"), reason="oracle/_ref not built")
+def test_literal_mode_equals_reference_rotated_moving():
+    scene = H.make_scene(48, 1, 1, 60, seed=102)
+    scene["rot"] = H.random_rotations(60, seed=9)
+    rs = np.random.RandomState(3)
+    scene["move"] = rs.uniform(-0.2, 0.2, (60, 3)).astype(np.float32)
+    _run_literal_vs_l0(scene, 20)
+
+
+@pytest.mark.skipif(not L0World.available("fabs"), reason="oracle/_ref not built")
+def test_literal_mode_equals_reference_float_abs_build():
+    from prototype2_b200 import capi
+    scene = H.make_scene(64, 4, 2, 50, seed=103)
+    scene["model_transform"] = [0.5, 0.25, -1.0, 0.9914449, 0.0, 0.1305262, 0.0, 1.25, 1.0, 1.25]
+    _run_literal_vs_l0(scene, 12, variant="fabs", abs_mode=capi.ABS_FLOAT)
+
+
+@pytest.mark.skipif(not L0World.available("traced"), reason="oracle/_ref not built")
+def test_literal_mode_c2_shape_600_capsules():
+    """the 12 % of characters that see a different candidate sequence in canonical order (finding 3 / H4) are
+    bit-identical here"""
+    scene = H.make_scene(120, 2, 2, 600, seed=21, separated=True)
+    _run_literal_vs_l0(scene, 6, trace_frames=(0, 5))
+
+
+import glob
+import os
+
+GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[:-4] for p in GOLDEN])
+def test_golden_vectors_from_the_reference(path):
+    """known-answer vectors generated from the reference's own code (tests/golden/make_golden.py): LITERAL order
+    must reproduce every one, CANONICAL order those flagged canonical_ok, in both abs resolutions"""
+    from prototype2_b200 import capi
+    g = np.load(path)
+    cap = g["capsule"]
+    scene = {"xyz": g["xyz"], "mesh_first": g["mesh_first"], "mesh_count": g["mesh_count"],
+             "model_transform": list(g["model_transform"]), "capsule": (float(cap[0]), float(cap[1]), tuple(float(x) for x in cap[2:5])),
+             "pos": g["pos"], "vel": g["vel"], "rot": g["rot"], "move": g["move"], "n": len(g["pos"])}
+    for tag, absm in (("int", capi.ABS_INT), ("flt", capi.ABS_FLOAT)):
+        modes = [capi.ORDER_LITERAL] + ([capi.ORDER_CANONICAL] if bool(g["canonical_ok_%s" % tag]) else [])
+        for mode in modes:
+            ctx, tf, ph = H.build_gpu(scene, order_mode=mode, abs_mode=absm)
+            for f in range(int(g["frames"])):
+                if f == 0 and tag == "int" and mode == capi.ORDER_LITERAL:
+                    tg = ctx.update_characters_traced(float(g["dt"]), tf, ph)
+                    for k in LITERAL_KEYS:
+                        assert H.same(tg[k], g["trace_" + k]), "trace %s" % k
+                else:
+                    ctx.update_characters(float(g["dt"]), tf, ph)
+                s = H.gpu_state(tf, ph)
+                for k in ("pos", "vel", "gnormal", "grounded"):
+                    assert H.same(s[k], g["%s_%s" % (tag, k)][f]), "%s mode %d frame %d %s" % (tag, mode, f, k)
