@@ -144,6 +144,10 @@ int prtc_update_capsule(prtc_ctx * ctx, uint32_t id, float height, float radius,
  * the reference's right-first DFS order and uploads.  Called implicitly by the step functions when needed. */
 int prtc_commit(prtc_ctx * ctx);
 
+/* PhysicsSystem::removeCollider(tag) for a MODEL tag -> removeModelCollider  physics_system.cpp:108-149: the model's
+ * mesh leaves leave the tree.  (Ids of other colliders stay stable here; the reference renumbers later meshes.) */
+int prtc_remove_model(prtc_ctx * ctx, uint32_t model_id);
+
 /* PhysicsSystem::updateModelColliders(ColliderTag const*, Transform const*, size_t)  physics_system.cpp:161-202 */
 int prtc_update_models(prtc_ctx * ctx, const uint32_t * model_ids, const prtc_transform * transforms, uint32_t n);
 

@@ -18,7 +18,7 @@ OPT_FRAME_CACHE, OPT_QUICK_REJECT = 1, 2
 # every symbol include/prtc.h declares (tests check the library exports exactly these)
 SYMBOLS = (
     "prtc_default_config", "prtc_last_error", "prtc_device_count", "prtc_create", "prtc_destroy",
-    "prtc_add_model", "prtc_add_capsule", "prtc_update_capsule", "prtc_commit", "prtc_update_models",
+    "prtc_add_model", "prtc_add_capsule", "prtc_update_capsule", "prtc_commit", "prtc_update_models", "prtc_remove_model",
     "prtc_step_characters", "prtc_step_characters_device", "prtc_step_characters_traced", "prtc_raycast",
     "prtc_set_stream", "prtc_synchronize", "prtc_get_counters", "prtc_set_option", "prtc_get_tree_info", "prtc_get_leaf_order",
     "prtc_get_world_vertices", "prtc_query_box", "prtc_host_build_tree",
@@ -182,6 +182,19 @@ class PhysicsContext:
         ids = np.ascontiguousarray(model_ids, np.uint32)
         assert transforms.dtype == TRANSFORM_DTYPE
         self._check(self.lib.prtc_update_models(self.h, _vp(ids), _vp(transforms), ctypes.c_uint32(len(ids))))
+
+    def remove_model_collider(self, model_id):
+        self._check(self.lib.prtc_remove_model(self.h, ctypes.c_uint32(model_id)))
+
+    def raycast(self, origins, directions, max_distances):
+        """PhysicsSystem::raycast, batched: returns (hit_mask[n] bool, hit_xyz[n,3])"""
+        o = np.ascontiguousarray(origins, np.float32).reshape(-1, 3)
+        d = np.ascontiguousarray(directions, np.float32).reshape(-1, 3)
+        m = np.ascontiguousarray(np.broadcast_to(np.asarray(max_distances, np.float32), (len(o),)), np.float32)
+        hit = np.zeros((len(o), 3), np.float32)
+        mask = np.zeros(len(o), np.uint8)
+        self._check(self.lib.prtc_raycast(self.h, ctypes.c_uint32(len(o)), _vp(o), _vp(d), _vp(m), _vp(hit), _vp(mask)))
+        return mask.astype(bool), hit
 
     def commit(self):
         self._check(self.lib.prtc_commit(self.h))

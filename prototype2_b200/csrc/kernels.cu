@@ -466,7 +466,102 @@ __global__ void k_query_box(const float4 * __restrict__ nodes, uint32_t n_nodes,
     *out_count = found;
 }
 
+// PhysicsSystem::raycast (physics_system.cpp:205-242): one thread per ray.  DynamicAABBTree::queryRaycast
+// (aabb_tree.cpp:70-93) with AABB::intersectRay (aabb.cpp:13-48, Ericson's slab test), then
+// intersectLineSegmentTriangle (physics_util.cpp:181-216) on every triangle of every mesh leaf hit; the result is
+// the minimum t, so the visiting order does not matter.  Capsule leaves of a unified tree are skipped (:215).
+__device__ __forceinline__ bool ray_box(float4 lo, float4 hi, V3 o, V3 d, float maxDistance) {
+    float tmin = 0.0f;
+    float tmax = maxDistance;
+    const float lov[3] = {lo.x, lo.y, lo.z}, hiv[3] = {hi.x, hi.y, hi.z};
+    const float ov[3] = {o.x, o.y, o.z}, dv[3] = {d.x, d.y, d.z};
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        if (double(fabsf(dv[i])) < 0.00001) {                     // `std::abs(direction[i]) < 0.00001`: a double compare
+            if (ov[i] < lov[i] || ov[i] > hiv[i]) return false;
+        } else {
+            const float ood = fdiv(1.0f, dv[i]);
+            float t1 = (lov[i] - ov[i]) * ood;
+            float t2 = (hiv[i] - ov[i]) * ood;
+            if (t1 > t2) { const float tmp = t1; t1 = t2; t2 = tmp; }
+            if (t1 > tmin) tmin = t1;
+            if (t2 < tmax) tmax = t2;
+            if (tmin > tmax) return false;
+        }
+    }
+    return true;
+}
+
+__device__ __forceinline__ bool segment_triangle(V3 origin, V3 end, V3 a, V3 b, V3 c, float & t) {
+    const V3 ab = b - a;
+    const V3 ac = c - a;
+    const V3 qp = origin - end;
+    const V3 n = cross(ab, ac);
+    const float d = dot(qp, n);
+    if (d <= 0.0f) return false;
+    const V3 ap = origin - a;
+    t = dot(ap, n);
+    if (t < 0.0f) return false;
+    if (t > d) return false;
+    const V3 e = cross(qp, ap);
+    const float v = dot(ac, e);
+    if (v < 0.0f || v > d) return false;
+    const float w = -dot(ab, e);
+    if (w < 0.0f || v + w > d) return false;
+    const float ood = fdiv(1.0f, d);
+    t = t * ood;
+    return true;
+}
+
+__global__ void k_raycast(const float4 * __restrict__ nodes, uint32_t n_nodes, const float4 * __restrict__ tris, uint32_t n_rays,
+                          const float * __restrict__ origins, const float * __restrict__ dirs, const float * __restrict__ maxd,
+                          float * __restrict__ hit_xyz, unsigned char * __restrict__ hit_mask) {
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_rays) return;
+    const V3 o = v3(origins[3 * r], origins[3 * r + 1], origins[3 * r + 2]);
+    const V3 d = v3(dirs[3 * r], dirs[3 * r + 1], dirs[3 * r + 2]);
+    const float md = maxd[r];
+    const V3 end = o + d * md;
+    float best = 3.402823466e+38f;                                // std::numeric_limits<float>::max()
+    bool any = false;
+    uint32_t node = 0;
+    while (node < n_nodes) {
+        const float4 lo = nodes[2 * node];
+        const float4 hi = nodes[2 * node + 1];
+        const bool ov = ray_box(lo, hi, o, d, md);
+        const int link = __float_as_int(lo.w);
+        const int cnt = __float_as_int(hi.w);
+        if (cnt < 0) {
+            node = ov ? node + 1 : uint32_t(link);
+        } else {
+            if (ov && !(cnt & PRT_CAPSULE_LEAF)) {
+                for (uint32_t t = uint32_t(link); t < uint32_t(link) + uint32_t(cnt); ++t) {
+                    const float4 t0 = tris[3 * size_t(t)], t1 = tris[3 * size_t(t) + 1], t2 = tris[3 * size_t(t) + 2];
+                    float tt;
+                    if (segment_triangle(o, end, v3(t0.x, t0.y, t0.z), v3(t1.x, t1.y, t1.z), v3(t2.x, t2.y, t2.z), tt)) {
+                        any = true;
+                        best = (tt < best) ? tt : best;           // std::min(intersectionTime, t)
+                    }
+                }
+            }
+            node = node + 1;
+        }
+    }
+    hit_mask[r] = any ? 1 : 0;
+    if (any) {
+        const V3 h = o + (d * best) * md;                         // origin + direction * intersectionTime * maxDistance
+        hit_xyz[3 * r] = h.x; hit_xyz[3 * r + 1] = h.y; hit_xyz[3 * r + 2] = h.z;
+    }
+}
+
 } // namespace
+
+void launch_raycast(const float4 * nodes, uint32_t n_nodes, const float4 * tris, uint32_t n_rays, const float * origins,
+                    const float * dirs, const float * maxd, float * hit_xyz, unsigned char * hit_mask, cudaStream_t stream) {
+    if (n_rays == 0) return;
+    const uint32_t block = 64;
+    k_raycast<<<(n_rays + block - 1) / block, block, 0, stream>>>(nodes, n_nodes, tris, n_rays, origins, dirs, maxd, hit_xyz, hit_mask);
+}
 
 void launch_step(StepParams const & p, bool traced, bool literal, cudaStream_t stream) {
     if (p.n == 0) return;

@@ -74,6 +74,9 @@ void launch_transform_refit(const float * raw_xyz, float * world_xyz, const Mesh
 // leaf-ordered triangle records with precomputed unit normals
 void launch_tri_setup(const float * world_xyz, const uint32_t * tri_src_vertex, uint32_t n_tris, float4 * tris,
                       cudaStream_t stream);
+// K7: batched PhysicsSystem::raycast
+void launch_raycast(const float4 * nodes, uint32_t n_nodes, const float4 * tris, uint32_t n_rays, const float * origins,
+                    const float * dirs, const float * maxd, float * hit_xyz, unsigned char * hit_mask, cudaStream_t stream);
 // single box query (introspection / tests)
 void launch_query_box(const float4 * nodes, uint32_t n_nodes, const uint32_t * node_leaf_id, const float * aabb6,
                       uint32_t * out_ids, uint32_t capacity, uint32_t * out_count, cudaStream_t stream);

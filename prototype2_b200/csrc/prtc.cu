@@ -179,7 +179,8 @@ int commit_impl(prtc_ctx * c) {
         for (float v : aabbs) { float a = std::fabs(v); if (a > c->world_max_abs) c->world_max_abs = a; }   // NaN never wins
         // new meshes: DynamicAABBTree::insert in registration order, physics_system.cpp:102
         for (uint32_t m = c->meshes_in_tree; m < n_meshes; ++m)
-            c->meshes[m].tree_index = c->tree.insert_leaf(m, LEAF_MESH, box_of(m));
+            if (c->models[c->meshes[m].model].n_meshes != 0)      // not removed before its first commit
+                c->meshes[m].tree_index = c->tree.insert_leaf(m, LEAF_MESH, box_of(m));
         c->meshes_in_tree = n_meshes;
         c->meshes_on_device = n_meshes;
         c->geometry_dirty = false;
@@ -690,9 +691,47 @@ int prtc_step_characters_traced(prtc_ctx * c, float dt, uint32_t n, prtc_transfo
     return gather_trace(c, n, TRACE_CAP_CAND, TRACE_CAP_HITS, tr);
 }
 
-int prtc_raycast(prtc_ctx * c, uint32_t, const float *, const float *, const float *, float *, uint8_t *) {
-    if (!c) return fail(PRTC_ERR_INVALID, "prtc_raycast: null context");
-    return fail(PRTC_ERR_INVALID, "prtc_raycast: not available in this build");
+int prtc_raycast(prtc_ctx * c, uint32_t n, const float * origins, const float * directions, const float * max_distances,
+                 float * hit_xyz, uint8_t * hit_mask) {
+    if (!c || (n && (!origins || !directions || !max_distances || !hit_xyz || !hit_mask)))
+        return fail(PRTC_ERR_INVALID, "prtc_raycast: null argument");
+    PRTC_CUDA(cudaSetDevice(c->cfg.device));
+    if (c->geometry_dirty || c->tree_dirty || c->capsules_dirty) { int rc = commit_impl(c); if (rc) return rc; }
+    if (n == 0) return PRTC_OK;
+    cudaStream_t s = c->stream;
+    PRTC_CUDA(c->d_scratch_f.reserve(size_t(n) * 10));
+    PRTC_CUDA(c->d_scratch_u.reserve((size_t(n) + 3) / 4 + 1));
+    float * d_o = c->d_scratch_f.ptr, * d_d = d_o + 3 * size_t(n), * d_m = d_d + 3 * size_t(n), * d_h = d_m + n;
+    unsigned char * d_mask = reinterpret_cast<unsigned char *>(c->d_scratch_u.ptr);
+    PRTC_CUDA(cudaMemcpyAsync(d_o, origins, size_t(n) * 3 * sizeof(float), cudaMemcpyHostToDevice, s));
+    PRTC_CUDA(cudaMemcpyAsync(d_d, directions, size_t(n) * 3 * sizeof(float), cudaMemcpyHostToDevice, s));
+    PRTC_CUDA(cudaMemcpyAsync(d_m, max_distances, size_t(n) * sizeof(float), cudaMemcpyHostToDevice, s));
+    PRTC_CUDA(cudaMemsetAsync(d_h, 0, size_t(n) * 3 * sizeof(float), s));
+    launch_raycast(c->d_nodes.ptr, uint32_t(c->flat.nodes.size()), c->d_tris.ptr, n, d_o, d_d, d_m, d_h, d_mask, s);
+    PRTC_CUDA(cudaGetLastError());
+    std::vector<float> h(size_t(n) * 3);
+    PRTC_CUDA(cudaMemcpyAsync(h.data(), d_h, h.size() * sizeof(float), cudaMemcpyDeviceToHost, s));
+    PRTC_CUDA(cudaMemcpyAsync(hit_mask, d_mask, n, cudaMemcpyDeviceToHost, s));
+    PRTC_CUDA(cudaStreamSynchronize(s));
+    for (uint32_t i = 0; i < n; ++i)
+        if (hit_mask[i]) { hit_xyz[3 * i] = h[3 * size_t(i)]; hit_xyz[3 * i + 1] = h[3 * size_t(i) + 1]; hit_xyz[3 * i + 2] = h[3 * size_t(i) + 2]; }
+    return PRTC_OK;
+}
+
+int prtc_remove_model(prtc_ctx * c, uint32_t model_id) {
+    if (!c || model_id >= c->models.size()) return fail(PRTC_ERR_INVALID, "prtc_remove_model: bad model id");
+    ModelHost & mh = c->models[model_id];
+    // DynamicAABBTree::remove over the model's mesh leaves in order (physics_system.cpp:136)
+    for (uint32_t m = mh.first_mesh; m < mh.first_mesh + mh.n_meshes; ++m) {
+        MeshHost & me = c->meshes[m];
+        if (m < c->meshes_in_tree && me.tree_index >= 0) c->tree.remove(me.tree_index);
+        me.tree_index = -1;
+        me.n_vertices = 0;          // the vertices stay in the registry but are never referenced again
+    }
+    mh.n_meshes = 0;
+    c->geometry_dirty = true;
+    c->tree_dirty = true;
+    return PRTC_OK;
 }
 
 int prtc_get_counters(prtc_ctx * c, prtc_counters * out, int reset) {

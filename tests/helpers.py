@@ -166,3 +166,12 @@ def compare_with_literal(t_lit, t_can, s_lit, s_can, n_chars):
         stats["out_of_sync_max_pos_dev"] = float(d.max())
         stats["out_of_sync_median_pos_dev"] = float(np.median(d))
     return stats
+
+
+def c1_scene(g):
+    """scene dict of the shipped-level fixture tests/golden/c1_level.npz (see tests/golden/make_c1.py)"""
+    cap = g["capsule"]
+    return {"xyz": g["xyz"], "mesh_first": g["mesh_first"], "mesh_count": g["mesh_count"],
+            "model_transform": list(g["model_transform"]), "capsule": (float(cap[0]), float(cap[1]), tuple(float(x) for x in cap[2:5])),
+            "pos": g["pos"], "vel": np.zeros((1, 3), np.float32), "rot": np.array([[1, 0, 0, 0]], np.float32),
+            "move": np.zeros((1, 3), np.float32), "n": 1}

@@ -12,7 +12,8 @@ import helpers as H
 from oraclelib import L0World, L1World, Trace
 
 DT = 1.0 / 30.0
-GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+GOLDEN = sorted(p for p in glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")) if not os.path.basename(p).startswith("c1_"))
+C1_PATH = os.path.join(os.path.dirname(__file__), "golden", "c1_level.npz")
 needs_l0 = pytest.mark.skipif(not L0World.available("traced"), reason="oracle/_ref not built (needs /root/reference)")
 
 
@@ -127,3 +128,22 @@ def test_canonical_vs_literal_deviation_report():
         assert st["chars_in_sync"] >= scene["n"] * 0.6
         s = l0.get_state()
         l1.set_state(pos=s["pos"], vel=s["vel"], gnormal=s["gnormal"], grounded=s["grounded"])
+
+
+@pytest.mark.parametrize("tag,absm", [("int", "int"), ("flt", "float")])
+def test_l1_reproduces_c1_shipped_level(tag, absm):
+    """C1: the repo's shipped level (res/models/level1, 3007 triangles in 172 mesh colliders) with the player capsule
+    of res/scenes/cavern.prt, 300 scripted frames (fall, land, run, jump) recorded from the reference's own code"""
+    g = np.load(C1_PATH)
+    w = H.build_oracle(H.c1_scene(g), "l1", order="literal", abs_mode=absm)
+    for f in range(int(g["frames"])):
+        s = w.get_state()
+        vel = s["vel"].copy()
+        if g["jump_script"][f]:
+            vel[0, 1] = np.float32(0.35)
+        w.set_state(vel=vel, move=g["move_script"][f:f + 1])
+        w.step(float(g["dt"]))
+        s = w.get_state()
+        for k in ("pos", "vel", "gnormal", "grounded"):
+            assert H.same(s[k], g["%s_%s" % (tag, k)][f]), "frame %d %s" % (f, k)
+    assert g["int_grounded"].sum() > 200 and abs(float(g["int_pos"][-1][0][1])) < 1e-5    # ends standing on the ground floor
