@@ -1,0 +1,117 @@
+// Engine-side caller used to demonstrate the drop-in (TEST code).  It only uses the public PhysicsSystem API of the
+// reference (physics_system.h:24-77) plus the engine types around it, exactly as Scene / CharacterSystem /
+// SceneSerialization do (scene.cpp:185-220, character_system.cpp:55-78, scene_serialization.cpp:145-166).
+// tests/cpp/Makefile compiles THIS SAME FILE twice:
+//   driver_reference  against the reference's own physics sources (unmodified, from /root/reference)
+//   driver_dropin     against prototype2_b200/engine/physics_system.{h,cpp} + libprtc.so
+// and tests/test_dropin.py requires the two programs to print byte-identical state dumps.
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "src/game/system/physics/physics_system.h"
+#include "src/game/scene/scene.h"
+
+void (*prt_oracle_contact_hook)(EntityID) = nullptr;   // the shadow Character header's per-contact hook (unused here)
+
+static uint32_t rng_state = 12345u;
+static float frand() {                                  // small LCG: identical streams in both builds
+    rng_state = rng_state * 1664525u + 1013904223u;
+    return float(rng_state >> 8) / 16777216.0f;
+}
+static float height(float x, float z) { return 0.75f * float(std::sin(0.07 * double(x))) * float(std::cos(0.05 * double(z))); }
+
+static void put(std::vector<uint8_t> & out, void const * p, size_t n) {
+    uint8_t const * b = static_cast<uint8_t const *>(p);
+    out.insert(out.end(), b, b + n);
+}
+
+int main(int argc, char ** argv) {
+    int const N = argc > 1 ? std::atoi(argv[1]) : 24;          // terrain cells per side
+    int const nChars = argc > 2 ? std::atoi(argv[2]) : 12;
+    int const frames = argc > 3 ? std::atoi(argv[3]) : 40;
+    char const * outPath = argc > 4 ? argv[4] : "dump.bin";
+
+    PhysicsSystem physics;
+    Scene scene;
+
+    // a terrain model with one mesh per 2x2 cells, registered like SceneSerialization does for a MODEL collider
+    Model model;
+    for (int bx = 0; bx < N; bx += 2) for (int bz = 0; bz < N; bz += 2) {
+        Model::Mesh mesh;
+        mesh.startIndex = model.indexBuffer.size();
+        for (int x = bx; x < bx + 2 && x < N; ++x) for (int z = bz; z < bz + 2 && z < N; ++z) {
+            float const xs[4] = {float(x), float(x), float(x + 1), float(x + 1)};
+            float const zs[4] = {float(z), float(z + 1), float(z + 1), float(z)};
+            int const order[6] = {0, 1, 2, 0, 2, 3};
+            for (int k = 0; k < 6; ++k) {
+                Model::Vertex v;
+                v.pos = glm::vec3(xs[order[k]], height(xs[order[k]], zs[order[k]]), zs[order[k]]);
+                model.indexBuffer.push_back(uint32_t(model.vertexBuffer.size()));
+                model.vertexBuffer.push_back(v);
+            }
+        }
+        mesh.numIndices = model.indexBuffer.size() - mesh.startIndex;
+        model.meshes.push_back(mesh);
+    }
+    Transform mapTransform;
+    mapTransform.scale = glm::vec3(1.5f, 1.0f, 1.5f);
+    ColliderTag mapTag = physics.addModelCollider(model, mapTransform);
+
+    // characters with capsule colliders (cavern.prt:9 values), some of them overlapping each other
+    std::vector<Transform> transforms{static_cast<size_t>(nChars)};
+    for (int i = 0; i < nChars; ++i) {
+        ColliderTag tag = physics.addCapsuleCollider(0.5f, 0.5f, glm::vec3(0.0f, 0.5f, 0.0f));
+        Character c;
+        c.id = EntityID(i);
+        c.physics.colliderTag = tag;
+        float const x = 3.0f + frand() * (1.5f * float(N) - 6.0f), z = 3.0f + frand() * (1.5f * float(N) - 6.0f);
+        transforms[size_t(i)].position = glm::vec3(x, 1.5f + frand(), z);
+        float const yaw = 6.2831853f * frand();
+        transforms[size_t(i)].rotation = glm::quat(std::cos(0.5f * yaw), 0.0f, std::sin(0.5f * yaw), 0.0f);
+        c.physics.velocity = glm::vec3(-0.2f + 0.4f * frand(), -0.2f * frand(), -0.2f + 0.4f * frand());
+        scene.getCharacterSystem().chars.push_back(c);
+    }
+    if (nChars >= 2) transforms[1].position = transforms[0].position + glm::vec3(0.3f, 0.0f, 0.1f);   // a touching pair
+
+    std::vector<uint8_t> dump;
+    for (int f = 0; f < frames; ++f) {
+        for (int i = 0; i < nChars; ++i) {               // gameplay input, like CharacterSystem::updateCharacters
+            CharacterPhysics & p = scene.getCharacterSystem().getCharacter(size_t(i)).physics;
+            p.movementVector = (f / 10) % 2 == 0 ? glm::vec3(0.1f, 0.0f, 0.05f) : glm::vec3(0.0f, 0.0f, 0.0f);
+            if (f == 15 && p.isGrounded) p.velocity.y = 0.35f;            // jump (character_system.cpp:92)
+        }
+        if (f == 20) {                                   // the editor moves the map (editor.cpp:40 -> scene.cpp:190-211)
+            mapTransform.position = glm::vec3(0.25f, -0.1f, 0.0f);
+            physics.updateModelColliders(&mapTag, &mapTransform, 1);
+        }
+        if (f == 25 && nChars > 2)                       // the editor edits a capsule (editor_gui.cpp:293-301)
+            physics.updateCapsuleCollider(scene.getCharacterSystem().getCharacter(2).physics.colliderTag, 0.8f, 0.4f, glm::vec3(0.0f, 0.4f, 0.0f));
+        physics.updateCharacters(1.0f / 30.0f, scene, transforms.data());
+        for (int i = 0; i < nChars; ++i) {
+            CharacterPhysics const & p = scene.getCharacterSystem().getCharacter(size_t(i)).physics;
+            put(dump, &transforms[size_t(i)].position, sizeof(glm::vec3));
+            put(dump, &p.velocity, sizeof(glm::vec3));
+            put(dump, &p.groundNormal, sizeof(glm::vec3));
+            uint8_t g = p.isGrounded ? 1 : 0;
+            put(dump, &g, 1);
+        }
+        // camera occlusion rays (scene.cpp:248-255)
+        for (int k = 0; k < 4; ++k) {
+            glm::vec3 origin = transforms[0].position + glm::vec3(0.0f, 1.0f, 0.0f);
+            glm::vec3 dir = glm::normalize(glm::vec3(float(k) - 1.5f, -0.8f, 1.0f));
+            glm::vec3 hit(0.0f);
+            uint8_t r = physics.raycast(origin, dir, 5.0f, hit) ? 1 : 0;
+            put(dump, &r, 1);
+            if (r) put(dump, &hit, sizeof(glm::vec3));
+        }
+    }
+    FILE * fp = std::fopen(outPath, "wb");
+    if (!fp) return 2;
+    std::fwrite(dump.data(), 1, dump.size(), fp);
+    std::fclose(fp);
+    std::printf("%s: %d characters, %d frames, %zu bytes, gravity %.1f\n", outPath, nChars, frames, dump.size(), double(physics.getGravity()));
+    return 0;
+}
