@@ -190,7 +190,7 @@ def run_reference(args):
                                  "the verbatim build cannot hold >65534 mesh colliders), std::thread over capsules"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 # ----------------------------------------------------------------------------------------------------------
@@ -378,13 +378,30 @@ def run_ours(args):
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": args.steps, "clocks": clocks,
             "setup": {"commit_s": t_commit, "nodes": info["nodes"], "leaves": info["leaves"]},
         }
-        print(json.dumps(line))
+        emit(line)
     if dist is not None:
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def emit(line):
+    """the ONE JSON line goes to the process's real stdout; everything else (NCCL banners, warnings) to stderr"""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
+    global _REAL_STDOUT
     args = parse_args()
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)                       # libraries that print to fd 1 (e.g. "NCCL version ...") must not pollute the JSON line
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -51,7 +51,7 @@ enum prtc_order_mode { PRTC_ORDER_LITERAL = 0, PRTC_ORDER_CANONICAL = 1 };
 
 /* Dynamic-vs-dynamic (capsule-capsule) pass in CANONICAL order:
  *   PRTC_DYN_OFF     capsules do not see one another (static pass only)
- *   PRTC_DYN_JACOBI  every capsule collides against the start-of-frame pose of its neighbours */
+ *   PRTC_DYN_JACOBI  every capsule collides against the start-of-frame pose of its neighbours (see prtc_dyn_*) */
 enum prtc_dyn_mode { PRTC_DYN_OFF = 0, PRTC_DYN_JACOBI = 2 };
 
 /* Compile-time constants of the reference turned into fields (defaults = reference values). */
@@ -166,6 +166,19 @@ int prtc_step_characters_traced(prtc_ctx * ctx, float dt, uint32_t n, prtc_trans
  * n rays; hit_xyz[3*i..] is written and hit_mask[i]=1 where ray i hits a mesh collider. */
 int prtc_raycast(prtc_ctx * ctx, uint32_t n, const float * origins, const float * directions,
                  const float * max_distances, float * hit_xyz, uint8_t * hit_mask);
+
+/* Dynamic-vs-dynamic pass at scale (PRTC_ORDER_CANONICAL + PRTC_DYN_JACOBI): every character
+ * collides with the start-of-frame pose of every other character whose STORED fat box (the hysteresis of
+ * DynamicAABBTree::update / insertLeaf, aabb_tree.cpp:102-111,140-141) overlaps its query box, in ascending global
+ * character index (collideCapsuleCapsule, collision_system.cpp:158-234; pass order physics_system.cpp:369-389).
+ * On one GPU nothing extra has to be called.  With characters partitioned over ranks, per frame and rank:
+ *   prtc_dyn_configure(ctx, first, n_global)             once: this rank owns global indices [first, first + n)
+ *   prtc_dyn_prepare(ctx, dt, n, d_transforms, d_physics) writes this rank's records (64 bytes per character)
+ *   prtc_dyn_buffer(...) -> the caller all-gathers the record array IN PLACE (e.g. ncclAllGather over NVLink)
+ *   prtc_step_characters_device(...)                      grid over all records + the step                       */
+int prtc_dyn_configure(prtc_ctx * ctx, uint32_t first_global, uint32_t n_global);
+int prtc_dyn_prepare(prtc_ctx * ctx, float dt, uint32_t n, const prtc_transform * d_transforms, const prtc_char_physics * d_physics);
+int prtc_dyn_buffer(prtc_ctx * ctx, void ** d_records, size_t * record_bytes, uint32_t * first_global, uint32_t * n_global);
 
 /* stream control for callers that own device memory (bench / multi-GPU drivers) */
 int prtc_set_stream(prtc_ctx * ctx, void * cuda_stream);

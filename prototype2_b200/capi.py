@@ -20,7 +20,7 @@ SYMBOLS = (
     "prtc_default_config", "prtc_last_error", "prtc_device_count", "prtc_create", "prtc_destroy",
     "prtc_add_model", "prtc_add_capsule", "prtc_update_capsule", "prtc_commit", "prtc_update_models", "prtc_remove_model",
     "prtc_step_characters", "prtc_step_characters_device", "prtc_step_characters_traced", "prtc_raycast",
-    "prtc_set_stream", "prtc_synchronize", "prtc_get_counters", "prtc_set_option", "prtc_get_tree_info", "prtc_get_leaf_order",
+    "prtc_set_stream", "prtc_synchronize", "prtc_get_counters", "prtc_set_option", "prtc_dyn_configure", "prtc_dyn_prepare", "prtc_dyn_buffer", "prtc_get_tree_info", "prtc_get_leaf_order",
     "prtc_get_world_vertices", "prtc_query_box", "prtc_host_build_tree",
 )
 
@@ -236,6 +236,19 @@ class PhysicsContext:
                "h_query": arr["h_query"][:nh], "h_poly": arr["h_poly"][:nh], "h_impulse": arr["h_impulse"][:nh],
                "h_normal": arr["h_normal"][:nh], "h_pos": arr["h_pos"][:nh]}
         return out
+
+    def dyn_configure(self, first_global, n_global):
+        self._check(self.lib.prtc_dyn_configure(self.h, ctypes.c_uint32(first_global), ctypes.c_uint32(n_global)))
+
+    def dyn_prepare(self, dt, n, d_transforms_ptr, d_physics_ptr):
+        self._check(self.lib.prtc_dyn_prepare(self.h, ctypes.c_float(dt), ctypes.c_uint32(n), ctypes.c_void_p(d_transforms_ptr),
+                                              ctypes.c_void_p(d_physics_ptr)))
+
+    def dyn_buffer(self):
+        """(device pointer, bytes per record, first global index, global count) of the record array to all-gather"""
+        ptr, rb, first, ng = ctypes.c_void_p(), ctypes.c_size_t(), ctypes.c_uint32(), ctypes.c_uint32()
+        self._check(self.lib.prtc_dyn_buffer(self.h, ctypes.byref(ptr), ctypes.byref(rb), ctypes.byref(first), ctypes.byref(ng)))
+        return ptr.value, rb.value, first.value, ng.value
 
     def set_option(self, option, value):
         self._check(self.lib.prtc_set_option(self.h, ctypes.c_int(option), ctypes.c_int(value)))

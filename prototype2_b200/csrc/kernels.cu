@@ -28,6 +28,15 @@ __device__ __forceinline__ bool node_overlaps(float4 lo, float4 hi, Box const & 
     return !(lo.x > q.hi.x || hi.x < q.lo.x || lo.y > q.hi.y || hi.y < q.lo.y || lo.z > q.hi.z || hi.z < q.lo.z);
 }
 
+// uniform xz grid of the JACOBI pass: cell coordinate of a world coordinate, clamped to the grid (clamping is safe,
+// the box-box test stays exact)
+__device__ __forceinline__ int dyn_cell(float v, float origin, float inv_cell, uint32_t g) {
+    const float f = floorf((v - origin) * inv_cell);
+    int c = (f >= float(g)) ? int(g) - 1 : (f < 0.0f ? 0 : int(f));
+    if (!(f == f)) c = 0;                                          // NaN boxes land in cell 0; they overlap everything anyway
+    return c;
+}
+
 // Conservative per-triangle pre-cull.  A contact needs `inside || intersects` (collision_system.cpp:101):
 //   intersects -> a point of the triangle lies within `radius` of `center`, and `center` lies on the segment AB;
 //   inside     -> point0 = center - n*dist lies in the triangle with 0 <= dist < dmax (the range cull :71-72), so
@@ -49,6 +58,8 @@ __device__ __forceinline__ bool quick_reject(V3 smin, V3 smax, float radius, flo
 }
 
 constexpr int STEP_BLOCK = 128;
+constexpr int MODE_STATIC = 0, MODE_LITERAL = 1, MODE_JACOBI = 2;
+constexpr int DYN_CAP = 16;      // capsule neighbours buffered per lane and pass of the JACOBI pass
 constexpr int TRI_RING = 2;      // triangles in flight per lane (cp.async ring in shared memory)
 constexpr int LEAF_CAP = 8;      // candidate leaves buffered per lane and pass (more => another pass)
 
@@ -59,14 +70,17 @@ constexpr int LEAF_CAP = 8;      // candidate leaves buffered per lane and pass 
 //            pre-cull) until one needs the exact test; the warp votes and all pending exact tests run together.
 // History (profiles/): v1 let each lane run its own loops -> 2.55 of 32 lanes active per instruction; v2 made the
 // loops vote-driven (13.5 lanes) but interleaved traversal and testing leaf by leaf.
-template <bool TRACE, bool LITERAL>
+template <bool TRACE, int MODE>
 __global__ void __launch_bounds__(STEP_BLOCK) k_step(StepParams p) {
+    constexpr bool LITERAL = MODE == MODE_LITERAL;
+    constexpr bool JACOBI = MODE == MODE_JACOBI;
     constexpr unsigned FULL = 0xffffffffu;
     __shared__ uint2 s_leaf[LEAF_CAP][STEP_BLOCK];
     __shared__ uint32_t s_cache[LEAF_CAP][STEP_BLOCK];     // frame cache: leaves (node indices) overlapping s_region
     __shared__ float s_region[6][STEP_BLOCK];
     // per-lane ring of candidate triangles streamed in with cp.async while the exact tests run
     __shared__ float4 s_tri[TRI_RING][3][STEP_BLOCK];
+    __shared__ uint32_t s_dyn[JACOBI ? DYN_CAP : 1][STEP_BLOCK];      // JACOBI: neighbour capsules, ascending
     const uint32_t tid = threadIdx.x;
     const uint32_t i = blockIdx.x * blockDim.x + tid;
     const bool valid = i < p.n;
@@ -174,6 +188,90 @@ __global__ void __launch_bounds__(STEP_BLOCK) k_step(StepParams p) {
             qb.lo = v3(0.0f); qb.hi = v3(0.0f);
         }
 
+        if (JACOBI) {
+            // ---- capsule-capsule pass, CANONICAL order: neighbours = every other capsule whose
+            // STORED fat box (hysteresis of aabb_tree.cpp:102-111,140-141) overlaps the query box, visited in
+            // ascending global index, each seen at its start-of-frame pose (the snapshot all ranks share).  The
+            // stored boxes are binned in a uniform xz grid; a pair is reported from the one cell that holds the
+            // lower corner of the two boxes' common cell range, so nothing is reported twice.
+            const uint32_t self = p.dyn_first + i;
+            int cx0 = 0, cx1 = -1, cz0 = 0, cz1 = -1;
+            if (alive) {
+                cx0 = dyn_cell(qb.lo.x, p.dyn_origin_x, p.dyn_inv_cell, p.dyn_gx); cx1 = dyn_cell(qb.hi.x, p.dyn_origin_x, p.dyn_inv_cell, p.dyn_gx);
+                cz0 = dyn_cell(qb.lo.z, p.dyn_origin_z, p.dyn_inv_cell, p.dyn_gz); cz1 = dyn_cell(qb.hi.z, p.dyn_origin_z, p.dyn_inv_cell, p.dyn_gz);
+            }
+            uint32_t t_caps = 0;
+            long long last = -1;                                  // largest neighbour index already processed
+            while (true) {
+                uint32_t ncand = 0;
+                bool more = false;
+                for (int cz = cz0; cz <= cz1; ++cz) {
+                    for (int cx = cx0; cx <= cx1; ++cx) {
+                        const uint32_t cell = uint32_t(cz) * p.dyn_gx + uint32_t(cx);
+                        const uint32_t beg = __ldg(p.dyn_cell_start + cell), end = __ldg(p.dyn_cell_start + cell + 1);
+                        for (uint32_t k = beg; k < end; ++k) {
+                            const uint32_t j = __ldg(p.dyn_items + k);
+                            if (j == self || (long long)j <= last) continue;
+                            const float4 blo = __ldg(p.dyn_records + 4 * size_t(j) + 2);
+                            const float4 bhi = __ldg(p.dyn_records + 4 * size_t(j) + 3);
+                            if (!node_overlaps(blo, bhi, qb)) continue;
+                            const int bx0 = dyn_cell(blo.x, p.dyn_origin_x, p.dyn_inv_cell, p.dyn_gx);
+                            const int bz0 = dyn_cell(blo.z, p.dyn_origin_z, p.dyn_inv_cell, p.dyn_gz);
+                            if (max(bx0, cx0) != cx || max(bz0, cz0) != cz) continue;      // reported from another cell
+                            // keep the DYN_CAP smallest indices, sorted
+                            if (ncand == DYN_CAP) {
+                                more = true;
+                                if (j > s_dyn[DYN_CAP - 1][tid]) continue;
+                                --ncand;
+                            }
+                            uint32_t q = ncand;
+                            while (q > 0 && s_dyn[q - 1][tid] > j) { s_dyn[q][tid] = s_dyn[q - 1][tid]; --q; }
+                            s_dyn[q][tid] = j;
+                            ++ncand;
+                        }
+                    }
+                }
+                __syncwarp(FULL);
+                const uint32_t rounds = __reduce_max_sync(FULL, ncand);
+                if (rounds == 0) break;
+                for (uint32_t r = 0; r < rounds; ++r) {
+                    if (r < ncand) {
+                        const uint32_t j = s_dyn[r][tid];
+                        if (TRACE) {
+                            if (t_caps < p.trace.cap_cand) p.trace.caps_ids[size_t(slot) * p.trace.cap_cand + t_caps] = j;
+                            ++t_caps;
+                        }
+                        const float4 sA = __ldg(p.dyn_records + 4 * size_t(j)), sB = __ldg(p.dyn_records + 4 * size_t(j) + 1);
+                        V3 aA, aB;
+                        segment_ends(fr, pos, aA, aB);
+                        Contact ct;
+                        ++c_cc;
+                        if (capsule_capsule(aA, aB, radius, v3(sA.x, sA.y, sA.z), v3(sB.x, sB.y, sB.z), sA.w, ct)) {
+                            pos = pos + ct.impulse;               // handleCollision (collision_system.cpp:242-252)
+                            ++c_contact;
+                            if (dot(ct.normal, v3(0.0f, 1.0f, 0.0f)) > p.ground_dot) {
+                                grounded = 1;
+                                gn = ct.normal;
+                            }
+                            if (TRACE) {
+                                if (t_hits < p.trace.cap_hits) {
+                                    TraceHit * h = p.trace.hits + size_t(slot) * p.trace.cap_hits + t_hits;
+                                    h->poly = -1;
+                                    h->impulse[0] = ct.impulse.x; h->impulse[1] = ct.impulse.y; h->impulse[2] = ct.impulse.z;
+                                    h->normal[0] = ct.normal.x; h->normal[1] = ct.normal.y; h->normal[2] = ct.normal.z;
+                                    h->pos[0] = pos.x; h->pos[1] = pos.y; h->pos[2] = pos.z;
+                                }
+                                ++t_hits;
+                            }
+                        }
+                    }
+                }
+                if (ncand) last = (long long)s_dyn[ncand - 1][tid];
+                if (!more) { cx1 = cx0 - 1; cz1 = cz0 - 1; }       // this lane is finished: empty cell range
+            }
+            if (TRACE && alive) p.trace.queries[slot].n_caps = t_caps;
+            ps = make_pose(fr, pos);
+        }
         if (LITERAL) {
             // ---- capsule-capsule pass (physics_system.cpp:369-389): every capsule leaf of the unified tree that the
             // query box overlaps, in emission order, BEFORE any triangle.  Character j is seen at its end-of-frame
@@ -364,7 +462,7 @@ __global__ void __launch_bounds__(STEP_BLOCK) k_step(StepParams p) {
         if (alive) {
             if (TRACE) {
                 TraceQuery * tq = p.trace.queries + slot;
-                tq->executed = 1; tq->n_mesh = t_mesh; if (!LITERAL) tq->n_caps = 0; tq->n_hits = t_hits; tq->tri_tests = t_tris;
+                tq->executed = 1; tq->n_mesh = t_mesh; if (!LITERAL && !JACOBI) tq->n_caps = 0; tq->n_hits = t_hits; tq->tri_tests = t_tris;
             }
             if (!found || stepsLeft == 0) alive = false;          // `if (meshColIDs.empty()) break;`  :391-393
         }
@@ -392,9 +490,9 @@ __global__ void __launch_bounds__(STEP_BLOCK) k_step(StepParams p) {
     c_tri = __reduce_add_sync(FULL, c_tri);
     c_node = __reduce_add_sync(FULL, c_node);
     c_contact = __reduce_add_sync(FULL, c_contact);
-    if (LITERAL) c_cc = __reduce_add_sync(FULL, c_cc);
+    if (LITERAL || JACOBI) c_cc = __reduce_add_sync(FULL, c_cc);
     if ((tid & 31u) == 0 && p.counters) {
-        if (LITERAL) atomicAdd(p.counters + 4, (unsigned long long)c_cc);
+        if (LITERAL || JACOBI) atomicAdd(p.counters + 4, (unsigned long long)c_cc);
         atomicAdd(p.counters + 0, (unsigned long long)c_sub);
         atomicAdd(p.counters + 1, (unsigned long long)c_tri);
         atomicAdd(p.counters + 2, (unsigned long long)c_node);
@@ -464,6 +562,65 @@ __global__ void k_query_box(const float4 * __restrict__ nodes, uint32_t n_nodes,
         }
     }
     *out_count = found;
+}
+
+// K1 for the dynamic pass: per own character, the phase-1 predicted box (physics_system.cpp:263-273: pose box united
+// with the box after `velocity + gravity*dt`, displacement applied in the capsule's rotated frame), the stored fat box
+// hysteresis of DynamicAABBTree::update/insertLeaf (aabb_tree.cpp:102-111,140-141) and the start-of-frame segment.
+// Record = 4 float4: (A.xyz, radius) (B.xyz, 0) (stored.lo, 0) (stored.hi, 0) at global index dyn_first + i.
+__global__ void k_dyn_prep(const prtc_transform * __restrict__ tf, const prtc_char_physics * __restrict__ ph,
+                           const CapsuleDev * __restrict__ capsules, uint32_t n, uint32_t first, float4 * __restrict__ records,
+                           float dt, float gravity, float margin, uint32_t init) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const CapsuleDev cap = capsules[ph[i].collider];
+    Quat q; q.x = tf[i].rotation[0]; q.y = tf[i].rotation[1]; q.z = tf[i].rotation[2]; q.w = tf[i].rotation[3];
+    const Rot3 R = rotation_of(q);
+    const CapsuleFrame fr = capsule_frame(cap, R);
+    const V3 pos = v3(tf[i].position[0], tf[i].position[1], tf[i].position[2]);
+    V3 A, B;
+    segment_ends(fr, pos, A, B);
+    Box e = capsule_box(A, B, cap.radius);
+    const V3 vel = v3(ph[i].velocity[0], ph[i].velocity[1], ph[i].velocity[2]);
+    const V3 d = vel + (v3(0.0f, -1.0f, 0.0f) * gravity) * dt;
+    const V3 pos2 = ((R.c0 * d.x + R.c1 * d.y) + R.c2 * d.z) + pos;
+    V3 A2, B2;
+    segment_ends(fr, pos2, A2, B2);
+    e = box_union(e, capsule_box(A2, B2, cap.radius));
+    float4 * rec = records + 4 * size_t(first + i);
+    Box stored;
+    if (init) {                                                    // the leaf is created at the identity pose (physics_system.cpp:36-39)
+        Quat qi; qi.x = qi.y = qi.z = 0.0f; qi.w = 1.0f;
+        V3 iA, iB;
+        segment_ends(capsule_frame(cap, rotation_of(qi)), v3(0.0f), iA, iB);
+        const Box ib = capsule_box(iA, iB, cap.radius);
+        stored.lo = ib.lo - margin; stored.hi = ib.hi + margin;
+    } else {
+        const float4 lo = rec[2], hi = rec[3];
+        stored.lo = v3(lo.x, lo.y, lo.z); stored.hi = v3(hi.x, hi.y, hi.z);
+    }
+    if (!box_contains(stored, e)) { stored.lo = e.lo - margin; stored.hi = e.hi + margin; }
+    rec[0] = make_float4(A.x, A.y, A.z, cap.radius);
+    rec[1] = make_float4(B.x, B.y, B.z, 0.0f);
+    rec[2] = make_float4(stored.lo.x, stored.lo.y, stored.lo.z, 0.0f);
+    rec[3] = make_float4(stored.hi.x, stored.hi.y, stored.hi.z, 0.0f);
+}
+
+// counting-sort build of the uniform grid over ALL capsules' stored boxes (pass 0 counts, pass 1 fills)
+__global__ void k_dyn_grid(const float4 * __restrict__ records, uint32_t n, float ox, float oz, float inv_cell, uint32_t gx, uint32_t gz,
+                           uint32_t * __restrict__ cell_count, const uint32_t * __restrict__ cell_start, uint32_t * __restrict__ items, int fill) {
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    const float4 lo = records[4 * size_t(j) + 2], hi = records[4 * size_t(j) + 3];
+    const int x0 = dyn_cell(lo.x, ox, inv_cell, gx), x1 = dyn_cell(hi.x, ox, inv_cell, gx);
+    const int z0 = dyn_cell(lo.z, oz, inv_cell, gz), z1 = dyn_cell(hi.z, oz, inv_cell, gz);
+    // a NaN corner puts the box in every cell it could matter for: (0,0)..(x1,z1) is what dyn_cell yields
+    for (int z = z0; z <= z1; ++z)
+        for (int x = x0; x <= x1; ++x) {
+            const uint32_t cell = uint32_t(z) * gx + uint32_t(x);
+            const uint32_t slot = atomicAdd(cell_count + cell, 1u);
+            if (fill) items[cell_start[cell] + slot] = j;
+        }
 }
 
 // PhysicsSystem::raycast (physics_system.cpp:205-242): one thread per ray.  DynamicAABBTree::queryRaycast
@@ -563,17 +720,32 @@ void launch_raycast(const float4 * nodes, uint32_t n_nodes, const float4 * tris,
     k_raycast<<<(n_rays + block - 1) / block, block, 0, stream>>>(nodes, n_nodes, tris, n_rays, origins, dirs, maxd, hit_xyz, hit_mask);
 }
 
-void launch_step(StepParams const & p, bool traced, bool literal, cudaStream_t stream) {
+void launch_step(StepParams const & p, bool traced, int mode, cudaStream_t stream) {
     if (p.n == 0) return;
     const uint32_t block = STEP_BLOCK;
     const uint32_t grid = (p.n + block - 1) / block;
-    if (literal) {
-        if (traced) k_step<true, true><<<grid, block, 0, stream>>>(p);
-        else k_step<false, true><<<grid, block, 0, stream>>>(p);
+    if (mode == MODE_LITERAL) {
+        if (traced) k_step<true, MODE_LITERAL><<<grid, block, 0, stream>>>(p);
+        else k_step<false, MODE_LITERAL><<<grid, block, 0, stream>>>(p);
+    } else if (mode == MODE_JACOBI) {
+        if (traced) k_step<true, MODE_JACOBI><<<grid, block, 0, stream>>>(p);
+        else k_step<false, MODE_JACOBI><<<grid, block, 0, stream>>>(p);
     } else {
-        if (traced) k_step<true, false><<<grid, block, 0, stream>>>(p);
-        else k_step<false, false><<<grid, block, 0, stream>>>(p);
+        if (traced) k_step<true, MODE_STATIC><<<grid, block, 0, stream>>>(p);
+        else k_step<false, MODE_STATIC><<<grid, block, 0, stream>>>(p);
     }
+}
+
+void launch_dyn_prep(const prtc_transform * tf, const prtc_char_physics * ph, const CapsuleDev * capsules, uint32_t n, uint32_t first,
+                     float4 * records, float dt, float gravity, float margin, bool init, cudaStream_t stream) {
+    if (n == 0) return;
+    k_dyn_prep<<<(n + 127) / 128, 128, 0, stream>>>(tf, ph, capsules, n, first, records, dt, gravity, margin, init ? 1u : 0u);
+}
+
+void launch_dyn_grid(const float4 * records, uint32_t n, float ox, float oz, float inv_cell, uint32_t gx, uint32_t gz,
+                     uint32_t * cell_count, const uint32_t * cell_start, uint32_t * items, bool fill, cudaStream_t stream) {
+    if (n == 0) return;
+    k_dyn_grid<<<(n + 127) / 128, 128, 0, stream>>>(records, n, ox, oz, inv_cell, gx, gz, cell_count, cell_start, items, fill ? 1 : 0);
 }
 
 void launch_transform_refit(const float * raw_xyz, float * world_xyz, const MeshDev * meshes, uint32_t first_mesh,

@@ -52,6 +52,13 @@ struct StepParams {
     const float4 * seg_start;       // 2 float4 per character: (A.xyz, radius) (B.xyz, 0) at the start-of-frame pose
     const float4 * seg_prev;        // same at the end-of-frame pose of the previous fixpoint round
     float * last_box;               // out, 6 floats per character: the last executed substep's query box
+    // CANONICAL order, JACOBI dynamic pass: records of ALL characters (4 float4 each) + uniform xz grid over their stored boxes
+    const float4 * dyn_records;
+    const uint32_t * dyn_cell_start;  // [gx*gz + 1]
+    const uint32_t * dyn_items;
+    uint32_t dyn_first;             // global index of this launch's character 0
+    uint32_t dyn_gx, dyn_gz;
+    float dyn_origin_x, dyn_origin_z, dyn_inv_cell;
     // constants (prtc_config)
     float dt, gravity, ground_dot, friction, stick;
     uint32_t substeps, abs_mode;
@@ -63,7 +70,13 @@ struct StepParams {
     TraceBuffers trace;
 };
 
-void launch_step(StepParams const & p, bool traced, bool literal, cudaStream_t stream);
+enum StepMode { STEP_STATIC = 0, STEP_LITERAL = 1, STEP_JACOBI = 2 };
+void launch_step(StepParams const & p, bool traced, int mode, cudaStream_t stream);
+// dynamic pass, CANONICAL / JACOBI: per-character record (4 float4) and the uniform grid over all stored boxes
+void launch_dyn_prep(const prtc_transform * tf, const prtc_char_physics * ph, const CapsuleDev * capsules, uint32_t n, uint32_t first,
+                     float4 * records, float dt, float gravity, float margin, bool init, cudaStream_t stream);
+void launch_dyn_grid(const float4 * records, uint32_t n, float ox, float oz, float inv_cell, uint32_t gx, uint32_t gz,
+                     uint32_t * cell_count, const uint32_t * cell_start, uint32_t * items, bool fill, cudaStream_t stream);
 
 // K8: world-space vertex cache + per-mesh AABB (physics_system.cpp:68-93 / :161-202)
 struct MeshDev { uint32_t first_vertex, n_vertices, model; uint32_t pad; };

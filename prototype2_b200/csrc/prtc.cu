@@ -3,6 +3,7 @@
 // There is no CPU implementation of the compute path in this library: without a compute-capability-10 device
 // prtc_create fails and nothing else can be called.
 #include <cuda_runtime.h>
+#include <cub/device/device_scan.cuh>
 
 #include <algorithm>
 #include <cstdio>
@@ -107,7 +108,17 @@ struct prtc_ctx {
     DevBuf<uint32_t> d_cap2char;
     DevBuf<float4> d_seg_start, d_seg_prev;
     DevBuf<float> d_last_box;
+    // CANONICAL order, JACOBI dynamic pass
+    DevBuf<float4> d_dyn_records;
+    DevBuf<uint32_t> d_dyn_count, d_dyn_start, d_dyn_items;
+    DevBuf<unsigned char> d_cub_temp;
+    uint32_t dyn_first = 0, dyn_global = 0;  // this context's slice [dyn_first, dyn_first + n) of dyn_global characters
+    bool dyn_configured = false;             // prtc_dyn_configure called (multi-rank); otherwise the slice is the whole batch
+    bool dyn_initialized = false;            // stored boxes exist (first prepare creates them at the identity pose)
+    bool dyn_prepared = false;               // prtc_dyn_prepare ran for the coming step (records may have been exchanged since)
+    float world_lo[3] = {0, 0, 0}, world_hi[3] = {0, 0, 0};
     bool literal() const { return cfg.order_mode == PRTC_ORDER_LITERAL; }
+    bool jacobi() const { return cfg.order_mode == PRTC_ORDER_CANONICAL && cfg.dyn_mode == PRTC_DYN_JACOBI; }
 };
 
 namespace {
@@ -177,6 +188,12 @@ int commit_impl(prtc_ctx * c) {
         c->moved_models.clear();
         c->world_max_abs = 0.0f;
         for (float v : aabbs) { float a = std::fabs(v); if (a > c->world_max_abs) c->world_max_abs = a; }   // NaN never wins
+        for (int k = 0; k < 3; ++k) { c->world_lo[k] = 3.0e38f; c->world_hi[k] = -3.0e38f; }
+        for (uint32_t m = 0; m < n_meshes; ++m)
+            for (int k = 0; k < 3; ++k) {
+                if (aabbs[6 * size_t(m) + k] < c->world_lo[k]) c->world_lo[k] = aabbs[6 * size_t(m) + k];
+                if (aabbs[6 * size_t(m) + 3 + k] > c->world_hi[k]) c->world_hi[k] = aabbs[6 * size_t(m) + 3 + k];
+            }
         // new meshes: DynamicAABBTree::insert in registration order, physics_system.cpp:102
         for (uint32_t m = c->meshes_in_tree; m < n_meshes; ++m)
             if (c->models[c->meshes[m].model].n_meshes != 0)      // not removed before its first commit
@@ -254,9 +271,8 @@ int check_mode(prtc_ctx * c, bool device_pointers) {
     if (c->literal() && device_pointers)
         return fail(PRTC_ERR_INVALID, "PRTC_ORDER_LITERAL maintains the unified tree on the host every frame and needs the "
                                       "host-buffer entry points (prtc_step_characters / _traced)");
-    if (c->cfg.dyn_mode != PRTC_DYN_OFF && !c->literal())
-        return fail(PRTC_ERR_INVALID, "dyn_mode PRTC_DYN_JACOBI is not available in this build; use PRTC_DYN_OFF "
-                                      "(PRTC_ORDER_LITERAL always runs the reference's capsule-capsule pass)");
+    if (c->cfg.dyn_mode != PRTC_DYN_OFF && c->cfg.dyn_mode != PRTC_DYN_JACOBI)
+        return fail(PRTC_ERR_INVALID, "unknown dyn_mode");
     return PRTC_OK;
 }
 
@@ -330,6 +346,58 @@ int prepare_trace(prtc_ctx * c, uint32_t n, StepParams & p) {
     return PRTC_OK;
 }
 
+// JACOBI dynamic pass: records of this context's characters (phase-1 box, stored-box hysteresis, start-of-frame segment)
+int dyn_prepare(prtc_ctx * c, float dt, uint32_t n, const prtc_transform * d_tf, const prtc_char_physics * d_ph) {
+    if (!c->dyn_configured) { c->dyn_first = 0; c->dyn_global = n; }
+    if (uint64_t(c->dyn_first) + n > c->dyn_global) return fail(PRTC_ERR_INVALID, "prtc_dyn_prepare: slice exceeds the configured global count");
+    if (c->d_dyn_records.cap < size_t(c->dyn_global) * 4) {
+        if (c->dyn_initialized) return fail(PRTC_ERR_INVALID, "prtc_dyn_prepare: the global character count may not grow after the first frame");
+        PRTC_CUDA(c->d_dyn_records.reserve(size_t(c->dyn_global) * 4));
+        PRTC_CUDA(cudaMemsetAsync(c->d_dyn_records.ptr, 0, size_t(c->dyn_global) * 4 * sizeof(float4), c->stream));
+    }
+    launch_dyn_prep(d_tf, d_ph, c->d_capsules.ptr, n, c->dyn_first, c->d_dyn_records.ptr, dt, c->cfg.gravity, c->cfg.leaf_margin,
+                    !c->dyn_initialized, c->stream);
+    PRTC_CUDA(cudaGetLastError());
+    c->dyn_initialized = true;
+    c->dyn_prepared = true;
+    return PRTC_OK;
+}
+
+// uniform xz grid over the stored boxes of ALL characters (counting sort), wired into the launch parameters
+int dyn_build_grid(prtc_ctx * c, StepParams & p) {
+    cudaStream_t s = c->stream;
+    float lox = c->world_lo[0], loz = c->world_lo[2], hix = c->world_hi[0], hiz = c->world_hi[2];
+    if (!(hix > lox) || !(hiz > loz)) { lox = loz = 0.0f; hix = hiz = 1.0f; }          // no static geometry: one cell
+    lox -= 2.0f; loz -= 2.0f; hix += 2.0f; hiz += 2.0f;
+    const float ext = std::max(hix - lox, hiz - loz);
+    const float cell = std::max(2.5f, ext / 1024.0f);
+    const uint32_t gx = std::max(1u, uint32_t(std::ceil((hix - lox) / cell))), gz = std::max(1u, uint32_t(std::ceil((hiz - loz) / cell)));
+    const size_t cells = size_t(gx) * gz;
+    const uint32_t ng = c->dyn_global;
+    PRTC_CUDA(c->d_dyn_count.reserve(cells + 1));
+    PRTC_CUDA(c->d_dyn_start.reserve(cells + 1));
+    PRTC_CUDA(cudaMemsetAsync(c->d_dyn_count.ptr, 0, (cells + 1) * sizeof(uint32_t), s));
+    launch_dyn_grid(c->d_dyn_records.ptr, ng, lox, loz, 1.0f / cell, gx, gz, c->d_dyn_count.ptr, nullptr, nullptr, false, s);
+    size_t temp_bytes = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, temp_bytes, c->d_dyn_count.ptr, c->d_dyn_start.ptr, int(cells + 1), s);
+    PRTC_CUDA(c->d_cub_temp.reserve(temp_bytes));
+    PRTC_CUDA(cub::DeviceScan::ExclusiveSum(c->d_cub_temp.ptr, temp_bytes, c->d_dyn_count.ptr, c->d_dyn_start.ptr, int(cells + 1), s));
+    uint32_t total = 0;
+    PRTC_CUDA(cudaMemcpyAsync(&total, c->d_dyn_start.ptr + cells, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    PRTC_CUDA(cudaStreamSynchronize(s));
+    PRTC_CUDA(c->d_dyn_items.reserve(size_t(total) + 1));
+    PRTC_CUDA(cudaMemsetAsync(c->d_dyn_count.ptr, 0, (cells + 1) * sizeof(uint32_t), s));
+    launch_dyn_grid(c->d_dyn_records.ptr, ng, lox, loz, 1.0f / cell, gx, gz, c->d_dyn_count.ptr, c->d_dyn_start.ptr, c->d_dyn_items.ptr, true, s);
+    PRTC_CUDA(cudaGetLastError());
+    p.dyn_records = c->d_dyn_records.ptr;
+    p.dyn_cell_start = c->d_dyn_start.ptr;
+    p.dyn_items = c->d_dyn_items.ptr;
+    p.dyn_first = c->dyn_first;
+    p.dyn_gx = gx; p.dyn_gz = gz;
+    p.dyn_origin_x = lox; p.dyn_origin_z = loz; p.dyn_inv_cell = 1.0f / cell;
+    return PRTC_OK;
+}
+
 // One frame in LITERAL order (host buffers).  Everything the reference does to its unified tree per frame is
 // replayed on the host with the same algorithm; the device runs the collide phase; the reference's sequential
 // visibility between characters (T18) is reached as the fixpoint of repeated whole-batch launches.
@@ -396,7 +464,7 @@ int literal_step(prtc_ctx * c, float dt, uint32_t n, prtc_transform * tf, prtc_c
         fill_params(c, dt, n, c->d_tf.ptr, c->d_ph.ptr, p);
         p.cap2char = c->d_cap2char.ptr; p.seg_start = c->d_seg_start.ptr; p.seg_prev = c->d_seg_prev.ptr; p.last_box = c->d_last_box.ptr;
         if (tr) { rc = prepare_trace(c, n, p); if (rc) return rc; }
-        launch_step(p, tr != nullptr, true, s);
+        launch_step(p, tr != nullptr, STEP_LITERAL, s);
         PRTC_CUDA(cudaGetLastError());
         PRTC_CUDA(cudaMemcpyAsync(out_tf.data(), c->d_tf.ptr, size_t(n) * sizeof(prtc_transform), cudaMemcpyDeviceToHost, s));
         PRTC_CUDA(cudaMemcpyAsync(out_ph.data(), c->d_ph.ptr, size_t(n) * sizeof(prtc_char_physics), cudaMemcpyDeviceToHost, s));
@@ -513,6 +581,7 @@ void prtc_destroy(prtc_ctx * c) {
     c->d_tq.release(); c->d_tmesh.release(); c->d_tcaps.release(); c->d_thits.release();
     c->d_scratch_f.release(); c->d_scratch_u.release();
     c->d_cap2char.release(); c->d_seg_start.release(); c->d_seg_prev.release(); c->d_last_box.release();
+    c->d_dyn_records.release(); c->d_dyn_count.release(); c->d_dyn_start.release(); c->d_dyn_items.release(); c->d_cub_temp.release();
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -637,7 +706,15 @@ int prtc_step_characters_device(prtc_ctx * c, float dt, uint32_t n, prtc_transfo
     if (c->capsules.empty() && n) return fail(PRTC_ERR_INVALID, "prtc_step_characters: no capsule collider registered");
     StepParams p;
     fill_params(c, dt, n, d_tf, d_ph, p);
-    launch_step(p, false, false, c->stream);
+    int mode = STEP_STATIC;
+    if (c->jacobi()) {
+        if (!c->dyn_prepared) { rc = dyn_prepare(c, dt, n, d_tf, d_ph); if (rc) return rc; }
+        rc = dyn_build_grid(c, p);
+        if (rc) return rc;
+        c->dyn_prepared = false;
+        mode = STEP_JACOBI;
+    }
+    launch_step(p, false, mode, c->stream);
     PRTC_CUDA(cudaGetLastError());
     return PRTC_OK;
 }
@@ -684,7 +761,15 @@ int prtc_step_characters_traced(prtc_ctx * c, float dt, uint32_t n, prtc_transfo
     fill_params(c, dt, n, c->d_tf.ptr, c->d_ph.ptr, p);
     rc = prepare_trace(c, n, p);
     if (rc) return rc;
-    launch_step(p, true, false, s);
+    int mode = STEP_STATIC;
+    if (c->jacobi()) {
+        if (!c->dyn_prepared) { rc = dyn_prepare(c, dt, n, c->d_tf.ptr, c->d_ph.ptr); if (rc) return rc; }
+        rc = dyn_build_grid(c, p);
+        if (rc) return rc;
+        c->dyn_prepared = false;
+        mode = STEP_JACOBI;
+    }
+    launch_step(p, true, mode, s);
     PRTC_CUDA(cudaGetLastError());
     PRTC_CUDA(cudaMemcpyAsync(tf, c->d_tf.ptr, size_t(n) * sizeof(prtc_transform), cudaMemcpyDeviceToHost, s));
     PRTC_CUDA(cudaMemcpyAsync(ph, c->d_ph.ptr, size_t(n) * sizeof(prtc_char_physics), cudaMemcpyDeviceToHost, s));
@@ -742,6 +827,33 @@ int prtc_get_counters(prtc_ctx * c, prtc_counters * out, int reset) {
     if (reset) PRTC_CUDA(cudaMemsetAsync(c->d_counters.ptr, 0, sizeof(h), c->stream));
     PRTC_CUDA(cudaStreamSynchronize(c->stream));
     out->substeps = h[0]; out->tri_tests = h[1]; out->node_tests = h[2]; out->contacts = h[3]; out->cc_tests = h[4];
+    return PRTC_OK;
+}
+
+int prtc_dyn_configure(prtc_ctx * c, uint32_t first_global, uint32_t n_global) {
+    if (!c) return fail(PRTC_ERR_INVALID, "prtc_dyn_configure: null context");
+    if (c->dyn_initialized && (n_global != c->dyn_global)) return fail(PRTC_ERR_INVALID, "prtc_dyn_configure: the global count is fixed after the first frame");
+    c->dyn_first = first_global;
+    c->dyn_global = n_global;
+    c->dyn_configured = true;
+    return PRTC_OK;
+}
+
+int prtc_dyn_prepare(prtc_ctx * c, float dt, uint32_t n, const prtc_transform * d_tf, const prtc_char_physics * d_ph) {
+    if (!c || (n && (!d_tf || !d_ph))) return fail(PRTC_ERR_INVALID, "prtc_dyn_prepare: null argument");
+    if (!c->jacobi()) return fail(PRTC_ERR_INVALID, "prtc_dyn_prepare: context is not in PRTC_ORDER_CANONICAL + PRTC_DYN_JACOBI");
+    PRTC_CUDA(cudaSetDevice(c->cfg.device));
+    if (c->geometry_dirty || c->tree_dirty || c->capsules_dirty) { int rc = commit_impl(c); if (rc) return rc; }
+    return dyn_prepare(c, dt, n, d_tf, d_ph);
+}
+
+int prtc_dyn_buffer(prtc_ctx * c, void ** d_records, size_t * record_bytes, uint32_t * first_global, uint32_t * n_global) {
+    if (!c || !d_records) return fail(PRTC_ERR_INVALID, "prtc_dyn_buffer: null argument");
+    if (!c->d_dyn_records.ptr) return fail(PRTC_ERR_INVALID, "prtc_dyn_buffer: call prtc_dyn_prepare first");
+    *d_records = c->d_dyn_records.ptr;
+    if (record_bytes) *record_bytes = 4 * sizeof(float4);
+    if (first_global) *first_global = c->dyn_first;
+    if (n_global) *n_global = c->dyn_global;
     return PRTC_OK;
 }
 

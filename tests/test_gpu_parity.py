@@ -349,3 +349,66 @@ def test_remove_and_move_model_colliders():
     fresh.commit()
     nv = len(xyz)
     assert H.same(ctx.world_vertices()[:nv], fresh.world_vertices()[:nv])
+
+
+# ------------------------------------------------------------------------------------------------------------
+# CANONICAL order + JACOBI dynamic pass (C5 shape): neighbours from the stored fat boxes in ascending index, seen at
+# their start-of-frame pose.  Oracle = L1 canonical/jacobi (brute force over all pairs).
+# ------------------------------------------------------------------------------------------------------------
+def _run_jacobi(scene, frames, trace_frames=(0, 1, 2)):
+    from prototype2_b200 import capi
+    orc = H.build_oracle(scene, "l1", order="canonical", dyn="jacobi")
+    ctx, tf, ph = H.build_gpu(scene, dyn_mode=capi.DYN_JACOBI)
+    cc_hits = 0
+    for f in range(frames):
+        if f in trace_frames:
+            to = orc.step(DT, trace=True)
+            tg = ctx.update_characters_traced(DT, tf, ph)
+            assert H.trace_diff(to, tg, LITERAL_KEYS) == [], "frame %d trace" % f
+            cc_hits += int((to.h_poly < 0).sum())
+        else:
+            orc.step(DT)
+            ctx.update_characters(DT, tf, ph)
+        assert H.state_diff(orc.get_state(), H.gpu_state(tf, ph)) == [], "frame %d state" % f
+    co, cg = orc.counters(), ctx.counters()
+    for k in ("substeps", "tri_tests", "contacts", "cc_tests"):
+        assert co[k] == cg[k], k
+    return cc_hits
+
+
+def test_jacobi_dynamic_pass_crowded():
+    scene = H.make_scene(48, 2, 2, 700, seed=55)             # ~0.35 capsules per unit area: plenty of contacts
+    assert _run_jacobi(scene, 8, trace_frames=(0, 1, 4, 7)) > 0
+
+
+def test_jacobi_dynamic_pass_more_neighbours_than_the_buffer():
+    """a pile of 90 capsules on a 6x6 patch: far more than 16 neighbours per query -> multi-pass neighbour lists"""
+    scene = H.make_scene(32, 2, 2, 90, seed=56)
+    rs = np.random.RandomState(2)
+    scene["pos"][:, 0] = 12.0 + rs.uniform(0, 6, 90).astype(np.float32)
+    scene["pos"][:, 2] = 12.0 + rs.uniform(0, 6, 90).astype(np.float32)
+    scene["pos"][:, 1] = H.scenes.height(scene["pos"][:, 0], scene["pos"][:, 2]) + rs.uniform(0, 2, 90).astype(np.float32)
+    assert _run_jacobi(scene, 5) > 50
+
+
+def test_jacobi_rotated_capsules_and_no_static_geometry():
+    from prototype2_b200 import capi
+    scene = H.make_scene(40, 2, 2, 300, seed=57)
+    scene["rot"] = H.random_rotations(300, seed=3)
+    _run_jacobi(scene, 5)
+    # capsules only (no mesh collider at all): the pass still runs before the early break (T7)
+    orc = H.L1World("canonical", dyn="jacobi")
+    ctx = capi.PhysicsContext(dyn_mode=capi.DYN_JACOBI)
+    rs = np.random.RandomState(9)
+    pos = rs.uniform(0, 6, (80, 3)).astype(np.float32)
+    vel = rs.uniform(-0.1, 0.1, (80, 3)).astype(np.float32)
+    for _ in range(80):
+        orc.add_capsule()
+        ctx.add_capsule_collider()
+    orc.set_state(pos=pos, vel=vel)
+    tf, ph = capi.make_transforms(pos), capi.make_physics(vel)
+    for f in range(4):
+        orc.step(DT)
+        ctx.update_characters(DT, tf, ph)
+        assert H.state_diff(orc.get_state(), H.gpu_state(tf, ph)) == []
+    assert ctx.counters()["cc_tests"] > 0
