@@ -29,6 +29,7 @@ WORKLOADS = {
     #        terrain N, block x, block z, capsules per GPU
     "C4": (2237, 2, 2, 1000000),
     "C3": (708, 4, 2, 64000),
+    "C5": (708, 2, 2, 256000),      # GLOBAL capsule count, partitioned over the ranks; dynamic-vs-dynamic pass on
     "C2": (224, 1, 1, 1000),
 }
 METRIC = "ellipsoid (capsule) sweep queries/sec"
@@ -55,6 +56,8 @@ def workload(args):
     n_terrain, bx, bz, n_caps = WORKLOADS[args.workload]
     if args.capsules:
         n_caps = args.capsules
+    if args.workload == "C5":                     # strong scaling: the global batch is split over the ranks
+        n_caps //= max(1, int(os.environ.get("WORLD_SIZE", "1")))
     if args.terrain_n:
         n_terrain = args.terrain_n
     return n_terrain, bx, bz, n_caps
@@ -68,8 +71,9 @@ def make_capsules(n_caps, n_terrain, rank):
 
 def describe(args, n_terrain, bx, bz, n_caps, n_tris, world):
     return {
-        "workload": "%s: %d capsules/GPU x %d-triangle terrain (%dx%d-cell mesh colliders), 4 substeps/frame, static pass, "
-                    "canonical order" % (args.workload, n_caps, n_tris, bx, bz),
+        "workload": "%s: %d capsules/GPU x %d-triangle terrain (%dx%d-cell mesh colliders), 4 substeps/frame, %s, "
+                    "canonical order" % (args.workload, n_caps, n_tris, bx, bz,
+                                         "static + dynamic-vs-dynamic pass (JACOBI, records all-gathered per frame)" if args.workload == "C5" else "static pass"),
         "capsules_per_gpu": n_caps, "global_capsules": n_caps * world, "triangles": n_tris, "terrain_n": n_terrain,
         "substeps": 4, "dt": DT, "abs_mode": "int", "parallelism": "capsules sharded x%d, static geometry replicated" % world,
         "l2_policy": "inputs larger than L2: nodes+triangles+capsule state touched per step exceed 126 MB at C4; "
@@ -216,9 +220,19 @@ def run_ours(args):
     n_terrain, bx, bz, n_caps = workload(args)
     xyz, mf, mc = scenes.terrain(n_terrain, bx, bz)
     n_tris = len(xyz) // 3
-    pos, vel = make_capsules(n_caps, n_terrain, rank)
+    dynamic = args.workload == "C5"
+    if dynamic:
+        # one global batch in Morton order, contiguous slices per rank (ascending-index neighbour order is global)
+        from prototype2_b200 import sharding
+        gpos, gvel = make_capsules(n_caps * world, n_terrain, 0)
+        first, _ = sharding.partition(n_caps * world, world, rank)
+        pos, vel = gpos[first:first + n_caps], gvel[first:first + n_caps]
+    else:
+        pos, vel = make_capsules(n_caps, n_terrain, rank)
 
-    ctx = capi.PhysicsContext(device=local)
+    ctx = capi.PhysicsContext(device=local, dyn_mode=capi.DYN_JACOBI if dynamic else capi.DYN_OFF)
+    if dynamic:
+        ctx.dyn_configure(first, n_caps * world)
     ctx.add_model_collider(xyz, mf, mc)
     cid = ctx.add_capsule_collider()                      # one shared collider shape (h=0.5 r=0.5 off=(0,0.5,0))
     t_commit = time.perf_counter()
@@ -261,12 +275,20 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         return [float(v) for v in t.tolist()]
 
+    def device_step():
+        if dynamic and world > 1:
+            # the one exchange of the path: 64-byte records of every character, all-gathered in place over NVLink
+            ctx.dyn_prepare(DT, n_caps, d_tf.data_ptr(), d_ph.data_ptr())
+            rec, rfirst = sharding.records_tensor(ctx)
+            sharding.allgather_records(rec, rfirst, n_caps)
+        ctx.update_characters_device(DT, n_caps, d_tf.data_ptr(), d_ph.data_ptr())
+
     # ---- device-resident leg: `value` --------------------------------------------------------------------
     reset_host()
     d_tf.copy_(h_tf)
     d_ph.copy_(h_ph)
     for _ in range(args.warmup):
-        ctx.update_characters_device(DT, n_caps, d_tf.data_ptr(), d_ph.data_ptr())
+        device_step()
     torch.cuda.synchronize()
     ctx.counters(reset=True)
     sampler = ClockSampler(local)
@@ -275,13 +297,21 @@ def run_ours(args):
     sampler.start()
     ev[0].record(stream)
     for k in range(args.steps):
-        ctx.update_characters_device(DT, n_caps, d_tf.data_ptr(), d_ph.data_ptr())
+        device_step()
         ev[k + 1].record(stream)
     barrier()
     clocks = sampler.stop()
     total_ms = ev[0].elapsed_time(ev[args.steps])
     kernel_ms = [ev[k].elapsed_time(ev[k + 1]) for k in range(args.steps)]
     cnt = ctx.counters(reset=True)
+    state_crc = None
+    if dynamic:
+        # one global batch: the state after W+K frames must not depend on the number of ranks -> checksum over all
+        # characters in global order (compare the value printed by an N=1 and an N>1 run)
+        import zlib
+        mine = torch.cat([d_tf.view(n_caps, 40), d_ph.view(n_caps, 44)], dim=1).contiguous()
+        allrows = sharding.gather_rows(mine)
+        state_crc = zlib.crc32(allrows.cpu().numpy().tobytes())
     el = max_over_ranks(total_ms * 1e-3)
     substeps, tri_tests, node_tests = sum_over_ranks([cnt["substeps"], cnt["tri_tests"], cnt["node_tests"]])
     value = substeps / el
@@ -294,14 +324,24 @@ def run_ours(args):
     d_tf.copy_(h_tf)
     d_ph.copy_(h_ph)
     ctx.set_option(capi.OPT_FRAME_CACHE, 0)
+    if dynamic:                                      # stored boxes carry over between frames: start the replay from a fresh context state
+        ctx2 = capi.PhysicsContext(device=local, dyn_mode=capi.DYN_JACOBI)
+        ctx2.add_model_collider(xyz, mf, mc)
+        ctx2.add_capsule_collider()
+        ctx2.dyn_configure(first, n_caps * world)
+        ctx2.set_stream(stream.cuda_stream)
+        ctx, ctx_timed = ctx2, ctx
+        ctx.set_option(capi.OPT_FRAME_CACHE, 0)
     for _ in range(args.warmup):
-        ctx.update_characters_device(DT, n_caps, d_tf.data_ptr(), d_ph.data_ptr())
+        device_step()
     torch.cuda.synchronize()
     ctx.counters(reset=True)
     for _ in range(args.steps):
-        ctx.update_characters_device(DT, n_caps, d_tf.data_ptr(), d_ph.data_ptr())
+        device_step()
     torch.cuda.synchronize()
     ref_cnt = ctx.counters(reset=True)
+    if dynamic:
+        ctx = ctx_timed
     ctx.set_option(capi.OPT_FRAME_CACHE, 1)
     assert ref_cnt["substeps"] == cnt["substeps"] and ref_cnt["tri_tests"] == cnt["tri_tests"], (ref_cnt, cnt)
     gpu_node_tests = cnt["node_tests"]
@@ -334,7 +374,7 @@ def run_ours(args):
 
     # ---- end-to-end leg: host buffers through prtc_step_characters (H2D + kernel + D2H every step) ----------
     e2e = None
-    if not args.no_e2e:
+    if not args.no_e2e and not (dynamic and world > 1):       # the host-buffer entry point has no exchange hook
         own = torch.cuda.Stream()
         ctx.set_stream(own.cuda_stream)
         reset_host()
@@ -372,12 +412,14 @@ def run_ours(args):
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": 1e3 * el / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": 1e3 * el / args.steps, "higher_is_better": True, "scaling": "strong" if dynamic else "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "config": describe(args, n_terrain, bx, bz, n_caps, n_tris, world),
             "tri_tests_per_s": tri_tests / el, "node_tests_per_s": node_tests / el,
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": args.steps, "clocks": clocks,
             "setup": {"commit_s": t_commit, "nodes": info["nodes"], "leaves": info["leaves"]},
         }
+        if state_crc is not None:
+            line["state_crc32"] = state_crc
         emit(line)
     if dist is not None:
         dist.destroy_process_group()

@@ -412,3 +412,41 @@ def test_jacobi_rotated_capsules_and_no_static_geometry():
         ctx.update_characters(DT, tf, ph)
         assert H.state_diff(orc.get_state(), H.gpu_state(tf, ph)) == []
     assert ctx.counters()["cc_tests"] > 0
+
+
+def test_jacobi_two_ranks_emulated_on_one_gpu_equal_one_rank():
+    """multi-rank dynamic pass without a second GPU: two contexts on cuda:0 each own half of the characters, prepare
+    their records, exchange them (device copies standing in for the NCCL all-gather), step -- and the concatenated
+    result must be byte-identical to one context stepping everybody (results independent of G)."""
+    import torch
+    from prototype2_b200 import capi, sharding
+    scene = H.make_scene(48, 2, 2, 600, seed=61)
+    n = scene["n"]
+    one, tf1, ph1 = H.build_gpu(scene, dyn_mode=capi.DYN_JACOBI)
+    ranks = []
+    for r in range(2):
+        first, count = sharding.partition(n, 2, r)
+        ctx, tf, ph = H.build_gpu(scene, dyn_mode=capi.DYN_JACOBI)        # every rank registers the same colliders
+        ctx.dyn_configure(first, n)
+        d_tf = torch.from_numpy(tf[first:first + count].view(np.uint8).reshape(-1)).cuda()
+        d_ph = torch.from_numpy(ph[first:first + count].view(np.uint8).reshape(-1)).cuda()
+        ranks.append((ctx, first, count, d_tf, d_ph))
+    for f in range(6):
+        one.update_characters(DT, tf1, ph1)
+        recs = []
+        for ctx, first, count, d_tf, d_ph in ranks:
+            ctx.dyn_prepare(DT, count, d_tf.data_ptr(), d_ph.data_ptr())
+            ctx.synchronize()
+            recs.append(sharding.records_tensor(ctx)[0])
+        for r, (ctx, first, count, _, _) in enumerate(ranks):              # "all-gather": copy every slice everywhere
+            for q, (_, qfirst, qcount, _, _) in enumerate(ranks):
+                if q != r:
+                    recs[r][qfirst:qfirst + qcount].copy_(recs[q][qfirst:qfirst + qcount])
+        torch.cuda.synchronize()
+        for ctx, first, count, d_tf, d_ph in ranks:
+            ctx.update_characters_device(DT, count, d_tf.data_ptr(), d_ph.data_ptr())
+            ctx.synchronize()
+        got_tf = np.concatenate([d_tf.cpu().numpy().view(capi.TRANSFORM_DTYPE) for _, _, _, d_tf, _ in ranks])
+        got_ph = np.concatenate([d_ph.cpu().numpy().view(capi.PHYSICS_DTYPE) for _, _, _, _, d_ph in ranks])
+        assert H.state_diff(H.gpu_state(tf1, ph1), H.gpu_state(got_tf, got_ph)) == [], "frame %d" % f
+    assert one.counters()["cc_tests"] > 0
