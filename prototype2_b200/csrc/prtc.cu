@@ -66,6 +66,10 @@ struct prtc_ctx {
     prtc_config cfg;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
+    // host-buffer steps of large batches are cut into chunks pipelined over these streams (copy-in, step, copy-out)
+    static constexpr int PIPE_STREAMS = 3;
+    cudaStream_t pipe[PIPE_STREAMS] = {nullptr, nullptr, nullptr};
+    cudaEvent_t pipe_ready = nullptr;
 
     // host registry
     std::vector<float> raw;                 // model-space xyz of every registered model, back to back
@@ -583,6 +587,8 @@ void prtc_destroy(prtc_ctx * c) {
     c->d_cap2char.release(); c->d_seg_start.release(); c->d_seg_prev.release(); c->d_last_box.release();
     c->d_dyn_records.release(); c->d_dyn_count.release(); c->d_dyn_start.release(); c->d_dyn_items.release(); c->d_cub_temp.release();
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+    for (int k = 0; k < prtc_ctx::PIPE_STREAMS; ++k) if (c->pipe[k]) cudaStreamDestroy(c->pipe[k]);
+    if (c->pipe_ready) cudaEventDestroy(c->pipe_ready);
     delete c;
 }
 
@@ -728,6 +734,34 @@ int prtc_step_characters(prtc_ctx * c, float dt, uint32_t n, prtc_transform * tf
     if (c->literal()) return literal_step(c, dt, n, tf, ph, nullptr);
     PRTC_CUDA(c->d_tf.reserve(n));
     PRTC_CUDA(c->d_ph.reserve(n));
+    // Static pass, big batch: characters are independent, so the batch is cut into chunks and the chunks' host->device
+    // copies, steps and device->host copies overlap on a few streams (PCIe is full duplex).  Results are identical
+    // to one launch -- every character's frame is computed by one thread either way.
+    const uint32_t kChunk = 65536;
+    if (!c->jacobi() && n >= 4 * kChunk) {
+        if (c->geometry_dirty || c->tree_dirty || c->capsules_dirty) { rc = commit_impl(c); if (rc) return rc; }
+        if (!c->pipe_ready) {
+            PRTC_CUDA(cudaEventCreateWithFlags(&c->pipe_ready, cudaEventDisableTiming));
+            for (int k = 0; k < prtc_ctx::PIPE_STREAMS; ++k) PRTC_CUDA(cudaStreamCreateWithFlags(&c->pipe[k], cudaStreamNonBlocking));
+        }
+        PRTC_CUDA(cudaEventRecord(c->pipe_ready, c->stream));          // whatever the context's stream still has queued
+        for (int k = 0; k < prtc_ctx::PIPE_STREAMS; ++k) PRTC_CUDA(cudaStreamWaitEvent(c->pipe[k], c->pipe_ready, 0));
+        uint32_t k = 0;
+        for (uint32_t first = 0; first < n; first += kChunk, ++k) {
+            const uint32_t cnt = std::min(kChunk, n - first);
+            cudaStream_t s = c->pipe[k % prtc_ctx::PIPE_STREAMS];
+            PRTC_CUDA(cudaMemcpyAsync(c->d_tf.ptr + first, tf + first, size_t(cnt) * sizeof(prtc_transform), cudaMemcpyHostToDevice, s));
+            PRTC_CUDA(cudaMemcpyAsync(c->d_ph.ptr + first, ph + first, size_t(cnt) * sizeof(prtc_char_physics), cudaMemcpyHostToDevice, s));
+            StepParams p;
+            fill_params(c, dt, cnt, c->d_tf.ptr + first, c->d_ph.ptr + first, p);
+            launch_step(p, false, STEP_STATIC, s);
+            PRTC_CUDA(cudaGetLastError());
+            PRTC_CUDA(cudaMemcpyAsync(tf + first, c->d_tf.ptr + first, size_t(cnt) * sizeof(prtc_transform), cudaMemcpyDeviceToHost, s));
+            PRTC_CUDA(cudaMemcpyAsync(ph + first, c->d_ph.ptr + first, size_t(cnt) * sizeof(prtc_char_physics), cudaMemcpyDeviceToHost, s));
+        }
+        for (int q = 0; q < prtc_ctx::PIPE_STREAMS; ++q) PRTC_CUDA(cudaStreamSynchronize(c->pipe[q]));
+        return PRTC_OK;
+    }
     if (n) {
         PRTC_CUDA(cudaMemcpyAsync(c->d_tf.ptr, tf, size_t(n) * sizeof(prtc_transform), cudaMemcpyHostToDevice, c->stream));
         PRTC_CUDA(cudaMemcpyAsync(c->d_ph.ptr, ph, size_t(n) * sizeof(prtc_char_physics), cudaMemcpyHostToDevice, c->stream));

@@ -450,3 +450,22 @@ def test_jacobi_two_ranks_emulated_on_one_gpu_equal_one_rank():
         got_ph = np.concatenate([d_ph.cpu().numpy().view(capi.PHYSICS_DTYPE) for _, _, _, _, d_ph in ranks])
         assert H.state_diff(H.gpu_state(tf1, ph1), H.gpu_state(got_tf, got_ph)) == [], "frame %d" % f
     assert one.counters()["cc_tests"] > 0
+
+
+def test_chunked_host_step_equals_device_step():
+    """big host batches are cut into chunks pipelined over several streams: same bits as one device-resident launch"""
+    import torch
+    from prototype2_b200 import capi
+    n = 300000
+    scene = H.make_scene(200, 2, 2, n, seed=71)
+    ctx, tf, ph = H.build_gpu(scene)
+    tf2, ph2 = tf.copy(), ph.copy()
+    d_tf = torch.from_numpy(tf2.view(np.uint8).reshape(-1)).cuda()
+    d_ph = torch.from_numpy(ph2.view(np.uint8).reshape(-1)).cuda()
+    for f in range(3):
+        ctx.update_characters(DT, tf, ph)                         # host buffers: chunked pipeline
+        ctx.update_characters_device(DT, n, d_tf.data_ptr(), d_ph.data_ptr())
+        ctx.synchronize()
+        got_tf = d_tf.cpu().numpy().view(capi.TRANSFORM_DTYPE)
+        got_ph = d_ph.cpu().numpy().view(capi.PHYSICS_DTYPE)
+        assert H.state_diff(H.gpu_state(tf, ph), H.gpu_state(got_tf, got_ph)) == [], "frame %d" % f
