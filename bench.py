@@ -370,7 +370,9 @@ def run_ours(args):
                 "algorithmic_bytes_per_launch": alg_bytes / args.steps,
                 "avg_launch_ms": float(np.mean(kernel_ms)), "formula": "96*S + 32*V + 36*T + 64*capsules (SURVEY.md 8d)",
                 "per_query": {"V_q": cnt["node_tests"] / max(1, cnt["substeps"]), "T_q": cnt["tri_tests"] / max(1, cnt["substeps"]),
-                              "gpu_node_tests_per_query": gpu_node_tests / max(1, cnt["substeps"])}}
+                              "gpu_node_tests_per_query": gpu_node_tests / max(1, cnt["substeps"]),
+                              "exact_tests_per_query": cnt["exact_tests"] / max(1, cnt["substeps"]),
+                              "contacts_per_query": cnt["contacts"] / max(1, cnt["substeps"])}}
 
     # ---- end-to-end leg: host buffers through prtc_step_characters (H2D + kernel + D2H every step) ----------
     e2e = None

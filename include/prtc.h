@@ -93,6 +93,7 @@ typedef struct prtc_counters {
     uint64_t node_tests;   /* BVH nodes tested by the GPU traversal */
     uint64_t contacts;     /* handleCollision calls (collision_system.cpp:236) */
     uint64_t cc_tests;     /* capsule-capsule narrowphase tests */
+    uint64_t exact_tests;  /* triangles that survived the pre-cull and ran the exact capsule-triangle test */
 } prtc_counters;
 
 /* Parity trace of one traced step (prtc_step_characters_traced); same record layout the CPU checkers under tests/ use.

@@ -33,7 +33,7 @@ class Config(ctypes.Structure):
 
 
 class Counters(ctypes.Structure):
-    _fields_ = [(k, ctypes.c_uint64) for k in ("substeps", "tri_tests", "node_tests", "contacts", "cc_tests")]
+    _fields_ = [(k, ctypes.c_uint64) for k in ("substeps", "tri_tests", "node_tests", "contacts", "cc_tests", "exact_tests")]
 
 
 _u32p = ctypes.POINTER(ctypes.c_uint32)

@@ -94,7 +94,7 @@ __global__ void __launch_bounds__(STEP_BLOCK) k_step(StepParams p) {
     fr.sa1 = fr.sa2 = fr.sb1 = fr.sb2 = v3(0.0f);
     fr.radius = 0.0f;
     float radius = 0.0f, qr_eps = 0.0f;
-    uint32_t my_capsule = 0xFFFFFFFFu, c_cc = 0;
+    uint32_t my_capsule = 0xFFFFFFFFu, c_cc = 0, c_exact = 0;
     if (valid) {
         pos = v3(tf->position[0], tf->position[1], tf->position[2]);
         Quat q; q.x = tf->rotation[0]; q.y = tf->rotation[1]; q.z = tf->rotation[2]; q.w = tf->rotation[3];
@@ -414,7 +414,13 @@ __global__ void __launch_bounds__(STEP_BLOCK) k_step(StepParams p) {
                 uint32_t my_poly = 0;
                 const V3 smin = gmin(ps.A, ps.B), smax = gmax(ps.A, ps.B);
                 while (n_consumed != n_fetched) {                 // filter loop: cheap, per lane
-                    if (n_fetched - n_consumed > 1) cp_async_wait<TRI_RING - 1>(); else cp_async_wait<0>();
+                    {   // the oldest outstanding group is the triangle to consume: allow (outstanding - 1) younger ones
+                        const uint32_t outstanding = n_fetched - n_consumed;
+                        if (TRI_RING >= 4 && outstanding >= 4) cp_async_wait<3>();
+                        else if (TRI_RING >= 3 && outstanding == 3) cp_async_wait<2>();
+                        else if (outstanding == 2) cp_async_wait<1>();
+                        else cp_async_wait<0>();
+                    }
                     const uint32_t slot = n_consumed % TRI_RING;
                     t0 = s_tri[slot][0][tid];
                     t1 = s_tri[slot][1][tid];
@@ -432,6 +438,7 @@ __global__ void __launch_bounds__(STEP_BLOCK) k_step(StepParams p) {
                 if (!__any_sync(FULL, pending)) break;
                 if (pending) {
                     Contact ct;
+                    ++c_exact;
                     if (capsule_triangle(ps, radius, p.abs_mode, v3(t0.x, t0.y, t0.z), v3(t1.x, t1.y, t1.z),
                                          v3(t2.x, t2.y, t2.z), v3(t0.w, t1.w, t2.w), ct)) {
                         // handleCollision (collision_system.cpp:242-252)
@@ -490,9 +497,11 @@ __global__ void __launch_bounds__(STEP_BLOCK) k_step(StepParams p) {
     c_tri = __reduce_add_sync(FULL, c_tri);
     c_node = __reduce_add_sync(FULL, c_node);
     c_contact = __reduce_add_sync(FULL, c_contact);
+    c_exact = __reduce_add_sync(FULL, c_exact);
     if (LITERAL || JACOBI) c_cc = __reduce_add_sync(FULL, c_cc);
     if ((tid & 31u) == 0 && p.counters) {
         if (LITERAL || JACOBI) atomicAdd(p.counters + 4, (unsigned long long)c_cc);
+        atomicAdd(p.counters + 5, (unsigned long long)c_exact);
         atomicAdd(p.counters + 0, (unsigned long long)c_sub);
         atomicAdd(p.counters + 1, (unsigned long long)c_tri);
         atomicAdd(p.counters + 2, (unsigned long long)c_node);

@@ -860,7 +860,7 @@ int prtc_get_counters(prtc_ctx * c, prtc_counters * out, int reset) {
     PRTC_CUDA(cudaMemcpyAsync(h, c->d_counters.ptr, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
     if (reset) PRTC_CUDA(cudaMemsetAsync(c->d_counters.ptr, 0, sizeof(h), c->stream));
     PRTC_CUDA(cudaStreamSynchronize(c->stream));
-    out->substeps = h[0]; out->tri_tests = h[1]; out->node_tests = h[2]; out->contacts = h[3]; out->cc_tests = h[4];
+    out->substeps = h[0]; out->tri_tests = h[1]; out->node_tests = h[2]; out->contacts = h[3]; out->cc_tests = h[4]; out->exact_tests = h[5];
     return PRTC_OK;
 }
 

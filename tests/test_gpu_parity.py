@@ -469,3 +469,84 @@ def test_chunked_host_step_equals_device_step():
         got_tf = d_tf.cpu().numpy().view(capi.TRANSFORM_DTYPE)
         got_ph = d_ph.cpu().numpy().view(capi.PHYSICS_DTYPE)
         assert H.state_diff(H.gpu_state(tf, ph), H.gpu_state(got_tf, got_ph)) == [], "frame %d" % f
+
+
+# ------------------------------------------------------------------------------------------------------------
+# BASELINE.json sizes
+# ------------------------------------------------------------------------------------------------------------
+def test_c3_full_size_bit_exact():
+    """C3 at full size: 64 000 capsules x 1 002 528 triangles (62 658 leaves of 16), 3 collide-and-slide iterations,
+    against the multi-threaded L1 port"""
+    scene = H.make_scene(708, 4, 2, 64000, seed=12345)
+    orc = H.build_oracle(scene, "l1", order="canonical", substeps=3, threads=os.cpu_count() or 1)
+    ctx, tf, ph = H.build_gpu(scene, substeps=3)
+    for f in range(3):
+        orc.step(DT)
+        ctx.update_characters(DT, tf, ph)
+        assert H.state_diff(orc.get_state(), H.gpu_state(tf, ph)) == [], "frame %d" % f
+    co, cg = orc.counters(), ctx.counters()
+    for k in ("substeps", "tri_tests", "contacts"):
+        assert co[k] == cg[k], k
+
+
+def test_c4_full_size_properties():
+    """C4 at full size (1 M capsules x 10 M triangles): too big for the CPU oracle to replay in a test, so the
+    size-independent properties of the path are checked instead:
+      * work-saving devices off (walk per substep, no pre-cull) == on, bit for bit, and the counters obey
+        substeps/tri_tests/contacts equal, exact_tests(on) <= tri_tests;
+      * batch independence: stepping two halves separately == stepping the whole batch (characters are independent);
+      * permutation equivariance: permuting the characters permutes the result;
+      * a 4096-character sample replayed by the CPU oracle against the full terrain is bit-identical."""
+    import torch
+    from prototype2_b200 import capi
+    n = 1000000
+    scene = H.make_scene(2237, 2, 2, n, seed=12345)
+    order = H.scenes.morton_order(scene["pos"], 2237)
+    for k in ("pos", "vel", "rot", "move"):
+        scene[k] = np.ascontiguousarray(scene[k][order])
+    ctx = capi.PhysicsContext()
+    ctx.add_model_collider(scene["xyz"], scene["mesh_first"], scene["mesh_count"])
+    cid = ctx.add_capsule_collider()
+    ctx.commit()
+    tf0 = capi.make_transforms(scene["pos"])
+    ph0 = capi.make_physics(scene["vel"], collider=np.full(n, cid, np.uint32))
+
+    def run(frames, tf, ph, **opts):
+        for o, v in opts.items():
+            ctx.set_option(getattr(capi, o), v)
+        ctx.counters(reset=True)
+        for _ in range(frames):
+            ctx.update_characters(DT, tf, ph)
+        c = ctx.counters(reset=True)
+        ctx.set_option(capi.OPT_FRAME_CACHE, 1)
+        ctx.set_option(capi.OPT_QUICK_REJECT, 1)
+        return c
+    tf_a, ph_a = tf0.copy(), ph0.copy()
+    ca = run(3, tf_a, ph_a)
+    tf_b, ph_b = tf0.copy(), ph0.copy()
+    cb = run(3, tf_b, ph_b, OPT_FRAME_CACHE=0, OPT_QUICK_REJECT=0)
+    assert H.state_diff(H.gpu_state(tf_a, ph_a), H.gpu_state(tf_b, ph_b)) == []
+    for k in ("substeps", "tri_tests", "contacts"):
+        assert ca[k] == cb[k], k
+    assert ca["exact_tests"] < cb["exact_tests"] <= cb["tri_tests"]
+    assert ca["node_tests"] < cb["node_tests"]
+    # halves
+    tf_c, ph_c = tf0.copy(), ph0.copy()
+    for _ in range(3):
+        ctx.update_characters(DT, tf_c[:n // 2], ph_c[:n // 2])
+        ctx.update_characters(DT, tf_c[n // 2:], ph_c[n // 2:])
+    assert H.state_diff(H.gpu_state(tf_a, ph_a), H.gpu_state(tf_c, ph_c)) == []
+    # permutation
+    perm = np.random.RandomState(3).permutation(n)
+    tf_d, ph_d = tf0[perm].copy(), ph0[perm].copy()
+    for _ in range(3):
+        ctx.update_characters(DT, tf_d, ph_d)
+    assert H.state_diff(H.gpu_state(tf_a[perm], ph_a[perm]), H.gpu_state(tf_d, ph_d)) == []
+    # oracle on a sample against the full terrain
+    sel = np.linspace(0, n - 1, 4096).astype(np.int64)
+    sub = dict(scene, pos=scene["pos"][sel], vel=scene["vel"][sel], rot=scene["rot"][sel], move=scene["move"][sel], n=len(sel))
+    orc = H.build_oracle(sub, "l1", order="canonical", threads=os.cpu_count() or 1)
+    for _ in range(3):
+        orc.step(DT)
+    so, sg = orc.get_state(), H.gpu_state(tf_a[sel], ph_a[sel])
+    assert H.state_diff(so, sg) == []
