@@ -192,8 +192,10 @@ int prtc_get_counters(prtc_ctx * ctx, prtc_counters * out, int reset);
  *                          frame's motion; substeps re-test only the cached leaves.  With 0 the device walks the
  *                          tree once per substep exactly like DynamicAABBTree::query, and prtc_counters.node_tests
  *                          then equals the reference's count (the numerator of the roofline's algorithmic bytes).
- *   PRTC_OPT_QUICK_REJECT  (default 1) conservative per-triangle pre-cull ahead of the exact test. */
-enum prtc_option { PRTC_OPT_FRAME_CACHE = 1, PRTC_OPT_QUICK_REJECT = 2 };
+ *   PRTC_OPT_QUICK_REJECT  (default 1) conservative per-triangle pre-cull ahead of the exact test.
+ *   PRTC_OPT_PERSISTENT    (default 1) static pass runs as a persistent kernel whose lanes advance through their
+ *                          characters independently (0: one character per lane in lock step). */
+enum prtc_option { PRTC_OPT_FRAME_CACHE = 1, PRTC_OPT_QUICK_REJECT = 2, PRTC_OPT_PERSISTENT = 3 };
 int prtc_set_option(prtc_ctx * ctx, int option, int value);
 
 /* Introspection for parity tests: the flattened tree.  leaf_mesh_ids receives the mesh-collider ids of all

@@ -57,6 +57,22 @@ __device__ __forceinline__ bool quick_reject(V3 smin, V3 smax, float radius, flo
            (loz - ez > smax.z) || (hiz + ez < smin.z);
 }
 
+// Cold per-lane state of k_step_stream lives in shared memory ([field][lane], conflict free)
+enum Park { P_VEL = 0, P_PREVVEL = 3, P_STEPV = 6, P_GN = 9, P_SA1 = 12, P_SA2 = 15, P_SB1 = 18, P_SB2 = 21,
+            P_PREVA = 24, P_PREVB = 27, P_COUNT = 30 };
+struct Parked {
+    float (*s)[32];
+    uint32_t tid;
+    __device__ __forceinline__ V3 get(int f) const { return v3(s[f][tid], s[f + 1][tid], s[f + 2][tid]); }
+    __device__ __forceinline__ void put(int f, V3 v) const { s[f][tid] = v.x; s[f + 1][tid] = v.y; s[f + 2][tid] = v.z; }
+    __device__ __forceinline__ CapsuleFrame frame(float radius) const {
+        CapsuleFrame fr;
+        fr.sa1 = get(P_SA1); fr.sa2 = get(P_SA2); fr.sb1 = get(P_SB1); fr.sb2 = get(P_SB2);
+        fr.radius = radius;
+        return fr;
+    }
+};
+
 constexpr int STEP_BLOCK = 32;      // one warp per block: a finished warp frees its slot at once (2.79 -> 2.71 ms at C4 vs 128)
 constexpr int MODE_STATIC = 0, MODE_LITERAL = 1, MODE_JACOBI = 2;
 constexpr int DYN_CAP = 16;      // capsule neighbours buffered per lane and pass of the JACOBI pass
@@ -573,6 +589,306 @@ __global__ void k_query_box(const float4 * __restrict__ nodes, uint32_t n_nodes,
     *out_count = found;
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// k_step_stream: the static pass (MODE_STATIC, untraced) as a PERSISTENT, lane-decoupled kernel.
+//
+// k_step keeps one character per lane and walks all lanes through "substep -> filter -> exact test" in lock step,
+// so a warp's cost per substep is set by its slowest lane (ncu: 14 of 32 lanes active per instruction).  Here every
+// lane is a small state machine that moves through its character's substeps on its own:
+//     LOAD     fetch the next character from a global counter, pre-step, one tree walk for the frame cache
+//     SUBSTEP  advance, query box, candidate leaves (cache or ordered walk), start the triangle stream
+//     STREAM   filter loop over the cp.async triangle ring until a triangle needs the exact test
+// and the only converged section is the expensive one, the exact capsule-triangle test, which runs whenever any lane
+// has a pending triangle.  LOAD and SUBSTEP are batched (they run when enough lanes wait for them or nobody has
+// anything else to do) so that their divergent code is shared by several lanes.  Arithmetic, order of triangles per
+// character and all results are the same as k_step's -- only the interleaving between characters differs.
+// ------------------------------------------------------------------------------------------------------------
+constexpr int ST_LOAD = 0, ST_SUBSTEP = 1, ST_STREAM = 2, ST_DONE = 3;
+constexpr int LOAD_BATCH = 16;       // lanes that must wait for new work before the (expensive) LOAD stage runs
+constexpr int SUBSTEP_BATCH = 8;     // same for the SUBSTEP stage
+
+__global__ void __launch_bounds__(32, 20) k_step_stream(StepParams p) {
+    constexpr unsigned FULL = 0xffffffffu;
+    __shared__ uint32_t s_leaf[LEAF_CAP][32];              // candidate leaves of the substep: node indices, emission order
+    __shared__ uint32_t s_cache[LEAF_CAP][32];
+    __shared__ float s_region[6][32];
+    __shared__ float4 s_tri[TRI_RING][3][32];
+    __shared__ float s_park[P_COUNT][32];
+    const uint32_t tid = threadIdx.x;
+    const Parked park{s_park, tid};
+    const unsigned lt_mask = (1u << tid) - 1u;
+    uint32_t c_sub = 0, c_tri = 0, c_node = 0, c_contact = 0, c_exact = 0;
+
+    int state = ST_LOAD;
+    uint32_t i = 0xFFFFFFFFu;
+    V3 pos = v3(0.0f);
+    uint32_t grounded = 0, stepsLeft = 0;
+    float radius = 0.0f, qr_eps = 0.0f, dmax = 0.0f;
+    bool cache_ok = false, found = true;
+    uint32_t ncache = 0, node = 0, nleaf = 0;
+    Box qb; qb.lo = v3(0.0f); qb.hi = v3(0.0f);
+    Pose ps = make_pose(park.frame(0.0f), pos);
+    uint32_t f_leaf = 0, f_cur = 0, f_end = 0, n_fetched = 0, n_consumed = 0;
+    bool pending = false;
+    float4 t0 = make_float4(0, 0, 0, 0), t1 = t0, t2 = t0;
+    const bool use_qr = p.qr_enable != 0u;
+    const bool use_cache = !(p.tune & 1u);
+    const int load_batch = ((p.tune >> 8) & 0xFFu) ? int((p.tune >> 8) & 0xFFu) : LOAD_BATCH;
+    const int substep_batch = ((p.tune >> 16) & 0xFFu) ? int((p.tune >> 16) & 0xFFu) : SUBSTEP_BATCH;
+    for (int f = 0; f < P_COUNT; ++f) s_park[f][tid] = 0.0f;
+
+    auto fetch_one = [&]() {
+        while (f_cur == f_end) {
+            if (f_leaf == nleaf) return;
+            const uint32_t leaf = s_leaf[f_leaf][tid];
+            ++f_leaf;
+            f_cur = uint32_t(__float_as_int(__ldg(p.nodes + 2 * leaf).w));
+            f_end = f_cur + uint32_t(__float_as_int(__ldg(p.nodes + 2 * leaf + 1).w));
+        }
+        const uint32_t slot = n_fetched % TRI_RING;
+        const float4 * src = p.tris + 3 * size_t(f_cur);
+        cp_async16(&s_tri[slot][0][tid], src);
+        cp_async16(&s_tri[slot][1][tid], src + 1);
+        cp_async16(&s_tri[slot][2][tid], src + 2);
+        cp_async_commit();
+        ++f_cur;
+        ++n_fetched;
+    };
+    // ordered stackless walk (DynamicAABBTree::query order) from `node`, buffering up to LEAF_CAP leaves
+    auto ordered_walk = [&]() {
+        nleaf = 0;
+        while (node < p.n_nodes && nleaf < LEAF_CAP) {
+            const float4 lo = __ldg(p.nodes + 2 * node);
+            const float4 hi = __ldg(p.nodes + 2 * node + 1);
+            const bool ov = node_overlaps(lo, hi, qb);
+            const int link = __float_as_int(lo.w);
+            const int cnt = __float_as_int(hi.w);
+            ++c_node;
+            if (cnt < 0) {
+                node = ov ? node + 1 : uint32_t(link);
+            } else {
+                if (ov) { s_leaf[nleaf][tid] = node; ++nleaf; }
+                node = node + 1;
+            }
+        }
+    };
+    auto start_stream = [&]() {
+        f_leaf = 0; f_cur = 0; f_end = 0; n_fetched = 0; n_consumed = 0;
+#pragma unroll
+        for (int r = 0; r < TRI_RING; ++r) fetch_one();
+    };
+
+    for (;;) {
+        const unsigned m_load = __ballot_sync(FULL, state == ST_LOAD);
+        const unsigned m_done = __ballot_sync(FULL, state == ST_DONE);
+        if (m_done == FULL) break;
+        const unsigned m_sub = __ballot_sync(FULL, state == ST_SUBSTEP);
+        const unsigned m_stream = __ballot_sync(FULL, state == ST_STREAM);
+
+        // ---------------- LOAD: new characters + their frame cache ----------------
+        if (m_load && (__popc(m_load) >= load_batch || (m_sub | m_stream) == 0u)) {
+            unsigned base = 0;
+            if (tid == 0) base = atomicAdd(p.work_counter, (unsigned)__popc(m_load));
+            base = __shfl_sync(FULL, base, 0);
+            Box R; R.lo = v3(0.0f); R.hi = v3(0.0f);
+            uint32_t wnode = p.n_nodes;
+            bool loaded_now = false;
+            if (state == ST_LOAD) {
+                const uint32_t idx = base + __popc(m_load & lt_mask);
+                if (idx >= p.n) {
+                    state = ST_DONE;
+                } else {
+                    i = idx;
+                    const prtc_transform * tf = p.transforms + i;
+                    const prtc_char_physics * ph = p.physics + i;
+                    pos = v3(tf->position[0], tf->position[1], tf->position[2]);
+                    Quat q; q.x = tf->rotation[0]; q.y = tf->rotation[1]; q.z = tf->rotation[2]; q.w = tf->rotation[3];
+                    V3 vel = v3(ph->velocity[0], ph->velocity[1], ph->velocity[2]);
+                    const V3 gn = v3(ph->ground_normal[0], ph->ground_normal[1], ph->ground_normal[2]);
+                    const float mvx = ph->movement[0], mvz = ph->movement[2];
+                    const CapsuleDev cap = p.capsules[ph->collider];
+                    const CapsuleFrame fr = capsule_frame(cap, rotation_of(q));
+                    radius = cap.radius;
+                    qr_eps = p.qr_eps + 1e-5f * (fabsf(cap.radius) + fabsf(cap.height) + fabsf(cap.ox) + fabsf(cap.oy) + fabsf(cap.oz));
+                    dmax = (p.abs_mode == 1u) ? radius : floorf(radius) + 1.0f;
+                    // ---- phase 1 (physics_system.cpp:277-285) ----
+                    park.put(P_PREVVEL, vel);
+                    if (ph->grounded) vel = vel + ((-p.stick * p.gravity) * p.dt) * gn;
+                    vel.x = vel.x + mvx;
+                    vel.z = vel.z + mvz;
+                    grounded = 0;
+                    park.put(P_VEL, vel);
+                    park.put(P_STEPV, vel / float(p.substeps));
+                    park.put(P_GN, gn);
+                    park.put(P_SA1, fr.sa1); park.put(P_SA2, fr.sa2); park.put(P_SB1, fr.sb1); park.put(P_SB2, fr.sb2);
+                    V3 a0, b0;
+                    segment_ends(fr, pos, a0, b0);                // prevTform                      :344
+                    park.put(P_PREVA, a0); park.put(P_PREVB, b0);
+                    stepsLeft = p.substeps;
+                    found = true;
+                    cache_ok = false;
+                    ncache = 0;
+                    state = ST_SUBSTEP;
+                    loaded_now = true;
+                    if (use_cache) {                              // frame region (see k_step)
+                        V3 eA, eB;
+                        segment_ends(fr, pos + vel, eA, eB);
+                        R = box_union(capsule_box(a0, b0, radius), capsule_box(eA, eB, radius));
+                        R.lo = R.lo - v3(0.25f); R.hi = R.hi + v3(0.25f);
+                        wnode = 0;
+                    }
+                }
+            }
+            if (use_cache) {
+                while (__any_sync(FULL, wnode < p.n_nodes)) {
+                    if (wnode < p.n_nodes) {
+                        const float4 lo = __ldg(p.nodes + 2 * wnode);
+                        const float4 hi = __ldg(p.nodes + 2 * wnode + 1);
+                        const bool ov = node_overlaps(lo, hi, R);
+                        const int cnt = __float_as_int(hi.w);
+                        ++c_node;
+                        if (cnt < 0) {
+                            wnode = ov ? wnode + 1 : uint32_t(__float_as_int(lo.w));
+                        } else {
+                            if (ov) {
+                                if (ncache < LEAF_CAP) { s_cache[ncache][tid] = wnode; ++ncache; wnode = wnode + 1; }
+                                else { wnode = 0xFFFFFFFFu; }
+                            } else wnode = wnode + 1;
+                        }
+                    }
+                }
+                if (loaded_now) {
+                    cache_ok = wnode != 0xFFFFFFFFu;
+                    s_region[0][tid] = R.lo.x; s_region[1][tid] = R.lo.y; s_region[2][tid] = R.lo.z;
+                    s_region[3][tid] = R.hi.x; s_region[4][tid] = R.hi.y; s_region[5][tid] = R.hi.z;
+                }
+            }
+            continue;
+        }
+
+        // ---------------- SUBSTEP: finish the frame or start the next substep ----------------
+        if (m_sub && (__popc(m_sub) >= substep_batch || m_stream == 0u)) {
+            if (state == ST_SUBSTEP) {
+                if (!found || stepsLeft == 0) {
+                    // `if (meshColIDs.empty()) break;` (:391-393) / loop end; remaining motion (:437); phase 3 (:298-317)
+                    prtc_transform * tf = p.transforms + i;
+                    prtc_char_physics * ph = p.physics + i;
+                    pos = pos + (float(stepsLeft) * park.get(P_VEL)) / float(p.substeps);
+                    V3 vel = park.get(P_PREVVEL);
+                    const float frictionRatio = fdiv(1.0f, 1.0f + (p.dt * p.friction));
+                    vel.x = vel.x * frictionRatio;
+                    vel.z = vel.z * frictionRatio;
+                    if (grounded) vel.y = gmax((0.0f * p.gravity) * p.dt, vel.y);
+                    else vel.y = vel.y + ((-1.0f * p.gravity) * p.dt);
+                    const V3 gn = park.get(P_GN);
+                    tf->position[0] = pos.x; tf->position[1] = pos.y; tf->position[2] = pos.z;
+                    ph->velocity[0] = vel.x; ph->velocity[1] = vel.y; ph->velocity[2] = vel.z;
+                    ph->ground_normal[0] = gn.x; ph->ground_normal[1] = gn.y; ph->ground_normal[2] = gn.z;
+                    ph->grounded = grounded;
+                    state = ST_LOAD;
+                } else {
+                    --stepsLeft;
+                    pos = pos + park.get(P_STEPV);                //                                 :350
+                    const CapsuleFrame fr = park.frame(radius);
+                    ps = make_pose(fr, pos);
+                    qb = box_union(capsule_box(park.get(P_PREVA), park.get(P_PREVB), radius), capsule_box(ps.A, ps.B, radius));   // :355-356
+                    park.put(P_PREVA, ps.A); park.put(P_PREVB, ps.B);     // prevTform = tform       :358
+                    ++c_sub;
+                    found = false;
+                    nleaf = 0;
+                    if (cache_ok &&
+                        s_region[0][tid] <= qb.lo.x && s_region[1][tid] <= qb.lo.y && s_region[2][tid] <= qb.lo.z &&
+                        s_region[3][tid] >= qb.hi.x && s_region[4][tid] >= qb.hi.y && s_region[5][tid] >= qb.hi.z) {
+                        for (uint32_t j = 0; j < ncache; ++j) {
+                            const uint32_t leaf = s_cache[j][tid];
+                            const float4 lo = __ldg(p.nodes + 2 * leaf);
+                            const float4 hi = __ldg(p.nodes + 2 * leaf + 1);
+                            ++c_node;
+                            if (node_overlaps(lo, hi, qb)) {
+                                s_leaf[nleaf][tid] = leaf;
+                                ++nleaf;
+                            }
+                        }
+                        node = p.n_nodes;
+                    } else {
+                        node = 0;
+                        ordered_walk();
+                    }
+                    if (nleaf) found = true;
+                    start_stream();
+                    state = ST_STREAM;
+                }
+            }
+            continue;
+        }
+
+        // ---------------- STREAM: filter until a triangle needs the exact test ----------------
+        if (state == ST_STREAM && !pending) {
+            const V3 smin = gmin(ps.A, ps.B), smax = gmax(ps.A, ps.B);
+            for (;;) {
+                while (n_consumed != n_fetched) {
+                    if (n_fetched - n_consumed >= 2) cp_async_wait<1>(); else cp_async_wait<0>();
+                    const uint32_t slot = n_consumed % TRI_RING;
+                    t0 = s_tri[slot][0][tid];
+                    t1 = s_tri[slot][1][tid];
+                    t2 = s_tri[slot][2][tid];
+                    ++n_consumed;
+                    fetch_one();
+                    ++c_tri;
+                    if (__float_as_uint(t0.w) == PRT_DEGENERATE_BITS) continue;       // length(n) == 0   :53
+                    if (use_qr && quick_reject(smin, smax, radius, dmax, qr_eps, t0, t1, t2)) continue;
+                    pending = true;
+                    break;
+                }
+                if (pending) break;
+                if (node < p.n_nodes) {                           // more leaves than the buffer holds: next pass
+                    ordered_walk();
+                    if (nleaf) found = true;
+                    start_stream();
+                    if (n_fetched == 0) { state = ST_SUBSTEP; break; }
+                } else {
+                    state = ST_SUBSTEP;                           // this substep's candidates are exhausted
+                    break;
+                }
+            }
+        }
+
+        // ---------------- exact tests, converged ----------------
+        if (__any_sync(FULL, pending)) {
+            if (pending) {
+                pending = false;
+                Contact ct;
+                ++c_exact;
+                if (capsule_triangle(ps, radius, p.abs_mode, v3(t0.x, t0.y, t0.z), v3(t1.x, t1.y, t1.z),
+                                     v3(t2.x, t2.y, t2.z), v3(t0.w, t1.w, t2.w), ct)) {
+                    pos = pos + ct.impulse;                       // handleCollision (collision_system.cpp:242-252)
+                    ++c_contact;
+                    if (dot(ct.normal, v3(0.0f, 1.0f, 0.0f)) > p.ground_dot) {
+                        grounded = 1;
+                        park.put(P_GN, ct.normal);
+                    }
+                    if (ct.impulse.x != 0.0f || ct.impulse.y != 0.0f || ct.impulse.z != 0.0f)
+                        ps = make_pose(park.frame(radius), pos);  // tform is rebuilt per triangle     :40
+                }
+            }
+            __syncwarp(FULL);
+        }
+    }
+
+    c_sub = __reduce_add_sync(FULL, c_sub);
+    c_tri = __reduce_add_sync(FULL, c_tri);
+    c_node = __reduce_add_sync(FULL, c_node);
+    c_contact = __reduce_add_sync(FULL, c_contact);
+    c_exact = __reduce_add_sync(FULL, c_exact);
+    if (tid == 0 && p.counters) {
+        atomicAdd(p.counters + 0, (unsigned long long)c_sub);
+        atomicAdd(p.counters + 1, (unsigned long long)c_tri);
+        atomicAdd(p.counters + 2, (unsigned long long)c_node);
+        atomicAdd(p.counters + 3, (unsigned long long)c_contact);
+        atomicAdd(p.counters + 5, (unsigned long long)c_exact);
+    }
+}
+
 // K1 for the dynamic pass: per own character, the phase-1 predicted box (physics_system.cpp:263-273: pose box united
 // with the box after `velocity + gravity*dt`, displacement applied in the capsule's rotated frame), the stored fat box
 // hysteresis of DynamicAABBTree::update/insertLeaf (aabb_tree.cpp:102-111,140-141) and the start-of-frame segment.
@@ -741,6 +1057,13 @@ void launch_step(StepParams const & p, bool traced, int mode, cudaStream_t strea
         else k_step<false, MODE_JACOBI><<<grid, block, 0, stream>>>(p);
     } else {
         if (traced) k_step<true, MODE_STATIC><<<grid, block, 0, stream>>>(p);
+        else if (p.work_counter) {
+            // persistent: one warp per block, as many blocks as fit (16 per SM), work handed out by a counter
+            cudaMemsetAsync(p.work_counter, 0, sizeof(unsigned), stream);
+            const uint32_t want = (p.n + 31) / 32;
+            const uint32_t resident = uint32_t(p.persistent_blocks);
+            k_step_stream<<<want < resident ? want : resident, 32, 0, stream>>>(p);
+        }
         else k_step<false, MODE_STATIC><<<grid, block, 0, stream>>>(p);
     }
 }

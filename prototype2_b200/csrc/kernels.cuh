@@ -67,6 +67,8 @@ struct StepParams {
     uint32_t qr_enable;
     uint32_t tune;                  // bit 0: frame cache OFF (walk the tree every substep, reference-equivalent counters)
     unsigned long long * counters;  // prtc_counters layout
+    unsigned * work_counter;        // k_step_stream: next character to hand out (null => lock-step kernel)
+    uint32_t persistent_blocks;     // k_step_stream: resident blocks to launch
     TraceBuffers trace;
 };
 

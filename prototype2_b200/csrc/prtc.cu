@@ -89,6 +89,9 @@ struct prtc_ctx {
     bool capsules_dirty = false;
     float world_max_abs = 0.0f;             // largest |coordinate| of any mesh AABB (margin of the pre-cull)
     int frame_cache = 1;                    // PRTC_OPT_FRAME_CACHE
+    int persistent = 1;                     // PRTC_OPT_PERSISTENT
+    uint32_t tune_hi = 0;                   // PRTC_TUNE: batch thresholds of k_step_stream (bits 8-15 load, 16-23 substep), experiments
+    int sm_count = 148;
     int quick_reject = 1;                   // PRTC_OPT_QUICK_REJECT
     std::vector<uint32_t> moved_models;     // models whose transform changed (prtc_update_models)
 
@@ -100,6 +103,7 @@ struct prtc_ctx {
     DevBuf<uint32_t> d_node_leaf_id, d_tri_src;
     DevBuf<CapsuleDev> d_capsules;
     DevBuf<unsigned long long> d_counters;
+    DevBuf<unsigned> d_work;                // work counters of the persistent kernel, one per concurrently running launch
     DevBuf<prtc_transform> d_tf;
     DevBuf<prtc_char_physics> d_ph;
     // trace scratch
@@ -264,7 +268,9 @@ int fill_params(prtc_ctx * c, float dt, uint32_t n, prtc_transform * d_tf, prtc_
         float ulp = std::nextafter(m, INFINITY) - m;
         p.qr_eps = std::max(1e-3f, 64.0f * ulp);
         p.qr_enable = (c->quick_reject && m < 1.0e6f) ? 1u : 0u;
-        p.tune = c->frame_cache ? 0u : 1u;
+        p.tune = (c->frame_cache ? 0u : 1u) | c->tune_hi;
+        p.work_counter = c->persistent ? c->d_work.ptr : nullptr;
+        p.persistent_blocks = uint32_t(c->sm_count) * 20u;
     }
     return PRTC_OK;
 }
@@ -561,13 +567,16 @@ int prtc_create(const prtc_config * cfg, prtc_ctx ** out) {
     // environment overrides of the option defaults, for A/B measurements without touching the caller
     if (const char * e = std::getenv("PRTC_QUICK_REJECT")) ctx->quick_reject = std::atoi(e);
     if (const char * e = std::getenv("PRTC_FRAME_CACHE")) ctx->frame_cache = std::atoi(e);
+    if (const char * e = std::getenv("PRTC_PERSISTENT")) ctx->persistent = std::atoi(e);
+    if (const char * e = std::getenv("PRTC_TUNE")) ctx->tune_hi = uint32_t(std::strtoul(e, nullptr, 0)) & 0xFFFFFF00u;
+    ctx->sm_count = prop.multiProcessorCount;
     ctx->tree.set_margin(c.leaf_margin);
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
         delete ctx;
         return fail(PRTC_ERR_CUDA, "prtc_create: cudaStreamCreate failed");
     }
     ctx->own_stream = true;
-    if (ctx->d_counters.reserve(8) != cudaSuccess || cudaMemsetAsync(ctx->d_counters.ptr, 0, 8 * sizeof(unsigned long long), ctx->stream) != cudaSuccess) {
+    if (ctx->d_work.reserve(16) != cudaSuccess || ctx->d_counters.reserve(8) != cudaSuccess || cudaMemsetAsync(ctx->d_counters.ptr, 0, 8 * sizeof(unsigned long long), ctx->stream) != cudaSuccess) {
         prtc_destroy(ctx);
         return fail(PRTC_ERR_CUDA, "prtc_create: counter allocation failed");
     }
@@ -581,7 +590,7 @@ void prtc_destroy(prtc_ctx * c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     c->d_raw.release(); c->d_world.release(); c->d_aabbs.release(); c->d_meshes.release(); c->d_xforms.release();
     c->d_nodes.release(); c->d_tris.release(); c->d_node_leaf_id.release(); c->d_tri_src.release();
-    c->d_capsules.release(); c->d_counters.release(); c->d_tf.release(); c->d_ph.release();
+    c->d_capsules.release(); c->d_counters.release(); c->d_work.release(); c->d_tf.release(); c->d_ph.release();
     c->d_tq.release(); c->d_tmesh.release(); c->d_tcaps.release(); c->d_thits.release();
     c->d_scratch_f.release(); c->d_scratch_u.release();
     c->d_cap2char.release(); c->d_seg_start.release(); c->d_seg_prev.release(); c->d_last_box.release();
@@ -737,7 +746,8 @@ int prtc_step_characters(prtc_ctx * c, float dt, uint32_t n, prtc_transform * tf
     // Static pass, big batch: characters are independent, so the batch is cut into chunks and the chunks' host->device
     // copies, steps and device->host copies overlap on a few streams (PCIe is full duplex).  Results are identical
     // to one launch -- every character's frame is computed by one thread either way.
-    const uint32_t kChunk = 65536;
+    static const uint32_t kChunk = [] { const char * e = std::getenv("PRTC_CHUNK"); return e ? uint32_t(std::atoi(e)) : 65536u; }();
+    static const bool kChunkPersistent = [] { const char * e = std::getenv("PRTC_CHUNK_PERSISTENT"); return e ? std::atoi(e) != 0 : false; }();   // chunks overlap: the lock-step kernel has no per-launch drain tail (3.13 vs 3.70 ms)
     if (!c->jacobi() && n >= 4 * kChunk) {
         if (c->geometry_dirty || c->tree_dirty || c->capsules_dirty) { rc = commit_impl(c); if (rc) return rc; }
         if (!c->pipe_ready) {
@@ -754,6 +764,8 @@ int prtc_step_characters(prtc_ctx * c, float dt, uint32_t n, prtc_transform * tf
             PRTC_CUDA(cudaMemcpyAsync(c->d_ph.ptr + first, ph + first, size_t(cnt) * sizeof(prtc_char_physics), cudaMemcpyHostToDevice, s));
             StepParams p;
             fill_params(c, dt, cnt, c->d_tf.ptr + first, c->d_ph.ptr + first, p);
+            if (!kChunkPersistent) p.work_counter = nullptr;
+            if (p.work_counter) p.work_counter += 1 + k % prtc_ctx::PIPE_STREAMS;     // launches on one stream are ordered
             launch_step(p, false, STEP_STATIC, s);
             PRTC_CUDA(cudaGetLastError());
             PRTC_CUDA(cudaMemcpyAsync(tf + first, c->d_tf.ptr + first, size_t(cnt) * sizeof(prtc_transform), cudaMemcpyDeviceToHost, s));
@@ -896,6 +908,7 @@ int prtc_set_option(prtc_ctx * c, int option, int value) {
     switch (option) {
         case PRTC_OPT_FRAME_CACHE: c->frame_cache = value != 0; return PRTC_OK;
         case PRTC_OPT_QUICK_REJECT: c->quick_reject = value != 0; return PRTC_OK;
+        case PRTC_OPT_PERSISTENT: c->persistent = value != 0; return PRTC_OK;
         default: return fail(PRTC_ERR_INVALID, "prtc_set_option: unknown option");
     }
 }

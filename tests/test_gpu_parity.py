@@ -46,8 +46,8 @@ def test_c2_shape_canonical_bit_exact(abs_mode):
               dict(abs_mode=capi.ABS_INT if abs_mode == "int" else capi.ABS_FLOAT))
 
 
-@pytest.mark.parametrize("frame_cache,quick_reject", [(0, 0), (0, 1), (1, 0)])
-def test_work_saving_options_do_not_change_results(frame_cache, quick_reject):
+@pytest.mark.parametrize("frame_cache,quick_reject,persistent", [(0, 0, 0), (0, 1, 0), (1, 0, 0), (1, 1, 0), (0, 0, 1), (0, 1, 1), (1, 0, 1)])
+def test_work_saving_options_do_not_change_results(frame_cache, quick_reject, persistent):
     """PRTC_OPT_FRAME_CACHE / PRTC_OPT_QUICK_REJECT off: same bits; with the frame cache off the node-test counter
     is the reference's own count"""
     from prototype2_b200 import capi
@@ -57,10 +57,15 @@ def test_work_saving_options_do_not_change_results(frame_cache, quick_reject):
     ctx, tf, ph = H.build_gpu(scene)
     ctx.set_option(capi.OPT_FRAME_CACHE, frame_cache)
     ctx.set_option(capi.OPT_QUICK_REJECT, quick_reject)
+    ctx.set_option(capi.OPT_PERSISTENT, persistent)
     for f in range(5):
-        to = orc.step(DT, trace=True)
-        tg = ctx.update_characters_traced(DT, tf, ph)
-        assert H.trace_diff(to, tg) == []
+        if f % 2 == 0:
+            to = orc.step(DT, trace=True)
+            tg = ctx.update_characters_traced(DT, tf, ph)                 # traced launches use the lock-step kernel
+            assert H.trace_diff(to, tg) == []
+        else:
+            orc.step(DT)
+            ctx.update_characters(DT, tf, ph)                             # untraced: persistent kernel when enabled
         assert H.state_diff(orc.get_state(), H.gpu_state(tf, ph)) == []
     co, cg = orc.counters(), ctx.counters()
     for k in ("substeps", "tri_tests", "contacts") + (("node_tests",) if not frame_cache else ()):
