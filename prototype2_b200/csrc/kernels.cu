@@ -98,8 +98,11 @@ __global__ void __launch_bounds__(STEP_BLOCK, 512 / STEP_BLOCK) k_step(StepParam
     __shared__ float4 s_tri[TRI_RING][3][STEP_BLOCK];
     __shared__ uint32_t s_dyn[JACOBI ? DYN_CAP : 1][STEP_BLOCK];      // JACOBI: neighbour capsules, ascending
     const uint32_t tid = threadIdx.x;
-    const uint32_t i = blockIdx.x * blockDim.x + tid;
-    const bool valid = i < p.n;
+    // small batches: only the first `lanes_per_warp` lanes of every warp carry a character, so that the batch is
+    // spread over all resident warps and latency is hidden across warps instead of paid inside one
+    const uint32_t lpw = p.lanes_per_warp ? p.lanes_per_warp : 32u;
+    const uint32_t i = (blockIdx.x * (blockDim.x / 32u) + tid / 32u) * lpw + (tid & 31u);
+    const bool valid = (tid & 31u) < lpw && i < p.n;
     uint32_t c_sub = 0, c_tri = 0, c_node = 0, c_contact = 0;
 
     prtc_transform * tf = p.transforms + (valid ? i : 0);
@@ -1045,10 +1048,19 @@ void launch_raycast(const float4 * nodes, uint32_t n_nodes, const float4 * tris,
     k_raycast<<<(n_rays + block - 1) / block, block, 0, stream>>>(nodes, n_nodes, tris, n_rays, origins, dirs, maxd, hit_xyz, hit_mask);
 }
 
-void launch_step(StepParams const & p, bool traced, int mode, cudaStream_t stream) {
-    if (p.n == 0) return;
+void launch_step(StepParams const & p_in, bool traced, int mode, cudaStream_t stream) {
+    if (p_in.n == 0) return;
+    StepParams p = p_in;
     const uint32_t block = STEP_BLOCK;
-    const uint32_t grid = (p.n + block - 1) / block;
+    // fewer characters than resident lanes: thin the warps out (1..32 characters per warp)
+    const uint32_t resident_warps = p.persistent_blocks ? p.persistent_blocks : 2368u;
+    uint32_t lpw = (p.n + resident_warps - 1) / resident_warps;
+    lpw = lpw < 1u ? 1u : (lpw > 8u ? 32u : lpw);       // measured: thinning pays up to ~8 lanes/warp (C2 0.29 -> 0.11 ms), not at 22 (C3)
+    const bool small = lpw < 32u;
+    p.lanes_per_warp = lpw;
+    if (small) p.work_counter = nullptr;                 // the persistent kernel is for batches that fill the machine
+    const uint32_t warps = (p.n + lpw - 1) / lpw;
+    const uint32_t grid = (warps * 32u + block - 1) / block;
     if (mode == MODE_LITERAL) {
         if (traced) k_step<true, MODE_LITERAL><<<grid, block, 0, stream>>>(p);
         else k_step<false, MODE_LITERAL><<<grid, block, 0, stream>>>(p);

@@ -69,6 +69,7 @@ struct StepParams {
     unsigned long long * counters;  // prtc_counters layout
     unsigned * work_counter;        // k_step_stream: next character to hand out (null => lock-step kernel)
     uint32_t persistent_blocks;     // k_step_stream: resident blocks to launch
+    uint32_t lanes_per_warp;        // k_step: characters per warp (set by launch_step; < 32 for small batches)
     TraceBuffers trace;
 };
 
