@@ -82,7 +82,9 @@ typedef struct prtc_char_physics {
     float velocity[3];         /* in/out */
     float movement[3];         /* in      movementVector */
     float ground_normal[3];    /* in/out  groundNormal */
-    uint32_t collider;         /* in      colliderTag.index (capsule id from prtc_add_capsule) */
+    uint32_t collider;         /* in      colliderTag.index (capsule id from prtc_add_capsule); an id that was never
+                                *         added is not dereferenced: the step returns PRTC_ERR_INVALID and that
+                                *         character's result is undefined */
     uint32_t grounded;         /* in/out  isGrounded (0/1) */
 } prtc_char_physics;
 

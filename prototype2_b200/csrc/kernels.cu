@@ -121,8 +121,13 @@ __global__ void __launch_bounds__(STEP_BLOCK, 512 / STEP_BLOCK) k_step(StepParam
         gn = v3(ph->ground_normal[0], ph->ground_normal[1], ph->ground_normal[2]);
         grounded = ph->grounded;
         const float mvx = ph->movement[0], mvz = ph->movement[2];
-        const CapsuleDev cap = p.capsules[ph->collider];
-        my_capsule = ph->collider;
+        uint32_t cid = ph->collider;
+        if (cid >= p.n_capsules) {                                // unknown capsule id: never dereferenced; reported, result undefined
+            if (p.counters) atomicAdd(p.counters + 6, 1ull);
+            cid = 0;
+        }
+        const CapsuleDev cap = p.capsules[cid];
+        my_capsule = cid;
         fr = capsule_frame(cap, rotation_of(q));
         radius = cap.radius;
         qr_eps = p.qr_eps + 1e-5f * (fabsf(cap.radius) + fabsf(cap.height) + fabsf(cap.ox) + fabsf(cap.oy) + fabsf(cap.oz));
@@ -704,12 +709,17 @@ __global__ void __launch_bounds__(32, 20) k_step_stream(StepParams p) {
                     i = idx;
                     const prtc_transform * tf = p.transforms + i;
                     const prtc_char_physics * ph = p.physics + i;
+                    uint32_t cid = ph->collider;
+                    if (cid >= p.n_capsules) {                    // unknown capsule id: never dereferenced; reported, result undefined
+                        if (p.counters) atomicAdd(p.counters + 6, 1ull);
+                        cid = 0;
+                    }
                     pos = v3(tf->position[0], tf->position[1], tf->position[2]);
                     Quat q; q.x = tf->rotation[0]; q.y = tf->rotation[1]; q.z = tf->rotation[2]; q.w = tf->rotation[3];
                     V3 vel = v3(ph->velocity[0], ph->velocity[1], ph->velocity[2]);
                     const V3 gn = v3(ph->ground_normal[0], ph->ground_normal[1], ph->ground_normal[2]);
                     const float mvx = ph->movement[0], mvz = ph->movement[2];
-                    const CapsuleDev cap = p.capsules[ph->collider];
+                    const CapsuleDev cap = p.capsules[cid];
                     const CapsuleFrame fr = capsule_frame(cap, rotation_of(q));
                     radius = cap.radius;
                     qr_eps = p.qr_eps + 1e-5f * (fabsf(cap.radius) + fabsf(cap.height) + fabsf(cap.ox) + fabsf(cap.oy) + fabsf(cap.oz));

@@ -275,6 +275,18 @@ int fill_params(prtc_ctx * c, float dt, uint32_t n, prtc_transform * d_tf, prtc_
     return PRTC_OK;
 }
 
+// characters whose collider id names no registered capsule are skipped by the kernels and counted in slot 6
+int check_bad_colliders(prtc_ctx * c) {
+    unsigned long long bad = 0;
+    PRTC_CUDA(cudaMemcpyAsync(&bad, c->d_counters.ptr + 6, sizeof(bad), cudaMemcpyDeviceToHost, c->stream));
+    PRTC_CUDA(cudaStreamSynchronize(c->stream));
+    if (bad) {
+        PRTC_CUDA(cudaMemsetAsync(c->d_counters.ptr + 6, 0, sizeof(bad), c->stream));
+        return fail(PRTC_ERR_INVALID, "prtc_step_characters: " + std::to_string(bad) + " character(s) name a capsule collider that was never added; their results are undefined");
+    }
+    return PRTC_OK;
+}
+
 int check_mode(prtc_ctx * c, bool device_pointers) {
     if (c->cfg.order_mode != PRTC_ORDER_CANONICAL && c->cfg.order_mode != PRTC_ORDER_LITERAL)
         return fail(PRTC_ERR_INVALID, "unknown order_mode");
@@ -708,8 +720,7 @@ int prtc_set_stream(prtc_ctx * c, void * cuda_stream) {
 
 int prtc_synchronize(prtc_ctx * c) {
     if (!c) return fail(PRTC_ERR_INVALID, "prtc_synchronize: null context");
-    PRTC_CUDA(cudaStreamSynchronize(c->stream));
-    return PRTC_OK;
+    return check_bad_colliders(c);          // synchronises; reports characters skipped by device-pointer steps
 }
 
 int prtc_step_characters_device(prtc_ctx * c, float dt, uint32_t n, prtc_transform * d_tf, prtc_char_physics * d_ph) {
@@ -772,7 +783,7 @@ int prtc_step_characters(prtc_ctx * c, float dt, uint32_t n, prtc_transform * tf
             PRTC_CUDA(cudaMemcpyAsync(ph + first, c->d_ph.ptr + first, size_t(cnt) * sizeof(prtc_char_physics), cudaMemcpyDeviceToHost, s));
         }
         for (int q = 0; q < prtc_ctx::PIPE_STREAMS; ++q) PRTC_CUDA(cudaStreamSynchronize(c->pipe[q]));
-        return PRTC_OK;
+        return check_bad_colliders(c);
     }
     if (n) {
         PRTC_CUDA(cudaMemcpyAsync(c->d_tf.ptr, tf, size_t(n) * sizeof(prtc_transform), cudaMemcpyHostToDevice, c->stream));
@@ -784,8 +795,7 @@ int prtc_step_characters(prtc_ctx * c, float dt, uint32_t n, prtc_transform * tf
         PRTC_CUDA(cudaMemcpyAsync(tf, c->d_tf.ptr, size_t(n) * sizeof(prtc_transform), cudaMemcpyDeviceToHost, c->stream));
         PRTC_CUDA(cudaMemcpyAsync(ph, c->d_ph.ptr, size_t(n) * sizeof(prtc_char_physics), cudaMemcpyDeviceToHost, c->stream));
     }
-    PRTC_CUDA(cudaStreamSynchronize(c->stream));
-    return PRTC_OK;
+    return check_bad_colliders(c);
 }
 
 int prtc_step_characters_traced(prtc_ctx * c, float dt, uint32_t n, prtc_transform * tf, prtc_char_physics * ph, prtc_trace * tr) {

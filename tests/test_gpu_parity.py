@@ -555,3 +555,17 @@ def test_c4_full_size_properties():
         orc.step(DT)
     so, sg = orc.get_state(), H.gpu_state(tf_a[sel], ph_a[sel])
     assert H.state_diff(so, sg) == []
+
+
+def test_unknown_collider_id_is_reported_not_dereferenced():
+    from prototype2_b200 import capi
+    scene = H.make_scene(24, 2, 2, 64, seed=2)
+    ctx, tf, ph = H.build_gpu(scene)
+    before = tf["position"].copy()
+    ph["collider"][5] = 9999
+    with pytest.raises(capi.PrtcError) as e:
+        ctx.update_characters(DT, tf, ph)
+    assert e.value.code == capi.PRTC_ERR_INVALID and "never added" in str(e.value)
+    assert not H.same(tf["position"][6], before[6])                # the others were stepped
+    ph["collider"][5] = 5
+    ctx.update_characters(DT, tf, ph)                              # and the context keeps working
