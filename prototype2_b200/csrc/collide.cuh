@@ -27,7 +27,7 @@ struct CapsuleDev {          // CapsuleCollider (colliders.h:14-18), padded to 3
 };
 
 // Per-capsule constants of `tform * a` / `tform * b` (collision_system.cpp:37-43) with tform = [R | pos]:
-//   A = (R0*a.x + R1*a.y) + (R2*a.z + pos)      -> A = sa1 + (sa2 + pos)
+//   A = (R0*a.x + R1*a.y) + (R2*a.z + pos)      -> A = sa1 + (sa2 + pos)   (+ pos*0, see segment_ends)
 struct CapsuleFrame {
     V3 sa1, sa2, sb1, sb2;
     float radius;
@@ -56,10 +56,18 @@ struct Pose {
     V3 pointA;               // A - cn * radius                                   :46-48
     V3 segv; float segd;     // normalize(B - A), distance(A, B): closestPointOnLineSegment(A, B, .)   :67
 };
-PRT_HD void segment_ends(CapsuleFrame const & f, V3 pos, V3 & A, V3 & B) {
-    A = f.sa1 + (f.sa2 + pos);
-    B = f.sb1 + (f.sb2 + pos);
+// `cols` is the position tform was built from.  translate(mat4(1), cols) computes its translation column as
+// ((m0*x + m1*y) + m2*z) + m3 with identity columns, i.e. every component picks up 0*x, 0*y, 0*z terms, and the 4x4
+// product with toMat4(q) then adds translation*0 to every rotation entry.  For finite positions all of that is +-0;
+// for a position with ANY inf/NaN component it is NaN everywhere -- which is how a character at y = inf gets an
+// all-NaN box (and therefore every mesh as candidate) in the reference.  `zs` carries exactly that.  `t` is the
+// matrix's translation column (== cols except for glm::translate(tform, v), physics_system.cpp:271).
+PRT_HD void segment_ends(CapsuleFrame const & f, V3 cols, V3 t, V3 & A, V3 & B) {
+    const float zs = (cols.x * 0.0f + cols.y * 0.0f) + cols.z * 0.0f;
+    A = (f.sa1 + (f.sa2 + t)) + zs;
+    B = (f.sb1 + (f.sb2 + t)) + zs;
 }
+PRT_HD void segment_ends(CapsuleFrame const & f, V3 pos, V3 & A, V3 & B) { segment_ends(f, pos, pos, A, B); }
 PRT_HD Pose make_pose(CapsuleFrame const & f, V3 pos) {
     Pose p;
     segment_ends(f, pos, p.A, p.B);

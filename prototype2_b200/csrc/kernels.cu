@@ -923,7 +923,7 @@ __global__ void k_dyn_prep(const prtc_transform * __restrict__ tf, const prtc_ch
     const V3 d = vel + (v3(0.0f, -1.0f, 0.0f) * gravity) * dt;
     const V3 pos2 = ((R.c0 * d.x + R.c1 * d.y) + R.c2 * d.z) + pos;
     V3 A2, B2;
-    segment_ends(fr, pos2, A2, B2);
+    segment_ends(fr, pos, pos2, A2, B2);
     e = box_union(e, capsule_box(A2, B2, cap.radius));
     float4 * rec = records + 4 * size_t(first + i);
     Box stored;

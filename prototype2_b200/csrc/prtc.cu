@@ -445,7 +445,7 @@ int literal_step(prtc_ctx * c, float dt, uint32_t n, prtc_transform * tf, prtc_c
         const V3 d = vel + (v3(0.0f, -1.0f, 0.0f) * c->cfg.gravity) * dt;
         const V3 pos2 = ((R.c0 * d.x + R.c1 * d.y) + R.c2 * d.z) + pos;       // translate(): m[0]*v.x + m[1]*v.y + m[2]*v.z + m[3]
         V3 A2, B2;
-        segment_ends(fr, pos2, A2, B2);
+        segment_ends(fr, pos, pos2, A2, B2);
         e = box_union(e, capsule_box(A2, B2, cap.radius));
         c->capsule_aabbs[ph[i].collider] = e;
         cap2char[ph[i].collider] = i;                                          // tagToCharacter, :275

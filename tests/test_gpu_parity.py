@@ -569,3 +569,79 @@ def test_unknown_collider_id_is_reported_not_dereferenced():
     assert not H.same(tf["position"][6], before[6])                # the others were stepped
     ph["collider"][5] = 5
     ctx.update_characters(DT, tf, ph)                              # and the context keeps working
+
+
+# ------------------------------------------------------------------------------------------------------------
+# robustness: heterogeneous capsules, odd substep counts, far-away worlds, NaN input
+# ------------------------------------------------------------------------------------------------------------
+def _hetero_worlds(scene, caps, oracle_kind, oracle_kw, gpu_kw):
+    from prototype2_b200 import capi
+    orc = H.L0World(oracle_kw.pop("variant")) if oracle_kind == "l0" else H.L1World(**oracle_kw)
+    ctx = capi.PhysicsContext(**gpu_kw)
+    orc.add_model(scene["xyz"], scene["mesh_first"], scene["mesh_count"], scene["model_transform"])
+    ctx.add_model_collider(scene["xyz"], scene["mesh_first"], scene["mesh_count"], scene["model_transform"])
+    for h, r, off in caps:
+        orc.add_capsule(h, r, off)
+        ctx.add_capsule_collider(h, r, off)
+    orc.set_state(pos=scene["pos"], rot=scene["rot"], vel=scene["vel"], move=scene["move"])
+    tf = capi.make_transforms(scene["pos"], rot_xyzw=scene["rot"][:, [1, 2, 3, 0]])
+    ph = capi.make_physics(scene["vel"], movement=scene["move"])
+    return orc, ctx, tf, ph
+
+
+def _random_capsules(n, seed):
+    rs = np.random.RandomState(seed)
+    return [(float(rs.uniform(0.2, 1.2)), float(rs.uniform(0.2, 0.8)), (float(rs.uniform(-0.1, 0.1)), float(rs.uniform(0.2, 0.8)), float(rs.uniform(-0.1, 0.1))))
+            for _ in range(n)]
+
+
+@pytest.mark.skipif(not L0World.available("plain"), reason="oracle/_ref not built")
+def test_heterogeneous_capsules_literal_vs_reference():
+    """every capsule its own height / radius / offset (capsule-capsule uses both radii, collision_system.cpp:212)"""
+    from prototype2_b200 import capi
+    scene = H.make_scene(36, 2, 2, 70, seed=81)
+    caps = _random_capsules(70, 5)
+    orc, ctx, tf, ph = _hetero_worlds(scene, caps, "l0", dict(variant="plain"), dict(order_mode=capi.ORDER_LITERAL))
+    for f in range(15):
+        orc.step(DT)
+        ctx.update_characters(DT, tf, ph)
+        assert H.state_diff(orc.get_state(), H.gpu_state(tf, ph)) == [], "frame %d" % f
+    assert ctx.counters()["cc_tests"] > 0
+
+
+@pytest.mark.parametrize("dyn", ["off", "jacobi"])
+def test_heterogeneous_capsules_canonical(dyn):
+    from prototype2_b200 import capi
+    scene = H.make_scene(36, 2, 2, 200, seed=82)
+    caps = _random_capsules(200, 6)
+    orc, ctx, tf, ph = _hetero_worlds(scene, caps, "l1", dict(order="canonical", dyn=dyn),
+                                      dict(dyn_mode=capi.DYN_JACOBI if dyn == "jacobi" else capi.DYN_OFF))
+    for f in range(8):
+        orc.step(DT)
+        ctx.update_characters(DT, tf, ph)
+        assert H.state_diff(orc.get_state(), H.gpu_state(tf, ph)) == [], "frame %d" % f
+
+
+@pytest.mark.parametrize("substeps", [1, 2, 7])
+def test_other_substep_counts(substeps):
+    scene = H.make_scene(48, 2, 2, 300, seed=83)
+    _run_pair(scene, 4, dict(order="canonical", substeps=substeps), dict(substeps=substeps))
+
+
+def test_world_far_from_the_origin_disables_the_pre_cull():
+    """coordinates around 3e6: the pre-cull's margin argument no longer holds and it switches itself off
+    (StepParams::qr_enable); float spacing there is 0.25, results must still equal the oracle's bit for bit"""
+    scene = H.make_scene(32, 2, 2, 120, seed=84)
+    scene["model_transform"] = [3.0e6, 0.0, -2.0e6, 1, 0, 0, 0, 1, 1, 1]
+    scene["pos"] = (scene["pos"] + np.array([3.0e6, 0.0, -2.0e6], np.float32)).astype(np.float32)
+    _run_pair(scene, 4, dict(order="canonical"), dict())
+
+
+def test_nan_and_inf_characters_do_not_hang_or_poison_the_others():
+    """a NaN box overlaps every node (AABB::intersect is written with negated compares, aabb.cpp:3-10, trap T14), so
+    such a character tests every triangle of the scene -- like in the reference -- and its neighbours are unaffected"""
+    scene = H.make_scene(20, 2, 2, 48, seed=85)
+    scene["pos"][3] = np.nan
+    scene["vel"][7, 1] = np.inf
+    scene["pos"][11, 0] = np.float32(3.0e38)
+    _run_pair(scene, 3, dict(order="canonical"), dict(), trace_frames=())      # (a NaN query has more candidates than a trace slot holds)
