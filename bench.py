@@ -199,6 +199,19 @@ def reference_verbatim():
         return {"error": str(e)}
 
 
+def host_info():
+    model = "unknown"
+    try:
+        for ln in open("/proc/cpuinfo"):
+            if ln.startswith("model name"):
+                model = ln.split(":", 1)[1].strip()
+                break
+    except OSError:
+        pass
+    return {"cpu_model": model, "nproc": os.cpu_count(),
+            "build": "g++ -std=c++17 -O3 -DNDEBUG -ffp-contract=off (oracle/Makefile), no sanitizers"}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -221,7 +234,7 @@ def run_reference(args):
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": describe(args, n_terrain, bx, bz, n_caps, len(xyz) // 3, max(1, args.gpus)),
         "tri_tests_per_s": r["tri_tests"] / r["seconds"],
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample_txt,
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample_txt, "host": host_info(),
                          "note": "oracle/l1_oracle.cpp (restatement pinned bit-identical to the reference's own sources; "
                                  "the verbatim build cannot hold >65534 mesh colliders), std::thread over capsules"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -439,7 +452,9 @@ def run_ours(args):
         sel = np.linspace(0, n_caps - 1, sample).astype(np.int64)
         threads = os.cpu_count() or 1
         r = cpu_run(xyz, mf, mc, pos[sel], vel[sel], 1000, 1, threads, seconds_cap=args.cpu_seconds)
-        cpu = {"value": r["substeps"] / r["seconds"], "unit": UNIT, "cores": threads, "kind": "port",
+        r1 = cpu_run(xyz, mf, mc, pos[sel[::8]], vel[sel[::8]], 1000, 1, 1, seconds_cap=4.0)
+        cpu = {"value": r["substeps"] / r["seconds"], "unit": UNIT, "cores": threads, "kind": "port", "host": host_info(),
+               "single_thread_value": r1["substeps"] / r1["seconds"],
                "sample": "%d of %d capsules (every %d-th in Morton order) x %d frames against the full terrain, %.1f s" % (
                    sample, n_caps, max(1, n_caps // sample), r["steps"], r["seconds"]),
                "tri_tests_per_s": r["tri_tests"] / r["seconds"]}
@@ -447,7 +462,8 @@ def run_ours(args):
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": 1e3 * el / args.steps, "higher_is_better": True, "scaling": "strong" if dynamic else "weak", "vs_baseline": None,
+            "ms_per_step": 1e3 * el / args.steps, "ms_per_step_median": float(np.median(kernel_ms)), "ms_per_step_min": float(np.min(kernel_ms)),
+            "higher_is_better": True, "scaling": "strong" if dynamic else "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "config": describe(args, n_terrain, bx, bz, n_caps, n_tris, world),
             "tri_tests_per_s": tri_tests / el, "node_tests_per_s": node_tests / el,
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": args.steps, "clocks": clocks,
