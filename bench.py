@@ -466,7 +466,7 @@ def run_ours(args):
             "higher_is_better": True, "scaling": "strong" if dynamic else "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "config": describe(args, n_terrain, bx, bz, n_caps, n_tris, world),
             "tri_tests_per_s": tri_tests / el, "node_tests_per_s": node_tests / el,
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": args.steps, "clocks": clocks,
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(cnt["launches"]), "clocks": clocks,
             "setup": {"commit_s": t_commit, "nodes": info["nodes"], "leaves": info["leaves"]},
         }
         if state_crc is not None:

@@ -96,6 +96,7 @@ typedef struct prtc_counters {
     uint64_t contacts;     /* handleCollision calls (collision_system.cpp:236) */
     uint64_t cc_tests;     /* capsule-capsule narrowphase tests */
     uint64_t exact_tests;  /* triangles that survived the pre-cull and ran the exact capsule-triangle test */
+    uint64_t launches;     /* kernels launched by the step entry points (host-side count) */
 } prtc_counters;
 
 /* Parity trace of one traced step (prtc_step_characters_traced); same record layout the CPU checkers under tests/ use.
@@ -196,8 +197,12 @@ int prtc_get_counters(prtc_ctx * ctx, prtc_counters * out, int reset);
  *                          then equals the reference's count (the numerator of the roofline's algorithmic bytes).
  *   PRTC_OPT_QUICK_REJECT  (default 1) conservative per-triangle pre-cull ahead of the exact test.
  *   PRTC_OPT_PERSISTENT    (default 1) static pass runs as a persistent kernel whose lanes advance through their
- *                          characters independently (0: one character per lane in lock step). */
-enum prtc_option { PRTC_OPT_FRAME_CACHE = 1, PRTC_OPT_QUICK_REJECT = 2, PRTC_OPT_PERSISTENT = 3 };
+ *                          characters independently (0: one character per lane in lock step).
+ *   PRTC_OPT_CROSS_FRAME_CACHE (default 1) the persistent kernel keeps every character slot's leaf list (valid for
+ *                          an enlarged region around it) in device memory between frames; a character whose
+ *                          frame still fits inside that region skips the tree walk.  The list is a pure function
+ *                          of (tree, region), so it does not matter which character occupies the slot. */
+enum prtc_option { PRTC_OPT_FRAME_CACHE = 1, PRTC_OPT_QUICK_REJECT = 2, PRTC_OPT_PERSISTENT = 3, PRTC_OPT_CROSS_FRAME_CACHE = 4 };
 int prtc_set_option(prtc_ctx * ctx, int option, int value);
 
 /* Introspection for parity tests: the flattened tree.  leaf_mesh_ids receives the mesh-collider ids of all

@@ -58,8 +58,8 @@ __device__ __forceinline__ bool quick_reject(V3 smin, V3 smax, float radius, flo
 }
 
 // Cold per-lane state of k_step_stream lives in shared memory ([field][lane], conflict free)
-enum Park { P_VEL = 0, P_PREVVEL = 3, P_STEPV = 6, P_GN = 9, P_SA1 = 12, P_SA2 = 15, P_SB1 = 18, P_SB2 = 21,
-            P_PREVA = 24, P_PREVB = 27, P_COUNT = 30 };
+enum Park { P_VEL = 0, P_STEPV = 3, P_GN = 6, P_SA1 = 9, P_SA2 = 12, P_SB1 = 15, P_SB2 = 18,
+            P_PREVA = 21, P_PREVB = 24, P_QR_EPS = 27, P_COUNT = 28 };
 struct Parked {
     float (*s)[32];
     uint32_t tid;
@@ -76,6 +76,7 @@ struct Parked {
 constexpr int STEP_BLOCK = 32;      // one warp per block: a finished warp frees its slot at once (2.79 -> 2.71 ms at C4 vs 128)
 constexpr int MODE_STATIC = 0, MODE_LITERAL = 1, MODE_JACOBI = 2;
 constexpr int DYN_CAP = 16;      // capsule neighbours buffered per lane and pass of the JACOBI pass
+constexpr int XC_CAP = 12;       // leaves per cached region slot (k_xc_refresh / k_step_stream)
 constexpr int TRI_RING = 2;      // triangles in flight per lane (cp.async ring in shared memory)
 constexpr int LEAF_CAP = 8;      // candidate leaves buffered per lane and pass (more => another pass)
 
@@ -597,6 +598,65 @@ __global__ void k_query_box(const float4 * __restrict__ nodes, uint32_t n_nodes,
     *out_count = found;
 }
 
+// k_xc_refresh: keeps the per-slot frame cache of k_step_stream valid for the coming frame.  One thread per
+// character: the region its frame can need (box of the current pose united with the pose after the pre-stepped
+// velocity, +0.25 for push-outs); if the slot's stored region (built for this tree version) already contains it, done --
+// resting or slow characters never walk the tree again; else one stackless walk with the region grown by xc_margin
+// collects the overlapping leaves (emission order) and the slot is rewritten.  The list is a pure function of
+// (tree, region): it does not matter which character occupied the slot before, and k_step_stream re-checks
+// "query box inside region" at every substep, so a stale or too-small region can only cost time, never correctness.
+__global__ void __launch_bounds__(128) k_xc_refresh(StepParams p, int reuse) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= p.n) return;
+    const prtc_transform * tf = p.transforms + i;
+    const prtc_char_physics * ph = p.physics + i;
+    const V3 pos = v3(tf->position[0], tf->position[1], tf->position[2]);
+    Quat q; q.x = tf->rotation[0]; q.y = tf->rotation[1]; q.z = tf->rotation[2]; q.w = tf->rotation[3];
+    V3 vel = v3(ph->velocity[0], ph->velocity[1], ph->velocity[2]);
+    uint32_t cid = ph->collider;
+    if (cid >= p.n_capsules) cid = 0;
+    const CapsuleDev cap = p.capsules[cid];
+    const CapsuleFrame fr = capsule_frame(cap, rotation_of(q));
+    if (ph->grounded) vel = vel + ((-p.stick * p.gravity) * p.dt) * v3(ph->ground_normal[0], ph->ground_normal[1], ph->ground_normal[2]);
+    vel.x = vel.x + ph->movement[0];
+    vel.z = vel.z + ph->movement[2];
+    V3 a0, b0, eA, eB;
+    segment_ends(fr, pos, a0, b0);
+    segment_ends(fr, pos + vel, eA, eB);
+    Box R = box_union(capsule_box(a0, b0, cap.radius), capsule_box(eA, eB, cap.radius));
+    R.lo = R.lo - v3(0.25f); R.hi = R.hi + v3(0.25f);
+    const size_t s = size_t(p.xc_first) + i;
+    if (reuse && p.xc_version[s] == p.tree_version) {
+        if (p.xc_region[0 * size_t(p.xc_stride) + s] <= R.lo.x && p.xc_region[1 * size_t(p.xc_stride) + s] <= R.lo.y &&
+            p.xc_region[2 * size_t(p.xc_stride) + s] <= R.lo.z && p.xc_region[3 * size_t(p.xc_stride) + s] >= R.hi.x &&
+            p.xc_region[4 * size_t(p.xc_stride) + s] >= R.hi.y && p.xc_region[5 * size_t(p.xc_stride) + s] >= R.hi.z)
+            return;
+    }
+    if (reuse) { R.lo = R.lo - v3(p.xc_margin); R.hi = R.hi + v3(p.xc_margin); }
+    uint32_t node = 0, ncache = 0;
+    while (node < p.n_nodes) {
+        const float4 lo = __ldg(p.nodes + 2 * node);
+        const float4 hi = __ldg(p.nodes + 2 * node + 1);
+        const bool ov = node_overlaps(lo, hi, R);
+        const int cnt = __float_as_int(hi.w);
+        if (cnt < 0) {
+            node = ov ? node + 1 : uint32_t(__float_as_int(lo.w));
+        } else {
+            if (ov) {
+                if (ncache == XC_CAP) { ncache = 0xFFFFFFFFu; break; }
+                p.xc_leaf[size_t(ncache) * p.xc_stride + s] = node;
+                ++ncache;
+            }
+            node = node + 1;
+        }
+    }
+    if (ncache == 0xFFFFFFFFu) { p.xc_version[s] = 0u; return; }   // too many leaves for a slot: this character walks per substep
+    p.xc_region[0 * size_t(p.xc_stride) + s] = R.lo.x; p.xc_region[1 * size_t(p.xc_stride) + s] = R.lo.y; p.xc_region[2 * size_t(p.xc_stride) + s] = R.lo.z;
+    p.xc_region[3 * size_t(p.xc_stride) + s] = R.hi.x; p.xc_region[4 * size_t(p.xc_stride) + s] = R.hi.y; p.xc_region[5 * size_t(p.xc_stride) + s] = R.hi.z;
+    p.xc_count[s] = ncache;
+    p.xc_version[s] = p.tree_version;
+}
+
 // ------------------------------------------------------------------------------------------------------------
 // k_step_stream: the static pass (MODE_STATIC, untraced) as a PERSISTENT, lane-decoupled kernel.
 //
@@ -618,22 +678,28 @@ constexpr int SUBSTEP_BATCH = 8;     // same for the SUBSTEP stage
 __global__ void __launch_bounds__(32, 20) k_step_stream(StepParams p) {
     constexpr unsigned FULL = 0xffffffffu;
     __shared__ uint32_t s_leaf[LEAF_CAP][32];              // candidate leaves of the substep: node indices, emission order
-    __shared__ uint32_t s_cache[LEAF_CAP][32];
+    __shared__ uint32_t s_cache[XC_CAP][32];
     __shared__ float s_region[6][32];
     __shared__ float4 s_tri[TRI_RING][3][32];
     __shared__ float s_park[P_COUNT][32];
     const uint32_t tid = threadIdx.x;
     const Parked park{s_park, tid};
     const unsigned lt_mask = (1u << tid) - 1u;
-    uint32_t c_sub = 0, c_tri = 0, c_node = 0, c_contact = 0, c_exact = 0;
+    uint32_t c_tri = 0, c_node = 0;
+    __shared__ uint32_t s_cnt[4][32];                      // rarely bumped counters + ncache live here, not in registers
+    s_cnt[0][tid] = 0; s_cnt[1][tid] = 0; s_cnt[2][tid] = 0; s_cnt[3][tid] = 0;
+#define C_SUB s_cnt[0][tid]
+#define C_CONTACT s_cnt[1][tid]
+#define C_EXACT s_cnt[2][tid]
+#define NCACHE s_cnt[3][tid]
 
     int state = ST_LOAD;
     uint32_t i = 0xFFFFFFFFu;
     V3 pos = v3(0.0f);
     uint32_t grounded = 0, stepsLeft = 0;
-    float radius = 0.0f, qr_eps = 0.0f, dmax = 0.0f;
+    float radius = 0.0f;
     bool cache_ok = false, found = true;
-    uint32_t ncache = 0, node = 0, nleaf = 0;
+    uint32_t node = 0, nleaf = 0;
     Box qb; qb.lo = v3(0.0f); qb.hi = v3(0.0f);
     Pose ps = make_pose(park.frame(0.0f), pos);
     uint32_t f_leaf = 0, f_cur = 0, f_end = 0, n_fetched = 0, n_consumed = 0;
@@ -698,8 +764,6 @@ __global__ void __launch_bounds__(32, 20) k_step_stream(StepParams p) {
             unsigned base = 0;
             if (tid == 0) base = atomicAdd(p.work_counter, (unsigned)__popc(m_load));
             base = __shfl_sync(FULL, base, 0);
-            Box R; R.lo = v3(0.0f); R.hi = v3(0.0f);
-            uint32_t wnode = p.n_nodes;
             bool loaded_now = false;
             if (state == ST_LOAD) {
                 const uint32_t idx = base + __popc(m_load & lt_mask);
@@ -722,10 +786,8 @@ __global__ void __launch_bounds__(32, 20) k_step_stream(StepParams p) {
                     const CapsuleDev cap = p.capsules[cid];
                     const CapsuleFrame fr = capsule_frame(cap, rotation_of(q));
                     radius = cap.radius;
-                    qr_eps = p.qr_eps + 1e-5f * (fabsf(cap.radius) + fabsf(cap.height) + fabsf(cap.ox) + fabsf(cap.oy) + fabsf(cap.oz));
-                    dmax = (p.abs_mode == 1u) ? radius : floorf(radius) + 1.0f;
+                    s_park[P_QR_EPS][tid] = p.qr_eps + 1e-5f * (fabsf(cap.radius) + fabsf(cap.height) + fabsf(cap.ox) + fabsf(cap.oy) + fabsf(cap.oz));
                     // ---- phase 1 (physics_system.cpp:277-285) ----
-                    park.put(P_PREVVEL, vel);
                     if (ph->grounded) vel = vel + ((-p.stick * p.gravity) * p.dt) * gn;
                     vel.x = vel.x + mvx;
                     vel.z = vel.z + mvz;
@@ -740,40 +802,25 @@ __global__ void __launch_bounds__(32, 20) k_step_stream(StepParams p) {
                     stepsLeft = p.substeps;
                     found = true;
                     cache_ok = false;
-                    ncache = 0;
+                    NCACHE = 0;
                     state = ST_SUBSTEP;
                     loaded_now = true;
-                    if (use_cache) {                              // frame region (see k_step)
-                        V3 eA, eB;
-                        segment_ends(fr, pos + vel, eA, eB);
-                        R = box_union(capsule_box(a0, b0, radius), capsule_box(eA, eB, radius));
-                        R.lo = R.lo - v3(0.25f); R.hi = R.hi + v3(0.25f);
-                        wnode = 0;
-                    }
                 }
             }
-            if (use_cache) {
-                while (__any_sync(FULL, wnode < p.n_nodes)) {
-                    if (wnode < p.n_nodes) {
-                        const float4 lo = __ldg(p.nodes + 2 * wnode);
-                        const float4 hi = __ldg(p.nodes + 2 * wnode + 1);
-                        const bool ov = node_overlaps(lo, hi, R);
-                        const int cnt = __float_as_int(hi.w);
-                        ++c_node;
-                        if (cnt < 0) {
-                            wnode = ov ? wnode + 1 : uint32_t(__float_as_int(lo.w));
-                        } else {
-                            if (ov) {
-                                if (ncache < LEAF_CAP) { s_cache[ncache][tid] = wnode; ++ncache; wnode = wnode + 1; }
-                                else { wnode = 0xFFFFFFFFu; }
-                            } else wnode = wnode + 1;
-                        }
+            // The frame cache (candidate leaves valid for a region around the character, kept per character slot in
+            // device memory and refreshed by k_xc_refresh right before this kernel) is only read here.
+            if (loaded_now) {
+                cache_ok = false;
+                if (use_cache) {
+                    const size_t s = size_t(p.xc_first) + i;
+                    if (p.xc_version[s] == p.tree_version) {
+                        const uint32_t nc = p.xc_count[s];
+                        NCACHE = nc;
+                        for (uint32_t j = 0; j < nc; ++j) s_cache[j][tid] = p.xc_leaf[size_t(j) * p.xc_stride + s];
+#pragma unroll
+                        for (int f = 0; f < 6; ++f) s_region[f][tid] = p.xc_region[size_t(f) * p.xc_stride + s];
+                        cache_ok = true;
                     }
-                }
-                if (loaded_now) {
-                    cache_ok = wnode != 0xFFFFFFFFu;
-                    s_region[0][tid] = R.lo.x; s_region[1][tid] = R.lo.y; s_region[2][tid] = R.lo.z;
-                    s_region[3][tid] = R.hi.x; s_region[4][tid] = R.hi.y; s_region[5][tid] = R.hi.z;
                 }
             }
             continue;
@@ -787,7 +834,7 @@ __global__ void __launch_bounds__(32, 20) k_step_stream(StepParams p) {
                     prtc_transform * tf = p.transforms + i;
                     prtc_char_physics * ph = p.physics + i;
                     pos = pos + (float(stepsLeft) * park.get(P_VEL)) / float(p.substeps);
-                    V3 vel = park.get(P_PREVVEL);
+                    V3 vel = v3(ph->velocity[0], ph->velocity[1], ph->velocity[2]);   // prevVelocities[i]: still untouched in memory (:277,304)
                     const float frictionRatio = fdiv(1.0f, 1.0f + (p.dt * p.friction));
                     vel.x = vel.x * frictionRatio;
                     vel.z = vel.z * frictionRatio;
@@ -806,23 +853,27 @@ __global__ void __launch_bounds__(32, 20) k_step_stream(StepParams p) {
                     ps = make_pose(fr, pos);
                     qb = box_union(capsule_box(park.get(P_PREVA), park.get(P_PREVB), radius), capsule_box(ps.A, ps.B, radius));   // :355-356
                     park.put(P_PREVA, ps.A); park.put(P_PREVB, ps.B);     // prevTform = tform       :358
-                    ++c_sub;
+                    ++C_SUB;
                     found = false;
                     nleaf = 0;
                     if (cache_ok &&
                         s_region[0][tid] <= qb.lo.x && s_region[1][tid] <= qb.lo.y && s_region[2][tid] <= qb.lo.z &&
                         s_region[3][tid] >= qb.hi.x && s_region[4][tid] >= qb.hi.y && s_region[5][tid] >= qb.hi.z) {
+                        bool fits = true;
+                        const uint32_t ncache = NCACHE;
                         for (uint32_t j = 0; j < ncache; ++j) {
                             const uint32_t leaf = s_cache[j][tid];
                             const float4 lo = __ldg(p.nodes + 2 * leaf);
                             const float4 hi = __ldg(p.nodes + 2 * leaf + 1);
                             ++c_node;
                             if (node_overlaps(lo, hi, qb)) {
+                                if (nleaf == LEAF_CAP) { fits = false; break; }
                                 s_leaf[nleaf][tid] = leaf;
                                 ++nleaf;
                             }
                         }
                         node = p.n_nodes;
+                        if (!fits) { node = 0; ordered_walk(); }  // more candidates than one pass holds: walk in passes
                     } else {
                         node = 0;
                         ordered_walk();
@@ -838,6 +889,8 @@ __global__ void __launch_bounds__(32, 20) k_step_stream(StepParams p) {
         // ---------------- STREAM: filter until a triangle needs the exact test ----------------
         if (state == ST_STREAM && !pending) {
             const V3 smin = gmin(ps.A, ps.B), smax = gmax(ps.A, ps.B);
+            const float qr_eps = s_park[P_QR_EPS][tid];
+            const float dmax = (p.abs_mode == 1u) ? radius : floorf(radius) + 1.0f;   // largest plane distance surviving the range cull
             for (;;) {
                 while (n_consumed != n_fetched) {
                     if (n_fetched - n_consumed >= 2) cp_async_wait<1>(); else cp_async_wait<0>();
@@ -871,11 +924,11 @@ __global__ void __launch_bounds__(32, 20) k_step_stream(StepParams p) {
             if (pending) {
                 pending = false;
                 Contact ct;
-                ++c_exact;
+                ++C_EXACT;
                 if (capsule_triangle(ps, radius, p.abs_mode, v3(t0.x, t0.y, t0.z), v3(t1.x, t1.y, t1.z),
                                      v3(t2.x, t2.y, t2.z), v3(t0.w, t1.w, t2.w), ct)) {
                     pos = pos + ct.impulse;                       // handleCollision (collision_system.cpp:242-252)
-                    ++c_contact;
+                    ++C_CONTACT;
                     if (dot(ct.normal, v3(0.0f, 1.0f, 0.0f)) > p.ground_dot) {
                         grounded = 1;
                         park.put(P_GN, ct.normal);
@@ -888,11 +941,11 @@ __global__ void __launch_bounds__(32, 20) k_step_stream(StepParams p) {
         }
     }
 
-    c_sub = __reduce_add_sync(FULL, c_sub);
+    const uint32_t c_sub = __reduce_add_sync(FULL, C_SUB);
     c_tri = __reduce_add_sync(FULL, c_tri);
     c_node = __reduce_add_sync(FULL, c_node);
-    c_contact = __reduce_add_sync(FULL, c_contact);
-    c_exact = __reduce_add_sync(FULL, c_exact);
+    const uint32_t c_contact = __reduce_add_sync(FULL, C_CONTACT);
+    const uint32_t c_exact = __reduce_add_sync(FULL, C_EXACT);
     if (tid == 0 && p.counters) {
         atomicAdd(p.counters + 0, (unsigned long long)c_sub);
         atomicAdd(p.counters + 1, (unsigned long long)c_tri);
@@ -901,6 +954,11 @@ __global__ void __launch_bounds__(32, 20) k_step_stream(StepParams p) {
         atomicAdd(p.counters + 5, (unsigned long long)c_exact);
     }
 }
+
+#undef C_SUB
+#undef C_CONTACT
+#undef C_EXACT
+#undef NCACHE
 
 // K1 for the dynamic pass: per own character, the phase-1 predicted box (physics_system.cpp:263-273: pose box united
 // with the box after `velocity + gravity*dt`, displacement applied in the capsule's rotated frame), the stored fat box
@@ -1058,8 +1116,9 @@ void launch_raycast(const float4 * nodes, uint32_t n_nodes, const float4 * tris,
     k_raycast<<<(n_rays + block - 1) / block, block, 0, stream>>>(nodes, n_nodes, tris, n_rays, origins, dirs, maxd, hit_xyz, hit_mask);
 }
 
-void launch_step(StepParams const & p_in, bool traced, int mode, cudaStream_t stream) {
-    if (p_in.n == 0) return;
+int launch_step(StepParams const & p_in, bool traced, int mode, cudaStream_t stream) {
+    if (p_in.n == 0) return 0;
+    int launches = 1;
     StepParams p = p_in;
     const uint32_t block = STEP_BLOCK;
     // fewer characters than resident lanes: thin the warps out (1..32 characters per warp)
@@ -1082,12 +1141,14 @@ void launch_step(StepParams const & p_in, bool traced, int mode, cudaStream_t st
         else if (p.work_counter) {
             // persistent: one warp per block, as many blocks as fit (16 per SM), work handed out by a counter
             cudaMemsetAsync(p.work_counter, 0, sizeof(unsigned), stream);
+            if (!(p.tune & 1u)) { k_xc_refresh<<<(p.n + 127) / 128, 128, 0, stream>>>(p, p.xc_reuse ? 1 : 0); ++launches; }
             const uint32_t want = (p.n + 31) / 32;
             const uint32_t resident = uint32_t(p.persistent_blocks);
             k_step_stream<<<want < resident ? want : resident, 32, 0, stream>>>(p);
         }
         else k_step<false, MODE_STATIC><<<grid, block, 0, stream>>>(p);
     }
+    return launches;
 }
 
 void launch_dyn_prep(const prtc_transform * tf, const prtc_char_physics * ph, const CapsuleDev * capsules, uint32_t n, uint32_t first,

@@ -68,13 +68,22 @@ struct StepParams {
     uint32_t tune;                  // bit 0: frame cache OFF (walk the tree every substep, reference-equivalent counters)
     unsigned long long * counters;  // prtc_counters layout
     unsigned * work_counter;        // k_step_stream: next character to hand out (null => lock-step kernel)
+    // k_step_stream: cross-frame leaf cache, one slot per character index (SoA, stride xc_stride); null => off
+    uint32_t * xc_version;          // tree version the slot was built for (0 = empty)
+    float * xc_region;              // [6][stride] region the leaf list is complete for
+    uint32_t * xc_count;            // [stride]
+    uint32_t * xc_leaf;             // [LEAF_CAP][stride] node indices, emission order
+    uint32_t xc_stride, xc_first;   // slot of this launch's character 0
+    uint32_t tree_version;          // bumped on every re-flatten (>= 1)
+    float xc_margin;                // how far beyond the frame's needed region a fresh list reaches
+    uint32_t xc_reuse;              // 1: keep slots across frames (PRTC_OPT_CROSS_FRAME_CACHE), 0: rebuild every frame
     uint32_t persistent_blocks;     // k_step_stream: resident blocks to launch
     uint32_t lanes_per_warp;        // k_step: characters per warp (set by launch_step; < 32 for small batches)
     TraceBuffers trace;
 };
 
 enum StepMode { STEP_STATIC = 0, STEP_LITERAL = 1, STEP_JACOBI = 2 };
-void launch_step(StepParams const & p, bool traced, int mode, cudaStream_t stream);
+int launch_step(StepParams const & p, bool traced, int mode, cudaStream_t stream);   // returns the number of kernels launched
 // dynamic pass, CANONICAL / JACOBI: per-character record (4 float4) and the uniform grid over all stored boxes
 void launch_dyn_prep(const prtc_transform * tf, const prtc_char_physics * ph, const CapsuleDev * capsules, uint32_t n, uint32_t first,
                      float4 * records, float dt, float gravity, float margin, bool init, cudaStream_t stream);

@@ -103,6 +103,14 @@ struct prtc_ctx {
     DevBuf<uint32_t> d_node_leaf_id, d_tri_src;
     DevBuf<CapsuleDev> d_capsules;
     DevBuf<unsigned long long> d_counters;
+    // cross-frame leaf cache of the persistent kernel (PRTC_OPT_CROSS_FRAME_CACHE)
+    DevBuf<uint32_t> d_xc_version, d_xc_count, d_xc_leaf;
+    DevBuf<float> d_xc_region;
+    uint32_t xc_capacity = 0;
+    uint32_t tree_version = 1;
+    uint64_t launches = 0;                  // kernels launched by step calls since the last counter reset
+    int cross_frame = 1;
+    float xc_margin = 0.5f;
     DevBuf<unsigned> d_work;                // work counters of the persistent kernel, one per concurrently running launch
     DevBuf<prtc_transform> d_tf;
     DevBuf<prtc_char_physics> d_ph;
@@ -215,6 +223,7 @@ int commit_impl(prtc_ctx * c) {
     if (c->tree_dirty) {
         c->tri_src.clear();
         c->tri_src.reserve(n_vertices / 3);
+        ++c->tree_version;                       // every cached leaf list refers to node indices of the old layout
         c->tree.flatten(c->flat, [&](uint32_t mesh_id, uint32_t & first, uint32_t & count) {
             MeshHost const & mh = c->meshes[mesh_id];
             first = uint32_t(c->tri_src.size());
@@ -271,6 +280,20 @@ int fill_params(prtc_ctx * c, float dt, uint32_t n, prtc_transform * d_tf, prtc_
         p.tune = (c->frame_cache ? 0u : 1u) | c->tune_hi;
         p.work_counter = c->persistent ? c->d_work.ptr : nullptr;
         p.persistent_blocks = uint32_t(c->sm_count) * 20u;
+        p.tree_version = c->tree_version;
+        p.xc_margin = c->xc_margin;
+        if (c->persistent && n > c->xc_capacity) {
+            const uint32_t cap = n;
+            PRTC_CUDA(c->d_xc_version.reserve(cap)); PRTC_CUDA(c->d_xc_count.reserve(cap));
+            PRTC_CUDA(c->d_xc_region.reserve(size_t(cap) * 6)); PRTC_CUDA(c->d_xc_leaf.reserve(size_t(cap) * 12));
+            PRTC_CUDA(cudaMemsetAsync(c->d_xc_version.ptr, 0, size_t(cap) * sizeof(uint32_t), c->stream));
+            c->xc_capacity = cap;
+        }
+        if (c->persistent) {
+            p.xc_version = c->d_xc_version.ptr; p.xc_region = c->d_xc_region.ptr; p.xc_count = c->d_xc_count.ptr; p.xc_leaf = c->d_xc_leaf.ptr;
+            p.xc_stride = c->xc_capacity; p.xc_first = 0;
+            p.xc_reuse = c->cross_frame ? 1u : 0u;
+        }
     }
     return PRTC_OK;
 }
@@ -486,7 +509,7 @@ int literal_step(prtc_ctx * c, float dt, uint32_t n, prtc_transform * tf, prtc_c
         fill_params(c, dt, n, c->d_tf.ptr, c->d_ph.ptr, p);
         p.cap2char = c->d_cap2char.ptr; p.seg_start = c->d_seg_start.ptr; p.seg_prev = c->d_seg_prev.ptr; p.last_box = c->d_last_box.ptr;
         if (tr) { rc = prepare_trace(c, n, p); if (rc) return rc; }
-        launch_step(p, tr != nullptr, STEP_LITERAL, s);
+        c->launches += uint64_t(launch_step(p, tr != nullptr, STEP_LITERAL, s));
         PRTC_CUDA(cudaGetLastError());
         PRTC_CUDA(cudaMemcpyAsync(out_tf.data(), c->d_tf.ptr, size_t(n) * sizeof(prtc_transform), cudaMemcpyDeviceToHost, s));
         PRTC_CUDA(cudaMemcpyAsync(out_ph.data(), c->d_ph.ptr, size_t(n) * sizeof(prtc_char_physics), cudaMemcpyDeviceToHost, s));
@@ -580,6 +603,8 @@ int prtc_create(const prtc_config * cfg, prtc_ctx ** out) {
     if (const char * e = std::getenv("PRTC_QUICK_REJECT")) ctx->quick_reject = std::atoi(e);
     if (const char * e = std::getenv("PRTC_FRAME_CACHE")) ctx->frame_cache = std::atoi(e);
     if (const char * e = std::getenv("PRTC_PERSISTENT")) ctx->persistent = std::atoi(e);
+    if (const char * e = std::getenv("PRTC_CROSS_FRAME")) ctx->cross_frame = std::atoi(e);
+    if (const char * e = std::getenv("PRTC_XC_MARGIN")) ctx->xc_margin = float(std::atof(e));
     if (const char * e = std::getenv("PRTC_TUNE")) ctx->tune_hi = uint32_t(std::strtoul(e, nullptr, 0)) & 0xFFFFFF00u;
     ctx->sm_count = prop.multiProcessorCount;
     ctx->tree.set_margin(c.leaf_margin);
@@ -602,7 +627,8 @@ void prtc_destroy(prtc_ctx * c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     c->d_raw.release(); c->d_world.release(); c->d_aabbs.release(); c->d_meshes.release(); c->d_xforms.release();
     c->d_nodes.release(); c->d_tris.release(); c->d_node_leaf_id.release(); c->d_tri_src.release();
-    c->d_capsules.release(); c->d_counters.release(); c->d_work.release(); c->d_tf.release(); c->d_ph.release();
+    c->d_capsules.release(); c->d_counters.release(); c->d_work.release();
+    c->d_xc_version.release(); c->d_xc_count.release(); c->d_xc_leaf.release(); c->d_xc_region.release(); c->d_tf.release(); c->d_ph.release();
     c->d_tq.release(); c->d_tmesh.release(); c->d_tcaps.release(); c->d_thits.release();
     c->d_scratch_f.release(); c->d_scratch_u.release();
     c->d_cap2char.release(); c->d_seg_start.release(); c->d_seg_prev.release(); c->d_last_box.release();
@@ -740,7 +766,8 @@ int prtc_step_characters_device(prtc_ctx * c, float dt, uint32_t n, prtc_transfo
         c->dyn_prepared = false;
         mode = STEP_JACOBI;
     }
-    launch_step(p, false, mode, c->stream);
+    c->launches += uint64_t(launch_step(p, false, mode, c->stream));
+    if (mode == STEP_JACOBI) c->launches += 3;                // k_dyn_prep + two k_dyn_grid passes (+ cub scan)
     PRTC_CUDA(cudaGetLastError());
     return PRTC_OK;
 }
@@ -777,7 +804,7 @@ int prtc_step_characters(prtc_ctx * c, float dt, uint32_t n, prtc_transform * tf
             fill_params(c, dt, cnt, c->d_tf.ptr + first, c->d_ph.ptr + first, p);
             if (!kChunkPersistent) p.work_counter = nullptr;
             if (p.work_counter) p.work_counter += 1 + k % prtc_ctx::PIPE_STREAMS;     // launches on one stream are ordered
-            launch_step(p, false, STEP_STATIC, s);
+            c->launches += uint64_t(launch_step(p, false, STEP_STATIC, s));
             PRTC_CUDA(cudaGetLastError());
             PRTC_CUDA(cudaMemcpyAsync(tf + first, c->d_tf.ptr + first, size_t(cnt) * sizeof(prtc_transform), cudaMemcpyDeviceToHost, s));
             PRTC_CUDA(cudaMemcpyAsync(ph + first, c->d_ph.ptr + first, size_t(cnt) * sizeof(prtc_char_physics), cudaMemcpyDeviceToHost, s));
@@ -825,7 +852,7 @@ int prtc_step_characters_traced(prtc_ctx * c, float dt, uint32_t n, prtc_transfo
         c->dyn_prepared = false;
         mode = STEP_JACOBI;
     }
-    launch_step(p, true, mode, s);
+    c->launches += uint64_t(launch_step(p, true, mode, s));
     PRTC_CUDA(cudaGetLastError());
     PRTC_CUDA(cudaMemcpyAsync(tf, c->d_tf.ptr, size_t(n) * sizeof(prtc_transform), cudaMemcpyDeviceToHost, s));
     PRTC_CUDA(cudaMemcpyAsync(ph, c->d_ph.ptr, size_t(n) * sizeof(prtc_char_physics), cudaMemcpyDeviceToHost, s));
@@ -883,6 +910,8 @@ int prtc_get_counters(prtc_ctx * c, prtc_counters * out, int reset) {
     if (reset) PRTC_CUDA(cudaMemsetAsync(c->d_counters.ptr, 0, sizeof(h), c->stream));
     PRTC_CUDA(cudaStreamSynchronize(c->stream));
     out->substeps = h[0]; out->tri_tests = h[1]; out->node_tests = h[2]; out->contacts = h[3]; out->cc_tests = h[4]; out->exact_tests = h[5];
+    out->launches = c->launches;
+    if (reset) c->launches = 0;
     return PRTC_OK;
 }
 
@@ -919,6 +948,7 @@ int prtc_set_option(prtc_ctx * c, int option, int value) {
         case PRTC_OPT_FRAME_CACHE: c->frame_cache = value != 0; return PRTC_OK;
         case PRTC_OPT_QUICK_REJECT: c->quick_reject = value != 0; return PRTC_OK;
         case PRTC_OPT_PERSISTENT: c->persistent = value != 0; return PRTC_OK;
+        case PRTC_OPT_CROSS_FRAME_CACHE: c->cross_frame = value != 0; return PRTC_OK;
         default: return fail(PRTC_ERR_INVALID, "prtc_set_option: unknown option");
     }
 }

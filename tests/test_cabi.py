@@ -32,7 +32,7 @@ def test_struct_layouts_match_the_reference_types():
     assert capi.TRANSFORM_DTYPE.itemsize == 40
     assert capi.TRANSFORM_DTYPE.fields["rotation"][1] == 12 and capi.TRANSFORM_DTYPE.fields["scale"][1] == 28
     assert capi.PHYSICS_DTYPE.itemsize == 44
-    assert ctypes.sizeof(capi.Config) == 40 and ctypes.sizeof(capi.Counters) == 48
+    assert ctypes.sizeof(capi.Config) == 40 and ctypes.sizeof(capi.Counters) == 56
 
 
 def test_default_config_holds_the_reference_constants():
