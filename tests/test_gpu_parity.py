@@ -645,3 +645,50 @@ def test_nan_and_inf_characters_do_not_hang_or_poison_the_others():
     scene["vel"][7, 1] = np.inf
     scene["pos"][11, 0] = np.float32(3.0e38)
     _run_pair(scene, 3, dict(order="canonical"), dict(), trace_frames=())      # (a NaN query has more candidates than a trace slot holds)
+
+
+def test_cross_frame_cache_does_not_care_who_sits_in_a_slot():
+    """the persistent kernel's per-slot leaf cache survives between frames; it is a pure function of (tree, region), so
+    shuffling the characters between frames (different character in every slot), teleporting some of them and moving
+    the model (tree re-flattened) must change nothing -- checked against the oracle and against a context with the
+    cache switched off"""
+    from prototype2_b200 import capi
+    n = 30000                                                 # more than 8 characters per resident warp: persistent kernel
+    scene = H.make_scene(200, 2, 2, n, seed=91)
+    scene["vel"] *= np.float32(2.0)
+    orc = H.build_oracle(scene, "l1", order="canonical", threads=os.cpu_count() or 1)
+    on, tf, ph = H.build_gpu(scene)
+    off, tf2, ph2 = H.build_gpu(scene)
+    off.set_option(capi.OPT_CROSS_FRAME_CACHE, 0)
+    rs = np.random.RandomState(0)
+    for f in range(8):
+        if f in (2, 5):                                       # shuffle slots
+            perm = rs.permutation(n)
+            tf, ph, tf2, ph2 = tf[perm].copy(), ph[perm].copy(), tf2[perm].copy(), ph2[perm].copy()
+            s = orc.get_state()
+            orc.set_state(pos=s["pos"][perm], vel=s["vel"][perm], gnormal=s["gnormal"][perm], grounded=s["grounded"][perm],
+                          rot=scene["rot"][perm])
+            scene["rot"] = scene["rot"][perm]
+        if f == 4:                                            # teleport a tenth of them
+            idx = rs.choice(n, n // 10, replace=False)
+            newpos = tf["position"].copy()
+            newpos[idx, 0] = rs.uniform(4, 190, len(idx)).astype(np.float32)
+            newpos[idx, 2] = rs.uniform(4, 190, len(idx)).astype(np.float32)
+            tf["position"] = newpos
+            tf2["position"] = newpos
+            orc.set_state(pos=newpos)
+        orc.step(DT)
+        on.update_characters(DT, tf, ph)
+        off.update_characters(DT, tf2, ph2)
+        assert H.state_diff(H.gpu_state(tf, ph), H.gpu_state(tf2, ph2)) == [], "frame %d on/off" % f
+        assert H.state_diff(orc.get_state(), H.gpu_state(tf, ph)) == [], "frame %d oracle" % f
+    # a moved model re-flattens the tree: cached node indices must be dropped (tree_version)
+    t = np.zeros(1, capi.TRANSFORM_DTYPE)
+    t["position"][0] = (0.5, -0.25, 0.25); t["rotation"][0] = (0, 0, 0, 1); t["scale"][0] = (1, 1, 1)
+    on.update_model_colliders([0], t)
+    off.update_model_colliders([0], t)
+    for f in range(3):
+        on.update_characters(DT, tf, ph)
+        off.update_characters(DT, tf2, ph2)
+        assert H.state_diff(H.gpu_state(tf, ph), H.gpu_state(tf2, ph2)) == [], "after move, frame %d" % f
+    assert on.counters()["launches"] == off.counters()["launches"] > 0
