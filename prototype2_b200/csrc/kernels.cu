@@ -93,7 +93,7 @@ __global__ void __launch_bounds__(STEP_BLOCK, 512 / STEP_BLOCK) k_step(StepParam
     constexpr bool JACOBI = MODE == MODE_JACOBI;
     constexpr unsigned FULL = 0xffffffffu;
     __shared__ uint2 s_leaf[LEAF_CAP][STEP_BLOCK];
-    __shared__ uint32_t s_cache[LEAF_CAP][STEP_BLOCK];     // frame cache: leaves (node indices) overlapping s_region
+    __shared__ uint32_t s_cache[XC_CAP][STEP_BLOCK];       // frame cache: leaves (node indices) overlapping s_region
     __shared__ float s_region[6][STEP_BLOCK];
     // per-lane ring of candidate triangles streamed in with cp.async while the exact tests run
     __shared__ float4 s_tri[TRI_RING][3][STEP_BLOCK];
@@ -158,7 +158,19 @@ __global__ void __launch_bounds__(STEP_BLOCK, 512 / STEP_BLOCK) k_step(StepParam
     // lane whose cache overflowed -- simply walks the tree as before.
     bool cache_ok = false;
     uint32_t ncache = 0;
-    if (!LITERAL && !(p.tune & 1u)) {
+    if (!LITERAL && !TRACE && !(p.tune & 1u) && p.xc_version) {
+        // per-slot lists kept valid by k_xc_refresh (see there); nothing to walk here
+        if (alive) {
+            const size_t s = size_t(p.xc_first) + i;
+            if (p.xc_version[s] == p.tree_version) {
+                ncache = p.xc_count[s];
+                for (uint32_t j = 0; j < ncache; ++j) s_cache[j][tid] = p.xc_leaf[size_t(j) * p.xc_stride + s];
+#pragma unroll
+                for (int f = 0; f < 6; ++f) s_region[f][tid] = p.xc_region[size_t(f) * p.xc_stride + s];
+                cache_ok = true;
+            }
+        }
+    } else if (!LITERAL && !(p.tune & 1u)) {
         Box R;
         R.lo = v3(0.0f); R.hi = v3(0.0f);
         uint32_t node = p.n_nodes;
@@ -373,6 +385,7 @@ __global__ void __launch_bounds__(STEP_BLOCK, 512 / STEP_BLOCK) k_step(StepParam
                 const float4 hi = __ldg(p.nodes + 2 * leaf + 1);
                 ++c_node;
                 if (node_overlaps(lo, hi, qb)) {
+                    if (nleaf == LEAF_CAP) { nleaf = 0xFFFFFFFFu; break; }    // more than one pass holds: ordered walk below
                     if (TRACE) {
                         if (t_mesh < p.trace.cap_cand) p.trace.mesh_ids[size_t(slot) * p.trace.cap_cand + t_mesh] = p.node_leaf_id[leaf];
                         ++t_mesh;
@@ -382,6 +395,7 @@ __global__ void __launch_bounds__(STEP_BLOCK, 512 / STEP_BLOCK) k_step(StepParam
                 }
             }
             node = p.n_nodes;
+            if (nleaf == 0xFFFFFFFFu) { nleaf = 0; node = 0; if (TRACE) t_mesh = 0; }
         }
         while (true) {
             // ---- phase A: stackless traversal in right-first preorder == DynamicAABBTree::query's emission order
@@ -1130,6 +1144,13 @@ int launch_step(StepParams const & p_in, bool traced, int mode, cudaStream_t str
     if (small) p.work_counter = nullptr;                 // the persistent kernel is for batches that fill the machine
     const uint32_t warps = (p.n + lpw - 1) / lpw;
     const uint32_t grid = (warps * 32u + block - 1) / block;
+    // untraced CANONICAL launches read per-slot leaf lists: bring them up to date first
+    // (only where the extra launch pays: the persistent kernel and big JACOBI batches; thinned / chunked lock-step
+    //  launches walk inside k_step -- measured: C2 0.113 vs 0.148 ms, chunked e2e 3.21 vs 3.32 ms)
+    const bool slots = !traced && mode != MODE_LITERAL && p.xc_version != nullptr && !(p.tune & 1u) &&
+                       ((mode == MODE_STATIC && p.work_counter != nullptr) || (mode == MODE_JACOBI && !small));
+    if (!slots) p.xc_version = nullptr;
+    if (slots) { k_xc_refresh<<<(p.n + 127) / 128, 128, 0, stream>>>(p, p.xc_reuse ? 1 : 0); ++launches; }
     if (mode == MODE_LITERAL) {
         if (traced) k_step<true, MODE_LITERAL><<<grid, block, 0, stream>>>(p);
         else k_step<false, MODE_LITERAL><<<grid, block, 0, stream>>>(p);
@@ -1139,9 +1160,8 @@ int launch_step(StepParams const & p_in, bool traced, int mode, cudaStream_t str
     } else {
         if (traced) k_step<true, MODE_STATIC><<<grid, block, 0, stream>>>(p);
         else if (p.work_counter) {
-            // persistent: one warp per block, as many blocks as fit (16 per SM), work handed out by a counter
+            // persistent: one warp per block, as many blocks as fit (20 per SM), work handed out by a counter
             cudaMemsetAsync(p.work_counter, 0, sizeof(unsigned), stream);
-            if (!(p.tune & 1u)) { k_xc_refresh<<<(p.n + 127) / 128, 128, 0, stream>>>(p, p.xc_reuse ? 1 : 0); ++launches; }
             const uint32_t want = (p.n + 31) / 32;
             const uint32_t resident = uint32_t(p.persistent_blocks);
             k_step_stream<<<want < resident ? want : resident, 32, 0, stream>>>(p);

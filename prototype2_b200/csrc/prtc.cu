@@ -794,6 +794,7 @@ int prtc_step_characters(prtc_ctx * c, float dt, uint32_t n, prtc_transform * tf
         }
         PRTC_CUDA(cudaEventRecord(c->pipe_ready, c->stream));          // whatever the context's stream still has queued
         for (int k = 0; k < prtc_ctx::PIPE_STREAMS; ++k) PRTC_CUDA(cudaStreamWaitEvent(c->pipe[k], c->pipe_ready, 0));
+        { StepParams whole; rc = fill_params(c, dt, n, c->d_tf.ptr, c->d_ph.ptr, whole); if (rc) return rc; }   // sizes the per-slot caches for n
         uint32_t k = 0;
         for (uint32_t first = 0; first < n; first += kChunk, ++k) {
             const uint32_t cnt = std::min(kChunk, n - first);
@@ -804,6 +805,7 @@ int prtc_step_characters(prtc_ctx * c, float dt, uint32_t n, prtc_transform * tf
             fill_params(c, dt, cnt, c->d_tf.ptr + first, c->d_ph.ptr + first, p);
             if (!kChunkPersistent) p.work_counter = nullptr;
             if (p.work_counter) p.work_counter += 1 + k % prtc_ctx::PIPE_STREAMS;     // launches on one stream are ordered
+            p.xc_first = first;                               // cache slots are indexed by the character's position in the batch
             c->launches += uint64_t(launch_step(p, false, STEP_STATIC, s));
             PRTC_CUDA(cudaGetLastError());
             PRTC_CUDA(cudaMemcpyAsync(tf + first, c->d_tf.ptr + first, size_t(cnt) * sizeof(prtc_transform), cudaMemcpyDeviceToHost, s));
