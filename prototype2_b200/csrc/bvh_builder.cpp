@@ -195,7 +195,8 @@ void RefTree::remove(int32_t index) {                       // aabb_tree.cpp:182
     release(index);
 }
 
-void RefTree::update(int32_t * tree_indices, Box const * aabbs, size_t n) {    // aabb_tree.cpp:102-111
+size_t RefTree::update(int32_t * tree_indices, Box const * aabbs, size_t n) {    // aabb_tree.cpp:102-111
+    size_t reinserted = 0;
     for (size_t i = 0; i < n; ++i) {
         Node const & node = nodes_[size_t(tree_indices[i])];
         if (!box_contains(node.box, aabbs[i])) {
@@ -203,8 +204,10 @@ void RefTree::update(int32_t * tree_indices, Box const * aabbs, size_t n) {    /
             LeafKind kind = node.kind;
             remove(tree_indices[i]);
             tree_indices[i] = insert_leaf(id, kind, aabbs[i]);
+            ++reinserted;
         }
     }
+    return reinserted;
 }
 
 } // namespace prt

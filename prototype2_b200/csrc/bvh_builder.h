@@ -51,7 +51,7 @@ public:
     // DynamicAABBTree::remove(int32_t) (aabb_tree.cpp:182-220)
     void remove(int32_t index);
     // DynamicAABBTree::update (aabb_tree.cpp:102-111): re-insert leaves whose stored fat box no longer contains aabb
-    void update(int32_t * tree_indices, Box const * aabbs, size_t n);
+    size_t update(int32_t * tree_indices, Box const * aabbs, size_t n);   // returns how many leaves were re-inserted
     Box const & node_box(int32_t index) const { return nodes_[size_t(index)].box; }
     int32_t size() const { return size_; }
     bool empty() const { return root_ == NIL; }

@@ -110,6 +110,7 @@ struct prtc_ctx {
     uint32_t tree_version = 1;
     uint64_t launches = 0;                  // kernels launched by step calls since the last counter reset
     int cross_frame = 1;
+    int warp_kernel = 1;                    // small batches: one warp per character (k_step_warp); 0 = thinned lock-step kernel
     float xc_margin = 0.5f;
     DevBuf<unsigned> d_work;                // work counters of the persistent kernel, one per concurrently running launch
     DevBuf<prtc_transform> d_tf;
@@ -277,7 +278,7 @@ int fill_params(prtc_ctx * c, float dt, uint32_t n, prtc_transform * d_tf, prtc_
         float ulp = std::nextafter(m, INFINITY) - m;
         p.qr_eps = std::max(1e-3f, 64.0f * ulp);
         p.qr_enable = (c->quick_reject && m < 1.0e6f) ? 1u : 0u;
-        p.tune = (c->frame_cache ? 0u : 1u) | c->tune_hi;
+        p.tune = (c->frame_cache ? 0u : 1u) | (c->warp_kernel ? 0u : 2u) | c->tune_hi;
         p.work_counter = c->persistent ? c->d_work.ptr : nullptr;
         p.persistent_blocks = uint32_t(c->sm_count) * 20u;
         p.tree_version = c->tree_version;
@@ -476,10 +477,10 @@ int literal_step(prtc_ctx * c, float dt, uint32_t n, prtc_transform * tf, prtc_c
         seg_start[2 * size_t(i) + 1] = make_float4(B.x, B.y, B.z, 0.0f);
     }
     // m_aabbData.tree.update(all capsule leaves) (physics_system.cpp:289)
-    if (!c->capsule_tree_index.empty())
-        c->tree.update(c->capsule_tree_index.data(), c->capsule_aabbs.data(), c->capsule_tree_index.size());
-    c->tree_dirty = true;
-    int rc = commit_impl(c);                                                    // re-flatten + upload (+ triangles in the new leaf order)
+    if (!c->capsule_tree_index.empty() &&
+        c->tree.update(c->capsule_tree_index.data(), c->capsule_aabbs.data(), c->capsule_tree_index.size()) != 0)
+        c->tree_dirty = true;                                                   // some leaf left its fat box: the tree changed shape
+    int rc = commit_impl(c);                                                    // re-flatten + upload (+ triangles in the new leaf order) if needed
     if (rc) return rc;
 
     PRTC_CUDA(c->d_tf.reserve(n));
@@ -604,6 +605,7 @@ int prtc_create(const prtc_config * cfg, prtc_ctx ** out) {
     if (const char * e = std::getenv("PRTC_FRAME_CACHE")) ctx->frame_cache = std::atoi(e);
     if (const char * e = std::getenv("PRTC_PERSISTENT")) ctx->persistent = std::atoi(e);
     if (const char * e = std::getenv("PRTC_CROSS_FRAME")) ctx->cross_frame = std::atoi(e);
+    if (const char * e = std::getenv("PRTC_WARP_KERNEL")) ctx->warp_kernel = std::atoi(e);
     if (const char * e = std::getenv("PRTC_XC_MARGIN")) ctx->xc_margin = float(std::atof(e));
     if (const char * e = std::getenv("PRTC_TUNE")) ctx->tune_hi = uint32_t(std::strtoul(e, nullptr, 0)) & 0xFFFFFF00u;
     ctx->sm_count = prop.multiProcessorCount;
