@@ -190,7 +190,8 @@ int prtc_synchronize(prtc_ctx * ctx);
 
 int prtc_get_counters(prtc_ctx * ctx, prtc_counters * out, int reset);
 
-/* Work-saving devices of the GPU path.  Neither changes any result bit; both change how much work is done.
+/* Work-saving devices and kernel choices of the GPU path.  None changes any result bit; they change how much work is
+ * done and how it is scheduled.
  *   PRTC_OPT_FRAME_CACHE   (default 1) one tree walk per character and frame with a box covering the whole
  *                          frame's motion; substeps re-test only the cached leaves.  With 0 the device walks the
  *                          tree once per substep exactly like DynamicAABBTree::query, and prtc_counters.node_tests
@@ -201,8 +202,11 @@ int prtc_get_counters(prtc_ctx * ctx, prtc_counters * out, int reset);
  *   PRTC_OPT_CROSS_FRAME_CACHE (default 1) the persistent kernel keeps every character slot's leaf list (valid for
  *                          an enlarged region around it) in device memory between frames; a character whose
  *                          frame still fits inside that region skips the tree walk.  The list is a pure function
- *                          of (tree, region), so it does not matter which character occupies the slot. */
-enum prtc_option { PRTC_OPT_FRAME_CACHE = 1, PRTC_OPT_QUICK_REJECT = 2, PRTC_OPT_PERSISTENT = 3, PRTC_OPT_CROSS_FRAME_CACHE = 4 };
+ *                          of (tree, region), so it does not matter which character occupies the slot.
+ *   PRTC_OPT_WARP_KERNEL   (default 1) batches small enough to give every character a resident warp run on the
+ *                          warp-cooperative kernel (0: the lock-step kernel with thinned-out warps). */
+enum prtc_option { PRTC_OPT_FRAME_CACHE = 1, PRTC_OPT_QUICK_REJECT = 2, PRTC_OPT_PERSISTENT = 3, PRTC_OPT_CROSS_FRAME_CACHE = 4,
+                   PRTC_OPT_WARP_KERNEL = 5 };
 int prtc_set_option(prtc_ctx * ctx, int option, int value);
 
 /* Introspection for parity tests: the flattened tree.  leaf_mesh_ids receives the mesh-collider ids of all

@@ -953,6 +953,7 @@ int prtc_set_option(prtc_ctx * c, int option, int value) {
         case PRTC_OPT_QUICK_REJECT: c->quick_reject = value != 0; return PRTC_OK;
         case PRTC_OPT_PERSISTENT: c->persistent = value != 0; return PRTC_OK;
         case PRTC_OPT_CROSS_FRAME_CACHE: c->cross_frame = value != 0; return PRTC_OK;
+        case PRTC_OPT_WARP_KERNEL: c->warp_kernel = value != 0; return PRTC_OK;
         default: return fail(PRTC_ERR_INVALID, "prtc_set_option: unknown option");
     }
 }

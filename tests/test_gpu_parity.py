@@ -692,3 +692,34 @@ def test_cross_frame_cache_does_not_care_who_sits_in_a_slot():
         off.update_characters(DT, tf2, ph2)
         assert H.state_diff(H.gpu_state(tf, ph), H.gpu_state(tf2, ph2)) == [], "after move, frame %d" % f
     assert on.counters()["launches"] == off.counters()["launches"] > 0
+
+
+def test_warp_kernel_overflow_and_equivalence_with_the_lock_step_kernel():
+    """small batches run one warp per character (k_step_warp).  A huge capsule and a NaN one overlap far more than
+    the 128 leaves / frontier nodes a warp buffers -> ordered passes; results must equal the oracle and the thinned
+    lock-step kernel (PRTC_OPT_WARP_KERNEL = 0), counters included"""
+    from prototype2_b200 import capi
+    xyz, mf, mc = H.scenes.terrain(32, 1, 1)                  # 1024 two-triangle leaves
+    rs = np.random.RandomState(7)
+    n = 24
+    pos = np.stack([rs.uniform(4, 28, n), rs.uniform(0.3, 1.5, n), rs.uniform(4, 28, n)], 1).astype(np.float32)
+    vel = rs.uniform(-0.1, 0.1, (n, 3)).astype(np.float32)
+    pos[5] = np.nan
+    caps = [(0.5, 0.5, (0.0, 0.5, 0.0))] * n
+    caps[2] = (1.0, 6.0, (0.0, 6.0, 0.0))                     # 13 units wide: ~200 candidate leaves
+    caps[9] = (0.2, 3.0, (0.0, 3.0, 0.0))
+    scene = {"xyz": xyz, "mesh_first": mf, "mesh_count": mc, "model_transform": None, "pos": pos, "vel": vel,
+             "rot": np.tile(np.array([1, 0, 0, 0], np.float32), (n, 1)), "move": np.zeros((n, 3), np.float32), "n": n}
+    orc, warp, tf, ph = _hetero_worlds(scene, caps, "l1", dict(order="canonical"), dict())
+    _, lock, tf2, ph2 = _hetero_worlds(scene, caps, "l1", dict(order="canonical"), dict())
+    lock.set_option(capi.OPT_WARP_KERNEL, 0)
+    for f in range(4):
+        orc.step(DT)
+        warp.update_characters(DT, tf, ph)
+        lock.update_characters(DT, tf2, ph2)
+        assert H.state_diff(orc.get_state(), H.gpu_state(tf, ph)) == [], "frame %d warp kernel vs oracle" % f
+        assert H.state_diff(H.gpu_state(tf, ph), H.gpu_state(tf2, ph2)) == [], "frame %d warp vs lock-step" % f
+    co, cw, cl = orc.counters(), warp.counters(), lock.counters()
+    for k in ("substeps", "tri_tests", "contacts"):
+        assert co[k] == cw[k] == cl[k], k
+    assert cw["node_tests"] == co["node_tests"]               # the frontier walk tests exactly the nodes the reference tests
