@@ -1,0 +1,382 @@
+// k_step_stream.cu -- the persistent, lane-decoupled static-pass kernel and the refresh of its per-slot leaf cache
+// Compile with -fmad=false: results must be bit-identical to the CPU reference (see prt_math.cuh).
+#include "step_common.cuh"
+
+namespace prt {
+
+namespace {
+
+// k_xc_refresh: keeps the per-slot frame cache of k_step_stream valid for the coming frame.  One thread per
+// character: the region its frame can need (box of the current pose united with the pose after the pre-stepped
+// velocity, +0.25 for push-outs); if the slot's stored region (built for this tree version) already contains it, done --
+// resting or slow characters never walk the tree again; else one stackless walk with the region grown by xc_margin
+// collects the overlapping leaves (emission order) and the slot is rewritten.  The list is a pure function of
+// (tree, region): it does not matter which character occupied the slot before, and k_step_stream re-checks
+// "query box inside region" at every substep, so a stale or too-small region can only cost time, never correctness.
+__global__ void __launch_bounds__(128) k_xc_refresh(StepParams p, int reuse) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= p.n) return;
+    const prtc_transform * tf = p.transforms + i;
+    const prtc_char_physics * ph = p.physics + i;
+    const V3 pos = v3(tf->position[0], tf->position[1], tf->position[2]);
+    Quat q; q.x = tf->rotation[0]; q.y = tf->rotation[1]; q.z = tf->rotation[2]; q.w = tf->rotation[3];
+    V3 vel = v3(ph->velocity[0], ph->velocity[1], ph->velocity[2]);
+    uint32_t cid = ph->collider;
+    if (cid >= p.n_capsules) cid = 0;
+    const CapsuleDev cap = p.capsules[cid];
+    const CapsuleFrame fr = capsule_frame(cap, rotation_of(q));
+    if (ph->grounded) vel = vel + ((-p.stick * p.gravity) * p.dt) * v3(ph->ground_normal[0], ph->ground_normal[1], ph->ground_normal[2]);
+    vel.x = vel.x + ph->movement[0];
+    vel.z = vel.z + ph->movement[2];
+    V3 a0, b0, eA, eB;
+    segment_ends(fr, pos, a0, b0);
+    segment_ends(fr, pos + vel, eA, eB);
+    Box R = box_union(capsule_box(a0, b0, cap.radius), capsule_box(eA, eB, cap.radius));
+    R.lo = R.lo - v3(0.25f); R.hi = R.hi + v3(0.25f);
+    const size_t s = size_t(p.xc_first) + i;
+    if (reuse && p.xc_version[s] == p.tree_version) {
+        if (p.xc_region[0 * size_t(p.xc_stride) + s] <= R.lo.x && p.xc_region[1 * size_t(p.xc_stride) + s] <= R.lo.y &&
+            p.xc_region[2 * size_t(p.xc_stride) + s] <= R.lo.z && p.xc_region[3 * size_t(p.xc_stride) + s] >= R.hi.x &&
+            p.xc_region[4 * size_t(p.xc_stride) + s] >= R.hi.y && p.xc_region[5 * size_t(p.xc_stride) + s] >= R.hi.z)
+            return;
+    }
+    if (reuse) { R.lo = R.lo - v3(p.xc_margin); R.hi = R.hi + v3(p.xc_margin); }
+    uint32_t node = 0, ncache = 0;
+    while (node < p.n_nodes) {
+        const float4 lo = __ldg(p.nodes + 2 * node);
+        const float4 hi = __ldg(p.nodes + 2 * node + 1);
+        const bool ov = node_overlaps(lo, hi, R);
+        const int cnt = __float_as_int(hi.w);
+        if (cnt < 0) {
+            node = ov ? node + 1 : uint32_t(__float_as_int(lo.w));
+        } else {
+            if (ov) {
+                if (ncache == XC_CAP) { ncache = 0xFFFFFFFFu; break; }
+                p.xc_leaf[size_t(ncache) * p.xc_stride + s] = node;
+                ++ncache;
+            }
+            node = node + 1;
+        }
+    }
+    if (ncache == 0xFFFFFFFFu) { p.xc_version[s] = 0u; return; }   // too many leaves for a slot: this character walks per substep
+    p.xc_region[0 * size_t(p.xc_stride) + s] = R.lo.x; p.xc_region[1 * size_t(p.xc_stride) + s] = R.lo.y; p.xc_region[2 * size_t(p.xc_stride) + s] = R.lo.z;
+    p.xc_region[3 * size_t(p.xc_stride) + s] = R.hi.x; p.xc_region[4 * size_t(p.xc_stride) + s] = R.hi.y; p.xc_region[5 * size_t(p.xc_stride) + s] = R.hi.z;
+    p.xc_count[s] = ncache;
+    p.xc_version[s] = p.tree_version;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// k_step_stream: the static pass (MODE_STATIC, untraced) as a PERSISTENT, lane-decoupled kernel.
+//
+// k_step keeps one character per lane and walks all lanes through "substep -> filter -> exact test" in lock step,
+// so a warp's cost per substep is set by its slowest lane (ncu: 14 of 32 lanes active per instruction).  Here every
+// lane is a small state machine that moves through its character's substeps on its own:
+//     LOAD     fetch the next character from a global counter, pre-step, one tree walk for the frame cache
+//     SUBSTEP  advance, query box, candidate leaves (cache or ordered walk), start the triangle stream
+//     STREAM   filter loop over the cp.async triangle ring until a triangle needs the exact test
+// and the only converged section is the expensive one, the exact capsule-triangle test, which runs whenever any lane
+// has a pending triangle.  LOAD and SUBSTEP are batched (they run when enough lanes wait for them or nobody has
+// anything else to do) so that their divergent code is shared by several lanes.  Arithmetic, order of triangles per
+// character and all results are the same as k_step's -- only the interleaving between characters differs.
+// ------------------------------------------------------------------------------------------------------------
+constexpr int ST_LOAD = 0, ST_SUBSTEP = 1, ST_STREAM = 2, ST_DONE = 3;
+constexpr int LOAD_BATCH = 16;       // lanes that must wait for new work before the (expensive) LOAD stage runs
+constexpr int SUBSTEP_BATCH = 8;     // same for the SUBSTEP stage
+
+__global__ void __launch_bounds__(32, 20) k_step_stream(StepParams p) {
+    constexpr unsigned FULL = 0xffffffffu;
+    __shared__ uint32_t s_leaf[LEAF_CAP][32];              // candidate leaves of the substep: node indices, emission order
+    __shared__ uint32_t s_cache[XC_CAP][32];
+    __shared__ float s_region[6][32];
+    __shared__ float4 s_tri[TRI_RING][3][32];
+    __shared__ float s_park[P_COUNT][32];
+    const uint32_t tid = threadIdx.x;
+    const Parked park{s_park, tid};
+    const unsigned lt_mask = (1u << tid) - 1u;
+    uint32_t c_tri = 0, c_node = 0;
+    __shared__ uint32_t s_cnt[4][32];                      // rarely bumped counters + ncache live here, not in registers
+    s_cnt[0][tid] = 0; s_cnt[1][tid] = 0; s_cnt[2][tid] = 0; s_cnt[3][tid] = 0;
+#define C_SUB s_cnt[0][tid]
+#define C_CONTACT s_cnt[1][tid]
+#define C_EXACT s_cnt[2][tid]
+#define NCACHE s_cnt[3][tid]
+
+    int state = ST_LOAD;
+    uint32_t i = 0xFFFFFFFFu;
+    V3 pos = v3(0.0f);
+    uint32_t grounded = 0, stepsLeft = 0;
+    float radius = 0.0f;
+    bool cache_ok = false, found = true;
+    uint32_t node = 0, nleaf = 0;
+    Box qb; qb.lo = v3(0.0f); qb.hi = v3(0.0f);
+    Pose ps = make_pose(park.frame(0.0f), pos);
+    uint32_t f_leaf = 0, f_cur = 0, f_end = 0, n_fetched = 0, n_consumed = 0;
+    bool pending = false;
+    float4 t0 = make_float4(0, 0, 0, 0), t1 = t0, t2 = t0;
+    const bool use_qr = p.qr_enable != 0u;
+    const bool use_cache = !(p.tune & 1u);
+    const int load_batch = ((p.tune >> 8) & 0xFFu) ? int((p.tune >> 8) & 0xFFu) : LOAD_BATCH;
+    const int substep_batch = ((p.tune >> 16) & 0xFFu) ? int((p.tune >> 16) & 0xFFu) : SUBSTEP_BATCH;
+    for (int f = 0; f < P_COUNT; ++f) s_park[f][tid] = 0.0f;
+
+    auto fetch_one = [&]() {
+        while (f_cur == f_end) {
+            if (f_leaf == nleaf) return;
+            const uint32_t leaf = s_leaf[f_leaf][tid];
+            ++f_leaf;
+            f_cur = uint32_t(__float_as_int(__ldg(p.nodes + 2 * leaf).w));
+            f_end = f_cur + uint32_t(__float_as_int(__ldg(p.nodes + 2 * leaf + 1).w));
+        }
+        const uint32_t slot = n_fetched % TRI_RING;
+        const float4 * src = p.tris + 3 * size_t(f_cur);
+        cp_async16(&s_tri[slot][0][tid], src);
+        cp_async16(&s_tri[slot][1][tid], src + 1);
+        cp_async16(&s_tri[slot][2][tid], src + 2);
+        cp_async_commit();
+        ++f_cur;
+        ++n_fetched;
+    };
+    // ordered stackless walk (DynamicAABBTree::query order) from `node`, buffering up to LEAF_CAP leaves
+    auto ordered_walk = [&]() {
+        nleaf = 0;
+        while (node < p.n_nodes && nleaf < LEAF_CAP) {
+            const float4 lo = __ldg(p.nodes + 2 * node);
+            const float4 hi = __ldg(p.nodes + 2 * node + 1);
+            const bool ov = node_overlaps(lo, hi, qb);
+            const int link = __float_as_int(lo.w);
+            const int cnt = __float_as_int(hi.w);
+            ++c_node;
+            if (cnt < 0) {
+                node = ov ? node + 1 : uint32_t(link);
+            } else {
+                if (ov) { s_leaf[nleaf][tid] = node; ++nleaf; }
+                node = node + 1;
+            }
+        }
+    };
+    auto start_stream = [&]() {
+        f_leaf = 0; f_cur = 0; f_end = 0; n_fetched = 0; n_consumed = 0;
+#pragma unroll
+        for (int r = 0; r < TRI_RING; ++r) fetch_one();
+    };
+
+    for (;;) {
+        const unsigned m_load = __ballot_sync(FULL, state == ST_LOAD);
+        const unsigned m_done = __ballot_sync(FULL, state == ST_DONE);
+        if (m_done == FULL) break;
+        const unsigned m_sub = __ballot_sync(FULL, state == ST_SUBSTEP);
+        const unsigned m_stream = __ballot_sync(FULL, state == ST_STREAM);
+
+        // ---------------- LOAD: new characters + their frame cache ----------------
+        if (m_load && (__popc(m_load) >= load_batch || (m_sub | m_stream) == 0u)) {
+            unsigned base = 0;
+            if (tid == 0) base = atomicAdd(p.work_counter, (unsigned)__popc(m_load));
+            base = __shfl_sync(FULL, base, 0);
+            bool loaded_now = false;
+            if (state == ST_LOAD) {
+                const uint32_t idx = base + __popc(m_load & lt_mask);
+                if (idx >= p.n) {
+                    state = ST_DONE;
+                } else {
+                    i = idx;
+                    const prtc_transform * tf = p.transforms + i;
+                    const prtc_char_physics * ph = p.physics + i;
+                    uint32_t cid = ph->collider;
+                    if (cid >= p.n_capsules) {                    // unknown capsule id: never dereferenced; reported, result undefined
+                        if (p.counters) atomicAdd(p.counters + 6, 1ull);
+                        cid = 0;
+                    }
+                    pos = v3(tf->position[0], tf->position[1], tf->position[2]);
+                    Quat q; q.x = tf->rotation[0]; q.y = tf->rotation[1]; q.z = tf->rotation[2]; q.w = tf->rotation[3];
+                    V3 vel = v3(ph->velocity[0], ph->velocity[1], ph->velocity[2]);
+                    const V3 gn = v3(ph->ground_normal[0], ph->ground_normal[1], ph->ground_normal[2]);
+                    const float mvx = ph->movement[0], mvz = ph->movement[2];
+                    const CapsuleDev cap = p.capsules[cid];
+                    const CapsuleFrame fr = capsule_frame(cap, rotation_of(q));
+                    radius = cap.radius;
+                    s_park[P_QR_EPS][tid] = p.qr_eps + 1e-5f * (fabsf(cap.radius) + fabsf(cap.height) + fabsf(cap.ox) + fabsf(cap.oy) + fabsf(cap.oz));
+                    // ---- phase 1 (physics_system.cpp:277-285) ----
+                    if (ph->grounded) vel = vel + ((-p.stick * p.gravity) * p.dt) * gn;
+                    vel.x = vel.x + mvx;
+                    vel.z = vel.z + mvz;
+                    grounded = 0;
+                    park.put(P_VEL, vel);
+                    park.put(P_STEPV, vel / float(p.substeps));
+                    park.put(P_GN, gn);
+                    park.put(P_SA1, fr.sa1); park.put(P_SA2, fr.sa2); park.put(P_SB1, fr.sb1); park.put(P_SB2, fr.sb2);
+                    V3 a0, b0;
+                    segment_ends(fr, pos, a0, b0);                // prevTform                      :344
+                    park.put(P_PREVA, a0); park.put(P_PREVB, b0);
+                    stepsLeft = p.substeps;
+                    found = true;
+                    cache_ok = false;
+                    NCACHE = 0;
+                    state = ST_SUBSTEP;
+                    loaded_now = true;
+                }
+            }
+            // The frame cache (candidate leaves valid for a region around the character, kept per character slot in
+            // device memory and refreshed by k_xc_refresh right before this kernel) is only read here.
+            if (loaded_now) {
+                cache_ok = false;
+                if (use_cache) {
+                    const size_t s = size_t(p.xc_first) + i;
+                    if (p.xc_version[s] == p.tree_version) {
+                        const uint32_t nc = p.xc_count[s];
+                        NCACHE = nc;
+                        for (uint32_t j = 0; j < nc; ++j) s_cache[j][tid] = p.xc_leaf[size_t(j) * p.xc_stride + s];
+#pragma unroll
+                        for (int f = 0; f < 6; ++f) s_region[f][tid] = p.xc_region[size_t(f) * p.xc_stride + s];
+                        cache_ok = true;
+                    }
+                }
+            }
+            continue;
+        }
+
+        // ---------------- SUBSTEP: finish the frame or start the next substep ----------------
+        if (m_sub && (__popc(m_sub) >= substep_batch || m_stream == 0u)) {
+            if (state == ST_SUBSTEP) {
+                if (!found || stepsLeft == 0) {
+                    // `if (meshColIDs.empty()) break;` (:391-393) / loop end; remaining motion (:437); phase 3 (:298-317)
+                    prtc_transform * tf = p.transforms + i;
+                    prtc_char_physics * ph = p.physics + i;
+                    pos = pos + (float(stepsLeft) * park.get(P_VEL)) / float(p.substeps);
+                    V3 vel = v3(ph->velocity[0], ph->velocity[1], ph->velocity[2]);   // prevVelocities[i]: still untouched in memory (:277,304)
+                    const float frictionRatio = fdiv(1.0f, 1.0f + (p.dt * p.friction));
+                    vel.x = vel.x * frictionRatio;
+                    vel.z = vel.z * frictionRatio;
+                    if (grounded) vel.y = gmax((0.0f * p.gravity) * p.dt, vel.y);
+                    else vel.y = vel.y + ((-1.0f * p.gravity) * p.dt);
+                    const V3 gn = park.get(P_GN);
+                    tf->position[0] = pos.x; tf->position[1] = pos.y; tf->position[2] = pos.z;
+                    ph->velocity[0] = vel.x; ph->velocity[1] = vel.y; ph->velocity[2] = vel.z;
+                    ph->ground_normal[0] = gn.x; ph->ground_normal[1] = gn.y; ph->ground_normal[2] = gn.z;
+                    ph->grounded = grounded;
+                    state = ST_LOAD;
+                } else {
+                    --stepsLeft;
+                    pos = pos + park.get(P_STEPV);                //                                 :350
+                    const CapsuleFrame fr = park.frame(radius);
+                    ps = make_pose(fr, pos);
+                    qb = box_union(capsule_box(park.get(P_PREVA), park.get(P_PREVB), radius), capsule_box(ps.A, ps.B, radius));   // :355-356
+                    park.put(P_PREVA, ps.A); park.put(P_PREVB, ps.B);     // prevTform = tform       :358
+                    ++C_SUB;
+                    found = false;
+                    nleaf = 0;
+                    if (cache_ok &&
+                        s_region[0][tid] <= qb.lo.x && s_region[1][tid] <= qb.lo.y && s_region[2][tid] <= qb.lo.z &&
+                        s_region[3][tid] >= qb.hi.x && s_region[4][tid] >= qb.hi.y && s_region[5][tid] >= qb.hi.z) {
+                        bool fits = true;
+                        const uint32_t ncache = NCACHE;
+                        for (uint32_t j = 0; j < ncache; ++j) {
+                            const uint32_t leaf = s_cache[j][tid];
+                            const float4 lo = __ldg(p.nodes + 2 * leaf);
+                            const float4 hi = __ldg(p.nodes + 2 * leaf + 1);
+                            ++c_node;
+                            if (node_overlaps(lo, hi, qb)) {
+                                if (nleaf == LEAF_CAP) { fits = false; break; }
+                                s_leaf[nleaf][tid] = leaf;
+                                ++nleaf;
+                            }
+                        }
+                        node = p.n_nodes;
+                        if (!fits) { node = 0; ordered_walk(); }  // more candidates than one pass holds: walk in passes
+                    } else {
+                        node = 0;
+                        ordered_walk();
+                    }
+                    if (nleaf) found = true;
+                    start_stream();
+                    state = ST_STREAM;
+                }
+            }
+            continue;
+        }
+
+        // ---------------- STREAM: filter until a triangle needs the exact test ----------------
+        if (state == ST_STREAM && !pending) {
+            const V3 smin = gmin(ps.A, ps.B), smax = gmax(ps.A, ps.B);
+            const float qr_eps = s_park[P_QR_EPS][tid];
+            const float dmax = (p.abs_mode == 1u) ? radius : floorf(radius) + 1.0f;   // largest plane distance surviving the range cull
+            for (;;) {
+                while (n_consumed != n_fetched) {
+                    if (n_fetched - n_consumed >= 2) cp_async_wait<1>(); else cp_async_wait<0>();
+                    const uint32_t slot = n_consumed % TRI_RING;
+                    t0 = s_tri[slot][0][tid];
+                    t1 = s_tri[slot][1][tid];
+                    t2 = s_tri[slot][2][tid];
+                    ++n_consumed;
+                    fetch_one();
+                    ++c_tri;
+                    if (__float_as_uint(t0.w) == PRT_DEGENERATE_BITS) continue;       // length(n) == 0   :53
+                    if (use_qr && quick_reject(smin, smax, radius, dmax, qr_eps, t0, t1, t2)) continue;
+                    pending = true;
+                    break;
+                }
+                if (pending) break;
+                if (node < p.n_nodes) {                           // more leaves than the buffer holds: next pass
+                    ordered_walk();
+                    if (nleaf) found = true;
+                    start_stream();
+                    if (n_fetched == 0) { state = ST_SUBSTEP; break; }
+                } else {
+                    state = ST_SUBSTEP;                           // this substep's candidates are exhausted
+                    break;
+                }
+            }
+        }
+
+        // ---------------- exact tests, converged ----------------
+        if (__any_sync(FULL, pending)) {
+            if (pending) {
+                pending = false;
+                Contact ct;
+                ++C_EXACT;
+                if (capsule_triangle(ps, radius, p.abs_mode, v3(t0.x, t0.y, t0.z), v3(t1.x, t1.y, t1.z),
+                                     v3(t2.x, t2.y, t2.z), v3(t0.w, t1.w, t2.w), ct)) {
+                    pos = pos + ct.impulse;                       // handleCollision (collision_system.cpp:242-252)
+                    ++C_CONTACT;
+                    if (dot(ct.normal, v3(0.0f, 1.0f, 0.0f)) > p.ground_dot) {
+                        grounded = 1;
+                        park.put(P_GN, ct.normal);
+                    }
+                    if (ct.impulse.x != 0.0f || ct.impulse.y != 0.0f || ct.impulse.z != 0.0f)
+                        ps = make_pose(park.frame(radius), pos);  // tform is rebuilt per triangle     :40
+                }
+            }
+            __syncwarp(FULL);
+        }
+    }
+
+    const uint32_t c_sub = __reduce_add_sync(FULL, C_SUB);
+    c_tri = __reduce_add_sync(FULL, c_tri);
+    c_node = __reduce_add_sync(FULL, c_node);
+    const uint32_t c_contact = __reduce_add_sync(FULL, C_CONTACT);
+    const uint32_t c_exact = __reduce_add_sync(FULL, C_EXACT);
+    if (tid == 0 && p.counters) {
+        atomicAdd(p.counters + 0, (unsigned long long)c_sub);
+        atomicAdd(p.counters + 1, (unsigned long long)c_tri);
+        atomicAdd(p.counters + 2, (unsigned long long)c_node);
+        atomicAdd(p.counters + 3, (unsigned long long)c_contact);
+        atomicAdd(p.counters + 5, (unsigned long long)c_exact);
+    }
+}
+
+#undef C_SUB
+#undef C_CONTACT
+#undef C_EXACT
+#undef NCACHE
+
+} // namespace
+
+void launch_k_xc_refresh(StepParams const & p, cudaStream_t stream) {
+    k_xc_refresh<<<(p.n + 127) / 128, 128, 0, stream>>>(p, p.xc_reuse ? 1 : 0);
+}
+
+void launch_k_step_stream(StepParams const & p, uint32_t blocks, cudaStream_t stream) {
+    cudaMemsetAsync(p.work_counter, 0, sizeof(unsigned), stream);
+    k_step_stream<<<blocks, 32, 0, stream>>>(p);
+}
+
+} // namespace prt

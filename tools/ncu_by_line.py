@@ -3,7 +3,7 @@
 
   ncu -i prof.ncu-rep --page source --csv > sass.csv
   cuobjdump -xelf all prototype2_b200/libprtc.so && nvdisasm --print-line-info kernels.sm_100a.cubin > kernels.sass
-  python tools/ncu_by_line.py sass.csv kernels.sass k_stepILb0 [top]
+  python tools/ncu_by_line.py sass.csv k_step_stream.sass k_step_stream [top]
 """
 import csv
 import re
