@@ -16,7 +16,8 @@ def pytest_configure(config):
 @pytest.fixture(scope="session", autouse=True)
 def _built_libraries():
     """Build what is missing (the driver normally runs __graft_entry__.build() first)."""
-    need = [os.path.join(ROOT, "prototype2_b200", "libprtc.so"), os.path.join(ROOT, "oracle", "_build", "libprt_l1.so")]
+    need = [os.path.join(ROOT, "prototype2_b200", "libprtc.so"), os.path.join(ROOT, "prototype2_b200", "libprtscene.so"),
+            os.path.join(ROOT, "oracle", "_build", "libprt_l1.so")]
     if not all(os.path.exists(p) for p in need):
         import __graft_entry__
         __graft_entry__.build()
