@@ -204,9 +204,13 @@ int prtc_get_counters(prtc_ctx * ctx, prtc_counters * out, int reset);
  *                          frame still fits inside that region skips the tree walk.  The list is a pure function
  *                          of (tree, region), so it does not matter which character occupies the slot.
  *   PRTC_OPT_WARP_KERNEL   (default 1) batches small enough to give every character a resident warp run on the
- *                          warp-cooperative kernel (0: the lock-step kernel with thinned-out warps). */
+ *                          warp-cooperative kernel (0: the lock-step kernel with thinned-out warps).
+ *   PRTC_OPT_STREAMED_COPY (default 1) prtc_step_characters on a big static batch (>= 262144 characters) runs ONE
+ *                          persistent launch that is fed by the host->device copy while it runs and hands finished
+ *                          chunks to the device->host copy while it is still computing (0: the batch is cut into
+ *                          chunks that are copied in, stepped and copied out on a few streams). */
 enum prtc_option { PRTC_OPT_FRAME_CACHE = 1, PRTC_OPT_QUICK_REJECT = 2, PRTC_OPT_PERSISTENT = 3, PRTC_OPT_CROSS_FRAME_CACHE = 4,
-                   PRTC_OPT_WARP_KERNEL = 5 };
+                   PRTC_OPT_WARP_KERNEL = 5, PRTC_OPT_STREAMED_COPY = 6 };
 int prtc_set_option(prtc_ctx * ctx, int option, int value);
 
 /* Introspection for parity tests: the flattened tree.  leaf_mesh_ids receives the mesh-collider ids of all

@@ -83,6 +83,12 @@ constexpr int ST_LOAD = 0, ST_SUBSTEP = 1, ST_STREAM = 2, ST_DONE = 3;
 constexpr int LOAD_BATCH = 16;       // lanes that must wait for new work before the (expensive) LOAD stage runs
 constexpr int SUBSTEP_BATCH = 8;     // same for the SUBSTEP stage
 
+//
+// GATED: the batch is still arriving over PCIe while the kernel runs (prtc_step_characters with host buffers).  The
+// copy-in stream publishes how many characters have landed in `*gate`; LOAD waits for its own indices.  Every finished
+// character is counted (per 1024, then per 65536) so the copy-out stream can start on a chunk the moment its last
+// character is written, while later chunks are still being computed.
+template <bool GATED>
 __global__ void __launch_bounds__(32, 20) k_step_stream(StepParams p) {
     constexpr unsigned FULL = 0xffffffffu;
     __shared__ uint32_t s_leaf[LEAF_CAP][32];              // candidate leaves of the substep: node indices, emission order
@@ -96,6 +102,9 @@ __global__ void __launch_bounds__(32, 20) k_step_stream(StepParams p) {
     uint32_t c_tri = 0, c_node = 0;
     __shared__ uint32_t s_cnt[4][32];                      // rarely bumped counters + ncache live here, not in registers
     s_cnt[0][tid] = 0; s_cnt[1][tid] = 0; s_cnt[2][tid] = 0; s_cnt[3][tid] = 0;
+    __shared__ uint32_t s_poll, s_arrived;                 // GATED: arrival count as last polled by lane 0
+    if (tid == 0) { s_poll = 0; s_arrived = 0; }
+    __syncwarp(FULL);
 #define C_SUB s_cnt[0][tid]
 #define C_CONTACT s_cnt[1][tid]
 #define C_EXACT s_cnt[2][tid]
@@ -168,17 +177,37 @@ __global__ void __launch_bounds__(32, 20) k_step_stream(StepParams p) {
         const unsigned m_stream = __ballot_sync(FULL, state == ST_STREAM);
 
         // ---------------- LOAD: new characters + their frame cache ----------------
+        // Lanes without a character claim the next index from the global counter.  GATED: an index whose records are
+        // still on the wire stays claimed while its lane waits in LOAD (the lanes that have work go on); the arrival
+        // count is polled sparsely as long as other lanes are busy.  Chunk boundaries are multiples of 32 characters =
+        // whole 128-byte lines of both record arrays, so no line with not-yet-arrived bytes was touched before.
         if (m_load && (__popc(m_load) >= load_batch || (m_sub | m_stream) == 0u)) {
-            unsigned base = 0;
-            if (tid == 0) base = atomicAdd(p.work_counter, (unsigned)__popc(m_load));
-            base = __shfl_sync(FULL, base, 0);
-            bool loaded_now = false;
-            if (state == ST_LOAD) {
-                const uint32_t idx = base + __popc(m_load & lt_mask);
-                if (idx >= p.n) {
-                    state = ST_DONE;
-                } else {
-                    i = idx;
+            const bool others_busy = (m_sub | m_stream) != 0u;
+            const unsigned m_claim = GATED ? __ballot_sync(FULL, state == ST_LOAD && i == 0xFFFFFFFFu) : m_load;
+            if (m_claim) {
+                unsigned base = 0;
+                if (tid == 0) base = atomicAdd(p.work_counter, (unsigned)__popc(m_claim));
+                base = __shfl_sync(FULL, base, 0);
+                if ((m_claim >> tid) & 1u) {
+                    i = base + __popc(m_claim & lt_mask);
+                    if (i >= p.n) state = ST_DONE;
+                }
+            }
+            bool take = state == ST_LOAD;
+            bool run = true;
+            if (GATED) {
+                if (tid == 0 && (!others_busy || (++s_poll & 7u) == 0u)) s_arrived = *reinterpret_cast<const volatile uint32_t *>(p.gate);
+                __syncwarp(FULL);
+                take = take && i < s_arrived;
+                const unsigned m_take = __ballot_sync(FULL, take);
+                const unsigned m_wait = __ballot_sync(FULL, state == ST_LOAD);
+                run = m_take != 0u && (__popc(m_take) >= load_batch || !others_busy || m_take == m_wait);
+                if (run) __threadfence();
+                else if (!others_busy) __nanosleep(300);
+            }
+            if (run) {
+                bool loaded_now = false;
+                if (take) {
                     const prtc_transform * tf = p.transforms + i;
                     const prtc_char_physics * ph = p.physics + i;
                     uint32_t cid = ph->collider;
@@ -214,24 +243,24 @@ __global__ void __launch_bounds__(32, 20) k_step_stream(StepParams p) {
                     state = ST_SUBSTEP;
                     loaded_now = true;
                 }
-            }
-            // The frame cache (candidate leaves valid for a region around the character, kept per character slot in
-            // device memory and refreshed by k_xc_refresh right before this kernel) is only read here.
-            if (loaded_now) {
-                cache_ok = false;
-                if (use_cache) {
-                    const size_t s = size_t(p.xc_first) + i;
-                    if (p.xc_version[s] == p.tree_version) {
-                        const uint32_t nc = p.xc_count[s];
-                        NCACHE = nc;
-                        for (uint32_t j = 0; j < nc; ++j) s_cache[j][tid] = p.xc_leaf[size_t(j) * p.xc_stride + s];
+                // The frame cache (candidate leaves valid for a region around the character, kept per character slot in
+                // device memory and refreshed by k_xc_refresh right before this kernel) is only read here.
+                if (loaded_now) {
+                    cache_ok = false;
+                    if (use_cache) {
+                        const size_t s = size_t(p.xc_first) + i;
+                        if (p.xc_version[s] == p.tree_version) {
+                            const uint32_t nc = p.xc_count[s];
+                            NCACHE = nc;
+                            for (uint32_t j = 0; j < nc; ++j) s_cache[j][tid] = p.xc_leaf[size_t(j) * p.xc_stride + s];
 #pragma unroll
-                        for (int f = 0; f < 6; ++f) s_region[f][tid] = p.xc_region[size_t(f) * p.xc_stride + s];
-                        cache_ok = true;
+                            for (int f = 0; f < 6; ++f) s_region[f][tid] = p.xc_region[size_t(f) * p.xc_stride + s];
+                            cache_ok = true;
+                        }
                     }
                 }
+                continue;
             }
-            continue;
         }
 
         // ---------------- SUBSTEP: finish the frame or start the next substep ----------------
@@ -253,6 +282,17 @@ __global__ void __launch_bounds__(32, 20) k_step_stream(StepParams p) {
                     ph->velocity[0] = vel.x; ph->velocity[1] = vel.y; ph->velocity[2] = vel.z;
                     ph->ground_normal[0] = gn.x; ph->ground_normal[1] = gn.y; ph->ground_normal[2] = gn.z;
                     ph->grounded = grounded;
+                    if (GATED) {
+                        __threadfence();
+                        const uint32_t sb = i >> INGEST_SUB_SHIFT;
+                        const uint32_t left = p.n - (sb << INGEST_SUB_SHIFT);
+                        const uint32_t sb_size = left < (1u << INGEST_SUB_SHIFT) ? left : (1u << INGEST_SUB_SHIFT);
+                        if (atomicAdd(p.done_sub + sb, 1u) + 1u == sb_size) {
+                            __threadfence_system();
+                            atomicAdd(p.done_chunk + (sb >> INGEST_CHUNK_SHIFT), 1u);
+                        }
+                        i = 0xFFFFFFFFu;                          // no index claimed
+                    }
                     state = ST_LOAD;
                 } else {
                     --stepsLeft;
@@ -374,9 +414,10 @@ void launch_k_xc_refresh(StepParams const & p, cudaStream_t stream) {
     k_xc_refresh<<<(p.n + 127) / 128, 128, 0, stream>>>(p, p.xc_reuse ? 1 : 0);
 }
 
-void launch_k_step_stream(StepParams const & p, uint32_t blocks, cudaStream_t stream) {
+void launch_k_step_stream(StepParams const & p, uint32_t blocks, bool gated, cudaStream_t stream) {
     cudaMemsetAsync(p.work_counter, 0, sizeof(unsigned), stream);
-    k_step_stream<<<blocks, 32, 0, stream>>>(p);
+    if (gated) k_step_stream<true><<<blocks, 32, 0, stream>>>(p);
+    else k_step_stream<false><<<blocks, 32, 0, stream>>>(p);
 }
 
 } // namespace prt

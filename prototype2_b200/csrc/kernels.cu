@@ -266,11 +266,28 @@ int launch_step(StepParams const & p_in, bool traced, int mode, cudaStream_t str
     } else if (mode == MODE_STATIC && !traced && p.work_counter) {
         // persistent: one warp per block, as many blocks as fit (20 per SM), work handed out by a counter
         const uint32_t want = (p.n + 31) / 32;
-        launch_k_step_stream(p, want < p.persistent_blocks ? want : p.persistent_blocks, stream);
+        launch_k_step_stream(p, want < p.persistent_blocks ? want : p.persistent_blocks, false, stream);
     } else {
         launch_k_step(p, traced, mode, grid, stream);
     }
     return launches;
+}
+
+int launch_step_ingest(StepParams const & p_in, cudaStream_t stream) {
+    if (p_in.n == 0) return 0;
+    StepParams p = p_in;
+    p.lanes_per_warp = 32;
+    if (p.tune & 1u) p.xc_version = nullptr;
+    const uint32_t want = (p.n + 31) / 32;
+    launch_k_step_stream(p, want < p.persistent_blocks ? want : p.persistent_blocks, true, stream);
+    if (!p.xc_version) return 1;
+    // the slots cannot be refreshed ahead of the kernel (the input is not there yet): refresh them behind it from the
+    // state this frame leaves, which is the next frame's input unless the caller edits it -- and then the per-substep
+    // "query box inside region" check of k_step_stream still decides, so a wrong guess costs a tree walk, never a result
+    StepParams r = p;
+    r.gate = nullptr;
+    launch_k_xc_refresh(r, stream);
+    return 2;
 }
 
 void launch_dyn_prep(const prtc_transform * tf, const prtc_char_physics * ph, const CapsuleDev * capsules, uint32_t n, uint32_t first,

@@ -78,12 +78,22 @@ struct StepParams {
     float xc_margin;                // how far beyond the frame's needed region a fresh list reaches
     uint32_t xc_reuse;              // 1: keep slots across frames (PRTC_OPT_CROSS_FRAME_CACHE), 0: rebuild every frame
     uint32_t persistent_blocks;     // k_step_stream: resident blocks to launch
+    // k_step_stream fed by a host->device copy that is still in flight (prtc_step_characters on big host batches):
+    const uint32_t * gate;          // characters [0, *gate) have arrived; advanced by the copy-in stream, polled by LOAD
+    uint32_t * done_sub;            // finished characters per block of 2^INGEST_SUB_SHIFT characters
+    uint32_t * done_chunk;          // finished blocks per chunk of 2^INGEST_CHUNK_SHIFT blocks: what the copy-out stream waits on
     uint32_t lanes_per_warp;        // k_step: characters per warp (set by launch_step; < 32 for small batches)
     TraceBuffers trace;
 };
 
+constexpr uint32_t INGEST_SUB_SHIFT = 10;      // 1024 characters per completion counter (keeps the atomics spread out)
+constexpr uint32_t INGEST_CHUNK_SHIFT = 6;     // 64 of those = 65536 characters per copy chunk (5.5 MB in, 5.5 MB out)
+
 enum StepMode { STEP_STATIC = 0, STEP_LITERAL = 1, STEP_JACOBI = 2 };
 int launch_step(StepParams const & p, bool traced, int mode, cudaStream_t stream);   // returns the number of kernels launched
+// static pass over a batch whose input is still being copied in (gate / done_* set): the persistent kernel alone, then the
+// refresh of the per-slot leaf lists for the NEXT frame from the state it leaves behind; returns the number of launches
+int launch_step_ingest(StepParams const & p, cudaStream_t stream);
 // dynamic pass, CANONICAL / JACOBI: per-character record (4 float4) and the uniform grid over all stored boxes
 void launch_dyn_prep(const prtc_transform * tf, const prtc_char_physics * ph, const CapsuleDev * capsules, uint32_t n, uint32_t first,
                      float4 * records, float dt, float gravity, float margin, bool init, cudaStream_t stream);

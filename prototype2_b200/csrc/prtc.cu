@@ -2,6 +2,7 @@
 // the device, reference-algorithm tree build on the host, flatten, upload) and the per-frame step launches.
 // There is no CPU implementation of the compute path in this library: without a compute-capability-10 device
 // prtc_create fails and nothing else can be called.
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <cub/device/device_scan.cuh>
 
@@ -110,9 +111,12 @@ struct prtc_ctx {
     uint32_t tree_version = 1;
     uint64_t launches = 0;                  // kernels launched by step calls since the last counter reset
     int cross_frame = 1;
+    int streamed_copy = 1;                  // PRTC_OPT_STREAMED_COPY: big host-buffer batches feed one persistent launch while it runs
     int warp_kernel = 1;                    // small batches: one warp per character (k_step_warp); 0 = thinned lock-step kernel
     float xc_margin = 0.5f;
     DevBuf<unsigned> d_work;                // work counters of the persistent kernel, one per concurrently running launch
+    DevBuf<uint32_t> d_ingest;              // streamed host-buffer step: [0] arrival gate, then per-chunk and per-block completion counters
+    cudaEvent_t ingest_reset = nullptr;
     DevBuf<prtc_transform> d_tf;
     DevBuf<prtc_char_physics> d_ph;
     // trace scratch
@@ -300,12 +304,13 @@ int fill_params(prtc_ctx * c, float dt, uint32_t n, prtc_transform * d_tf, prtc_
 }
 
 // characters whose collider id names no registered capsule are skipped by the kernels and counted in slot 6
-int check_bad_colliders(prtc_ctx * c) {
+int check_bad_colliders(prtc_ctx * c, cudaStream_t on = nullptr) {
+    cudaStream_t s = on ? on : c->stream;
     unsigned long long bad = 0;
-    PRTC_CUDA(cudaMemcpyAsync(&bad, c->d_counters.ptr + 6, sizeof(bad), cudaMemcpyDeviceToHost, c->stream));
-    PRTC_CUDA(cudaStreamSynchronize(c->stream));
+    PRTC_CUDA(cudaMemcpyAsync(&bad, c->d_counters.ptr + 6, sizeof(bad), cudaMemcpyDeviceToHost, s));
+    PRTC_CUDA(cudaStreamSynchronize(s));
     if (bad) {
-        PRTC_CUDA(cudaMemsetAsync(c->d_counters.ptr + 6, 0, sizeof(bad), c->stream));
+        PRTC_CUDA(cudaMemsetAsync(c->d_counters.ptr + 6, 0, sizeof(bad), s));
         return fail(PRTC_ERR_INVALID, "prtc_step_characters: " + std::to_string(bad) + " character(s) name a capsule collider that was never added; their results are undefined");
     }
     return PRTC_OK;
@@ -606,6 +611,7 @@ int prtc_create(const prtc_config * cfg, prtc_ctx ** out) {
     if (const char * e = std::getenv("PRTC_PERSISTENT")) ctx->persistent = std::atoi(e);
     if (const char * e = std::getenv("PRTC_CROSS_FRAME")) ctx->cross_frame = std::atoi(e);
     if (const char * e = std::getenv("PRTC_WARP_KERNEL")) ctx->warp_kernel = std::atoi(e);
+    if (const char * e = std::getenv("PRTC_STREAMED_COPY")) ctx->streamed_copy = std::atoi(e);
     if (const char * e = std::getenv("PRTC_XC_MARGIN")) ctx->xc_margin = float(std::atof(e));
     if (const char * e = std::getenv("PRTC_TUNE")) ctx->tune_hi = uint32_t(std::strtoul(e, nullptr, 0)) & 0xFFFFFF00u;
     ctx->sm_count = prop.multiProcessorCount;
@@ -629,7 +635,7 @@ void prtc_destroy(prtc_ctx * c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     c->d_raw.release(); c->d_world.release(); c->d_aabbs.release(); c->d_meshes.release(); c->d_xforms.release();
     c->d_nodes.release(); c->d_tris.release(); c->d_node_leaf_id.release(); c->d_tri_src.release();
-    c->d_capsules.release(); c->d_counters.release(); c->d_work.release();
+    c->d_capsules.release(); c->d_counters.release(); c->d_work.release(); c->d_ingest.release();
     c->d_xc_version.release(); c->d_xc_count.release(); c->d_xc_leaf.release(); c->d_xc_region.release(); c->d_tf.release(); c->d_ph.release();
     c->d_tq.release(); c->d_tmesh.release(); c->d_tcaps.release(); c->d_thits.release();
     c->d_scratch_f.release(); c->d_scratch_u.release();
@@ -638,6 +644,7 @@ void prtc_destroy(prtc_ctx * c) {
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
     for (int k = 0; k < prtc_ctx::PIPE_STREAMS; ++k) if (c->pipe[k]) cudaStreamDestroy(c->pipe[k]);
     if (c->pipe_ready) cudaEventDestroy(c->pipe_ready);
+    if (c->ingest_reset) cudaEventDestroy(c->ingest_reset);
     delete c;
 }
 
@@ -774,6 +781,94 @@ int prtc_step_characters_device(prtc_ctx * c, float dt, uint32_t n, prtc_transfo
     return PRTC_OK;
 }
 
+namespace {
+
+// cuStreamWriteValue32 / cuStreamWaitValue32 through the runtime's driver entry-point query: libprtc.so does not link
+// libcuda, so it still loads (and fails loudly in prtc_create) on a machine without a driver.
+struct StreamMemOps {
+    typedef CUresult (*WriteFn)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
+    typedef CUresult (*WaitFn)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
+    WriteFn write = nullptr;
+    WaitFn wait = nullptr;
+    bool ok = false;
+};
+StreamMemOps const & stream_memops() {
+    static const StreamMemOps ops = [] {
+        StreamMemOps o;
+        void * w = nullptr;
+        void * q = nullptr;
+        cudaDriverEntryPointQueryResult rw, rq;
+        if (cudaGetDriverEntryPoint("cuStreamWriteValue32", &w, cudaEnableDefault, &rw) == cudaSuccess && rw == cudaDriverEntryPointSuccess &&
+            cudaGetDriverEntryPoint("cuStreamWaitValue32", &q, cudaEnableDefault, &rq) == cudaSuccess && rq == cudaDriverEntryPointSuccess) {
+            o.write = reinterpret_cast<StreamMemOps::WriteFn>(w);
+            o.wait = reinterpret_cast<StreamMemOps::WaitFn>(q);
+            o.ok = o.write && o.wait;
+        }
+        (void)cudaGetLastError();
+        return o;
+    }();
+    return ops;
+}
+
+// Host-buffer step of a big static batch as ONE persistent launch fed while it runs:
+//   copy-in stream   chunk k of both record arrays, then `gate = characters arrived` (stream-ordered 32-bit write)
+//   compute stream   k_step_stream<GATED>: LOAD waits for its indices behind the gate, finished characters are counted
+//   copy-out stream  waits (stream-ordered 32-bit wait) until chunk k's counter is full, then copies chunk k back
+// so the first triangle test starts after 5.5 MB instead of 84 MB have crossed PCIe, and the last copy-out is one chunk
+// long.  The pipes already wait for the context's stream (pipe_ready).
+int ingest_step(prtc_ctx * c, float dt, uint32_t n, prtc_transform * tf, prtc_char_physics * ph) {
+    StreamMemOps const & ops = stream_memops();
+    cudaStream_t compute = c->pipe[0], in = c->pipe[1], out = c->pipe[2];
+    const uint32_t chunk = 1u << (INGEST_SUB_SHIFT + INGEST_CHUNK_SHIFT);
+    const uint32_t n_sub = (n + (1u << INGEST_SUB_SHIFT) - 1) >> INGEST_SUB_SHIFT;
+    const uint32_t n_chunks = (n + chunk - 1) / chunk;
+    PRTC_CUDA(c->d_ingest.reserve(size_t(1) + n_chunks + n_sub));
+    StepParams p;
+    int rc = fill_params(c, dt, n, c->d_tf.ptr, c->d_ph.ptr, p);
+    if (rc) return rc;
+    p.gate = c->d_ingest.ptr;
+    p.done_chunk = c->d_ingest.ptr + 1;
+    p.done_sub = c->d_ingest.ptr + 1 + n_chunks;
+    // compute stream first: it also carries the slot refresh of the previous call, which reads the record arrays
+    PRTC_CUDA(cudaMemsetAsync(c->d_ingest.ptr, 0, (size_t(1) + n_chunks + n_sub) * sizeof(uint32_t), compute));
+    PRTC_CUDA(cudaEventRecord(c->ingest_reset, compute));
+    PRTC_CUDA(cudaStreamWaitEvent(in, c->ingest_reset, 0));
+    PRTC_CUDA(cudaStreamWaitEvent(out, c->ingest_reset, 0));
+    // SUBMISSION ORDER MATTERS: everything the kernel waits for (the copies in and their gate writes) is submitted
+    // before the kernel, everything that waits for the kernel (the copies out) after it.  Hardware queues are FIFO, so
+    // even if the driver folds these streams onto one queue the worst case is "no overlap", never a kernel spinning on
+    // a write that is queued behind it.
+    // copy-in pieces: 32 Ki characters first so the kernel starts early, 64 Ki after that.  Measured at C4 (1 M characters):
+    // bigger pieces finish the copy sooner (1.7 vs 2.1 ms) but open the gate in coarser steps and the kernel ends later
+    // (e2e 3.08 ms at 256 Ki, 3.33 at 1 Mi vs 2.96); smaller ones pay per-operation gaps (3.27 ms at 32 Ki throughout)
+    static const uint32_t in_first = [] { const char * e = std::getenv("PRTC_INGEST_IN_FIRST"); return e ? uint32_t(std::atoi(e)) : 32768u; }();
+    static const uint32_t in_max = [] { const char * e = std::getenv("PRTC_INGEST_IN_MAX"); return e ? uint32_t(std::atoi(e)) : 65536u; }();
+    for (uint32_t first = 0, piece = in_first & ~31u; first < n; first += piece, piece = std::min(2 * piece, in_max & ~31u)) {
+        const uint32_t cnt = std::min(piece, n - first);
+        PRTC_CUDA(cudaMemcpyAsync(c->d_tf.ptr + first, tf + first, size_t(cnt) * sizeof(prtc_transform), cudaMemcpyHostToDevice, in));
+        PRTC_CUDA(cudaMemcpyAsync(c->d_ph.ptr + first, ph + first, size_t(cnt) * sizeof(prtc_char_physics), cudaMemcpyHostToDevice, in));
+        if (ops.write(in, CUdeviceptr(reinterpret_cast<uintptr_t>(p.gate)), first + cnt, CU_STREAM_WRITE_VALUE_DEFAULT) != CUDA_SUCCESS)
+            return fail(PRTC_ERR_CUDA, "cuStreamWriteValue32 failed");
+    }
+    c->launches += uint64_t(launch_step_ingest(p, compute));
+    PRTC_CUDA(cudaGetLastError());
+    for (uint32_t k = 0, first = 0; first < n; first += chunk, ++k) {
+        const uint32_t cnt = std::min(chunk, n - first);
+        const uint32_t blocks = (cnt + (1u << INGEST_SUB_SHIFT) - 1) >> INGEST_SUB_SHIFT;
+        if (ops.wait(out, CUdeviceptr(reinterpret_cast<uintptr_t>(p.done_chunk + k)), blocks, CU_STREAM_WAIT_VALUE_GEQ) != CUDA_SUCCESS)
+            return fail(PRTC_ERR_CUDA, "cuStreamWaitValue32 failed");
+        PRTC_CUDA(cudaMemcpyAsync(tf + first, c->d_tf.ptr + first, size_t(cnt) * sizeof(prtc_transform), cudaMemcpyDeviceToHost, out));
+        PRTC_CUDA(cudaMemcpyAsync(ph + first, c->d_ph.ptr + first, size_t(cnt) * sizeof(prtc_char_physics), cudaMemcpyDeviceToHost, out));
+    }
+    // the compute stream may still be refreshing slots for the next frame: later work on the context's stream follows
+    // it, this call only waits for the last copy-out (every character was counted after its bad-collider report)
+    PRTC_CUDA(cudaEventRecord(c->ingest_reset, compute));
+    PRTC_CUDA(cudaStreamWaitEvent(c->stream, c->ingest_reset, 0));
+    return check_bad_colliders(c, out);
+}
+
+} // namespace
+
 int prtc_step_characters(prtc_ctx * c, float dt, uint32_t n, prtc_transform * tf, prtc_char_physics * ph) {
     if (!c || (n && (!tf || !ph))) return fail(PRTC_ERR_INVALID, "prtc_step_characters: null argument");
     int rc = check_mode(c, false);
@@ -792,11 +887,13 @@ int prtc_step_characters(prtc_ctx * c, float dt, uint32_t n, prtc_transform * tf
         if (c->geometry_dirty || c->tree_dirty || c->capsules_dirty) { rc = commit_impl(c); if (rc) return rc; }
         if (!c->pipe_ready) {
             PRTC_CUDA(cudaEventCreateWithFlags(&c->pipe_ready, cudaEventDisableTiming));
+            PRTC_CUDA(cudaEventCreateWithFlags(&c->ingest_reset, cudaEventDisableTiming));
             for (int k = 0; k < prtc_ctx::PIPE_STREAMS; ++k) PRTC_CUDA(cudaStreamCreateWithFlags(&c->pipe[k], cudaStreamNonBlocking));
         }
+        { StepParams whole; rc = fill_params(c, dt, n, c->d_tf.ptr, c->d_ph.ptr, whole); if (rc) return rc; }   // sizes the per-slot caches for n
         PRTC_CUDA(cudaEventRecord(c->pipe_ready, c->stream));          // whatever the context's stream still has queued
         for (int k = 0; k < prtc_ctx::PIPE_STREAMS; ++k) PRTC_CUDA(cudaStreamWaitEvent(c->pipe[k], c->pipe_ready, 0));
-        { StepParams whole; rc = fill_params(c, dt, n, c->d_tf.ptr, c->d_ph.ptr, whole); if (rc) return rc; }   // sizes the per-slot caches for n
+        if (c->persistent && c->streamed_copy && stream_memops().ok) return ingest_step(c, dt, n, tf, ph);
         uint32_t k = 0;
         for (uint32_t first = 0; first < n; first += kChunk, ++k) {
             const uint32_t cnt = std::min(kChunk, n - first);
@@ -954,6 +1051,7 @@ int prtc_set_option(prtc_ctx * c, int option, int value) {
         case PRTC_OPT_PERSISTENT: c->persistent = value != 0; return PRTC_OK;
         case PRTC_OPT_CROSS_FRAME_CACHE: c->cross_frame = value != 0; return PRTC_OK;
         case PRTC_OPT_WARP_KERNEL: c->warp_kernel = value != 0; return PRTC_OK;
+        case PRTC_OPT_STREAMED_COPY: c->streamed_copy = value != 0; return PRTC_OK;
         default: return fail(PRTC_ERR_INVALID, "prtc_set_option: unknown option");
     }
 }

@@ -76,7 +76,7 @@ constexpr int LEAF_CAP = 8;      // candidate leaves buffered per lane and pass 
 void launch_k_step(StepParams const & p, bool traced, int mode, uint32_t grid, cudaStream_t stream);
 void launch_k_step_warp(StepParams const & p, int mode, cudaStream_t stream);
 void launch_k_xc_refresh(StepParams const & p, cudaStream_t stream);
-void launch_k_step_stream(StepParams const & p, uint32_t blocks, cudaStream_t stream);
+void launch_k_step_stream(StepParams const & p, uint32_t blocks, bool gated, cudaStream_t stream);
 
 } // namespace prt
 #endif

@@ -457,23 +457,39 @@ def test_jacobi_two_ranks_emulated_on_one_gpu_equal_one_rank():
     assert one.counters()["cc_tests"] > 0
 
 
-def test_chunked_host_step_equals_device_step():
-    """big host batches are cut into chunks pipelined over several streams: same bits as one device-resident launch"""
+@pytest.mark.parametrize("pinned,streamed", [(False, 1), (True, 1), (True, 0)])
+def test_streamed_host_step_equals_device_step(pinned, streamed):
+    """big host batches run as one persistent launch fed by the copy-in stream while it runs, results leaving chunk by
+    chunk: same bits as one device-resident launch -- from pageable and pinned buffers, with an odd tail chunk, and when
+    the caller edits the state between frames (the per-slot leaf lists were refreshed for a frame that did not come).
+    streamed=0 is the older arrangement (chunks copied in, stepped and copied out on three streams)."""
     import torch
     from prototype2_b200 import capi
-    n = 300000
+    n = 300000 + 37
     scene = H.make_scene(200, 2, 2, n, seed=71)
     ctx, tf, ph = H.build_gpu(scene)
-    tf2, ph2 = tf.copy(), ph.copy()
-    d_tf = torch.from_numpy(tf2.view(np.uint8).reshape(-1)).cuda()
-    d_ph = torch.from_numpy(ph2.view(np.uint8).reshape(-1)).cuda()
-    for f in range(3):
-        ctx.update_characters(DT, tf, ph)                         # host buffers: chunked pipeline
+    ctx.set_option(capi.OPT_STREAMED_COPY, streamed)
+    if pinned:
+        t_tf = torch.from_numpy(tf.view(np.uint8).reshape(-1).copy()).pin_memory()
+        t_ph = torch.from_numpy(ph.view(np.uint8).reshape(-1).copy()).pin_memory()
+        tf, ph = t_tf.numpy().view(capi.TRANSFORM_DTYPE), t_ph.numpy().view(capi.PHYSICS_DTYPE)
+    d_tf = torch.from_numpy(tf.view(np.uint8).reshape(-1).copy()).cuda()
+    d_ph = torch.from_numpy(ph.view(np.uint8).reshape(-1).copy()).cuda()
+    rs = np.random.RandomState(5)
+    for f in range(6):
+        if f == 3:                                                # a third of the crowd is told to run / teleported
+            who = rs.rand(n) < 0.33
+            ph["movement"][who, 0] = np.float32(0.2)
+            tf["position"][who, 0] += rs.uniform(-3, 3, int(who.sum())).astype(np.float32)
+            d_tf.copy_(torch.from_numpy(tf.view(np.uint8).reshape(-1)))
+            d_ph.copy_(torch.from_numpy(ph.view(np.uint8).reshape(-1)))
+        ctx.update_characters(DT, tf, ph)                         # host buffers: streamed
         ctx.update_characters_device(DT, n, d_tf.data_ptr(), d_ph.data_ptr())
         ctx.synchronize()
         got_tf = d_tf.cpu().numpy().view(capi.TRANSFORM_DTYPE)
         got_ph = d_ph.cpu().numpy().view(capi.PHYSICS_DTYPE)
         assert H.state_diff(H.gpu_state(tf, ph), H.gpu_state(got_tf, got_ph)) == [], "frame %d" % f
+        assert np.array_equal(tf["rotation"], got_tf["rotation"]) and np.array_equal(ph["collider"], got_ph["collider"])
 
 
 # ------------------------------------------------------------------------------------------------------------
