@@ -164,6 +164,23 @@ int l0_add_capsule(void * h, float height, float radius, const float * off3) {
     return int(tag.index);
 }
 
+// PhysicsSystem::updateModelColliders for one model collider (physics_system.cpp:161-202)
+void l0_update_model(void * h, uint32_t model_index, const float * tform10) {
+    World * w = static_cast<World *>(h);
+    Transform t;
+    t.position = glm::vec3(tform10[0], tform10[1], tform10[2]);
+    t.rotation = glm::quat(tform10[3], tform10[4], tform10[5], tform10[6]);
+    t.scale = glm::vec3(tform10[7], tform10[8], tform10[9]);
+    ColliderTag tag = { uint16_t(model_index), ColliderShape::COLLIDER_SHAPE_MODEL, ColliderType::COLLIDER_TYPE_COLLIDE };
+    w->ps.updateModelColliders(&tag, &t, 1);
+}
+// PhysicsSystem::updateCapsuleCollider (physics_system.cpp:151-159)
+void l0_update_capsule(void * h, uint32_t capsule_index, float height, float radius, const float * off3) {
+    World * w = static_cast<World *>(h);
+    ColliderTag tag = { uint16_t(capsule_index), ColliderShape::COLLIDER_SHAPE_CAPSULE, ColliderType::COLLIDER_TYPE_COLLIDE };
+    w->ps.updateCapsuleCollider(tag, height, radius, glm::vec3(off3[0], off3[1], off3[2]));
+}
+
 uint32_t l0_num_characters(void * h) { return uint32_t(static_cast<World *>(h)->transforms.size()); }
 
 void l0_set_state(void * h, const float * pos3, const float * quat4_wxyz, const float * vel3,

@@ -51,6 +51,7 @@ __global__ void __launch_bounds__(32) k_step_warp(StepParams p) {
     uint32_t cid = ph->collider;
     if (cid >= p.n_capsules) {
         if (lane == 0 && p.counters) atomicAdd(p.counters + 6, 1ull);
+        if (lane == 0 && p.host_flags) p.host_flags[1] = 1u;
         cid = 0;
     }
     const CapsuleDev cap = p.capsules[cid];
@@ -293,6 +294,7 @@ __global__ void __launch_bounds__(32) k_step_warp(StepParams p) {
             atomicAdd(p.counters + 3, (unsigned long long)c_contact);
             if (LITERAL) atomicAdd(p.counters + 4, (unsigned long long)c_cc);
         }
+        if (LITERAL && p.host_flags && c_cc) p.host_flags[0] = 1u;
     }
 }
 

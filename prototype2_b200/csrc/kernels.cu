@@ -273,6 +273,14 @@ int launch_step(StepParams const & p_in, bool traced, int mode, cudaStream_t str
     return launches;
 }
 
+__global__ void k_fold_counters(unsigned long long * main_counters, unsigned long long * scratch) {
+    const unsigned k = threadIdx.x;
+    if (k < 6) { if (scratch[k]) atomicAdd(main_counters + k, scratch[k]); scratch[k] = 0ull; }
+}
+void launch_fold_counters(unsigned long long * main_counters, unsigned long long * scratch, cudaStream_t stream) {
+    k_fold_counters<<<1, 32, 0, stream>>>(main_counters, scratch);
+}
+
 int launch_step_ingest(StepParams const & p_in, cudaStream_t stream) {
     if (p_in.n == 0) return 0;
     StepParams p = p_in;

@@ -67,6 +67,8 @@ struct StepParams {
     uint32_t qr_enable;
     uint32_t tune;                  // bit 0: frame cache OFF (walk the tree every substep, reference-equivalent counters)
     unsigned long long * counters;  // prtc_counters layout
+    uint32_t * host_flags;          // k_step_warp, small host-buffer batches: host-mapped words the kernel raises --
+                                    // [0] a capsule-capsule test ran (LITERAL), [1] a character named an unknown capsule
     unsigned * work_counter;        // k_step_stream: next character to hand out (null => lock-step kernel)
     // k_step_stream: cross-frame leaf cache, one slot per character index (SoA, stride xc_stride); null => off
     uint32_t * xc_version;          // tree version the slot was built for (0 = empty)
@@ -99,6 +101,9 @@ void launch_dyn_prep(const prtc_transform * tf, const prtc_char_physics * ph, co
                      float4 * records, float dt, float gravity, float margin, bool init, cudaStream_t stream);
 void launch_dyn_grid(const float4 * records, uint32_t n, float ox, float oz, float inv_cell, uint32_t gx, uint32_t gz,
                      uint32_t * cell_count, const uint32_t * cell_start, uint32_t * items, bool fill, cudaStream_t stream);
+
+// main[k] += scratch[k], scratch[k] = 0 for the device-side work counters (per-frame scratch of the LITERAL fixpoint rounds)
+void launch_fold_counters(unsigned long long * main_counters, unsigned long long * scratch, cudaStream_t stream);
 
 // K8: world-space vertex cache + per-mesh AABB (physics_system.cpp:68-93 / :161-202)
 struct MeshDev { uint32_t first_vertex, n_vertices, model; uint32_t pad; };

@@ -53,6 +53,29 @@ struct DevBuf {
     void release() { if (ptr) cudaFree(ptr); ptr = nullptr; cap = 0; }
 };
 
+// Pinned host memory the device reads and writes in place (unified addressing: one pointer for both sides).  Engine-sized
+// host-buffer steps stage their records here instead of paying two uploads, two downloads and a counter read-back.
+struct HostStage {
+    unsigned char * base = nullptr;
+    size_t bytes = 0;
+    cudaError_t reserve(size_t need) {
+        if (need <= bytes) return cudaSuccess;
+        if (base) cudaFreeHost(base);
+        base = nullptr; bytes = 0;
+        const size_t want = std::max<size_t>(need, size_t(64) << 10);
+        cudaError_t e = cudaHostAlloc(reinterpret_cast<void **>(&base), want, cudaHostAllocMapped);
+        if (e == cudaSuccess) bytes = want;
+        return e;
+    }
+    void release() { if (base) cudaFreeHost(base); base = nullptr; bytes = 0; }
+};
+// carves 64-byte aligned arrays out of a HostStage
+struct StageCursor {
+    unsigned char * p;
+    template <typename T> T * take(size_t n) { T * r = reinterpret_cast<T *>(p); p += (n * sizeof(T) + 63) & ~size_t(63); return r; }
+};
+constexpr uint32_t kSmallBatch = 256;       // the engine's entity table holds 100 (entity.h:15)
+
 struct MeshHost { uint32_t first_vertex, n_vertices, model; int32_t tree_index; };
 struct ModelHost { uint32_t first_mesh, n_meshes; prtc_transform transform; };
 
@@ -115,6 +138,8 @@ struct prtc_ctx {
     int warp_kernel = 1;                    // small batches: one warp per character (k_step_warp); 0 = thinned lock-step kernel
     float xc_margin = 0.5f;
     DevBuf<unsigned> d_work;                // work counters of the persistent kernel, one per concurrently running launch
+    HostStage stage;                        // small host-buffer batches: records staged in mapped pinned memory
+    int staged = 1;                         // PRTC_STAGED=0: small batches take the copy path too (A/B)
     DevBuf<uint32_t> d_ingest;              // streamed host-buffer step: [0] arrival gate, then per-chunk and per-block completion counters
     cudaEvent_t ingest_reset = nullptr;
     DevBuf<prtc_transform> d_tf;
@@ -199,7 +224,9 @@ int commit_impl(prtc_ctx * c) {
             return b;
         };
         // moved models first (they were registered earlier): DynamicAABBTree::update per model, physics_system.cpp:199-200
+        // (LITERAL order has done this in prtc_update_models already, where the reference does it)
         for (uint32_t model : c->moved_models) {
+            if (c->literal()) break;
             ModelHost const & mh = c->models[model];
             for (uint32_t m = mh.first_mesh; m < mh.first_mesh + mh.n_meshes && m < c->meshes_in_tree; ++m) {
                 Box b = box_of(m);
@@ -452,6 +479,74 @@ int dyn_build_grid(prtc_ctx * c, StepParams & p) {
 // One frame in LITERAL order (host buffers).  Everything the reference does to its unified tree per frame is
 // replayed on the host with the same algorithm; the device runs the collide phase; the reference's sequential
 // visibility between characters (T18) is reached as the fixpoint of repeated whole-batch launches.
+// literal_step for an engine-sized batch (no trace): the records live in mapped pinned memory for the duration of the
+// call, the warp-per-character kernel reads and writes them there, and "did any capsule-capsule test run" comes back as
+// a flag in the same memory -- one launch (+ the counter fold) and one synchronisation per fixpoint round instead of
+// six copies and three synchronisations.  Device counters of a round go to a scratch block so that only the last round
+// is added to the context's counters.
+int literal_step_staged(prtc_ctx * c, float dt, uint32_t n, prtc_transform * tf, prtc_char_physics * ph,
+                        std::vector<float4> const & seg_start, std::vector<uint32_t> const & cap2char) {
+    cudaStream_t s = c->stream;
+    const size_t bytes = 64 + 64 * 8 + size_t(n) * (sizeof(prtc_transform) + sizeof(prtc_char_physics) + 4 * sizeof(float4) + 6 * sizeof(float)) +
+                         cap2char.size() * sizeof(uint32_t);
+    PRTC_CUDA(c->stage.reserve(bytes));
+    StageCursor cur{c->stage.base};
+    uint32_t * flags = cur.take<uint32_t>(16);
+    prtc_transform * s_tf = cur.take<prtc_transform>(n);
+    prtc_char_physics * s_ph = cur.take<prtc_char_physics>(n);
+    float4 * s_seg_start = cur.take<float4>(2 * size_t(n));
+    float4 * s_seg_prev = cur.take<float4>(2 * size_t(n));
+    float * s_last_box = cur.take<float>(6 * size_t(n));
+    uint32_t * s_cap2char = cur.take<uint32_t>(cap2char.size());
+    std::memcpy(s_seg_start, seg_start.data(), seg_start.size() * sizeof(float4));
+    std::memcpy(s_seg_prev, seg_start.data(), seg_start.size() * sizeof(float4));
+    std::memcpy(s_cap2char, cap2char.data(), cap2char.size() * sizeof(uint32_t));
+    unsigned long long * scratch = c->d_counters.ptr + 8;
+
+    std::vector<prtc_transform> prev_tf;
+    const uint32_t max_rounds = n + 2;
+    for (uint32_t round = 0; round < max_rounds; ++round) {
+        std::memcpy(s_tf, tf, size_t(n) * sizeof(prtc_transform));
+        std::memcpy(s_ph, ph, size_t(n) * sizeof(prtc_char_physics));
+        flags[0] = 0u; flags[1] = 0u;
+        if (round > 0) PRTC_CUDA(cudaMemsetAsync(scratch, 0, 6 * sizeof(unsigned long long), s));       // only the last round counts
+        StepParams p;
+        fill_params(c, dt, n, s_tf, s_ph, p);
+        p.cap2char = s_cap2char; p.seg_start = s_seg_start; p.seg_prev = s_seg_prev; p.last_box = s_last_box;
+        p.counters = scratch;
+        p.host_flags = flags;
+        c->launches += uint64_t(launch_step(p, false, STEP_LITERAL, s));
+        PRTC_CUDA(cudaGetLastError());
+        PRTC_CUDA(cudaStreamSynchronize(s));
+        const bool any_capsule_test = flags[0] != 0u;
+        const bool settled = !prev_tf.empty() && std::memcmp(prev_tf.data(), s_tf, size_t(n) * sizeof(prtc_transform)) == 0;
+        if (!any_capsule_test || settled) break;
+        // next round: characters j < i are seen where this round left them
+        for (uint32_t i = 0; i < n; ++i) {
+            CapsuleDev const & cap = c->capsules[ph[i].collider];
+            Quat q; q.x = tf[i].rotation[0]; q.y = tf[i].rotation[1]; q.z = tf[i].rotation[2]; q.w = tf[i].rotation[3];
+            V3 A, B;
+            segment_ends(capsule_frame(cap, rotation_of(q)), v3(s_tf[i].position[0], s_tf[i].position[1], s_tf[i].position[2]), A, B);
+            s_seg_prev[2 * size_t(i)] = make_float4(A.x, A.y, A.z, cap.radius);
+            s_seg_prev[2 * size_t(i) + 1] = make_float4(B.x, B.y, B.z, 0.0f);
+        }
+        prev_tf.assign(s_tf, s_tf + n);
+    }
+    launch_fold_counters(c->d_counters.ptr, scratch, s);           // asynchronous: nobody waits for it here
+    c->launches += 1;
+    PRTC_CUDA(cudaGetLastError());
+    // m_aabbData.capsuleAABBs[tag.index] is left at the last executed substep's query box (physics_system.cpp:355-356)
+    for (uint32_t i = 0; i < n; ++i) {
+        Box b;
+        b.lo = v3(s_last_box[6 * size_t(i)], s_last_box[6 * size_t(i) + 1], s_last_box[6 * size_t(i) + 2]);
+        b.hi = v3(s_last_box[6 * size_t(i) + 3], s_last_box[6 * size_t(i) + 4], s_last_box[6 * size_t(i) + 5]);
+        c->capsule_aabbs[ph[i].collider] = b;
+    }
+    std::memcpy(tf, s_tf, size_t(n) * sizeof(prtc_transform));
+    std::memcpy(ph, s_ph, size_t(n) * sizeof(prtc_char_physics));
+    return PRTC_OK;
+}
+
 int literal_step(prtc_ctx * c, float dt, uint32_t n, prtc_transform * tf, prtc_char_physics * ph, prtc_trace * tr) {
     cudaStream_t s = c->stream;
     for (uint32_t i = 0; i < n; ++i)
@@ -487,6 +582,9 @@ int literal_step(prtc_ctx * c, float dt, uint32_t n, prtc_transform * tf, prtc_c
         c->tree_dirty = true;                                                   // some leaf left its fat box: the tree changed shape
     int rc = commit_impl(c);                                                    // re-flatten + upload (+ triangles in the new leaf order) if needed
     if (rc) return rc;
+
+    if (!tr && n > 0 && n <= kSmallBatch && cap2char.size() <= 16 * kSmallBatch && c->warp_kernel && c->staged)
+        return literal_step_staged(c, dt, n, tf, ph, seg_start, cap2char);
 
     PRTC_CUDA(c->d_tf.reserve(n));
     PRTC_CUDA(c->d_ph.reserve(n));
@@ -612,6 +710,7 @@ int prtc_create(const prtc_config * cfg, prtc_ctx ** out) {
     if (const char * e = std::getenv("PRTC_CROSS_FRAME")) ctx->cross_frame = std::atoi(e);
     if (const char * e = std::getenv("PRTC_WARP_KERNEL")) ctx->warp_kernel = std::atoi(e);
     if (const char * e = std::getenv("PRTC_STREAMED_COPY")) ctx->streamed_copy = std::atoi(e);
+    if (const char * e = std::getenv("PRTC_STAGED")) ctx->staged = std::atoi(e);
     if (const char * e = std::getenv("PRTC_XC_MARGIN")) ctx->xc_margin = float(std::atof(e));
     if (const char * e = std::getenv("PRTC_TUNE")) ctx->tune_hi = uint32_t(std::strtoul(e, nullptr, 0)) & 0xFFFFFF00u;
     ctx->sm_count = prop.multiProcessorCount;
@@ -621,7 +720,7 @@ int prtc_create(const prtc_config * cfg, prtc_ctx ** out) {
         return fail(PRTC_ERR_CUDA, "prtc_create: cudaStreamCreate failed");
     }
     ctx->own_stream = true;
-    if (ctx->d_work.reserve(16) != cudaSuccess || ctx->d_counters.reserve(8) != cudaSuccess || cudaMemsetAsync(ctx->d_counters.ptr, 0, 8 * sizeof(unsigned long long), ctx->stream) != cudaSuccess) {
+    if (ctx->d_work.reserve(16) != cudaSuccess || ctx->d_counters.reserve(16) != cudaSuccess || cudaMemsetAsync(ctx->d_counters.ptr, 0, 16 * sizeof(unsigned long long), ctx->stream) != cudaSuccess) {
         prtc_destroy(ctx);
         return fail(PRTC_ERR_CUDA, "prtc_create: counter allocation failed");
     }
@@ -635,7 +734,7 @@ void prtc_destroy(prtc_ctx * c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     c->d_raw.release(); c->d_world.release(); c->d_aabbs.release(); c->d_meshes.release(); c->d_xforms.release();
     c->d_nodes.release(); c->d_tris.release(); c->d_node_leaf_id.release(); c->d_tri_src.release();
-    c->d_capsules.release(); c->d_counters.release(); c->d_work.release(); c->d_ingest.release();
+    c->d_capsules.release(); c->d_counters.release(); c->d_work.release(); c->d_ingest.release(); c->stage.release();
     c->d_xc_version.release(); c->d_xc_count.release(); c->d_xc_leaf.release(); c->d_xc_region.release(); c->d_tf.release(); c->d_ph.release();
     c->d_tq.release(); c->d_tmesh.release(); c->d_tcaps.release(); c->d_thits.release();
     c->d_scratch_f.release(); c->d_scratch_u.release();
@@ -647,6 +746,21 @@ void prtc_destroy(prtc_ctx * c) {
     if (c->ingest_reset) cudaEventDestroy(c->ingest_reset);
     delete c;
 }
+
+namespace {
+// world-space AABB of one registered mesh under `xf`, with the arithmetic of k_transform_refit (physics_system.cpp:80-91)
+Box host_mesh_box(prtc_ctx const * c, MeshHost const & me, Affine const & xf) {
+    V3 mn = v3(3.402823466e+38f), mx = v3(-3.402823466e+38f);
+    for (uint32_t k = 0; k < me.n_vertices; ++k) {
+        const float * r = &c->raw[3 * size_t(me.first_vertex + k)];
+        V3 w = affine_point(xf, v3(r[0], r[1], r[2]));
+        mn = gmin(mn, w);
+        mx = gmax(mx, w);
+    }
+    Box b; b.lo = mn; b.hi = mx;
+    return b;
+}
+} // namespace
 
 int prtc_add_model(prtc_ctx * c, const float * xyz, uint32_t n_vertices, const uint32_t * mesh_first,
                    const uint32_t * mesh_count, uint32_t n_meshes, const prtc_transform * transform,
@@ -677,19 +791,11 @@ int prtc_add_model(prtc_ctx * c, const float * xyz, uint32_t n_vertices, const u
     if (c->literal()) {
         // the reference inserts the mesh leaves right here (physics_system.cpp:102), interleaved with capsule leaves
         // in call order, and the tree's shape depends on that order: derive the AABBs on the host with the same
-        // arithmetic as k_transform_refit (physics_system.cpp:80-91) instead of waiting for the commit
+        // arithmetic as k_transform_refit instead of waiting for the commit
         const Affine xf = affine_from(mh.transform);
         for (uint32_t m = mh.first_mesh; m < mh.first_mesh + n_meshes; ++m) {
             MeshHost & me = c->meshes[m];
-            V3 mn = v3(3.402823466e+38f), mx = v3(-3.402823466e+38f);
-            for (uint32_t k = 0; k < me.n_vertices; ++k) {
-                const float * r = &c->raw[3 * size_t(me.first_vertex + k)];
-                V3 w = affine_point(xf, v3(r[0], r[1], r[2]));
-                mn = gmin(mn, w);
-                mx = gmax(mx, w);
-            }
-            Box b; b.lo = mn; b.hi = mx;
-            me.tree_index = c->tree.insert_leaf(m, LEAF_MESH, b);
+            me.tree_index = c->tree.insert_leaf(m, LEAF_MESH, host_mesh_box(c, me, xf));
         }
         c->meshes_in_tree = uint32_t(c->meshes.size());
         c->tree_dirty = true;
@@ -740,6 +846,16 @@ int prtc_update_models(prtc_ctx * c, const uint32_t * model_ids, const prtc_tran
         if (model_ids[i] >= c->models.size()) return fail(PRTC_ERR_INVALID, "prtc_update_models: bad model id");
         c->models[model_ids[i]].transform = transforms[i];
         c->moved_models.push_back(model_ids[i]);
+        if (c->literal()) {
+            // the reference updates the model's leaves right here (physics_system.cpp:199-200), i.e. BEFORE the capsule
+            // leaves of the next updateCharacters move -- and the tree's shape depends on that order
+            ModelHost const & mh = c->models[model_ids[i]];
+            const Affine xf = affine_from(mh.transform);
+            for (uint32_t m = mh.first_mesh; m < mh.first_mesh + mh.n_meshes && m < c->meshes_in_tree; ++m) {
+                Box b = host_mesh_box(c, c->meshes[m], xf);
+                if (c->tree.update(&c->meshes[m].tree_index, &b, 1) != 0) c->tree_dirty = true;
+            }
+        }
     }
     if (n) c->geometry_dirty = true;
     return PRTC_OK;
@@ -913,6 +1029,28 @@ int prtc_step_characters(prtc_ctx * c, float dt, uint32_t n, prtc_transform * tf
         for (int q = 0; q < prtc_ctx::PIPE_STREAMS; ++q) PRTC_CUDA(cudaStreamSynchronize(c->pipe[q]));
         return check_bad_colliders(c);
     }
+    if (n > 0 && n <= kSmallBatch && !c->jacobi() && c->warp_kernel && c->staged) {
+        // engine-sized static batch: stage the records in mapped pinned memory, one launch, one synchronisation
+        if (c->geometry_dirty || c->tree_dirty || c->capsules_dirty) { rc = commit_impl(c); if (rc) return rc; }
+        PRTC_CUDA(c->stage.reserve(128 + size_t(n) * (sizeof(prtc_transform) + sizeof(prtc_char_physics)) + 128));
+        StageCursor cur{c->stage.base};
+        uint32_t * flags = cur.take<uint32_t>(16);
+        prtc_transform * s_tf = cur.take<prtc_transform>(n);
+        prtc_char_physics * s_ph = cur.take<prtc_char_physics>(n);
+        std::memcpy(s_tf, tf, size_t(n) * sizeof(prtc_transform));
+        std::memcpy(s_ph, ph, size_t(n) * sizeof(prtc_char_physics));
+        flags[0] = 0u; flags[1] = 0u;
+        StepParams p;
+        rc = fill_params(c, dt, n, s_tf, s_ph, p);
+        if (rc) return rc;
+        p.host_flags = flags;
+        c->launches += uint64_t(launch_step(p, false, STEP_STATIC, c->stream));
+        PRTC_CUDA(cudaGetLastError());
+        PRTC_CUDA(cudaStreamSynchronize(c->stream));
+        std::memcpy(tf, s_tf, size_t(n) * sizeof(prtc_transform));
+        std::memcpy(ph, s_ph, size_t(n) * sizeof(prtc_char_physics));
+        return flags[1] ? check_bad_colliders(c) : PRTC_OK;
+    }
     if (n) {
         PRTC_CUDA(cudaMemcpyAsync(c->d_tf.ptr, tf, size_t(n) * sizeof(prtc_transform), cudaMemcpyHostToDevice, c->stream));
         PRTC_CUDA(cudaMemcpyAsync(c->d_ph.ptr, ph, size_t(n) * sizeof(prtc_char_physics), cudaMemcpyHostToDevice, c->stream));
@@ -968,6 +1106,26 @@ int prtc_raycast(prtc_ctx * c, uint32_t n, const float * origins, const float * 
     if (c->geometry_dirty || c->tree_dirty || c->capsules_dirty) { int rc = commit_impl(c); if (rc) return rc; }
     if (n == 0) return PRTC_OK;
     cudaStream_t s = c->stream;
+    if (n <= kSmallBatch && c->staged) {
+        // the engine casts four rays per frame, one call each (scene.cpp:248-255): rays and answers live in mapped pinned
+        // memory, the call is one launch and one synchronisation instead of four uploads, a launch and two downloads
+        PRTC_CUDA(c->stage.reserve(size_t(n) * 11 * sizeof(float) + 6 * 64));
+        StageCursor cur{c->stage.base};
+        float * s_o = cur.take<float>(3 * size_t(n)), * s_d = cur.take<float>(3 * size_t(n)), * s_m = cur.take<float>(n);
+        float * s_h = cur.take<float>(3 * size_t(n));
+        unsigned char * s_mask = cur.take<unsigned char>(n);
+        std::memcpy(s_o, origins, size_t(n) * 3 * sizeof(float));
+        std::memcpy(s_d, directions, size_t(n) * 3 * sizeof(float));
+        std::memcpy(s_m, max_distances, size_t(n) * sizeof(float));
+        std::memset(s_h, 0, size_t(n) * 3 * sizeof(float));
+        launch_raycast(c->d_nodes.ptr, uint32_t(c->flat.nodes.size()), c->d_tris.ptr, n, s_o, s_d, s_m, s_h, s_mask, s);
+        PRTC_CUDA(cudaGetLastError());
+        PRTC_CUDA(cudaStreamSynchronize(s));
+        std::memcpy(hit_mask, s_mask, n);
+        for (uint32_t i = 0; i < n; ++i)
+            if (hit_mask[i]) { hit_xyz[3 * i] = s_h[3 * size_t(i)]; hit_xyz[3 * i + 1] = s_h[3 * size_t(i) + 1]; hit_xyz[3 * i + 2] = s_h[3 * size_t(i) + 2]; }
+        return PRTC_OK;
+    }
     PRTC_CUDA(c->d_scratch_f.reserve(size_t(n) * 10));
     PRTC_CUDA(c->d_scratch_u.reserve((size_t(n) + 3) / 4 + 1));
     float * d_o = c->d_scratch_f.ptr, * d_d = d_o + 3 * size_t(n), * d_m = d_d + 3 * size_t(n), * d_h = d_m + n;

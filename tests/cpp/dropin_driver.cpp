@@ -8,6 +8,8 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
+#include <algorithm>
+#include <chrono>
 #include <cstring>
 #include <vector>
 
@@ -76,7 +78,18 @@ int main(int argc, char ** argv) {
     }
     if (nChars >= 2) transforms[1].position = transforms[0].position + glm::vec3(0.3f, 0.0f, 0.1f);   // a touching pair
 
+    if (char const * initPath = std::getenv("PRT_DRIVER_DUMP_INIT")) {      // lets a Python harness rebuild exactly this scene
+        std::vector<uint8_t> init;
+        for (int i = 0; i < nChars; ++i) {
+            put(init, &transforms[size_t(i)].position, sizeof(glm::vec3));
+            put(init, &transforms[size_t(i)].rotation, sizeof(glm::quat));            // x, y, z, w
+            put(init, &scene.getCharacterSystem().getCharacter(size_t(i)).physics.velocity, sizeof(glm::vec3));
+        }
+        if (FILE * fi = std::fopen(initPath, "wb")) { std::fwrite(init.data(), 1, init.size(), fi); std::fclose(fi); }
+    }
     std::vector<uint8_t> dump;
+    std::vector<double> stepTimes, rayTimes;             // native cost of the two per-frame entry points, microseconds
+    typedef std::chrono::steady_clock Clock;
     for (int f = 0; f < frames; ++f) {
         for (int i = 0; i < nChars; ++i) {               // gameplay input, like CharacterSystem::updateCharacters
             CharacterPhysics & p = scene.getCharacterSystem().getCharacter(size_t(i)).physics;
@@ -89,7 +102,9 @@ int main(int argc, char ** argv) {
         }
         if (f == 25 && nChars > 2)                       // the editor edits a capsule (editor_gui.cpp:293-301)
             physics.updateCapsuleCollider(scene.getCharacterSystem().getCharacter(2).physics.colliderTag, 0.8f, 0.4f, glm::vec3(0.0f, 0.4f, 0.0f));
+        Clock::time_point const t0 = Clock::now();
         physics.updateCharacters(1.0f / 30.0f, scene, transforms.data());
+        stepTimes.push_back(std::chrono::duration<double, std::micro>(Clock::now() - t0).count());
         for (int i = 0; i < nChars; ++i) {
             CharacterPhysics const & p = scene.getCharacterSystem().getCharacter(size_t(i)).physics;
             put(dump, &transforms[size_t(i)].position, sizeof(glm::vec3));
@@ -99,6 +114,7 @@ int main(int argc, char ** argv) {
             put(dump, &g, 1);
         }
         // camera occlusion rays (scene.cpp:248-255)
+        Clock::time_point const t1 = Clock::now();
         for (int k = 0; k < 4; ++k) {
             glm::vec3 origin = transforms[0].position + glm::vec3(0.0f, 1.0f, 0.0f);
             glm::vec3 dir = glm::normalize(glm::vec3(float(k) - 1.5f, -0.8f, 1.0f));
@@ -107,6 +123,14 @@ int main(int argc, char ** argv) {
             put(dump, &r, 1);
             if (r) put(dump, &hit, sizeof(glm::vec3));
         }
+        rayTimes.push_back(std::chrono::duration<double, std::micro>(Clock::now() - t1).count());
+    }
+    if (std::getenv("PRT_DRIVER_TIMING") && frames > 10) {
+        std::sort(stepTimes.begin() + 5, stepTimes.end());   // the first frames carry one-off setup (tree build / upload)
+        std::sort(rayTimes.begin() + 5, rayTimes.end());
+        size_t const mid = 5 + (stepTimes.size() - 5) / 2;
+        std::fprintf(stderr, "timing: %d characters, updateCharacters median %.1f us, 4 raycasts median %.1f us\n", nChars,
+                     stepTimes[mid], rayTimes[mid]);
     }
     FILE * fp = std::fopen(outPath, "wb");
     if (!fp) return 2;

@@ -140,6 +140,12 @@ class L0World(_World):
     def available(variant="plain"):
         return os.path.exists(os.path.join(ORACLE_DIR, "_ref", L0World.LIBS[variant]))
 
+    def update_model(self, model_index, transform):
+        self._fn("update_model")(self.h, _u32(model_index), _ptr(_f32(transform)))
+
+    def update_capsule(self, capsule_index, height, radius, offset):
+        self._fn("update_capsule")(self.h, _u32(capsule_index), _f(height), _f(radius), _ptr(_f32(offset)))
+
     def dump_order(self):
         m = np.zeros(70000, np.uint16)
         c = np.zeros(70000, np.uint16)

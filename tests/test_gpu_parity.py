@@ -217,6 +217,53 @@ def test_literal_mode_equals_reference_rotated_moving():
     _run_literal_vs_l0(scene, 20)
 
 
+@pytest.mark.skipif(not L0World.available("traced"), reason="oracle/_ref not built")
+def test_literal_mode_with_models_moved_and_added_mid_run():
+    """the unified tree's shape depends on the ORDER of its operations: a model moved (updateModelColliders,
+    physics_system.cpp:161-202) or added between two frames changes leaves before that frame's capsule leaves move.
+    States and traces (candidate order included) against the reference's own code for 120 frames."""
+    from prototype2_b200 import capi
+    scene = H.make_scene(24, 2, 2, 16, seed=77, yaw=True)
+    scene["model_transform"] = [0.0, 0.0, 0.0, 1.0, 0.0, 0.0, 0.0, 1.5, 1.0, 1.5]
+    orc = H.build_oracle(scene, "l0", variant="traced")
+    ctx, tf, ph = H.build_gpu(scene, order_mode=capi.ORDER_LITERAL)
+    rs = np.random.RandomState(8)
+    slab = np.array([[0, 0, 0], [0, 0, 6], [6, 0, 6], [0, 0, 0], [6, 0, 6], [6, 0, 0]], np.float32)
+    extra = None
+    for f in range(120):
+        if f % 10 == 0:
+            move = np.zeros((16, 3), np.float32)
+            move[:, [0, 2]] = rs.uniform(-0.15, 0.15, (16, 2)).astype(np.float32)
+            ph["movement"][:] = move
+            orc.set_state(move=move)
+        if f in (20, 45, 70):                                     # the map slides / rescales
+            t = [0.25 * (f // 20), -0.1, 0.1 * (f // 20), 1.0, 0.0, 0.0, 0.0, 1.5, 1.0 + 0.01 * f, 1.5]
+            orc.update_model(0, t)
+            g = np.zeros(1, capi.TRANSFORM_DTYPE)
+            g["position"][0] = t[0:3]; g["rotation"][0] = (t[4], t[5], t[6], t[3]); g["scale"][0] = t[7:10]
+            ctx.update_model_colliders([0], g)
+        if f == 30:                                               # a second model appears
+            t2 = [10.0, 1.0, 10.0, 0.9961947, 0.0871557, 0.0, 0.0, 1.0, 1.0, 1.0]
+            orc.add_model(slab, [0], [6], t2)
+            extra, _ = ctx.add_model_collider(slab, np.uint32([0]), np.uint32([6]), t2)
+        if f == 60:                                               # ... and moves
+            t2 = [12.0, 1.5, 9.0, 0.9961947, 0.0871557, 0.0, 0.0, 1.0, 1.0, 2.0]
+            orc.update_model(1, t2)
+            g = np.zeros(1, capi.TRANSFORM_DTYPE)
+            g["position"][0] = t2[0:3]; g["rotation"][0] = (t2[4], t2[5], t2[6], t2[3]); g["scale"][0] = t2[7:10]
+            ctx.update_model_colliders([extra], g)
+        if f % 6 == 0 or f in (20, 21, 30, 31, 45, 46, 60, 61, 70, 71):
+            to = orc.step(DT, trace=True)
+            tg = ctx.update_characters_traced(DT, tf, ph)
+            assert H.trace_diff(to, tg, LITERAL_KEYS) == [], "frame %d trace" % f
+        else:
+            orc.step(DT)
+            ctx.update_characters(DT, tf, ph)
+        assert H.state_diff(orc.get_state(), H.gpu_state(tf, ph)) == [], "frame %d" % f
+        mo, co = orc.dump_order()
+        assert np.array_equal(mo, ctx.leaf_order()), "frame %d: mesh leaves in a different tree order" % f
+
+
 @pytest.mark.skipif(not L0World.available("fabs"), reason="oracle/_ref not built")
 def test_literal_mode_equals_reference_float_abs_build():
     from prototype2_b200 import capi
