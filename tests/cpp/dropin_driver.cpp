@@ -35,6 +35,7 @@ int main(int argc, char ** argv) {
     int const nChars = argc > 2 ? std::atoi(argv[2]) : 12;
     int const frames = argc > 3 ? std::atoi(argv[3]) : 40;
     char const * outPath = argc > 4 ? argv[4] : "dump.bin";
+    if (argc > 5) rng_state = uint32_t(std::strtoul(argv[5], nullptr, 10));   // another crowd on the same level
 
     PhysicsSystem physics;
     Scene scene;

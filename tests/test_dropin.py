@@ -42,11 +42,11 @@ def test_drop_in_keeps_the_reference_class_surface():
 # instead of before the capsule leaves of that frame) only showed as a different candidate order at frame 63 and as a
 # 1-ulp position difference at frame 84
 @pytest.mark.parametrize("args", [("24", "12", "40"), ("40", "60", "30"), ("16", "1", "60"), ("24", "12", "300"), ("48", "100", "300"),
-                                  ("32", "100", "150")])
+                                  ("32", "100", "150"), ("12", "30", "300", "3"), ("10", "100", "200", "5")])
 def test_same_caller_same_bytes(args, tmp_path):
     ref, dro = str(tmp_path / "ref.bin"), str(tmp_path / "dropin.bin")
-    subprocess.run([os.path.join(BIN, "driver_reference"), *args, ref], check=True)
-    subprocess.run([os.path.join(BIN, "driver_dropin"), *args, dro], check=True)
+    subprocess.run([os.path.join(BIN, "driver_reference"), *args[:3], ref, *args[3:]], check=True)      # [3] = seed of the crowd
+    subprocess.run([os.path.join(BIN, "driver_dropin"), *args[:3], dro, *args[3:]], check=True)
     a, b = open(ref, "rb").read(), open(dro, "rb").read()
     assert len(a) == len(b) and len(a) > 1000
     assert a == b, "first difference at byte %d" % next(i for i in range(len(a)) if a[i] != b[i])
