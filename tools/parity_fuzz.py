@@ -1,5 +1,5 @@
 """Parity fuzz of the CUDA path against the CPU checker (test infrastructure, like tests/): random levels, crowds, capsule
-shapes, rotations and inputs, run free for many frames in CANONICAL order (vs the L1 port) and in LITERAL order (vs the
+shapes, rotations and inputs, run free for many frames in CANONICAL order with and without the JACOBI dynamic pass (vs the L1 port) and in LITERAL order (vs the
 reference's own code when oracle/_ref is there); states compared bit for bit every frame, counters at the end.
 Usage on the GPU box:  PYTHONPATH=$PWD python tools/parity_fuzz.py [rounds] [seed]"""
 import os
@@ -23,6 +23,7 @@ for r in range(rounds):
     bx, bz = int(rs.choice([1, 2, 4])), int(rs.choice([1, 2]))
     n = int(rs.choice([1, 7, 40, 200, 700]))
     literal = bool(rs.rand() < 0.4) and n <= 200 and L0World.available("traced")
+    jacobi = (not literal) and bool(rs.rand() < 0.35) and n > 1
     cap = (float(rs.choice([0.5, 0.8, 0.25])), float(rs.choice([0.5, 0.3, 0.75])), (0.0, float(rs.choice([0.5, 0.3])), 0.0))
     scene = H.make_scene(n_terrain, bx, bz, n, seed=int(rs.randint(1 << 30)), capsule=cap)
     kind = rs.randint(3)
@@ -43,11 +44,12 @@ for r in range(rounds):
         orc = H.build_oracle(scene, "l0", variant="fabs" if abs_mode else "plain")
         ctx, tf, ph = H.build_gpu(scene, order_mode=capi.ORDER_LITERAL, abs_mode=abs_mode)
     else:
-        orc = H.build_oracle(scene, "l1", order="canonical", substeps=substeps, abs_mode="float" if abs_mode else "int", threads=8)
-        ctx, tf, ph = H.build_gpu(scene, substeps=substeps, abs_mode=abs_mode)
+        orc = H.build_oracle(scene, "l1", order="canonical", dyn="jacobi" if jacobi else "off", substeps=substeps,
+                             abs_mode="float" if abs_mode else "int", threads=8)
+        ctx, tf, ph = H.build_gpu(scene, substeps=substeps, abs_mode=abs_mode, dyn_mode=capi.DYN_JACOBI if jacobi else capi.DYN_OFF)
     frames = int(rs.choice([60, 120, 200]))
     desc = "round %d: %s terrain %d (%dx%d) n=%d cap=%s rot=%d xform=%s substeps=%d abs=%d frames=%d" % (
-        r, "LITERAL" if literal else "canonical", n_terrain, bx, bz, n, cap, kind, scene["model_transform"] is not None, substeps, abs_mode, frames)
+        r, "LITERAL" if literal else ("canonical+JACOBI" if jacobi else "canonical"), n_terrain, bx, bz, n, cap, kind, scene["model_transform"] is not None, substeps, abs_mode, frames)
     ok = True
     for f in range(frames):
         if f % 12 == 0:
@@ -73,7 +75,7 @@ for r in range(rounds):
             break
     if ok and not literal:
         co, cg = orc.counters(), ctx.counters()
-        for k in ("substeps", "tri_tests", "contacts"):
+        for k in ("substeps", "tri_tests", "contacts") + (("cc_tests",) if jacobi else ()):
             if co[k] != cg[k]:
                 print("COUNTER MISMATCH", desc, k, co[k], cg[k])
                 ok = False
