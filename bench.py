@@ -412,7 +412,9 @@ def run_ours(args):
         except Exception:
             traffic = None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                "kernel": "k_step<false>", "peak_source": peak_src,
+                "kernel": ("k_step<false, MODE_JACOBI>" if args.workload == "C5" else
+                           "k_step_warp<MODE_STATIC>" if n_caps <= 2960 else "k_step_stream<false>"),   # what launch_step picks
+                "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes / args.steps,
                 "avg_launch_ms": float(np.mean(kernel_ms)), "formula": "96*S + 32*V + 36*T + 64*capsules (SURVEY.md 8d)",
                 "per_query": {"V_q": cnt["node_tests"] / max(1, cnt["substeps"]), "T_q": cnt["tri_tests"] / max(1, cnt["substeps"]),
