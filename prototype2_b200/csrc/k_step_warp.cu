@@ -34,6 +34,7 @@ __global__ void __launch_bounds__(32) k_step_warp(StepParams p) {
     __shared__ uint32_t s_start[WF_CAP + 1];    // exclusive prefix sum of the leaves' triangle counts
     __shared__ uint32_t s_tbeg[WF_CAP];
     __shared__ uint32_t s_caps[WF_CAP];         // LITERAL: overlapping capsule leaves (node indices), sorted
+    __shared__ uint32_t s_rmesh[WF_CAP], s_rcaps[WF_CAP];   // the frame's cached candidates (emission order)
     const uint32_t lane = threadIdx.x;
     const unsigned lt = (1u << lane) - 1u;
     const uint32_t i = blockIdx.x;
@@ -69,6 +70,99 @@ __global__ void __launch_bounds__(32) k_step_warp(StepParams p) {
     const V3 stepv = vel / fsub;
     V3 prevA, prevB;
     segment_ends(fr, pos, prevA, prevB);
+    // Level-by-level frontier walk for box `b`: the overlapping mesh leaves end up in s_mesh, the capsule leaves
+    // (LITERAL) in s_caps, both sorted by node index = emission order.  false: a list or the frontier outgrew WF_CAP.
+    uint32_t c_node_lane = 0;                                      // node tests of this lane (summed at the end)
+    auto frontier_walk = [&](Box const & b, uint32_t & nmesh, uint32_t & ncaps) -> bool {
+        nmesh = 0; ncaps = 0;
+        const uint32_t tests_before = c_node_lane;                 // an overflowing walk is redone by ordered passes, which count themselves
+        uint32_t cur = 0, nfront = p.n_nodes ? 1u : 0u;
+        if (lane == 0) s_front[0][0] = 0u;
+        __syncwarp(FULL);
+        while (nfront != 0) {
+            uint32_t nnext = 0;
+            for (uint32_t base = 0; base < nfront; base += 32) {
+                const uint32_t k = base + lane;
+                bool internal = false, leaf_mesh = false, leaf_caps = false;
+                uint32_t idx = 0, second = 0;
+                if (k < nfront) {
+                    idx = s_front[cur][k];
+                    const float4 lo = __ldg(p.nodes + 2 * idx);
+                    const float4 hi = __ldg(p.nodes + 2 * idx + 1);
+                    ++c_node_lane;
+                    if (node_overlaps(lo, hi, b)) {
+                        const int cnt = __float_as_int(hi.w);
+                        if (cnt < 0) { internal = true; second = uint32_t(-cnt); }
+                        else if (!(cnt & PRT_CAPSULE_LEAF)) leaf_mesh = true;
+                        else if (LITERAL && uint32_t(__float_as_int(lo.w)) != cid) leaf_caps = true;
+                    }
+                }
+                const unsigned m_int = __ballot_sync(FULL, internal);
+                const unsigned m_mesh = __ballot_sync(FULL, leaf_mesh);
+                const unsigned m_caps = __ballot_sync(FULL, leaf_caps);
+                if (nnext + 2 * __popc(m_int) > WF_CAP || nmesh + __popc(m_mesh) > WF_CAP || ncaps + __popc(m_caps) > WF_CAP) {
+                    c_node_lane = tests_before;
+                    return false;
+                }
+                if (internal) {
+                    const uint32_t o = nnext + 2 * __popc(m_int & lt);
+                    s_front[cur ^ 1][o] = idx + 1;
+                    s_front[cur ^ 1][o + 1] = second;
+                }
+                if (leaf_mesh) s_found[nmesh + __popc(m_mesh & lt)] = idx;
+                if (leaf_caps) s_caps[ncaps + __popc(m_caps & lt)] = idx;
+                nnext += 2 * __popc(m_int);
+                nmesh += __popc(m_mesh);
+                ncaps += __popc(m_caps);
+            }
+            cur ^= 1;
+            nfront = nnext;
+            __syncwarp(FULL);
+        }
+        // sort by node index (rank by counting; the lists are short)
+        for (uint32_t j = lane; j < nmesh; j += 32) {
+            const uint32_t e = s_found[j];
+            uint32_t r = 0;
+            for (uint32_t t = 0; t < nmesh; ++t) r += s_found[t] < e;
+            s_mesh[r] = e;
+        }
+        if (LITERAL) {
+            uint32_t mine[WF_CAP / 32], rk[WF_CAP / 32];
+#pragma unroll
+            for (int q4 = 0; q4 < WF_CAP / 32; ++q4) {
+                const uint32_t j = lane + 32 * q4;
+                mine[q4] = j < ncaps ? s_caps[j] : 0xFFFFFFFFu;
+                rk[q4] = 0;
+                for (uint32_t t = 0; t < ncaps; ++t) rk[q4] += s_caps[t] < mine[q4];
+            }
+            __syncwarp(FULL);
+#pragma unroll
+            for (int q4 = 0; q4 < WF_CAP / 32; ++q4) if (lane + 32 * q4 < ncaps) s_caps[rk[q4]] = mine[q4];
+        }
+        __syncwarp(FULL);
+        return true;
+    };
+
+    // Frame cache (PRTC_OPT_FRAME_CACHE): ONE frontier walk with a box that covers the whole frame's motion (pose now,
+    // pose after the pre-stepped velocity, 0.25 of slack for push-outs); a substep whose query box lies inside that
+    // region only filters the cached leaves -- one memory round trip instead of one per tree level.  The cached lists
+    // are supersets in emission order, the filter is the exact box test, so the candidates are the walk's.
+    Box region; region.lo = v3(0.0f); region.hi = v3(0.0f);
+    bool region_ok = false;
+    uint32_t nr_mesh = 0, nr_caps = 0;
+    if (!(p.tune & 1u) && p.substeps > 1) {
+        V3 eA, eB;
+        segment_ends(fr, pos + vel, eA, eB);
+        region = box_union(capsule_box(prevA, prevB, radius), capsule_box(eA, eB, radius));
+        region.lo = region.lo - v3(0.25f); region.hi = region.hi + v3(0.25f);
+        region_ok = frontier_walk(region, nr_mesh, nr_caps);
+        if (region_ok) {
+            for (uint32_t j = lane; j < nr_mesh; j += 32) s_rmesh[j] = s_mesh[j];
+            for (uint32_t j = lane; j < nr_caps; j += 32) s_rcaps[j] = s_caps[j];
+            __syncwarp(FULL);
+        }
+    }
+
     uint32_t stepsLeft = p.substeps;
     while (stepsLeft != 0) {
         --stepsLeft;
@@ -82,79 +176,46 @@ __global__ void __launch_bounds__(32) k_step_warp(StepParams p) {
             lb[0] = qb.lo.x; lb[1] = qb.lo.y; lb[2] = qb.lo.z; lb[3] = qb.hi.x; lb[4] = qb.hi.y; lb[5] = qb.hi.z;
         }
 
-        // ---- broadphase: level-by-level frontier walk ----
-        uint32_t nmesh = 0, ncaps = 0, walk_tests = 0;
+        // ---- broadphase: the frame's cached candidates filtered by this substep's box, or a frontier walk ----
+        uint32_t nmesh = 0, ncaps = 0;
         bool overflow = false;
-        {
-            uint32_t cur = 0, nfront = p.n_nodes ? 1u : 0u;
-            if (lane == 0) s_front[0][0] = 0u;
-            __syncwarp(FULL);
-            while (nfront != 0 && !overflow) {
-                uint32_t nnext = 0;
-                for (uint32_t base = 0; base < nfront; base += 32) {
-                    const uint32_t k = base + lane;
-                    bool internal = false, leaf_mesh = false, leaf_caps = false;
-                    uint32_t idx = 0, second = 0;
-                    if (k < nfront) {
-                        idx = s_front[cur][k];
-                        const float4 lo = __ldg(p.nodes + 2 * idx);
-                        const float4 hi = __ldg(p.nodes + 2 * idx + 1);
-                        ++walk_tests;
-                        if (node_overlaps(lo, hi, qb)) {
-                            const int cnt = __float_as_int(hi.w);
-                            if (cnt < 0) { internal = true; second = uint32_t(-cnt); }
-                            else if (!(cnt & PRT_CAPSULE_LEAF)) leaf_mesh = true;
-                            else if (LITERAL && uint32_t(__float_as_int(lo.w)) != cid) leaf_caps = true;
-                        }
-                    }
-                    const unsigned m_int = __ballot_sync(FULL, internal);
-                    const unsigned m_mesh = __ballot_sync(FULL, leaf_mesh);
-                    const unsigned m_caps = __ballot_sync(FULL, leaf_caps);
-                    if (nnext + 2 * __popc(m_int) > WF_CAP || nmesh + __popc(m_mesh) > WF_CAP || ncaps + __popc(m_caps) > WF_CAP) { overflow = true; break; }
-                    if (internal) {
-                        const uint32_t o = nnext + 2 * __popc(m_int & lt);
-                        s_front[cur ^ 1][o] = idx + 1;
-                        s_front[cur ^ 1][o + 1] = second;
-                    }
-                    if (leaf_mesh) s_found[nmesh + __popc(m_mesh & lt)] = idx;
-                    if (leaf_caps) s_caps[ncaps + __popc(m_caps & lt)] = idx;     // sorted below (few)
-                    nnext += 2 * __popc(m_int);
-                    nmesh += __popc(m_mesh);
-                    ncaps += __popc(m_caps);
+        if (region_ok && box_contains(region, qb)) {
+            // both cached lists are in emission order and ballot compaction keeps it
+            for (uint32_t base = 0; base < nr_mesh; base += 32) {
+                const uint32_t k = base + lane;
+                bool ov = false;
+                uint32_t idx = 0;
+                if (k < nr_mesh) {
+                    idx = s_rmesh[k];
+                    ov = node_overlaps(__ldg(p.nodes + 2 * idx), __ldg(p.nodes + 2 * idx + 1), qb);
+                    ++c_node_lane;
                 }
-                cur ^= 1;
-                nfront = nnext;
-                __syncwarp(FULL);
+                const unsigned m = __ballot_sync(FULL, ov);
+                if (ov) s_mesh[nmesh + __popc(m & lt)] = idx;
+                nmesh += __popc(m);
             }
+            if (LITERAL) {
+                for (uint32_t base = 0; base < nr_caps; base += 32) {
+                    const uint32_t k = base + lane;
+                    bool ov = false;
+                    uint32_t idx = 0;
+                    if (k < nr_caps) {
+                        idx = s_rcaps[k];
+                        ov = node_overlaps(__ldg(p.nodes + 2 * idx), __ldg(p.nodes + 2 * idx + 1), qb);
+                        ++c_node_lane;
+                    }
+                    const unsigned m = __ballot_sync(FULL, ov);
+                    if (ov) s_caps[ncaps + __popc(m & lt)] = idx;
+                    ncaps += __popc(m);
+                }
+            }
+            __syncwarp(FULL);
+        } else {
+            overflow = !frontier_walk(qb, nmesh, ncaps);
         }
         // ordered passes (overflow only): the stackless right-first walk, executed uniformly by the whole warp
         uint32_t onode = p.n_nodes, cnode = p.n_nodes;            // resume positions of the mesh / capsule passes
         if (overflow) { onode = 0; cnode = 0; nmesh = 0; ncaps = 0; }
-        else {
-            c_node += __reduce_add_sync(FULL, walk_tests) ;
-            // sort by node index (rank by counting; the lists are short)
-            __syncwarp(FULL);
-            for (uint32_t j = lane; j < nmesh; j += 32) {
-                const uint32_t e = s_found[j];
-                uint32_t r = 0;
-                for (uint32_t t = 0; t < nmesh; ++t) r += s_found[t] < e;
-                s_mesh[r] = e;
-            }
-            if (LITERAL) {
-                uint32_t mine[WF_CAP / 32], rk[WF_CAP / 32];
-#pragma unroll
-                for (int s = 0; s < WF_CAP / 32; ++s) {
-                    const uint32_t j = lane + 32 * s;
-                    mine[s] = j < ncaps ? s_caps[j] : 0xFFFFFFFFu;
-                    rk[s] = 0;
-                    for (uint32_t t = 0; t < ncaps; ++t) rk[s] += s_caps[t] < mine[s];
-                }
-                __syncwarp(FULL);
-#pragma unroll
-                for (int s = 0; s < WF_CAP / 32; ++s) if (lane + 32 * s < ncaps) s_caps[rk[s]] = mine[s];
-            }
-            __syncwarp(FULL);
-        }
 
         // ---- LITERAL: capsule-capsule pass in tree order, before any triangle (physics_system.cpp:369-389) ----
         if (LITERAL) {
@@ -282,6 +343,7 @@ __global__ void __launch_bounds__(32) k_step_warp(StepParams p) {
     vel.z = vel.z * frictionRatio;
     if (grounded) vel.y = gmax((0.0f * p.gravity) * p.dt, vel.y);
     else vel.y = vel.y + ((-1.0f * p.gravity) * p.dt);
+    c_node += __reduce_add_sync(FULL, c_node_lane);
     if (lane == 0) {
         tf->position[0] = pos.x; tf->position[1] = pos.y; tf->position[2] = pos.z;
         ph->velocity[0] = vel.x; ph->velocity[1] = vel.y; ph->velocity[2] = vel.z;

@@ -776,16 +776,20 @@ def test_warp_kernel_overflow_and_equivalence_with_the_lock_step_kernel():
     orc, warp, tf, ph = _hetero_worlds(scene, caps, "l1", dict(order="canonical"), dict())
     _, lock, tf2, ph2 = _hetero_worlds(scene, caps, "l1", dict(order="canonical"), dict())
     lock.set_option(capi.OPT_WARP_KERNEL, 0)
+    _, walk, tf3, ph3 = _hetero_worlds(scene, caps, "l1", dict(order="canonical"), dict())
+    walk.set_option(capi.OPT_FRAME_CACHE, 0)                  # a frontier walk per substep instead of the frame's cached leaves
     for f in range(4):
         orc.step(DT)
         warp.update_characters(DT, tf, ph)
         lock.update_characters(DT, tf2, ph2)
+        walk.update_characters(DT, tf3, ph3)
         assert H.state_diff(orc.get_state(), H.gpu_state(tf, ph)) == [], "frame %d warp kernel vs oracle" % f
         assert H.state_diff(H.gpu_state(tf, ph), H.gpu_state(tf2, ph2)) == [], "frame %d warp vs lock-step" % f
-    co, cw, cl = orc.counters(), warp.counters(), lock.counters()
+        assert H.state_diff(H.gpu_state(tf, ph), H.gpu_state(tf3, ph3)) == [], "frame %d cached vs walked" % f
+    co, cw, cl, ck = orc.counters(), warp.counters(), lock.counters(), walk.counters()
     for k in ("substeps", "tri_tests", "contacts"):
-        assert co[k] == cw[k] == cl[k], k
-    assert cw["node_tests"] == co["node_tests"]               # the frontier walk tests exactly the nodes the reference tests
+        assert co[k] == cw[k] == cl[k] == ck[k], k
+    assert ck["node_tests"] == co["node_tests"]               # the per-substep frontier walk tests exactly the nodes the reference tests
 
 
 def test_randomised_long_runs():
