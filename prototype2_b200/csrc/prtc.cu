@@ -110,6 +110,9 @@ struct prtc_ctx {
     std::vector<Box> capsule_aabbs;         // m_aabbData.capsuleAABBs
     bool geometry_dirty = false;            // raw / meshes / xforms changed since the last upload
     bool tree_dirty = false;                // tree changed since the last flatten
+    bool leaf_ids_stale = true;             // d_node_leaf_id lags behind flat.node_leaf_id (upload_leaf_ids)
+    bool tri_dirty = true;                  // triangle records (layout or world positions) must be rebuilt
+    std::vector<uint32_t> mesh_tri_first;   // LITERAL: first triangle record of every mesh (registration order)
     bool capsules_dirty = false;
     float world_max_abs = 0.0f;             // largest |coordinate| of any mesh AABB (margin of the pre-cull)
     int frame_cache = 1;                    // PRTC_OPT_FRAME_CACHE
@@ -250,36 +253,60 @@ int commit_impl(prtc_ctx * c) {
         c->meshes_on_device = n_meshes;
         c->geometry_dirty = false;
         c->tree_dirty = true;
+        c->tri_dirty = true;                      // new / moved / removed geometry: the triangle records are stale
     }
 
     if (c->tree_dirty) {
-        c->tri_src.clear();
-        c->tri_src.reserve(n_vertices / 3);
+        // Triangle records are laid out in LEAF order in CANONICAL mode (the tree is built once; neighbours in the
+        // traversal are neighbours in memory) and in REGISTRATION order in LITERAL mode, where the tree changes shape
+        // whenever a capsule leaves its fat box: there a re-flatten only uploads the nodes, the triangles stay put.
+        const bool by_leaf_order = !c->literal();
+        const bool rebuild_tris = by_leaf_order || c->tri_dirty;
+        if (rebuild_tris) {
+            c->tri_src.clear();
+            c->tri_src.reserve(n_vertices / 3);
+            if (!by_leaf_order) {
+                c->mesh_tri_first.resize(n_meshes);
+                for (uint32_t m = 0; m < n_meshes; ++m) {
+                    MeshHost const & mh = c->meshes[m];
+                    c->mesh_tri_first[m] = uint32_t(c->tri_src.size());
+                    for (uint32_t k = 0; k < mh.n_vertices / 3; ++k) c->tri_src.push_back(mh.first_vertex + 3 * k);
+                }
+            }
+        }
         ++c->tree_version;                       // every cached leaf list refers to node indices of the old layout
         c->tree.flatten(c->flat, [&](uint32_t mesh_id, uint32_t & first, uint32_t & count) {
             MeshHost const & mh = c->meshes[mesh_id];
-            first = uint32_t(c->tri_src.size());
             count = mh.n_vertices / 3;
-            for (uint32_t k = 0; k < count; ++k) c->tri_src.push_back(mh.first_vertex + 3 * k);
+            if (by_leaf_order) {
+                first = uint32_t(c->tri_src.size());
+                for (uint32_t k = 0; k < count; ++k) c->tri_src.push_back(mh.first_vertex + 3 * k);
+            } else {
+                first = c->mesh_tri_first[mesh_id];
+            }
         });
         const size_t nn = c->flat.nodes.size();
         const size_t nt = c->tri_src.size();
         PRTC_CUDA(c->d_nodes.reserve(nn * 2));
         PRTC_CUDA(c->d_node_leaf_id.reserve(nn));
-        PRTC_CUDA(c->d_tri_src.reserve(nt));
-        PRTC_CUDA(c->d_tris.reserve(nt * 3));
         static_assert(sizeof(FlatNode) == 32, "FlatNode must be two float4");
         if (nn) {
+            // pageable sources: the runtime stages them before it returns, so the vectors may be rewritten afterwards
             PRTC_CUDA(cudaMemcpyAsync(c->d_nodes.ptr, c->flat.nodes.data(), nn * sizeof(FlatNode), cudaMemcpyHostToDevice, s));
-            PRTC_CUDA(cudaMemcpyAsync(c->d_node_leaf_id.ptr, c->flat.node_leaf_id.data(), nn * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+            c->leaf_ids_stale = true;            // only traces and prtc_query_box read them: uploaded on demand
         }
-        if (nt) {
-            PRTC_CUDA(cudaMemcpyAsync(c->d_tri_src.ptr, c->tri_src.data(), nt * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
-            launch_tri_setup(c->d_world.ptr, c->d_tri_src.ptr, uint32_t(nt), c->d_tris.ptr, s);
-            PRTC_CUDA(cudaGetLastError());
+        if (rebuild_tris) {
+            PRTC_CUDA(c->d_tri_src.reserve(nt));
+            PRTC_CUDA(c->d_tris.reserve(nt * 3));
+            if (nt) {
+                PRTC_CUDA(cudaMemcpyAsync(c->d_tri_src.ptr, c->tri_src.data(), nt * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+                launch_tri_setup(c->d_world.ptr, c->d_tri_src.ptr, uint32_t(nt), c->d_tris.ptr, s);
+                PRTC_CUDA(cudaGetLastError());
+            }
+            PRTC_CUDA(cudaStreamSynchronize(s));
         }
-        PRTC_CUDA(cudaStreamSynchronize(s));
         c->tree_dirty = false;
+        c->tri_dirty = false;
     }
     return PRTC_OK;
 }
@@ -412,7 +439,19 @@ int gather_trace(prtc_ctx * c, uint32_t n, uint32_t cap_cand, uint32_t cap_hits,
 
 constexpr uint32_t TRACE_CAP_CAND = 64, TRACE_CAP_HITS = 96;
 
+// collider id per node of the flattened tree: what traced kernels and prtc_query_box report
+int upload_leaf_ids(prtc_ctx * c) {
+    if (!c->leaf_ids_stale) return PRTC_OK;
+    const size_t nn = c->flat.node_leaf_id.size();
+    PRTC_CUDA(c->d_node_leaf_id.reserve(nn));
+    if (nn) PRTC_CUDA(cudaMemcpyAsync(c->d_node_leaf_id.ptr, c->flat.node_leaf_id.data(), nn * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+    c->leaf_ids_stale = false;
+    return PRTC_OK;
+}
+
 int prepare_trace(prtc_ctx * c, uint32_t n, StepParams & p) {
+    { int rc = upload_leaf_ids(c); if (rc) return rc; }
+    p.node_leaf_id = c->d_node_leaf_id.ptr;
     const size_t slots = size_t(n) * c->cfg.substeps;
     PRTC_CUDA(c->d_tq.reserve(slots));
     PRTC_CUDA(c->d_tmesh.reserve(slots * TRACE_CAP_CAND));
@@ -1266,6 +1305,7 @@ int prtc_query_box(prtc_ctx * c, const float aabb6[6], uint32_t * mesh_ids, uint
     if (!c || !aabb6 || !n_found || (capacity && !mesh_ids)) return fail(PRTC_ERR_INVALID, "prtc_query_box: null argument");
     PRTC_CUDA(cudaSetDevice(c->cfg.device));
     if (c->geometry_dirty || c->tree_dirty || c->capsules_dirty) { int rc = commit_impl(c); if (rc) return rc; }
+    { int rc = upload_leaf_ids(c); if (rc) return rc; }
     PRTC_CUDA(c->d_scratch_f.reserve(6));
     PRTC_CUDA(c->d_scratch_u.reserve(size_t(capacity) + 1));
     PRTC_CUDA(cudaMemcpyAsync(c->d_scratch_f.ptr, aabb6, 6 * sizeof(float), cudaMemcpyHostToDevice, c->stream));
