@@ -91,7 +91,7 @@ constexpr int SUBSTEP_BATCH = 8;     // same for the SUBSTEP stage
 template <bool GATED>
 __global__ void __launch_bounds__(32, 20) k_step_stream(StepParams p) {
     constexpr unsigned FULL = 0xffffffffu;
-    __shared__ uint32_t s_leaf[LEAF_CAP][32];              // candidate leaves of the substep: node indices, emission order
+    __shared__ uint32_t s_leaf[LEAF_CAP][32];              // candidate leaves of the substep (leaf_entry words), emission order
     __shared__ uint32_t s_cache[XC_CAP][32];
     __shared__ float s_region[6][32];
     __shared__ float4 s_tri[TRI_RING][3][32];
@@ -128,13 +128,25 @@ __global__ void __launch_bounds__(32, 20) k_step_stream(StepParams p) {
     const int substep_batch = ((p.tune >> 16) & 0xFFu) ? int((p.tune >> 16) & 0xFFu) : SUBSTEP_BATCH;
     for (int f = 0; f < P_COUNT; ++f) s_park[f][tid] = 0.0f;
 
+    // A candidate leaf is buffered as its triangle range when that fits one word (first < 2^24, count < 128: every
+    // synthetic shape), so the triangle stream does not wait for the node again; else as bit 31 | node index.
+    auto leaf_entry = [](uint32_t node_index, float4 lo, float4 hi) -> uint32_t {
+        const uint32_t first = uint32_t(__float_as_int(lo.w)), count = uint32_t(__float_as_int(hi.w));
+        return (first < (1u << 24) && count < 128u) ? (first | (count << 24)) : (0x80000000u | node_index);
+    };
     auto fetch_one = [&]() {
         while (f_cur == f_end) {
             if (f_leaf == nleaf) return;
-            const uint32_t leaf = s_leaf[f_leaf][tid];
+            const uint32_t e = s_leaf[f_leaf][tid];
             ++f_leaf;
-            f_cur = uint32_t(__float_as_int(__ldg(p.nodes + 2 * leaf).w));
-            f_end = f_cur + uint32_t(__float_as_int(__ldg(p.nodes + 2 * leaf + 1).w));
+            if (e & 0x80000000u) {
+                const uint32_t leaf = e & 0x7FFFFFFFu;
+                f_cur = uint32_t(__float_as_int(__ldg(p.nodes + 2 * leaf).w));
+                f_end = f_cur + uint32_t(__float_as_int(__ldg(p.nodes + 2 * leaf + 1).w));
+            } else {
+                f_cur = e & 0x00FFFFFFu;
+                f_end = f_cur + (e >> 24);
+            }
         }
         const uint32_t slot = n_fetched % TRI_RING;
         const float4 * src = p.tris + 3 * size_t(f_cur);
@@ -158,7 +170,7 @@ __global__ void __launch_bounds__(32, 20) k_step_stream(StepParams p) {
             if (cnt < 0) {
                 node = ov ? node + 1 : uint32_t(link);
             } else {
-                if (ov) { s_leaf[nleaf][tid] = node; ++nleaf; }
+                if (ov) { s_leaf[nleaf][tid] = leaf_entry(node, lo, hi); ++nleaf; }
                 node = node + 1;
             }
         }
@@ -309,15 +321,26 @@ __global__ void __launch_bounds__(32, 20) k_step_stream(StepParams p) {
                         s_region[3][tid] >= qb.hi.x && s_region[4][tid] >= qb.hi.y && s_region[5][tid] >= qb.hi.z) {
                         bool fits = true;
                         const uint32_t ncache = NCACHE;
-                        for (uint32_t j = 0; j < ncache; ++j) {
-                            const uint32_t leaf = s_cache[j][tid];
-                            const float4 lo = __ldg(p.nodes + 2 * leaf);
-                            const float4 hi = __ldg(p.nodes + 2 * leaf + 1);
+                        // two leaves per trip: four independent loads in flight instead of two behind every compare
+                        for (uint32_t j = 0; j < ncache && fits; j += 2) {
+                            const bool two = j + 1 < ncache;
+                            const uint32_t leaf0 = s_cache[j][tid];
+                            const uint32_t leaf1 = two ? s_cache[j + 1][tid] : leaf0;
+                            const float4 lo0 = __ldg(p.nodes + 2 * leaf0), hi0 = __ldg(p.nodes + 2 * leaf0 + 1);
+                            const float4 lo1 = __ldg(p.nodes + 2 * leaf1), hi1 = __ldg(p.nodes + 2 * leaf1 + 1);
                             ++c_node;
-                            if (node_overlaps(lo, hi, qb)) {
+                            if (node_overlaps(lo0, hi0, qb)) {
                                 if (nleaf == LEAF_CAP) { fits = false; break; }
-                                s_leaf[nleaf][tid] = leaf;
+                                s_leaf[nleaf][tid] = leaf_entry(leaf0, lo0, hi0);
                                 ++nleaf;
+                            }
+                            if (two) {
+                                ++c_node;
+                                if (node_overlaps(lo1, hi1, qb)) {
+                                    if (nleaf == LEAF_CAP) { fits = false; break; }
+                                    s_leaf[nleaf][tid] = leaf_entry(leaf1, lo1, hi1);
+                                    ++nleaf;
+                                }
                             }
                         }
                         node = p.n_nodes;
