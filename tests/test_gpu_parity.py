@@ -504,8 +504,10 @@ def test_jacobi_two_ranks_emulated_on_one_gpu_equal_one_rank():
     assert one.counters()["cc_tests"] > 0
 
 
-@pytest.mark.parametrize("pinned,streamed", [(False, 1), (True, 1), (True, 0)])
-def test_streamed_host_step_equals_device_step(pinned, streamed):
+@pytest.mark.parametrize("pinned,streamed,opts", [(False, 1, {}), (True, 1, {}), (True, 0, {}),
+                                                  (True, 1, {"OPT_CROSS_FRAME_CACHE": 0}), (True, 1, {"OPT_FRAME_CACHE": 0}),
+                                                  (True, 1, {"OPT_QUICK_REJECT": 0})])
+def test_streamed_host_step_equals_device_step(pinned, streamed, opts):
     """big host batches run as one persistent launch fed by the copy-in stream while it runs, results leaving chunk by
     chunk: same bits as one device-resident launch -- from pageable and pinned buffers, with an odd tail chunk, and when
     the caller edits the state between frames (the per-slot leaf lists were refreshed for a frame that did not come).
@@ -516,6 +518,8 @@ def test_streamed_host_step_equals_device_step(pinned, streamed):
     scene = H.make_scene(200, 2, 2, n, seed=71)
     ctx, tf, ph = H.build_gpu(scene)
     ctx.set_option(capi.OPT_STREAMED_COPY, streamed)
+    for k, v in opts.items():
+        ctx.set_option(getattr(capi, k), v)
     if pinned:
         t_tf = torch.from_numpy(tf.view(np.uint8).reshape(-1).copy()).pin_memory()
         t_ph = torch.from_numpy(ph.view(np.uint8).reshape(-1).copy()).pin_memory()
