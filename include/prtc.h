@@ -171,6 +171,19 @@ int prtc_step_characters_traced(prtc_ctx * ctx, float dt, uint32_t n, prtc_trans
 int prtc_raycast(prtc_ctx * ctx, uint32_t n, const float * origins, const float * directions,
                  const float * max_distances, float * hit_xyz, uint8_t * hit_mask);
 
+/* TIER B -- PARITY UNPINNED.  The swept ellipsoid-vs-triangle collide-and-slide of the engine's older collision code:
+ * n ellipsoids (centre, radius vector, displacement of this frame; world space) against the committed mesh colliders,
+ * `iterations` rounds of { earliest time of impact over all candidate triangles in ellipsoid space; stop very_close
+ * short of it; project the rest of the motion onto the slide plane }.  The snapshot of the reference has no caller
+ * for this any more (PhysicsSystem::collisionResponse is declared, physics_system.h:131-136, never defined); its
+ * helper functions survive in src/util/physics_util.cpp:51-178 and are what the kernel restates.  PRTC_ORDER_CANONICAL
+ * contexts only.  Outputs: out_pos / out_vel (3 floats per ellipsoid: where it ends up, what is left of the motion),
+ * and per (ellipsoid, iteration): hit_tri (triangle index in registration order, -1 = none), hit_toi (fraction of
+ * that iteration's motion), hit_normal (slide-plane normal in ellipsoid space, 3 floats). */
+int prtc_sweep_ellipsoids(prtc_ctx * ctx, uint32_t n, const float * centers, const float * radii, const float * velocities,
+                          uint32_t iterations, float very_close, float * out_pos, float * out_vel, int32_t * hit_tri,
+                          float * hit_toi, float * hit_normal);
+
 /* Dynamic-vs-dynamic pass at scale (PRTC_ORDER_CANONICAL + PRTC_DYN_JACOBI): every character
  * collides with the start-of-frame pose of every other character whose STORED fat box (the hysteresis of
  * DynamicAABBTree::update / insertLeaf, aabb_tree.cpp:102-111,140-141) overlaps its query box, in ascending global

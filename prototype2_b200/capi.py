@@ -19,7 +19,7 @@ OPT_FRAME_CACHE, OPT_QUICK_REJECT, OPT_PERSISTENT, OPT_CROSS_FRAME_CACHE, OPT_WA
 SYMBOLS = (
     "prtc_default_config", "prtc_last_error", "prtc_device_count", "prtc_create", "prtc_destroy",
     "prtc_add_model", "prtc_add_capsule", "prtc_update_capsule", "prtc_commit", "prtc_update_models", "prtc_remove_model",
-    "prtc_step_characters", "prtc_step_characters_device", "prtc_step_characters_traced", "prtc_raycast",
+    "prtc_step_characters", "prtc_step_characters_device", "prtc_step_characters_traced", "prtc_raycast", "prtc_sweep_ellipsoids",
     "prtc_set_stream", "prtc_synchronize", "prtc_get_counters", "prtc_set_option", "prtc_dyn_configure", "prtc_dyn_prepare", "prtc_dyn_buffer", "prtc_get_tree_info", "prtc_get_leaf_order",
     "prtc_get_world_vertices", "prtc_query_box", "prtc_host_build_tree",
 )
@@ -195,6 +195,21 @@ class PhysicsContext:
         mask = np.zeros(len(o), np.uint8)
         self._check(self.lib.prtc_raycast(self.h, ctypes.c_uint32(len(o)), _vp(o), _vp(d), _vp(m), _vp(hit), _vp(mask)))
         return mask.astype(bool), hit
+
+    def sweep_ellipsoids(self, centers, radii, velocities, iterations=3, very_close=0.005):
+        """TIER B (parity unpinned): swept ellipsoids with collide-and-slide.  Returns a dict: pos[n,3], vel[n,3] (what is left
+        of the motion), hit_tri[n,iterations] (-1 = none), hit_toi[n,iterations], hit_normal[n,iterations,3]."""
+        c = np.ascontiguousarray(centers, np.float32).reshape(-1, 3)
+        r = np.ascontiguousarray(np.broadcast_to(np.asarray(radii, np.float32), c.shape), np.float32)
+        v = np.ascontiguousarray(velocities, np.float32).reshape(-1, 3)
+        n = len(c)
+        out = {"pos": np.zeros((n, 3), np.float32), "vel": np.zeros((n, 3), np.float32),
+               "hit_tri": np.zeros((n, iterations), np.int32), "hit_toi": np.zeros((n, iterations), np.float32),
+               "hit_normal": np.zeros((n, iterations, 3), np.float32)}
+        self._check(self.lib.prtc_sweep_ellipsoids(self.h, ctypes.c_uint32(n), _vp(c), _vp(r), _vp(v), ctypes.c_uint32(iterations),
+                                                   ctypes.c_float(very_close), _vp(out["pos"]), _vp(out["vel"]), _vp(out["hit_tri"]),
+                                                   _vp(out["hit_toi"]), _vp(out["hit_normal"])))
+        return out
 
     def commit(self):
         self._check(self.lib.prtc_commit(self.h))

@@ -117,6 +117,19 @@ void launch_tri_setup(const float * world_xyz, const uint32_t * tri_src_vertex, 
 // K7: batched PhysicsSystem::raycast
 void launch_raycast(const float4 * nodes, uint32_t n_nodes, const float4 * tris, uint32_t n_rays, const float * origins,
                     const float * dirs, const float * maxd, float * hit_xyz, unsigned char * hit_mask, cudaStream_t stream);
+// TIER B (parity unpinned, see k_sweep.cu): swept ellipsoids with collide-and-slide, one warp per ellipsoid
+struct SweepParams {
+    const float4 * nodes; uint32_t n_nodes;
+    const float4 * tris;
+    const uint32_t * tri_src;       // per triangle record: index of its first vertex in registration order
+    uint32_t n, iterations;
+    float very_close;
+    const float * centers, * radii, * velocities;       // 3 floats per ellipsoid, world space
+    float * out_pos, * out_vel;
+    int32_t * hit_tri; float * hit_toi, * hit_normal;    // per (ellipsoid, iteration)
+    unsigned long long * counters;
+};
+void launch_sweep(SweepParams const & p, cudaStream_t stream);
 // single box query (introspection / tests)
 void launch_query_box(const float4 * nodes, uint32_t n_nodes, const uint32_t * node_leaf_id, const float * aabb6,
                       uint32_t * out_ids, uint32_t capacity, uint32_t * out_count, cudaStream_t stream);

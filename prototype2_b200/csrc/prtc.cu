@@ -1184,6 +1184,45 @@ int prtc_raycast(prtc_ctx * c, uint32_t n, const float * origins, const float * 
     return PRTC_OK;
 }
 
+int prtc_sweep_ellipsoids(prtc_ctx * c, uint32_t n, const float * centers, const float * radii, const float * velocities,
+                          uint32_t iterations, float very_close, float * out_pos, float * out_vel, int32_t * hit_tri,
+                          float * hit_toi, float * hit_normal) {
+    if (!c || (n && (!centers || !radii || !velocities || !out_pos || !out_vel || !hit_tri || !hit_toi || !hit_normal)) || iterations == 0)
+        return fail(PRTC_ERR_INVALID, "prtc_sweep_ellipsoids: null argument or zero iterations");
+    if (c->literal()) return fail(PRTC_ERR_INVALID, "prtc_sweep_ellipsoids needs a PRTC_ORDER_CANONICAL context (mesh colliders only in the tree)");
+    for (uint32_t i = 0; i < 3 * n; ++i)
+        if (!(radii[i] > 0.0f)) return fail(PRTC_ERR_INVALID, "prtc_sweep_ellipsoids: radii must be positive");
+    PRTC_CUDA(cudaSetDevice(c->cfg.device));
+    if (c->geometry_dirty || c->tree_dirty || c->capsules_dirty) { int rc = commit_impl(c); if (rc) return rc; }
+    if (n == 0) return PRTC_OK;
+    cudaStream_t s = c->stream;
+    const size_t hits = size_t(n) * iterations;
+    PRTC_CUDA(c->d_scratch_f.reserve(size_t(n) * 15 + hits * 4));
+    PRTC_CUDA(c->d_scratch_u.reserve(hits));
+    float * d_c = c->d_scratch_f.ptr, * d_r = d_c + 3 * size_t(n), * d_v = d_r + 3 * size_t(n), * d_p = d_v + 3 * size_t(n), * d_ov = d_p + 3 * size_t(n);
+    float * d_toi = d_ov + 3 * size_t(n), * d_nrm = d_toi + hits;
+    PRTC_CUDA(cudaMemcpyAsync(d_c, centers, size_t(n) * 3 * sizeof(float), cudaMemcpyHostToDevice, s));
+    PRTC_CUDA(cudaMemcpyAsync(d_r, radii, size_t(n) * 3 * sizeof(float), cudaMemcpyHostToDevice, s));
+    PRTC_CUDA(cudaMemcpyAsync(d_v, velocities, size_t(n) * 3 * sizeof(float), cudaMemcpyHostToDevice, s));
+    SweepParams p;
+    p.nodes = c->d_nodes.ptr; p.n_nodes = uint32_t(c->flat.nodes.size());
+    p.tris = c->d_tris.ptr; p.tri_src = c->d_tri_src.ptr;
+    p.n = n; p.iterations = iterations; p.very_close = very_close;
+    p.centers = d_c; p.radii = d_r; p.velocities = d_v; p.out_pos = d_p; p.out_vel = d_ov;
+    p.hit_tri = reinterpret_cast<int32_t *>(c->d_scratch_u.ptr); p.hit_toi = d_toi; p.hit_normal = d_nrm;
+    p.counters = c->d_counters.ptr;
+    launch_sweep(p, s);
+    c->launches += 1;
+    PRTC_CUDA(cudaGetLastError());
+    PRTC_CUDA(cudaMemcpyAsync(out_pos, d_p, size_t(n) * 3 * sizeof(float), cudaMemcpyDeviceToHost, s));
+    PRTC_CUDA(cudaMemcpyAsync(out_vel, d_ov, size_t(n) * 3 * sizeof(float), cudaMemcpyDeviceToHost, s));
+    PRTC_CUDA(cudaMemcpyAsync(hit_tri, p.hit_tri, hits * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    PRTC_CUDA(cudaMemcpyAsync(hit_toi, d_toi, hits * sizeof(float), cudaMemcpyDeviceToHost, s));
+    PRTC_CUDA(cudaMemcpyAsync(hit_normal, d_nrm, hits * 3 * sizeof(float), cudaMemcpyDeviceToHost, s));
+    PRTC_CUDA(cudaStreamSynchronize(s));
+    return PRTC_OK;
+}
+
 int prtc_remove_model(prtc_ctx * c, uint32_t model_id) {
     if (!c || model_id >= c->models.size()) return fail(PRTC_ERR_INVALID, "prtc_remove_model: bad model id");
     ModelHost & mh = c->models[model_id];

@@ -199,3 +199,27 @@ class L1World(_World):
         nm, nc = _u32(0), _u32(0)
         self.lib.l1_query(self.h, _u32(caller), _ptr(_f32(aabb6)), _ptr(m), ctypes.byref(nm), _ptr(c), ctypes.byref(nc), _u32(cap))
         return m[:nm.value], c[:nc.value]
+
+
+def sweep_reference_available():
+    return os.path.exists(os.path.join(ORACLE_DIR, "_ref", "libprt_l0_sweep.so"))
+
+
+def sweep_reference(tri_xyz, centers, radii, velocities, iterations=3, very_close=0.005):
+    """Checker of the Tier-B kernel (oracle/l0_sweep_driver.cpp): the reference's surviving Nettle helpers under our
+    restatement of the loop, brute force over all triangles.  tri_xyz: world-space vertices, 3 per triangle, registration order."""
+    lib = ctypes.CDLL(os.path.join(ORACLE_DIR, "_ref", "libprt_l0_sweep.so"))
+    t = _f32(tri_xyz, (-1, 3))
+    c = _f32(centers, (-1, 3))
+    r = np.ascontiguousarray(np.broadcast_to(np.asarray(radii, np.float32), c.shape), np.float32)
+    v = _f32(velocities, (-1, 3))
+    n = len(c)
+    out = {"pos": np.zeros((n, 3), np.float32), "vel": np.zeros((n, 3), np.float32),
+           "hit_tri": np.zeros((n, iterations), np.int32), "hit_toi": np.zeros((n, iterations), np.float32),
+           "hit_normal": np.zeros((n, iterations, 3), np.float32)}
+    tests = ctypes.c_uint64()
+    lib.l0_sweep.restype = None
+    lib.l0_sweep(_ptr(t), _u32(len(t) // 3), _u32(n), _ptr(c), _ptr(r), _ptr(v), _u32(iterations), _f(very_close), _ptr(out["pos"]),
+                 _ptr(out["vel"]), _ptr(out["hit_tri"]), _ptr(out["hit_toi"]), _ptr(out["hit_normal"]), ctypes.byref(tests))
+    out["tri_tests"] = tests.value
+    return out
