@@ -147,3 +147,24 @@ def test_l1_reproduces_c1_shipped_level(tag, absm):
         for k in ("pos", "vel", "gnormal", "grounded"):
             assert H.same(s[k], g["%s_%s" % (tag, k)][f]), "frame %d %s" % (f, k)
     assert g["int_grounded"].sum() > 200 and abs(float(g["int_pos"][-1][0][1])) < 1e-5    # ends standing on the ground floor
+
+
+def test_sweep_checker_known_answers():
+    """Tier-B checker (oracle/l0_sweep_driver.cpp: the reference's Nettle helpers under our loop; parity unpinned):
+    an ellipsoid dropped on a floor stops where its lowest point touches, keeps the tangential part of its motion,
+    and reports the impact at the fraction of the motion that geometry dictates."""
+    import oraclelib as O
+    if not O.sweep_reference_available():
+        pytest.skip("oracle/_ref/libprt_l0_sweep.so not built")
+    floor = np.array([[-10, 0, -10], [-10, 0, 10], [10, 0, 10], [-10, 0, -10], [10, 0, 10], [10, 0, -10]], np.float32)
+    r = O.sweep_reference(floor, [[0, 2, 0], [0, 0.8, 0], [3, 5, 1], [0, 2, 0]], [[0.5, 1.0, 0.5]] * 4,
+                          [[0.3, -2.0, 0.0], [0.5, -0.5, 0], [0, -0.1, 0], [0, 1, 0]], iterations=3, very_close=0.005)
+    # 1: bottom of the ellipsoid (y = 1) reaches the floor after half of the motion; slides the rest of the way in x
+    assert r["hit_tri"][0].tolist()[0] in (0, 1) and r["hit_tri"][0, 1] == -1
+    assert abs(r["hit_toi"][0, 0] - 0.5) < 1e-6 and abs(r["pos"][0, 1] - 1.005) < 1e-3 and abs(r["pos"][0, 0] - 0.3) < 2e-3
+    assert abs(r["hit_normal"][0, 0, 1] - 1.0) < 1e-5
+    # 2: starts cutting the floor: impact at time 0, vertical motion removed, tangential motion kept
+    assert r["hit_toi"][1, 0] == 0.0 and np.allclose(r["pos"][1], [0.5, 0.8, 0.0], atol=1e-6)
+    # 3: never reaches the floor; 4: moves away from it
+    assert (r["hit_tri"][2:] == -1).all() and np.allclose(r["pos"][2], [3, 4.9, 1]) and np.allclose(r["pos"][3], [0, 3, 0])
+    assert np.all(r["vel"] == 0.0)
