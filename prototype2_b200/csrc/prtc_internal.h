@@ -1,0 +1,181 @@
+// prtc_internal.h -- what the two host translation units of libprtc.so share: error reporting, device / staging buffers,
+// the context behind prtc_ctx and the commit / parameter helpers.  Not installed; include/prtc.h is the interface.
+#ifndef PRTC_INTERNAL_H
+#define PRTC_INTERNAL_H
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/prtc.h"
+#include "bvh_builder.h"
+#include "kernels.cuh"
+
+namespace prt {
+namespace host {
+
+int fail(int code, const std::string & msg);          // records the thread's last error text, returns `code`
+
+#define PRTC_CUDA(expr)                                                                                   \
+    do {                                                                                                  \
+        cudaError_t _e = (expr);                                                                          \
+        if (_e != cudaSuccess)                                                                            \
+            return fail(PRTC_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));               \
+    } while (0)
+
+template <class T>
+struct DevBuf {
+    T * ptr = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t n) {
+        if (n <= cap) return cudaSuccess;
+        if (ptr) cudaFree(ptr);
+        ptr = nullptr; cap = 0;
+        size_t want = std::max<size_t>(n, 16);
+        cudaError_t e = cudaMalloc(reinterpret_cast<void **>(&ptr), want * sizeof(T));
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (ptr) cudaFree(ptr); ptr = nullptr; cap = 0; }
+};
+
+// Pinned host memory the device reads and writes in place (unified addressing: one pointer for both sides).  Engine-sized
+// host-buffer steps stage their records here instead of paying two uploads, two downloads and a counter read-back.
+struct HostStage {
+    unsigned char * base = nullptr;
+    size_t bytes = 0;
+    cudaError_t reserve(size_t need) {
+        if (need <= bytes) return cudaSuccess;
+        if (base) cudaFreeHost(base);
+        base = nullptr; bytes = 0;
+        const size_t want = std::max<size_t>(need, size_t(64) << 10);
+        cudaError_t e = cudaHostAlloc(reinterpret_cast<void **>(&base), want, cudaHostAllocMapped);
+        if (e == cudaSuccess) bytes = want;
+        return e;
+    }
+    void release() { if (base) cudaFreeHost(base); base = nullptr; bytes = 0; }
+};
+// carves 64-byte aligned arrays out of a HostStage
+struct StageCursor {
+    unsigned char * p;
+    template <typename T> T * take(size_t n) { T * r = reinterpret_cast<T *>(p); p += (n * sizeof(T) + 63) & ~size_t(63); return r; }
+};
+constexpr uint32_t kSmallBatch = 256;       // the engine's entity table holds 100 (entity.h:15)
+
+struct MeshHost { uint32_t first_vertex, n_vertices, model; int32_t tree_index; };
+struct ModelHost { uint32_t first_mesh, n_meshes; prtc_transform transform; };
+
+inline Affine affine_from(prtc_transform const & t) {
+    Quat q; q.x = t.rotation[0]; q.y = t.rotation[1]; q.z = t.rotation[2]; q.w = t.rotation[3];
+    return affine_of(v3(t.position[0], t.position[1], t.position[2]), q, v3(t.scale[0], t.scale[1], t.scale[2]));
+}
+
+} // namespace host
+} // namespace prt
+
+struct prtc_ctx {
+    prtc_config cfg;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    // host-buffer steps of large batches are cut into chunks pipelined over these streams (copy-in, step, copy-out)
+    static constexpr int PIPE_STREAMS = 3;
+    cudaStream_t pipe[PIPE_STREAMS] = {nullptr, nullptr, nullptr};
+    cudaEvent_t pipe_ready = nullptr;
+
+    // host registry
+    std::vector<float> raw;                 // model-space xyz of every registered model, back to back
+    std::vector<prt::host::MeshHost> meshes;
+    std::vector<prt::host::ModelHost> models;
+    std::vector<prt::CapsuleDev> capsules;
+    prt::RefTree tree;
+    prt::FlatTree flat;
+    std::vector<uint32_t> tri_src;          // per leaf-ordered triangle: index of its first vertex in `raw`/`world`
+    uint32_t meshes_in_tree = 0;            // meshes that have a leaf in `tree`
+    uint32_t meshes_on_device = 0;          // meshes whose world cache / AABB the device has computed
+    // LITERAL order: the reference's unified tree also holds one leaf per capsule (physics_system.cpp:36-39)
+    std::vector<int32_t> capsule_tree_index;
+    std::vector<prt::Box> capsule_aabbs;         // m_aabbData.capsuleAABBs
+    bool geometry_dirty = false;            // raw / meshes / xforms changed since the last upload
+    bool tree_dirty = false;                // tree changed since the last flatten
+    bool leaf_ids_stale = true;             // d_node_leaf_id lags behind flat.node_leaf_id (upload_leaf_ids)
+    bool tri_dirty = true;                  // triangle records (layout or world positions) must be rebuilt
+    std::vector<uint32_t> mesh_tri_first;   // LITERAL: first triangle record of every mesh (registration order)
+    bool capsules_dirty = false;
+    float world_max_abs = 0.0f;             // largest |coordinate| of any mesh AABB (margin of the pre-cull)
+    int frame_cache = 1;                    // PRTC_OPT_FRAME_CACHE
+    int persistent = 1;                     // PRTC_OPT_PERSISTENT
+    uint32_t tune_hi = 0;                   // PRTC_TUNE: batch thresholds of k_step_stream (bits 8-15 load, 16-23 substep), experiments
+    int sm_count = 148;
+    int quick_reject = 1;                   // PRTC_OPT_QUICK_REJECT
+    std::vector<uint32_t> moved_models;     // models whose transform changed (prtc_update_models)
+
+    // device
+    prt::host::DevBuf<float> d_raw, d_world, d_aabbs;
+    prt::host::DevBuf<prt::MeshDev> d_meshes;
+    prt::host::DevBuf<prt::ModelXform> d_xforms;
+    prt::host::DevBuf<float4> d_nodes, d_tris;
+    prt::host::DevBuf<uint32_t> d_node_leaf_id, d_tri_src;
+    prt::host::DevBuf<prt::CapsuleDev> d_capsules;
+    prt::host::DevBuf<unsigned long long> d_counters;
+    // cross-frame leaf cache of the persistent kernel (PRTC_OPT_CROSS_FRAME_CACHE)
+    prt::host::DevBuf<uint32_t> d_xc_version, d_xc_count, d_xc_leaf;
+    prt::host::DevBuf<float> d_xc_region;
+    uint32_t xc_capacity = 0;
+    uint32_t tree_version = 1;
+    uint64_t launches = 0;                  // kernels launched by step calls since the last counter reset
+    int cross_frame = 1;
+    int streamed_copy = 1;                  // PRTC_OPT_STREAMED_COPY: big host-buffer batches feed one persistent launch while it runs
+    int warp_kernel = 1;                    // small batches: one warp per character (k_step_warp); 0 = thinned lock-step kernel
+    float xc_margin = 0.5f;
+    prt::host::DevBuf<unsigned> d_work;                // work counters of the persistent kernel, one per concurrently running launch
+    prt::host::HostStage stage;                        // small host-buffer batches: records staged in mapped pinned memory
+    int staged = 1;                         // PRTC_STAGED=0: small batches take the copy path too (A/B)
+    prt::host::DevBuf<uint32_t> d_ingest;              // streamed host-buffer step: [0] arrival gate, then per-chunk and per-block completion counters
+    cudaEvent_t ingest_reset = nullptr;
+    prt::host::DevBuf<prtc_transform> d_tf;
+    prt::host::DevBuf<prtc_char_physics> d_ph;
+    // trace scratch
+    prt::host::DevBuf<prt::TraceQuery> d_tq;
+    prt::host::DevBuf<uint32_t> d_tmesh, d_tcaps;
+    prt::host::DevBuf<prt::TraceHit> d_thits;
+    prt::host::DevBuf<float> d_scratch_f;
+    prt::host::DevBuf<uint32_t> d_scratch_u;
+    // LITERAL order
+    prt::host::DevBuf<uint32_t> d_cap2char;
+    prt::host::DevBuf<float4> d_seg_start, d_seg_prev;
+    prt::host::DevBuf<float> d_last_box;
+    // CANONICAL order, JACOBI dynamic pass
+    prt::host::DevBuf<float4> d_dyn_records;
+    prt::host::DevBuf<uint32_t> d_dyn_count, d_dyn_start, d_dyn_items;
+    prt::host::DevBuf<unsigned char> d_cub_temp;
+    uint32_t dyn_first = 0, dyn_global = 0;  // this context's slice [dyn_first, dyn_first + n) of dyn_global characters
+    bool dyn_configured = false;             // prtc_dyn_configure called (multi-rank); otherwise the slice is the whole batch
+    bool dyn_initialized = false;            // stored boxes exist (first prepare creates them at the identity pose)
+    bool dyn_prepared = false;               // prtc_dyn_prepare ran for the coming step (records may have been exchanged since)
+    float world_lo[3] = {0, 0, 0}, world_hi[3] = {0, 0, 0};
+    bool literal() const { return cfg.order_mode == PRTC_ORDER_LITERAL; }
+    bool jacobi() const { return cfg.order_mode == PRTC_ORDER_CANONICAL && cfg.dyn_mode == PRTC_DYN_JACOBI; }
+};
+
+namespace prt {
+namespace host {
+
+// ---- prtc.cu ---------------------------------------------------------------------------------------------------
+int commit_impl(prtc_ctx * c);
+int fill_params(prtc_ctx * c, float dt, uint32_t n, prtc_transform * d_tf, prtc_char_physics * d_ph, StepParams & p);
+int check_bad_colliders(prtc_ctx * c, cudaStream_t on = nullptr);
+int check_mode(prtc_ctx * c, bool device_pointers);
+int upload_leaf_ids(prtc_ctx * c);               // collider id per node, for traced kernels and prtc_query_box
+
+} // namespace host
+} // namespace prt
+
+#endif
