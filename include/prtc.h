@@ -209,11 +209,7 @@ int prtc_get_counters(prtc_ctx * ctx, prtc_counters * out, int reset);
  *                          frame's motion; substeps re-test only the cached leaves.  With 0 the device walks the
  *                          tree once per substep exactly like DynamicAABBTree::query, and prtc_counters.node_tests
  *                          then equals the reference's count (the numerator of the roofline's algorithmic bytes).
- *   PRTC_OPT_QUICK_REJECT  (default 1) conservative per-triangle pre-cull ahead of the exact test (box of the capsule
- *                          segment against the triangle's box grown by the reach of a contact).
- *   PRTC_OPT_TIGHT_REJECT  (default 1) second conservative pre-cull for the triangles the box test lets through:
- *                          plane distance and edge-plane distance of the capsule segment's end points bound the
- *                          distance between any sphere centre on the segment and the triangle from below.
+ *   PRTC_OPT_QUICK_REJECT  (default 1) conservative per-triangle pre-cull ahead of the exact test.
  *   PRTC_OPT_PERSISTENT    (default 1) static pass runs as a persistent kernel whose lanes advance through their
  *                          characters independently (0: one character per lane in lock step).
  *   PRTC_OPT_CROSS_FRAME_CACHE (default 1) the persistent kernel keeps every character slot's leaf list (valid for
@@ -227,7 +223,7 @@ int prtc_get_counters(prtc_ctx * ctx, prtc_counters * out, int reset);
  *                          chunks to the device->host copy while it is still computing (0: the batch is cut into
  *                          chunks that are copied in, stepped and copied out on a few streams). */
 enum prtc_option { PRTC_OPT_FRAME_CACHE = 1, PRTC_OPT_QUICK_REJECT = 2, PRTC_OPT_PERSISTENT = 3, PRTC_OPT_CROSS_FRAME_CACHE = 4,
-                   PRTC_OPT_WARP_KERNEL = 5, PRTC_OPT_STREAMED_COPY = 6, PRTC_OPT_TIGHT_REJECT = 7 };
+                   PRTC_OPT_WARP_KERNEL = 5, PRTC_OPT_STREAMED_COPY = 6 };
 int prtc_set_option(prtc_ctx * ctx, int option, int value);
 
 /* Introspection for parity tests: the flattened tree.  leaf_mesh_ids receives the mesh-collider ids of all

@@ -67,7 +67,7 @@ __global__ void __launch_bounds__(STEP_BLOCK, 512 / STEP_BLOCK) k_step(StepParam
     }
     // largest plane distance that survives the range cull (collision_system.cpp:72, see prtc_abs_mode)
     const float dmax = (p.abs_mode == 1u) ? radius : floorf(radius) + 1.0f;
-    const bool use_qr = (p.qr_enable & 1u) != 0u, use_tq = (p.qr_enable & 2u) != 0u;
+    const bool use_qr = p.qr_enable != 0u;
 
     // ---- phase 2: collideCharacterWithWorld (physics_system.cpp:330-438) ----
     const float fsub = float(p.substeps);
@@ -397,8 +397,6 @@ __global__ void __launch_bounds__(STEP_BLOCK, 512 / STEP_BLOCK) k_step(StepParam
                     my_poly = poly++;
                     if (__float_as_uint(t0.w) == PRT_DEGENERATE_BITS) continue;       // length(n) == 0   :53
                     if (use_qr && quick_reject(smin, smax, radius, dmax, qr_eps, t0, t1, t2)) continue;
-                    if (use_tq && tight_reject(ps.A, ps.B, radius, dmax, qr_eps, v3(t0.x, t0.y, t0.z), v3(t1.x, t1.y, t1.z),
-                                               v3(t2.x, t2.y, t2.z), v3(t0.w, t1.w, t2.w))) continue;
                     pending = true;
                     break;
                 }

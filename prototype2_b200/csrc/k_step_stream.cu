@@ -122,7 +122,7 @@ __global__ void __launch_bounds__(32, 20) k_step_stream(StepParams p) {
     uint32_t f_leaf = 0, f_cur = 0, f_end = 0, n_fetched = 0, n_consumed = 0;
     bool pending = false;
     float4 t0 = make_float4(0, 0, 0, 0), t1 = t0, t2 = t0;
-    const bool use_qr = (p.qr_enable & 1u) != 0u, use_tq = (p.qr_enable & 2u) != 0u;
+    const bool use_qr = p.qr_enable != 0u;
     const bool use_cache = !(p.tune & 1u);
     const int load_batch = ((p.tune >> 8) & 0xFFu) ? int((p.tune >> 8) & 0xFFu) : LOAD_BATCH;
     const int substep_batch = ((p.tune >> 16) & 0xFFu) ? int((p.tune >> 16) & 0xFFu) : SUBSTEP_BATCH;
@@ -374,8 +374,6 @@ __global__ void __launch_bounds__(32, 20) k_step_stream(StepParams p) {
                     ++c_tri;
                     if (__float_as_uint(t0.w) == PRT_DEGENERATE_BITS) continue;       // length(n) == 0   :53
                     if (use_qr && quick_reject(smin, smax, radius, dmax, qr_eps, t0, t1, t2)) continue;
-                    if (use_tq && tight_reject(ps.A, ps.B, radius, dmax, qr_eps, v3(t0.x, t0.y, t0.z), v3(t1.x, t1.y, t1.z),
-                                               v3(t2.x, t2.y, t2.z), v3(t0.w, t1.w, t2.w))) continue;
                     pending = true;
                     break;
                 }

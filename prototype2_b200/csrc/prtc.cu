@@ -180,7 +180,7 @@ int fill_params(prtc_ctx * c, float dt, uint32_t n, prtc_transform * d_tf, prtc_
         float m = c->world_max_abs;
         float ulp = std::nextafter(m, INFINITY) - m;
         p.qr_eps = std::max(1e-3f, 64.0f * ulp);
-        p.qr_enable = (m < 1.0e6f) ? ((c->quick_reject ? 1u : 0u) | (c->tight_reject ? 2u : 0u)) : 0u;
+        p.qr_enable = (c->quick_reject && m < 1.0e6f) ? 1u : 0u;
         p.tune = (c->frame_cache ? 0u : 1u) | (c->warp_kernel ? 0u : 2u) | c->tune_hi;
         p.work_counter = c->persistent ? c->d_work.ptr : nullptr;
         p.persistent_blocks = uint32_t(c->sm_count) * 20u;
@@ -293,7 +293,6 @@ int prtc_create(const prtc_config * cfg, prtc_ctx ** out) {
     ctx->cfg = c;
     // environment overrides of the option defaults, for A/B measurements without touching the caller
     if (const char * e = std::getenv("PRTC_QUICK_REJECT")) ctx->quick_reject = std::atoi(e);
-    if (const char * e = std::getenv("PRTC_TIGHT_REJECT")) ctx->tight_reject = std::atoi(e);
     if (const char * e = std::getenv("PRTC_FRAME_CACHE")) ctx->frame_cache = std::atoi(e);
     if (const char * e = std::getenv("PRTC_PERSISTENT")) ctx->persistent = std::atoi(e);
     if (const char * e = std::getenv("PRTC_CROSS_FRAME")) ctx->cross_frame = std::atoi(e);
@@ -492,7 +491,6 @@ int prtc_set_option(prtc_ctx * c, int option, int value) {
     switch (option) {
         case PRTC_OPT_FRAME_CACHE: c->frame_cache = value != 0; return PRTC_OK;
         case PRTC_OPT_QUICK_REJECT: c->quick_reject = value != 0; return PRTC_OK;
-        case PRTC_OPT_TIGHT_REJECT: c->tight_reject = value != 0; return PRTC_OK;
         case PRTC_OPT_PERSISTENT: c->persistent = value != 0; return PRTC_OK;
         case PRTC_OPT_CROSS_FRAME_CACHE: c->cross_frame = value != 0; return PRTC_OK;
         case PRTC_OPT_WARP_KERNEL: c->warp_kernel = value != 0; return PRTC_OK;
