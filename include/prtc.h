@@ -210,6 +210,9 @@ int prtc_get_counters(prtc_ctx * ctx, prtc_counters * out, int reset);
  *                          tree once per substep exactly like DynamicAABBTree::query, and prtc_counters.node_tests
  *                          then equals the reference's count (the numerator of the roofline's algorithmic bytes).
  *   PRTC_OPT_QUICK_REJECT  (default 1) conservative per-triangle pre-cull ahead of the exact test.
+ *   PRTC_OPT_TIGHT_REJECT  (default 1) persistent kernel only: second conservative pre-cull for the triangles the box test
+ *                          lets through -- plane distance and edge-plane distance of the capsule segment's end points
+ *                          bound the distance between any sphere centre on the segment and the triangle from below.
  *   PRTC_OPT_PERSISTENT    (default 1) static pass runs as a persistent kernel whose lanes advance through their
  *                          characters independently (0: one character per lane in lock step).
  *   PRTC_OPT_CROSS_FRAME_CACHE (default 1) the persistent kernel keeps every character slot's leaf list (valid for
@@ -221,9 +224,12 @@ int prtc_get_counters(prtc_ctx * ctx, prtc_counters * out, int reset);
  *   PRTC_OPT_STREAMED_COPY (default 1) prtc_step_characters on a big static batch (>= 262144 characters) runs ONE
  *                          persistent launch that is fed by the host->device copy while it runs and hands finished
  *                          chunks to the device->host copy while it is still computing (0: the batch is cut into
- *                          chunks that are copied in, stepped and copied out on a few streams). */
+ *                          chunks that are copied in, stepped and copied out on a few streams).
+ *   PRTC_OPT_TOP_STAGING   (default 1) the kernel that refills the per-slot leaf lists walks the top levels of the tree
+ *                          (<= 1024 nodes) out of shared memory, staged per block with one TMA bulk copy (0: every
+ *                          node comes from global memory).  CANONICAL order, trees of >= 4096 nodes. */
 enum prtc_option { PRTC_OPT_FRAME_CACHE = 1, PRTC_OPT_QUICK_REJECT = 2, PRTC_OPT_PERSISTENT = 3, PRTC_OPT_CROSS_FRAME_CACHE = 4,
-                   PRTC_OPT_WARP_KERNEL = 5, PRTC_OPT_STREAMED_COPY = 6 };
+                   PRTC_OPT_WARP_KERNEL = 5, PRTC_OPT_STREAMED_COPY = 6, PRTC_OPT_TOP_STAGING = 7, PRTC_OPT_TIGHT_REJECT = 8 };
 int prtc_set_option(prtc_ctx * ctx, int option, int value);
 
 /* Introspection for parity tests: the flattened tree.  leaf_mesh_ids receives the mesh-collider ids of all
@@ -243,6 +249,14 @@ int prtc_query_box(prtc_ctx * ctx, const float aabb6[6], uint32_t * mesh_ids, ui
  * indices in traversal order.  Lets the build / flatten logic be checked on a CPU-only box by the tests. */
 int prtc_host_build_tree(const float * aabbs6, uint32_t n, float margin, uint32_t * leaf_order, float * nodes8,
                          uint32_t nodes_capacity, uint32_t * n_nodes);
+/* Host-only utility: the top-of-tree table the device stages in shared memory (PRTC_OPT_TOP_STAGING) for a flattened
+ * tree in the layout above: all nodes of depth <= D (D the largest depth whose levels together fit `cap` entries), same
+ * preorder, 8 words per entry {lo.xyz, link, hi.xyz, count} with
+ *   internal above the cut: link = table index to go on at when the box is missed, count = -1;
+ *   internal at the cut:    link = index g of the node in the full array, count = -(skip index of g);
+ *   leaf:                   link = index g of the node in the full array, count = 0.
+ * n_top = 0 when the tree has fewer than 4 * cap nodes (no staging). */
+int prtc_host_top_table(const float * nodes8, uint32_t n_nodes, uint32_t cap, float * top8, uint32_t top_capacity, uint32_t * n_top);
 
 #ifdef __cplusplus
 }

@@ -13,7 +13,7 @@ PRTC_OK, PRTC_ERR_INVALID, PRTC_ERR_CUDA, PRTC_ERR_CAPACITY, PRTC_ERR_ALLOC = ra
 ABS_INT, ABS_FLOAT = 0, 1
 ORDER_LITERAL, ORDER_CANONICAL = 0, 1
 DYN_OFF, DYN_JACOBI = 0, 2
-OPT_FRAME_CACHE, OPT_QUICK_REJECT, OPT_PERSISTENT, OPT_CROSS_FRAME_CACHE, OPT_WARP_KERNEL, OPT_STREAMED_COPY = 1, 2, 3, 4, 5, 6
+OPT_FRAME_CACHE, OPT_QUICK_REJECT, OPT_PERSISTENT, OPT_CROSS_FRAME_CACHE, OPT_WARP_KERNEL, OPT_STREAMED_COPY, OPT_TOP_STAGING, OPT_TIGHT_REJECT = 1, 2, 3, 4, 5, 6, 7, 8
 
 # every symbol include/prtc.h declares (tests check the library exports exactly these)
 SYMBOLS = (
@@ -21,7 +21,7 @@ SYMBOLS = (
     "prtc_add_model", "prtc_add_capsule", "prtc_update_capsule", "prtc_commit", "prtc_update_models", "prtc_remove_model",
     "prtc_step_characters", "prtc_step_characters_device", "prtc_step_characters_traced", "prtc_raycast", "prtc_sweep_ellipsoids",
     "prtc_set_stream", "prtc_synchronize", "prtc_get_counters", "prtc_set_option", "prtc_dyn_configure", "prtc_dyn_prepare", "prtc_dyn_buffer", "prtc_get_tree_info", "prtc_get_leaf_order",
-    "prtc_get_world_vertices", "prtc_query_box", "prtc_host_build_tree",
+    "prtc_get_world_vertices", "prtc_query_box", "prtc_host_build_tree", "prtc_host_top_table",
 )
 
 
@@ -318,3 +318,15 @@ def host_build_tree(aabbs6, margin=0.05):
     if rc != PRTC_OK:
         raise PrtcError(rc, (lib().prtc_last_error() or b"").decode())
     return order[:n], nodes[:nn.value]
+
+
+def host_top_table(nodes8, cap=1024):
+    """prtc_host_top_table: the top-of-tree table the device stages in shared memory.  No device needed."""
+    nodes = np.ascontiguousarray(nodes8, np.float32).reshape(-1, 8)
+    top = np.zeros((max(cap, 1), 8), np.float32)
+    nt = ctypes.c_uint32()
+    rc = lib().prtc_host_top_table(_vp(nodes), ctypes.c_uint32(len(nodes)), ctypes.c_uint32(cap), _vp(top), ctypes.c_uint32(len(top)),
+                                   ctypes.byref(nt))
+    if rc != PRTC_OK:
+        raise PrtcError(rc, (lib().prtc_last_error() or b"").decode())
+    return top[:nt.value]

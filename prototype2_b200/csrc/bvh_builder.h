@@ -143,5 +143,51 @@ void RefTree::flatten(FlatTree & out, LeafRange && leaf_range) const {
     }
 }
 
+// Top of the flattened tree as a compact table for staging in shared memory (k_xc_refresh): every node of depth <= D,
+// D the largest depth whose levels together fit `cap` entries, in the same right-first preorder -- so a walk that runs
+// over the table and drops into the full array below it visits nodes in the order of the plain walk and emits the same
+// leaf sequence.  Entry = FlatNode with the two integer words re-used:
+//   internal, depth <  D:  link = TABLE index to continue at when the box is missed (table skip), count = -1
+//   internal, depth == D:  link = its index g in the full array, count = -(skip of g) <= -3: on overlap the walk goes on
+//                          in the full array over [g + 1, skip)
+//   leaf:                  link = its index g in the full array, count = 0: on overlap the walk visits [g, g + 1)
+// Returns an empty table when the whole tree is not bigger than a few tables (nothing to gain).
+inline void build_top_table(std::vector<FlatNode> const & nodes, uint32_t cap, std::vector<FlatNode> & top) {
+    top.clear();
+    const size_t n = nodes.size();
+    if (n < size_t(cap) * 4) return;
+    std::vector<uint8_t> depth(n, 0);
+    std::vector<uint32_t> per_depth;
+    for (size_t i = 0; i < n; ++i) {
+        const uint32_t d = depth[i];
+        if (d >= per_depth.size()) per_depth.resize(d + 1, 0);
+        ++per_depth[d];
+        if (nodes[i].count < 0) {
+            const uint8_t dc = uint8_t(d < 255 ? d + 1 : 255);
+            depth[i + 1] = dc;
+            depth[size_t(-nodes[i].count)] = dc;
+        }
+    }
+    uint32_t D = 0, kept = per_depth[0];
+    while (D + 1 < per_depth.size() && D + 1 < 255 && kept + per_depth[D + 1] <= cap) { ++D; kept += per_depth[D]; }
+    if (D == 0) return;
+    std::vector<int32_t> table_index(n + 1, -1);
+    int32_t k = 0;
+    for (size_t i = 0; i < n; ++i) if (depth[i] <= D) table_index[i] = k++;
+    table_index[n] = k;
+    top.reserve(size_t(k));
+    for (size_t i = 0; i < n; ++i) {
+        if (depth[i] > D) continue;
+        FlatNode f = nodes[i];
+        if (nodes[i].count < 0) {
+            if (depth[i] < D) { f.link = table_index[size_t(nodes[i].link)]; f.count = -1; }   // the node after a subtree is never deeper than its root
+            else { f.link = int32_t(i); f.count = -nodes[i].link; }
+        } else {
+            f.link = int32_t(i); f.count = 0;
+        }
+        top.push_back(f);
+    }
+}
+
 } // namespace prt
 #endif

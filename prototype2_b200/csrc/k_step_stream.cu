@@ -13,49 +13,114 @@ namespace {
 // collects the overlapping leaves (emission order) and the slot is rewritten.  The list is a pure function of
 // (tree, region): it does not matter which character occupied the slot before, and k_step_stream re-checks
 // "query box inside region" at every substep, so a stale or too-small region can only cost time, never correctness.
-__global__ void __launch_bounds__(128) k_xc_refresh(StepParams p, int reuse) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= p.n) return;
-    const prtc_transform * tf = p.transforms + i;
-    const prtc_char_physics * ph = p.physics + i;
-    const V3 pos = v3(tf->position[0], tf->position[1], tf->position[2]);
-    Quat q; q.x = tf->rotation[0]; q.y = tf->rotation[1]; q.z = tf->rotation[2]; q.w = tf->rotation[3];
-    V3 vel = v3(ph->velocity[0], ph->velocity[1], ph->velocity[2]);
-    uint32_t cid = ph->collider;
-    if (cid >= p.n_capsules) cid = 0;
-    const CapsuleDev cap = p.capsules[cid];
-    const CapsuleFrame fr = capsule_frame(cap, rotation_of(q));
-    if (ph->grounded) vel = vel + ((-p.stick * p.gravity) * p.dt) * v3(ph->ground_normal[0], ph->ground_normal[1], ph->ground_normal[2]);
-    vel.x = vel.x + ph->movement[0];
-    vel.z = vel.z + ph->movement[2];
-    V3 a0, b0, eA, eB;
-    segment_ends(fr, pos, a0, b0);
-    segment_ends(fr, pos + vel, eA, eB);
-    Box R = box_union(capsule_box(a0, b0, cap.radius), capsule_box(eA, eB, cap.radius));
-    R.lo = R.lo - v3(0.25f); R.hi = R.hi + v3(0.25f);
-    const size_t s = size_t(p.xc_first) + i;
-    if (reuse && p.xc_version[s] == p.tree_version) {
-        if (p.xc_region[0 * size_t(p.xc_stride) + s] <= R.lo.x && p.xc_region[1 * size_t(p.xc_stride) + s] <= R.lo.y &&
-            p.xc_region[2 * size_t(p.xc_stride) + s] <= R.lo.z && p.xc_region[3 * size_t(p.xc_stride) + s] >= R.hi.x &&
-            p.xc_region[4 * size_t(p.xc_stride) + s] >= R.hi.y && p.xc_region[5 * size_t(p.xc_stride) + s] >= R.hi.z)
-            return;
+//
+// Top-level staging (north_star: "shared-memory or TMA staging of top-level nodes").  Every walk starts with the same
+// few hundred nodes, so a block that has at least one slot to refill brings the top-of-tree table (all nodes of depth
+// <= D, <= TOP_CAP entries, same preorder -- bvh_builder.h build_top_table) into shared memory with ONE bulk copy of the
+// TMA unit (cp.async.bulk global -> shared, completion counted on an mbarrier; SASS: UBLKCP + SYNCS), issued by one thread
+// while the others are still computing their regions.  The walk then alternates between two cursors: `k` runs over the
+// table in shared memory; an overlapping entry of depth D (or a leaf) opens the range [node, node_end) of the full array,
+// which is walked exactly as before and hands back to the table when it is exhausted.  Same node visit order, same
+// leaf sequence.  A block whose slots are all still valid (the steady state) never issues the copy.
+constexpr int XC_BLOCK = 512;
+
+__device__ __forceinline__ void mbar_init(uint64_t * bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(uint32_t(__cvta_generic_to_shared(bar))), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_load(void * smem_dst, const void * gmem_src, uint32_t bytes, uint64_t * bar) {
+    const uint32_t b = uint32_t(__cvta_generic_to_shared(bar));
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(b), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(uint32_t(__cvta_generic_to_shared(smem_dst))), "l"(gmem_src), "r"(bytes), "r"(b) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t * bar, uint32_t parity) {
+    const uint32_t b = uint32_t(__cvta_generic_to_shared(bar));
+    uint32_t done = 0;
+    while (!done) {
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(done) : "r"(b), "r"(parity) : "memory");
     }
+}
+
+__global__ void __launch_bounds__(XC_BLOCK) k_xc_refresh(StepParams p, int reuse) {
+    __shared__ __align__(128) float4 s_top[2 * TOP_CAP];
+    __shared__ __align__(8) uint64_t s_bar;
+    const bool staged = p.top != nullptr;                         // uniform over the grid
+    if (staged && threadIdx.x == 0) mbar_init(&s_bar, 1);
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    bool walk = i < p.n;
+    Box R; R.lo = v3(0.0f); R.hi = v3(0.0f);
+    const size_t s = size_t(p.xc_first) + i;
+    if (walk) {
+        const prtc_transform * tf = p.transforms + i;
+        const prtc_char_physics * ph = p.physics + i;
+        const V3 pos = v3(tf->position[0], tf->position[1], tf->position[2]);
+        Quat q; q.x = tf->rotation[0]; q.y = tf->rotation[1]; q.z = tf->rotation[2]; q.w = tf->rotation[3];
+        V3 vel = v3(ph->velocity[0], ph->velocity[1], ph->velocity[2]);
+        uint32_t cid = ph->collider;
+        if (cid >= p.n_capsules) cid = 0;
+        const CapsuleDev cap = p.capsules[cid];
+        const CapsuleFrame fr = capsule_frame(cap, rotation_of(q));
+        if (ph->grounded) vel = vel + ((-p.stick * p.gravity) * p.dt) * v3(ph->ground_normal[0], ph->ground_normal[1], ph->ground_normal[2]);
+        vel.x = vel.x + ph->movement[0];
+        vel.z = vel.z + ph->movement[2];
+        V3 a0, b0, eA, eB;
+        segment_ends(fr, pos, a0, b0);
+        segment_ends(fr, pos + vel, eA, eB);
+        R = box_union(capsule_box(a0, b0, cap.radius), capsule_box(eA, eB, cap.radius));
+        R.lo = R.lo - v3(0.25f); R.hi = R.hi + v3(0.25f);
+        if (reuse && p.xc_version[s] == p.tree_version) {
+            if (p.xc_region[0 * size_t(p.xc_stride) + s] <= R.lo.x && p.xc_region[1 * size_t(p.xc_stride) + s] <= R.lo.y &&
+                p.xc_region[2 * size_t(p.xc_stride) + s] <= R.lo.z && p.xc_region[3 * size_t(p.xc_stride) + s] >= R.hi.x &&
+                p.xc_region[4 * size_t(p.xc_stride) + s] >= R.hi.y && p.xc_region[5 * size_t(p.xc_stride) + s] >= R.hi.z)
+                walk = false;
+        }
+    }
+    uint32_t n_top = 0;
+    if (staged) {
+        // the barrier is initialised (thread 0, above) before anyone can wait on it; the vote doubles as that fence
+        if (!__syncthreads_or(walk ? 1 : 0)) return;
+        if (threadIdx.x == 0) bulk_load(s_top, p.top, p.n_top * 32u, &s_bar);
+        n_top = p.n_top;
+    }
+    if (!walk) return;
     if (reuse) { R.lo = R.lo - v3(p.xc_margin); R.hi = R.hi + v3(p.xc_margin); }
-    uint32_t node = 0, ncache = 0;
-    while (node < p.n_nodes) {
-        const float4 lo = __ldg(p.nodes + 2 * node);
-        const float4 hi = __ldg(p.nodes + 2 * node + 1);
-        const bool ov = node_overlaps(lo, hi, R);
-        const int cnt = __float_as_int(hi.w);
-        if (cnt < 0) {
-            node = ov ? node + 1 : uint32_t(__float_as_int(lo.w));
-        } else {
-            if (ov) {
-                if (ncache == XC_CAP) { ncache = 0xFFFFFFFFu; break; }
-                p.xc_leaf[size_t(ncache) * p.xc_stride + s] = node;
-                ++ncache;
+    if (staged) mbar_wait(&s_bar, 0);
+    // k: cursor in the staged table; [node, node_end): open range of the full array (everything, when nothing is staged)
+    uint32_t k = 0, node = 0, node_end = staged ? 0u : p.n_nodes, ncache = 0;
+    for (;;) {
+        if (node != node_end) {
+            const float4 lo = __ldg(p.nodes + 2 * node);
+            const float4 hi = __ldg(p.nodes + 2 * node + 1);
+            const bool ov = node_overlaps(lo, hi, R);
+            const int cnt = __float_as_int(hi.w);
+            if (cnt < 0) {
+                node = ov ? node + 1 : uint32_t(__float_as_int(lo.w));
+            } else {
+                if (ov) {
+                    if (ncache == XC_CAP) { ncache = 0xFFFFFFFFu; break; }
+                    p.xc_leaf[size_t(ncache) * p.xc_stride + s] = node;
+                    ++ncache;
+                }
+                node = node + 1;
             }
-            node = node + 1;
+        } else {
+            if (k >= n_top) break;
+            const float4 lo = s_top[2 * k];
+            const float4 hi = s_top[2 * k + 1];
+            const bool ov = node_overlaps(lo, hi, R);
+            const int cnt = __float_as_int(hi.w);
+            const uint32_t link = uint32_t(__float_as_int(lo.w));
+            if (cnt == -1) {
+                k = ov ? k + 1 : link;
+            } else {
+                if (ov) {
+                    if (cnt == 0) { node = link; node_end = link + 1; }            // a leaf above the cut
+                    else { node = link + 1; node_end = uint32_t(-cnt); }           // subtree below the cut: its root overlaps, go on with the first child
+                }
+                ++k;
+            }
         }
     }
     if (ncache == 0xFFFFFFFFu) { p.xc_version[s] = 0u; return; }   // too many leaves for a slot: this character walks per substep
@@ -82,13 +147,23 @@ __global__ void __launch_bounds__(128) k_xc_refresh(StepParams p, int reuse) {
 constexpr int ST_LOAD = 0, ST_SUBSTEP = 1, ST_STREAM = 2, ST_DONE = 3;
 constexpr int LOAD_BATCH = 16;       // lanes that must wait for new work before the (expensive) LOAD stage runs
 constexpr int SUBSTEP_BATCH = 8;     // same for the SUBSTEP stage
+constexpr int EXACT_BATCH = 12;      // TRIPS: lanes that must hold a triangle before the exact test runs
 
 //
 // GATED: the batch is still arriving over PCIe while the kernel runs (prtc_step_characters with host buffers).  The
 // copy-in stream publishes how many characters have landed in `*gate`; LOAD waits for its own indices.  Every finished
 // character is counted (per 1024, then per 65536) so the copy-out stream can start on a chunk the moment its last
 // character is written, while later chunks are still being computed.
-template <bool GATED>
+//
+// TRIPS: how the STREAM stage is scheduled.  false: every streaming lane filters until IT has a triangle for the exact test
+// and the test runs as soon as any lane has one (v7-v9) -- the filter loop then ends with the slowest lane (geometric
+// tail: 9 of 32 lanes active on average), and the better the pre-cull, the longer that tail.  true: the streaming lanes
+// filter ONE triangle per trip, in lock step, and the trips go on until `exact_batch` lanes hold a triangle for the
+// exact test (or nobody is left to filter); lanes that found theirs early wait, but they are few until the batch is
+// full, and the exact test always runs with a full batch.  This is what makes the second-stage pre-cull
+// (tight_reject, collide.cuh) pay: it cuts the exact tests per query from 8.2 to 2.1 at C4 and, with trips, the longer
+// run of rejected triangles in front of each costs lock-step trips instead of a longer tail.
+template <bool GATED, bool TRIPS>
 __global__ void __launch_bounds__(32, 20) k_step_stream(StepParams p) {
     constexpr unsigned FULL = 0xffffffffu;
     __shared__ uint32_t s_leaf[LEAF_CAP][32];              // candidate leaves of the substep (leaf_entry words), emission order
@@ -122,10 +197,11 @@ __global__ void __launch_bounds__(32, 20) k_step_stream(StepParams p) {
     uint32_t f_leaf = 0, f_cur = 0, f_end = 0, n_fetched = 0, n_consumed = 0;
     bool pending = false;
     float4 t0 = make_float4(0, 0, 0, 0), t1 = t0, t2 = t0;
-    const bool use_qr = p.qr_enable != 0u;
+    const bool use_qr = (p.qr_enable & 1u) != 0u, use_tq = (p.qr_enable & 2u) != 0u;
     const bool use_cache = !(p.tune & 1u);
     const int load_batch = ((p.tune >> 8) & 0xFFu) ? int((p.tune >> 8) & 0xFFu) : LOAD_BATCH;
     const int substep_batch = ((p.tune >> 16) & 0xFFu) ? int((p.tune >> 16) & 0xFFu) : SUBSTEP_BATCH;
+    const int exact_batch = ((p.tune >> 24) & 0x3Fu) ? int((p.tune >> 24) & 0x3Fu) : EXACT_BATCH;
     for (int f = 0; f < P_COUNT; ++f) s_park[f][tid] = 0.0f;
 
     // A candidate leaf is buffered as its triangle range when that fits one word (first < 2^24, count < 128: every
@@ -358,6 +434,44 @@ __global__ void __launch_bounds__(32, 20) k_step_stream(StepParams p) {
         }
 
         // ---------------- STREAM: filter until a triangle needs the exact test ----------------
+        bool run_exact;
+        if (TRIPS) {
+            // lock-step trips: one triangle per streaming lane and trip
+            const V3 smin = gmin(ps.A, ps.B), smax = gmax(ps.A, ps.B);
+            const float qr_eps = s_park[P_QR_EPS][tid];
+            const float dmax = (p.abs_mode == 1u) ? radius : floorf(radius) + 1.0f;   // largest plane distance surviving the range cull
+            unsigned m_pend, m_filt;
+            for (;;) {
+                if (state == ST_STREAM && !pending) {
+                    if (n_consumed != n_fetched) {
+                        if (n_fetched - n_consumed >= 2) cp_async_wait<1>(); else cp_async_wait<0>();
+                        const uint32_t slot = n_consumed % TRI_RING;
+                        t0 = s_tri[slot][0][tid];
+                        t1 = s_tri[slot][1][tid];
+                        t2 = s_tri[slot][2][tid];
+                        ++n_consumed;
+                        fetch_one();
+                        ++c_tri;
+                        pending = __float_as_uint(t0.w) != PRT_DEGENERATE_BITS &&                         // length(n) == 0   :53
+                                  !(use_qr && quick_reject(smin, smax, radius, dmax, qr_eps, t0, t1, t2)) &&
+                                  !(use_tq && tight_reject(ps.A, ps.B, radius, dmax, qr_eps, v3(t0.x, t0.y, t0.z), v3(t1.x, t1.y, t1.z),
+                                                           v3(t2.x, t2.y, t2.z), v3(t0.w, t1.w, t2.w)));
+                    } else if (node < p.n_nodes) {                    // more leaves than the buffer holds: next pass
+                        ordered_walk();
+                        if (nleaf) found = true;
+                        start_stream();
+                        if (n_fetched == 0) state = ST_SUBSTEP;
+                    } else {
+                        state = ST_SUBSTEP;                           // this substep's candidates are exhausted
+                    }
+                }
+                m_pend = __ballot_sync(FULL, pending);
+                m_filt = __ballot_sync(FULL, state == ST_STREAM && !pending);
+                if (m_filt == 0u || __popc(m_pend) >= exact_batch) break;
+                if (__popc(__ballot_sync(FULL, state == ST_SUBSTEP)) >= substep_batch) break;   // let them start their next substep first
+            }
+            run_exact = m_pend != 0u && (m_filt == 0u || __popc(m_pend) >= exact_batch);
+        } else {
         if (state == ST_STREAM && !pending) {
             const V3 smin = gmin(ps.A, ps.B), smax = gmax(ps.A, ps.B);
             const float qr_eps = s_park[P_QR_EPS][tid];
@@ -374,6 +488,8 @@ __global__ void __launch_bounds__(32, 20) k_step_stream(StepParams p) {
                     ++c_tri;
                     if (__float_as_uint(t0.w) == PRT_DEGENERATE_BITS) continue;       // length(n) == 0   :53
                     if (use_qr && quick_reject(smin, smax, radius, dmax, qr_eps, t0, t1, t2)) continue;
+                    if (use_tq && tight_reject(ps.A, ps.B, radius, dmax, qr_eps, v3(t0.x, t0.y, t0.z), v3(t1.x, t1.y, t1.z),
+                                               v3(t2.x, t2.y, t2.z), v3(t0.w, t1.w, t2.w))) continue;
                     pending = true;
                     break;
                 }
@@ -389,9 +505,11 @@ __global__ void __launch_bounds__(32, 20) k_step_stream(StepParams p) {
                 }
             }
         }
+        run_exact = __any_sync(FULL, pending);
+        }
 
         // ---------------- exact tests, converged ----------------
-        if (__any_sync(FULL, pending)) {
+        if (run_exact) {
             if (pending) {
                 pending = false;
                 Contact ct;
@@ -434,13 +552,14 @@ __global__ void __launch_bounds__(32, 20) k_step_stream(StepParams p) {
 } // namespace
 
 void launch_k_xc_refresh(StepParams const & p, cudaStream_t stream) {
-    k_xc_refresh<<<(p.n + 127) / 128, 128, 0, stream>>>(p, p.xc_reuse ? 1 : 0);
+    k_xc_refresh<<<(p.n + XC_BLOCK - 1) / XC_BLOCK, XC_BLOCK, 0, stream>>>(p, p.xc_reuse ? 1 : 0);
 }
 
 void launch_k_step_stream(StepParams const & p, uint32_t blocks, bool gated, cudaStream_t stream) {
     cudaMemsetAsync(p.work_counter, 0, sizeof(unsigned), stream);
-    if (gated) k_step_stream<true><<<blocks, 32, 0, stream>>>(p);
-    else k_step_stream<false><<<blocks, 32, 0, stream>>>(p);
+    const bool trips = !(p.tune & 0x40000000u);                  // PRTC_TUNE bit 30: the v9 scheduling of the STREAM stage (A/B)
+    if (gated) { if (trips) k_step_stream<true, true><<<blocks, 32, 0, stream>>>(p); else k_step_stream<true, false><<<blocks, 32, 0, stream>>>(p); }
+    else { if (trips) k_step_stream<false, true><<<blocks, 32, 0, stream>>>(p); else k_step_stream<false, false><<<blocks, 32, 0, stream>>>(p); }
 }
 
 } // namespace prt

@@ -64,7 +64,7 @@ struct StepParams {
     uint32_t substeps, abs_mode;
     // conservative pre-cull (kernels.cu quick_reject): margin and enable, derived from the scene extent at commit
     float qr_eps;
-    uint32_t qr_enable;
+    uint32_t qr_enable;             // bit 0: box cull (quick_reject), bit 1: plane/edge cull (tight_reject, collide.cuh)
     uint32_t tune;                  // bit 0: frame cache OFF (walk the tree every substep, reference-equivalent counters)
     unsigned long long * counters;  // prtc_counters layout
     uint32_t * host_flags;          // k_step_warp, small host-buffer batches: host-mapped words the kernel raises --
@@ -79,6 +79,8 @@ struct StepParams {
     uint32_t tree_version;          // bumped on every re-flatten (>= 1)
     float xc_margin;                // how far beyond the frame's needed region a fresh list reaches
     uint32_t xc_reuse;              // 1: keep slots across frames (PRTC_OPT_CROSS_FRAME_CACHE), 0: rebuild every frame
+    const float4 * top;             // k_xc_refresh: top-of-tree table staged in shared memory (2 float4 per entry), null => plain walk
+    uint32_t n_top;
     uint32_t persistent_blocks;     // k_step_stream: resident blocks to launch
     // k_step_stream fed by a host->device copy that is still in flight (prtc_step_characters on big host batches):
     const uint32_t * gate;          // characters [0, *gate) have arrived; advanced by the copy-in stream, polled by LOAD
@@ -88,6 +90,7 @@ struct StepParams {
     TraceBuffers trace;
 };
 
+constexpr uint32_t TOP_CAP = 1024;             // entries of the top-of-tree table k_xc_refresh stages in shared memory (32 KB)
 constexpr uint32_t INGEST_SUB_SHIFT = 10;      // 1024 characters per completion counter (keeps the atomics spread out)
 constexpr uint32_t INGEST_CHUNK_SHIFT = 6;     // 64 of those = 65536 characters per copy chunk (5.5 MB in, 5.5 MB out)
 

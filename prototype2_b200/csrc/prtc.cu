@@ -140,6 +140,13 @@ int commit_impl(prtc_ctx * c) {
             PRTC_CUDA(cudaMemcpyAsync(c->d_nodes.ptr, c->flat.nodes.data(), nn * sizeof(FlatNode), cudaMemcpyHostToDevice, s));
             c->leaf_ids_stale = true;            // only traces and prtc_query_box read them: uploaded on demand
         }
+        // top levels as a compact table for k_xc_refresh (the LITERAL tree changes shape every frame and never gets there)
+        c->top.clear();
+        if (!c->literal()) build_top_table(c->flat.nodes, TOP_CAP, c->top);
+        if (!c->top.empty()) {
+            PRTC_CUDA(c->d_top.reserve(c->top.size() * 2));
+            PRTC_CUDA(cudaMemcpyAsync(c->d_top.ptr, c->top.data(), c->top.size() * sizeof(FlatNode), cudaMemcpyHostToDevice, s));
+        }
         if (rebuild_tris) {
             PRTC_CUDA(c->d_tri_src.reserve(nt));
             PRTC_CUDA(c->d_tris.reserve(nt * 3));
@@ -180,7 +187,7 @@ int fill_params(prtc_ctx * c, float dt, uint32_t n, prtc_transform * d_tf, prtc_
         float m = c->world_max_abs;
         float ulp = std::nextafter(m, INFINITY) - m;
         p.qr_eps = std::max(1e-3f, 64.0f * ulp);
-        p.qr_enable = (c->quick_reject && m < 1.0e6f) ? 1u : 0u;
+        p.qr_enable = (m < 1.0e6f) ? ((c->quick_reject ? 1u : 0u) | (c->tight_reject ? 2u : 0u)) : 0u;
         p.tune = (c->frame_cache ? 0u : 1u) | (c->warp_kernel ? 0u : 2u) | c->tune_hi;
         p.work_counter = c->persistent ? c->d_work.ptr : nullptr;
         p.persistent_blocks = uint32_t(c->sm_count) * 20u;
@@ -197,6 +204,7 @@ int fill_params(prtc_ctx * c, float dt, uint32_t n, prtc_transform * d_tf, prtc_
             p.xc_version = c->d_xc_version.ptr; p.xc_region = c->d_xc_region.ptr; p.xc_count = c->d_xc_count.ptr; p.xc_leaf = c->d_xc_leaf.ptr;
             p.xc_stride = c->xc_capacity; p.xc_first = 0;
             p.xc_reuse = c->cross_frame ? 1u : 0u;
+            if (c->top_staging && !c->top.empty()) { p.top = c->d_top.ptr; p.n_top = uint32_t(c->top.size()); }
         }
     }
     return PRTC_OK;
@@ -293,11 +301,13 @@ int prtc_create(const prtc_config * cfg, prtc_ctx ** out) {
     ctx->cfg = c;
     // environment overrides of the option defaults, for A/B measurements without touching the caller
     if (const char * e = std::getenv("PRTC_QUICK_REJECT")) ctx->quick_reject = std::atoi(e);
+    if (const char * e = std::getenv("PRTC_TIGHT_REJECT")) ctx->tight_reject = std::atoi(e);
     if (const char * e = std::getenv("PRTC_FRAME_CACHE")) ctx->frame_cache = std::atoi(e);
     if (const char * e = std::getenv("PRTC_PERSISTENT")) ctx->persistent = std::atoi(e);
     if (const char * e = std::getenv("PRTC_CROSS_FRAME")) ctx->cross_frame = std::atoi(e);
     if (const char * e = std::getenv("PRTC_WARP_KERNEL")) ctx->warp_kernel = std::atoi(e);
     if (const char * e = std::getenv("PRTC_STREAMED_COPY")) ctx->streamed_copy = std::atoi(e);
+    if (const char * e = std::getenv("PRTC_TOP_STAGING")) ctx->top_staging = std::atoi(e);
     if (const char * e = std::getenv("PRTC_STAGED")) ctx->staged = std::atoi(e);
     if (const char * e = std::getenv("PRTC_XC_MARGIN")) ctx->xc_margin = float(std::atof(e));
     if (const char * e = std::getenv("PRTC_TUNE")) ctx->tune_hi = uint32_t(std::strtoul(e, nullptr, 0)) & 0xFFFFFF00u;
@@ -321,7 +331,7 @@ void prtc_destroy(prtc_ctx * c) {
     cudaSetDevice(c->cfg.device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     c->d_raw.release(); c->d_world.release(); c->d_aabbs.release(); c->d_meshes.release(); c->d_xforms.release();
-    c->d_nodes.release(); c->d_tris.release(); c->d_node_leaf_id.release(); c->d_tri_src.release();
+    c->d_nodes.release(); c->d_top.release(); c->d_tris.release(); c->d_node_leaf_id.release(); c->d_tri_src.release();
     c->d_capsules.release(); c->d_counters.release(); c->d_work.release(); c->d_ingest.release(); c->stage.release();
     c->d_xc_version.release(); c->d_xc_count.release(); c->d_xc_leaf.release(); c->d_xc_region.release(); c->d_tf.release(); c->d_ph.release();
     c->d_tq.release(); c->d_tmesh.release(); c->d_tcaps.release(); c->d_thits.release();
@@ -495,6 +505,8 @@ int prtc_set_option(prtc_ctx * c, int option, int value) {
         case PRTC_OPT_CROSS_FRAME_CACHE: c->cross_frame = value != 0; return PRTC_OK;
         case PRTC_OPT_WARP_KERNEL: c->warp_kernel = value != 0; return PRTC_OK;
         case PRTC_OPT_STREAMED_COPY: c->streamed_copy = value != 0; return PRTC_OK;
+        case PRTC_OPT_TOP_STAGING: c->top_staging = value != 0; return PRTC_OK;
+        case PRTC_OPT_TIGHT_REJECT: c->tight_reject = value != 0; return PRTC_OK;
         default: return fail(PRTC_ERR_INVALID, "prtc_set_option: unknown option");
     }
 }
@@ -524,6 +536,19 @@ int prtc_host_build_tree(const float * aabbs6, uint32_t n, float margin, uint32_
     if (nodes8) {
         if (nodes_capacity < flat.nodes.size()) return fail(PRTC_ERR_CAPACITY, "prtc_host_build_tree: node buffer too small");
         std::memcpy(nodes8, flat.nodes.data(), flat.nodes.size() * sizeof(FlatNode));
+    }
+    return PRTC_OK;
+}
+
+int prtc_host_top_table(const float * nodes8, uint32_t n_nodes, uint32_t cap, float * top8, uint32_t top_capacity, uint32_t * n_top) {
+    if ((n_nodes && !nodes8) || !n_top) return fail(PRTC_ERR_INVALID, "prtc_host_top_table: null argument");
+    std::vector<FlatNode> nodes(n_nodes), top;
+    if (n_nodes) std::memcpy(nodes.data(), nodes8, size_t(n_nodes) * sizeof(FlatNode));
+    build_top_table(nodes, cap, top);
+    *n_top = uint32_t(top.size());
+    if (top8) {
+        if (top_capacity < top.size()) return fail(PRTC_ERR_CAPACITY, "prtc_host_top_table: table buffer too small");
+        if (!top.empty()) std::memcpy(top8, top.data(), top.size() * sizeof(FlatNode));
     }
     return PRTC_OK;
 }

@@ -115,6 +115,7 @@ struct prtc_ctx {
     uint32_t tune_hi = 0;                   // PRTC_TUNE: batch thresholds of k_step_stream (bits 8-15 load, 16-23 substep), experiments
     int sm_count = 148;
     int quick_reject = 1;                   // PRTC_OPT_QUICK_REJECT
+    int tight_reject = 1;                   // PRTC_OPT_TIGHT_REJECT (k_step_stream only)
     std::vector<uint32_t> moved_models;     // models whose transform changed (prtc_update_models)
 
     // device
@@ -122,6 +123,8 @@ struct prtc_ctx {
     prt::host::DevBuf<prt::MeshDev> d_meshes;
     prt::host::DevBuf<prt::ModelXform> d_xforms;
     prt::host::DevBuf<float4> d_nodes, d_tris;
+    prt::host::DevBuf<float4> d_top;        // top-of-tree table (bvh_builder.h build_top_table), CANONICAL order only
+    std::vector<prt::FlatNode> top;
     prt::host::DevBuf<uint32_t> d_node_leaf_id, d_tri_src;
     prt::host::DevBuf<prt::CapsuleDev> d_capsules;
     prt::host::DevBuf<unsigned long long> d_counters;
@@ -132,6 +135,7 @@ struct prtc_ctx {
     uint32_t tree_version = 1;
     uint64_t launches = 0;                  // kernels launched by step calls since the last counter reset
     int cross_frame = 1;
+    int top_staging = 1;                    // PRTC_OPT_TOP_STAGING: k_xc_refresh walks the top levels out of shared memory
     int streamed_copy = 1;                  // PRTC_OPT_STREAMED_COPY: big host-buffer batches feed one persistent launch while it runs
     int warp_kernel = 1;                    // small batches: one warp per character (k_step_warp); 0 = thinned lock-step kernel
     float xc_margin = 0.5f;

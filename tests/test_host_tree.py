@@ -111,3 +111,99 @@ def test_empty_and_single():
     order, nodes = capi.host_build_tree(np.array([[0, 0, 0, 1, 1, 1]], np.float32))
     assert list(order) == [0] and len(nodes) == 1 and nodes[0, 7].view(np.int32) == 1
     assert np.allclose(nodes[0, 0:3], -0.05) and np.allclose(nodes[0, 4:7], 1.05)
+
+
+def walk_staged(top, nodes, box):
+    """numpy restatement of k_xc_refresh's walk with the top-of-tree table (k_step_stream.cu): cursor k over the table,
+    [node, node_end) = open range of the full array; returns the emitted NODE indices and the two test counts"""
+    tl, tc = top[:, 3].view(np.int32), top[:, 7].view(np.int32)
+    nl, nc = nodes[:, 3].view(np.int32), nodes[:, 7].view(np.int32)
+
+    def ov(rec):
+        lo, hi = rec[0:3], rec[4:7]
+        return not (lo[0] > box[3] or hi[0] < box[0] or lo[1] > box[4] or hi[1] < box[1] or lo[2] > box[5] or hi[2] < box[2])
+    out, k, node, node_end, t_top, t_full = [], 0, 0, 0, 0, 0
+    while True:
+        if node != node_end:
+            t_full += 1
+            o = ov(nodes[node])
+            if nc[node] < 0:
+                node = node + 1 if o else int(nl[node])
+            else:
+                if o:
+                    out.append(node)
+                node += 1
+            assert node <= node_end
+        else:
+            if k >= len(top):
+                break
+            t_top += 1
+            o = ov(top[k])
+            if tc[k] == -1:
+                k = k + 1 if o else int(tl[k])
+            else:
+                if o:
+                    if tc[k] == 0:
+                        node, node_end = int(tl[k]), int(tl[k]) + 1
+                    else:
+                        node, node_end = int(tl[k]) + 1, -int(tc[k])
+                k += 1
+    return out, t_top, t_full
+
+
+def walk_nodes(nodes, box):
+    """plain walk returning node indices of the overlapping leaves"""
+    nl, nc = nodes[:, 3].view(np.int32), nodes[:, 7].view(np.int32)
+    out, i, tested = [], 0, 0
+    while i < len(nodes):
+        lo, hi = nodes[i, 0:3], nodes[i, 4:7]
+        tested += 1
+        o = not (lo[0] > box[3] or hi[0] < box[0] or lo[1] > box[4] or hi[1] < box[1] or lo[2] > box[5] or hi[2] < box[2])
+        if nc[i] < 0:
+            i = i + 1 if o else int(nl[i])
+        else:
+            if o:
+                out.append(i)
+            i += 1
+    return out, tested
+
+
+@pytest.mark.parametrize("cap", [16, 64, 1024])
+def test_top_table_walk_equals_plain_walk(cap):
+    """PRTC_OPT_TOP_STAGING: the walk over the staged top levels + the full array below the cut emits the same leaf
+    sequence as the plain walk, and tests each node of the plain walk once (leaves above the cut twice)"""
+    rng = np.random.default_rng(11)
+    xyz, mf, mc = scenes.terrain(96, 2, 2)
+    boxes = mesh_boxes(xyz, mf, mc)
+    extra = rng.uniform(0, 96, (3000, 3)).astype(np.float32)                 # an unbalanced part: clustered random boxes
+    extra[:, 1] = rng.uniform(-2, 6, 3000)
+    boxes = np.concatenate([boxes, np.concatenate([extra, extra + rng.uniform(0.1, 4, (3000, 3)).astype(np.float32)], axis=1)])
+    _, nodes = capi.host_build_tree(boxes)
+    top = capi.host_top_table(nodes, cap)
+    if len(nodes) < 4 * cap:
+        assert len(top) == 0
+        return
+    assert 0 < len(top) <= cap
+    tc = top[:, 7].view(np.int32)
+    assert (tc == -1).any() and (tc < -1).any()
+    # entries keep the boxes of the nodes they stand for
+    g = top[:, 3].view(np.int32)
+    for k in np.nonzero(tc != -1)[0][:200]:
+        assert np.array_equal(top[k, [0, 1, 2, 4, 5, 6]], nodes[g[k], [0, 1, 2, 4, 5, 6]])
+    for q in range(300):
+        c = rng.uniform(0, 96, 3)
+        c[1] = rng.uniform(-2, 3)
+        e = rng.uniform(0.2, 6.0, 3) if q % 10 else np.array([200.0, 200.0, 200.0])   # every 10th box covers everything
+        box = np.concatenate([c - e, c + e]).astype(np.float32)
+        plain, tested = walk_nodes(nodes, box)
+        staged, t_top, t_full = walk_staged(top, nodes, box)
+        assert staged == plain
+        leaf_hits_above_cut = sum(1 for k in range(len(top)) if tc[k] == 0 and not (
+            top[k, 0] > box[3] or top[k, 4] < box[0] or top[k, 1] > box[4] or top[k, 5] < box[1] or top[k, 2] > box[5] or top[k, 6] < box[2]))
+        assert t_top + t_full == tested + leaf_hits_above_cut
+
+
+def test_top_table_small_tree_is_not_staged():
+    _, nodes = capi.host_build_tree(np.array([[0, 0, 0, 1, 1, 1], [2, 0, 0, 3, 1, 1], [0, 2, 0, 1, 3, 1]], np.float32))
+    assert len(capi.host_top_table(nodes, 1024)) == 0
+    assert len(capi.host_top_table(np.zeros((0, 8), np.float32), 1024)) == 0
