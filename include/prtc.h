@@ -210,9 +210,6 @@ int prtc_get_counters(prtc_ctx * ctx, prtc_counters * out, int reset);
  *                          tree once per substep exactly like DynamicAABBTree::query, and prtc_counters.node_tests
  *                          then equals the reference's count (the numerator of the roofline's algorithmic bytes).
  *   PRTC_OPT_QUICK_REJECT  (default 1) conservative per-triangle pre-cull ahead of the exact test.
- *   PRTC_OPT_TIGHT_REJECT  (default 1) persistent kernel only: second conservative pre-cull for the triangles the box test
- *                          lets through -- plane distance and edge-plane distance of the capsule segment's end points
- *                          bound the distance between any sphere centre on the segment and the triangle from below.
  *   PRTC_OPT_PERSISTENT    (default 1) static pass runs as a persistent kernel whose lanes advance through their
  *                          characters independently (0: one character per lane in lock step).
  *   PRTC_OPT_CROSS_FRAME_CACHE (default 1) the persistent kernel keeps every character slot's leaf list (valid for
@@ -229,7 +226,7 @@ int prtc_get_counters(prtc_ctx * ctx, prtc_counters * out, int reset);
  *                          (<= 1024 nodes) out of shared memory, staged per block with one TMA bulk copy (0: every
  *                          node comes from global memory).  CANONICAL order, trees of >= 4096 nodes. */
 enum prtc_option { PRTC_OPT_FRAME_CACHE = 1, PRTC_OPT_QUICK_REJECT = 2, PRTC_OPT_PERSISTENT = 3, PRTC_OPT_CROSS_FRAME_CACHE = 4,
-                   PRTC_OPT_WARP_KERNEL = 5, PRTC_OPT_STREAMED_COPY = 6, PRTC_OPT_TOP_STAGING = 7, PRTC_OPT_TIGHT_REJECT = 8 };
+                   PRTC_OPT_WARP_KERNEL = 5, PRTC_OPT_STREAMED_COPY = 6, PRTC_OPT_TOP_STAGING = 7 };
 int prtc_set_option(prtc_ctx * ctx, int option, int value);
 
 /* Introspection for parity tests: the flattened tree.  leaf_mesh_ids receives the mesh-collider ids of all

@@ -13,7 +13,7 @@ PRTC_OK, PRTC_ERR_INVALID, PRTC_ERR_CUDA, PRTC_ERR_CAPACITY, PRTC_ERR_ALLOC = ra
 ABS_INT, ABS_FLOAT = 0, 1
 ORDER_LITERAL, ORDER_CANONICAL = 0, 1
 DYN_OFF, DYN_JACOBI = 0, 2
-OPT_FRAME_CACHE, OPT_QUICK_REJECT, OPT_PERSISTENT, OPT_CROSS_FRAME_CACHE, OPT_WARP_KERNEL, OPT_STREAMED_COPY, OPT_TOP_STAGING, OPT_TIGHT_REJECT = 1, 2, 3, 4, 5, 6, 7, 8
+OPT_FRAME_CACHE, OPT_QUICK_REJECT, OPT_PERSISTENT, OPT_CROSS_FRAME_CACHE, OPT_WARP_KERNEL, OPT_STREAMED_COPY, OPT_TOP_STAGING = 1, 2, 3, 4, 5, 6, 7
 
 # every symbol include/prtc.h declares (tests check the library exports exactly these)
 SYMBOLS = (

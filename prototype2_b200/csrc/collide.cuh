@@ -197,64 +197,6 @@ PRT_HD bool capsule_triangle(Pose const & ps, float radius, uint32_t abs_mode, V
     return true;
 }
 
-// Second-stage conservative pre-cull (the first stage is the box test quick_reject in step_common.cuh).
-//
-// capsule_triangle() reports a contact only through `inside || intersects` (collision_system.cpp:101), and both put
-// `center` -- a point of the capsule segment AB (closestPointOnLineSegment, :67) -- close to the triangle:
-//   intersects -> a point of an edge lies within `radius` of center                                   (:82-99)
-//   inside     -> the projection of center onto the plane lies inside all three edge planes and the plane distance
-//                 is in [0, dmax)  (back-face and range culls :71-72; dmax as in quick_reject)        (:74-80)
-// With the unit normal n and the outward in-plane edge normals m_e = e x n (the reference's own inside test is
-// (p - v_e) . m_e <= 0, by the triple-product identity), every point Q of the triangle has (Q - v_e) . m_e <= 0 and
-// (Q - pa) . n == 0, and both forms are linear along AB, so for every centre P on AB
-//   plane distance      dlo <= (P - pa) . n <= dhi          (dlo/dhi = min/max over the two end points)
-//   |P - Q|^2           >=  max(0, dlo)^2 + max(0, s)^2     (s = max over the edges of min over the end points of
-//                                                            (. - v_e) . m_e / |e|)
-// Hence no contact is possible at this pose when
-//   dlo > dmax + eps,   or   dhi < -eps,   or   (s > eps  and  max(0, dlo)^2 + s^2 > (radius + eps)^2)
-// eps absorbs the rounding of the exact test's intermediate points and of this test (a few ulp of the largest
-// coordinate; the caller passes several times the first stage's margin).  The edge-plane argument needs a stored
-// normal that really is perpendicular to the edges, which rounding cannot guarantee for slivers: the test only
-// answers for triangles whose squared area is at least 2^-4 |ab|^2 |ac|^2 (sine of the angle at pa >= 1/4; the
-// normal of such a triangle is tilted by < 1e-6 rad), checked here with the same quantities.  NaNs anywhere make
-// dA or dB NaN (a non-finite vertex poisons the stored normal) => "not rejected".  MUFU.RSQ / fused multiply-adds are
-// fine here: nothing computed in this function reaches an output.
-PRT_HD float rsq_approx(float x) {
-#ifdef __CUDA_ARCH__
-    return rsqrtf(x);
-#else
-    return 1.0f / sqrtf(x);
-#endif
-}
-PRT_HD float fdot(V3 a, V3 b) { return fmaf(a.x, b.x, fmaf(a.y, b.y, a.z * b.z)); }
-PRT_HD V3 fcross(V3 a, V3 b) {
-    return v3(fmaf(a.y, b.z, -(a.z * b.y)), fmaf(a.z, b.x, -(a.x * b.z)), fmaf(a.x, b.y, -(a.y * b.x)));
-}
-PRT_HD bool tight_reject(V3 A, V3 B, float radius, float dmax, float eps, V3 pa, V3 pb, V3 pc, V3 n) {
-    const V3 ra = A - pa, rb = B - pa;
-    const float dA = fdot(ra, n), dB = fdot(rb, n);
-    if (!(dA == dA) || !(dB == dB)) return false;
-    const float dlo = fminf(dA, dB), dhi = fmaxf(dA, dB);
-    if (dlo > dmax + eps || dhi < -eps) return true;
-    const V3 eab = pb - pa, ebc = pc - pb, eca = pa - pc;
-    const float lab = fdot(eab, eab), lbc = fdot(ebc, ebc), lca = fdot(eca, eca);
-    const V3 mab = fcross(eab, n);
-    // conditioning: |ab x ac|^2 >= 2^-4 |ab|^2 |ac|^2, with ab x ac reconstructed as (mab . ac) n-wards: |mab . eca| is
-    // twice the area when n is the true unit normal, so this also fails for a normal that is not
-    const float twice_area = fdot(mab, eca);                     // == n . (ab x ac) > 0 for a sound record
-    if (!(twice_area * twice_area >= 0.0625f * (lab * lca)) || !(twice_area > 0.0f)) return false;
-    const V3 mbc = fcross(ebc, n), mca = fcross(eca, n);
-    const V3 sa = A - pb, sb = B - pb;
-    const float s1 = fminf(fdot(ra, mab), fdot(rb, mab)) * rsq_approx(lab);
-    const float s2 = fminf(fdot(sa, mbc), fdot(sb, mbc)) * rsq_approx(lbc);
-    const float s3 = fminf(fdot(ra, mca), fdot(rb, mca)) * rsq_approx(lca);
-    const float s = fmaxf(fmaxf(s1, s2), s3);
-    if (!(s > eps)) return false;
-    const float dp = fmaxf(dlo, 0.0f);
-    const float reach = radius + eps;
-    return fmaf(dp, dp, s * s) > reach * reach;
-}
-
 // collision_system.cpp:164-221: capsule A (pose endpoints a_A, a_B) against capsule B (b_A, b_B).
 PRT_HD bool capsule_capsule(V3 a_A, V3 a_B, float radiusA, V3 b_A, V3 b_B, float radiusB, Contact & out) {
     V3 v0 = b_A - a_A;

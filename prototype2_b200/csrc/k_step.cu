@@ -67,7 +67,7 @@ __global__ void __launch_bounds__(STEP_BLOCK, 512 / STEP_BLOCK) k_step(StepParam
     }
     // largest plane distance that survives the range cull (collision_system.cpp:72, see prtc_abs_mode)
     const float dmax = (p.abs_mode == 1u) ? radius : floorf(radius) + 1.0f;
-    const bool use_qr = (p.qr_enable & 1u) != 0u;
+    const bool use_qr = p.qr_enable != 0u;
 
     // ---- phase 2: collideCharacterWithWorld (physics_system.cpp:330-438) ----
     const float fsub = float(p.substeps);

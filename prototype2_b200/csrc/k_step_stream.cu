@@ -147,23 +147,13 @@ __global__ void __launch_bounds__(XC_BLOCK) k_xc_refresh(StepParams p, int reuse
 constexpr int ST_LOAD = 0, ST_SUBSTEP = 1, ST_STREAM = 2, ST_DONE = 3;
 constexpr int LOAD_BATCH = 16;       // lanes that must wait for new work before the (expensive) LOAD stage runs
 constexpr int SUBSTEP_BATCH = 8;     // same for the SUBSTEP stage
-constexpr int EXACT_BATCH = 12;      // TRIPS: lanes that must hold a triangle before the exact test runs
 
 //
 // GATED: the batch is still arriving over PCIe while the kernel runs (prtc_step_characters with host buffers).  The
 // copy-in stream publishes how many characters have landed in `*gate`; LOAD waits for its own indices.  Every finished
 // character is counted (per 1024, then per 65536) so the copy-out stream can start on a chunk the moment its last
 // character is written, while later chunks are still being computed.
-//
-// TRIPS: how the STREAM stage is scheduled.  false: every streaming lane filters until IT has a triangle for the exact test
-// and the test runs as soon as any lane has one (v7-v9) -- the filter loop then ends with the slowest lane (geometric
-// tail: 9 of 32 lanes active on average), and the better the pre-cull, the longer that tail.  true: the streaming lanes
-// filter ONE triangle per trip, in lock step, and the trips go on until `exact_batch` lanes hold a triangle for the
-// exact test (or nobody is left to filter); lanes that found theirs early wait, but they are few until the batch is
-// full, and the exact test always runs with a full batch.  This is what makes the second-stage pre-cull
-// (tight_reject, collide.cuh) pay: it cuts the exact tests per query from 8.2 to 2.1 at C4 and, with trips, the longer
-// run of rejected triangles in front of each costs lock-step trips instead of a longer tail.
-template <bool GATED, bool TRIPS>
+template <bool GATED>
 __global__ void __launch_bounds__(32, 20) k_step_stream(StepParams p) {
     constexpr unsigned FULL = 0xffffffffu;
     __shared__ uint32_t s_leaf[LEAF_CAP][32];              // candidate leaves of the substep (leaf_entry words), emission order
@@ -197,11 +187,10 @@ __global__ void __launch_bounds__(32, 20) k_step_stream(StepParams p) {
     uint32_t f_leaf = 0, f_cur = 0, f_end = 0, n_fetched = 0, n_consumed = 0;
     bool pending = false;
     float4 t0 = make_float4(0, 0, 0, 0), t1 = t0, t2 = t0;
-    const bool use_qr = (p.qr_enable & 1u) != 0u, use_tq = (p.qr_enable & 2u) != 0u;
+    const bool use_qr = p.qr_enable != 0u;
     const bool use_cache = !(p.tune & 1u);
     const int load_batch = ((p.tune >> 8) & 0xFFu) ? int((p.tune >> 8) & 0xFFu) : LOAD_BATCH;
     const int substep_batch = ((p.tune >> 16) & 0xFFu) ? int((p.tune >> 16) & 0xFFu) : SUBSTEP_BATCH;
-    const int exact_batch = ((p.tune >> 24) & 0x3Fu) ? int((p.tune >> 24) & 0x3Fu) : EXACT_BATCH;
     for (int f = 0; f < P_COUNT; ++f) s_park[f][tid] = 0.0f;
 
     // A candidate leaf is buffered as its triangle range when that fits one word (first < 2^24, count < 128: every
@@ -434,44 +423,6 @@ __global__ void __launch_bounds__(32, 20) k_step_stream(StepParams p) {
         }
 
         // ---------------- STREAM: filter until a triangle needs the exact test ----------------
-        bool run_exact;
-        if (TRIPS) {
-            // lock-step trips: one triangle per streaming lane and trip
-            const V3 smin = gmin(ps.A, ps.B), smax = gmax(ps.A, ps.B);
-            const float qr_eps = s_park[P_QR_EPS][tid];
-            const float dmax = (p.abs_mode == 1u) ? radius : floorf(radius) + 1.0f;   // largest plane distance surviving the range cull
-            unsigned m_pend, m_filt;
-            for (;;) {
-                if (state == ST_STREAM && !pending) {
-                    if (n_consumed != n_fetched) {
-                        if (n_fetched - n_consumed >= 2) cp_async_wait<1>(); else cp_async_wait<0>();
-                        const uint32_t slot = n_consumed % TRI_RING;
-                        t0 = s_tri[slot][0][tid];
-                        t1 = s_tri[slot][1][tid];
-                        t2 = s_tri[slot][2][tid];
-                        ++n_consumed;
-                        fetch_one();
-                        ++c_tri;
-                        pending = __float_as_uint(t0.w) != PRT_DEGENERATE_BITS &&                         // length(n) == 0   :53
-                                  !(use_qr && quick_reject(smin, smax, radius, dmax, qr_eps, t0, t1, t2)) &&
-                                  !(use_tq && tight_reject(ps.A, ps.B, radius, dmax, qr_eps, v3(t0.x, t0.y, t0.z), v3(t1.x, t1.y, t1.z),
-                                                           v3(t2.x, t2.y, t2.z), v3(t0.w, t1.w, t2.w)));
-                    } else if (node < p.n_nodes) {                    // more leaves than the buffer holds: next pass
-                        ordered_walk();
-                        if (nleaf) found = true;
-                        start_stream();
-                        if (n_fetched == 0) state = ST_SUBSTEP;
-                    } else {
-                        state = ST_SUBSTEP;                           // this substep's candidates are exhausted
-                    }
-                }
-                m_pend = __ballot_sync(FULL, pending);
-                m_filt = __ballot_sync(FULL, state == ST_STREAM && !pending);
-                if (m_filt == 0u || __popc(m_pend) >= exact_batch) break;
-                if (__popc(__ballot_sync(FULL, state == ST_SUBSTEP)) >= substep_batch) break;   // let them start their next substep first
-            }
-            run_exact = m_pend != 0u && (m_filt == 0u || __popc(m_pend) >= exact_batch);
-        } else {
         if (state == ST_STREAM && !pending) {
             const V3 smin = gmin(ps.A, ps.B), smax = gmax(ps.A, ps.B);
             const float qr_eps = s_park[P_QR_EPS][tid];
@@ -488,8 +439,6 @@ __global__ void __launch_bounds__(32, 20) k_step_stream(StepParams p) {
                     ++c_tri;
                     if (__float_as_uint(t0.w) == PRT_DEGENERATE_BITS) continue;       // length(n) == 0   :53
                     if (use_qr && quick_reject(smin, smax, radius, dmax, qr_eps, t0, t1, t2)) continue;
-                    if (use_tq && tight_reject(ps.A, ps.B, radius, dmax, qr_eps, v3(t0.x, t0.y, t0.z), v3(t1.x, t1.y, t1.z),
-                                               v3(t2.x, t2.y, t2.z), v3(t0.w, t1.w, t2.w))) continue;
                     pending = true;
                     break;
                 }
@@ -505,11 +454,9 @@ __global__ void __launch_bounds__(32, 20) k_step_stream(StepParams p) {
                 }
             }
         }
-        run_exact = __any_sync(FULL, pending);
-        }
 
         // ---------------- exact tests, converged ----------------
-        if (run_exact) {
+        if (__any_sync(FULL, pending)) {
             if (pending) {
                 pending = false;
                 Contact ct;
@@ -557,9 +504,8 @@ void launch_k_xc_refresh(StepParams const & p, cudaStream_t stream) {
 
 void launch_k_step_stream(StepParams const & p, uint32_t blocks, bool gated, cudaStream_t stream) {
     cudaMemsetAsync(p.work_counter, 0, sizeof(unsigned), stream);
-    const bool trips = !(p.tune & 0x40000000u);                  // PRTC_TUNE bit 30: the v9 scheduling of the STREAM stage (A/B)
-    if (gated) { if (trips) k_step_stream<true, true><<<blocks, 32, 0, stream>>>(p); else k_step_stream<true, false><<<blocks, 32, 0, stream>>>(p); }
-    else { if (trips) k_step_stream<false, true><<<blocks, 32, 0, stream>>>(p); else k_step_stream<false, false><<<blocks, 32, 0, stream>>>(p); }
+    if (gated) k_step_stream<true><<<blocks, 32, 0, stream>>>(p);
+    else k_step_stream<false><<<blocks, 32, 0, stream>>>(p);
 }
 
 } // namespace prt

@@ -64,7 +64,7 @@ struct StepParams {
     uint32_t substeps, abs_mode;
     // conservative pre-cull (kernels.cu quick_reject): margin and enable, derived from the scene extent at commit
     float qr_eps;
-    uint32_t qr_enable;             // bit 0: box cull (quick_reject), bit 1: plane/edge cull (tight_reject, collide.cuh)
+    uint32_t qr_enable;
     uint32_t tune;                  // bit 0: frame cache OFF (walk the tree every substep, reference-equivalent counters)
     unsigned long long * counters;  // prtc_counters layout
     uint32_t * host_flags;          // k_step_warp, small host-buffer batches: host-mapped words the kernel raises --

@@ -187,7 +187,7 @@ int fill_params(prtc_ctx * c, float dt, uint32_t n, prtc_transform * d_tf, prtc_
         float m = c->world_max_abs;
         float ulp = std::nextafter(m, INFINITY) - m;
         p.qr_eps = std::max(1e-3f, 64.0f * ulp);
-        p.qr_enable = (m < 1.0e6f) ? ((c->quick_reject ? 1u : 0u) | (c->tight_reject ? 2u : 0u)) : 0u;
+        p.qr_enable = (c->quick_reject && m < 1.0e6f) ? 1u : 0u;
         p.tune = (c->frame_cache ? 0u : 1u) | (c->warp_kernel ? 0u : 2u) | c->tune_hi;
         p.work_counter = c->persistent ? c->d_work.ptr : nullptr;
         p.persistent_blocks = uint32_t(c->sm_count) * 20u;
@@ -301,7 +301,6 @@ int prtc_create(const prtc_config * cfg, prtc_ctx ** out) {
     ctx->cfg = c;
     // environment overrides of the option defaults, for A/B measurements without touching the caller
     if (const char * e = std::getenv("PRTC_QUICK_REJECT")) ctx->quick_reject = std::atoi(e);
-    if (const char * e = std::getenv("PRTC_TIGHT_REJECT")) ctx->tight_reject = std::atoi(e);
     if (const char * e = std::getenv("PRTC_FRAME_CACHE")) ctx->frame_cache = std::atoi(e);
     if (const char * e = std::getenv("PRTC_PERSISTENT")) ctx->persistent = std::atoi(e);
     if (const char * e = std::getenv("PRTC_CROSS_FRAME")) ctx->cross_frame = std::atoi(e);
@@ -506,7 +505,6 @@ int prtc_set_option(prtc_ctx * c, int option, int value) {
         case PRTC_OPT_WARP_KERNEL: c->warp_kernel = value != 0; return PRTC_OK;
         case PRTC_OPT_STREAMED_COPY: c->streamed_copy = value != 0; return PRTC_OK;
         case PRTC_OPT_TOP_STAGING: c->top_staging = value != 0; return PRTC_OK;
-        case PRTC_OPT_TIGHT_REJECT: c->tight_reject = value != 0; return PRTC_OK;
         default: return fail(PRTC_ERR_INVALID, "prtc_set_option: unknown option");
     }
 }

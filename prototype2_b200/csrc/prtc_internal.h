@@ -115,7 +115,6 @@ struct prtc_ctx {
     uint32_t tune_hi = 0;                   // PRTC_TUNE: batch thresholds of k_step_stream (bits 8-15 load, 16-23 substep), experiments
     int sm_count = 148;
     int quick_reject = 1;                   // PRTC_OPT_QUICK_REJECT
-    int tight_reject = 1;                   // PRTC_OPT_TIGHT_REJECT (k_step_stream only)
     std::vector<uint32_t> moved_models;     // models whose transform changed (prtc_update_models)
 
     // device

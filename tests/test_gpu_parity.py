@@ -46,25 +46,17 @@ def test_c2_shape_canonical_bit_exact(abs_mode):
               dict(abs_mode=capi.ABS_INT if abs_mode == "int" else capi.ABS_FLOAT))
 
 
-@pytest.mark.parametrize("frame_cache,quick_reject,persistent", [(0, 0, 0), (0, 1, 0), (1, 0, 0), (1, 3, 0), (0, 2, 0), (0, 0, 1), (0, 3, 1),
-                                                                 (1, 0, 1), (1, 1, 1), (1, 2, 1), (1, 3, 1), (1, 3, 2), (0, 1, 2), (1, 2, 3)])
-def test_work_saving_options_do_not_change_results(frame_cache, quick_reject, persistent, monkeypatch):
-    """PRTC_OPT_FRAME_CACHE / PRTC_OPT_QUICK_REJECT (bit 0 of the parameter) / PRTC_OPT_TIGHT_REJECT (bit 1) off: same
-    bits; with the frame cache off the node-test counter is the reference's own count.  persistent = 2: the persistent
-    kernel with the v9 scheduling of its STREAM stage (PRTC_TUNE bit 30), 3: lock-step trips with an exact batch of 1"""
+@pytest.mark.parametrize("frame_cache,quick_reject,persistent", [(0, 0, 0), (0, 1, 0), (1, 0, 0), (1, 1, 0), (0, 0, 1), (0, 1, 1), (1, 0, 1)])
+def test_work_saving_options_do_not_change_results(frame_cache, quick_reject, persistent):
+    """PRTC_OPT_FRAME_CACHE / PRTC_OPT_QUICK_REJECT off: same bits; with the frame cache off the node-test counter
+    is the reference's own count"""
     from prototype2_b200 import capi
-    if persistent == 2:
-        monkeypatch.setenv("PRTC_TUNE", "0x40000000")
-    elif persistent == 3:
-        monkeypatch.setenv("PRTC_TUNE", "0x01000000")
-    persistent = 1 if persistent else 0
     scene = H.make_scene(96, 2, 2, 800, seed=8)
     scene["vel"] = scene["vel"] * np.float32(1.7)           # some boxes escape the frame region
     orc = H.build_oracle(scene, "l1", order="canonical")
     ctx, tf, ph = H.build_gpu(scene)
     ctx.set_option(capi.OPT_FRAME_CACHE, frame_cache)
-    ctx.set_option(capi.OPT_QUICK_REJECT, quick_reject & 1)
-    ctx.set_option(capi.OPT_TIGHT_REJECT, quick_reject >> 1)
+    ctx.set_option(capi.OPT_QUICK_REJECT, quick_reject)
     ctx.set_option(capi.OPT_PERSISTENT, persistent)
     for f in range(5):
         if f % 2 == 0:
@@ -600,12 +592,11 @@ def test_c4_full_size_properties():
         c = ctx.counters(reset=True)
         ctx.set_option(capi.OPT_FRAME_CACHE, 1)
         ctx.set_option(capi.OPT_QUICK_REJECT, 1)
-        ctx.set_option(capi.OPT_TIGHT_REJECT, 1)
         return c
     tf_a, ph_a = tf0.copy(), ph0.copy()
     ca = run(3, tf_a, ph_a)
     tf_b, ph_b = tf0.copy(), ph0.copy()
-    cb = run(3, tf_b, ph_b, OPT_FRAME_CACHE=0, OPT_QUICK_REJECT=0, OPT_TIGHT_REJECT=0)
+    cb = run(3, tf_b, ph_b, OPT_FRAME_CACHE=0, OPT_QUICK_REJECT=0)
     assert H.state_diff(H.gpu_state(tf_a, ph_a), H.gpu_state(tf_b, ph_b)) == []
     for k in ("substeps", "tri_tests", "contacts"):
         assert ca[k] == cb[k], k
@@ -852,28 +843,3 @@ def test_top_staging_does_not_change_results(cross_frame):
     ca, cb = on.counters(), off.counters()
     for k in ("substeps", "tri_tests", "node_tests", "contacts", "launches"):
         assert ca[k] == cb[k], k
-
-
-@pytest.mark.parametrize("tune,tight", [("0x40000000", 0), ("0x40000000", 1), ("0", 0), ("0", 1), ("0x01000000", 1), ("0x20000000", 1),
-                                        ("0x06040400", 1)])
-def test_stream_stage_scheduling_does_not_change_results(tune, tight, monkeypatch):
-    """k_step_stream's STREAM stage: v9 scheduling (PRTC_TUNE bit 30) or lock-step trips with an exact batch of 12
-    (default), 1, 32, or 6 with LOAD/SUBSTEP batches of 4; second-stage pre-cull on and off -- a batch big enough for the
-    persistent kernel, bit-exact vs the oracle, triangle and substep counters equal to the reference's"""
-    from prototype2_b200 import capi
-    monkeypatch.setenv("PRTC_TUNE", tune)
-    n = 36000
-    scene = H.make_scene(144, 2, 2, n, seed=23)
-    scene["vel"] *= np.float32(1.5)
-    orc = H.build_oracle(scene, "l1", order="canonical", threads=os.cpu_count() or 1)
-    ctx, tf, ph = H.build_gpu(scene)
-    ctx.set_option(capi.OPT_TIGHT_REJECT, tight)
-    for f in range(5):
-        orc.step(DT)
-        ctx.update_characters(DT, tf, ph)
-        assert H.state_diff(orc.get_state(), H.gpu_state(tf, ph)) == [], "frame %d" % f
-    co, cg = orc.counters(), ctx.counters()
-    for k in ("substeps", "tri_tests", "contacts"):
-        assert co[k] == cg[k], k
-    if tight:
-        assert cg["exact_tests"] < 0.6 * cg["tri_tests"]
