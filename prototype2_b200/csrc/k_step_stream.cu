@@ -87,40 +87,58 @@ __global__ void __launch_bounds__(XC_BLOCK) k_xc_refresh(StepParams p, int reuse
     if (!walk) return;
     if (reuse) { R.lo = R.lo - v3(p.xc_margin); R.hi = R.hi + v3(p.xc_margin); }
     if (staged) mbar_wait(&s_bar, 0);
-    // k: cursor in the staged table; [node, node_end): open range of the full array (everything, when nothing is staged)
-    uint32_t k = 0, node = 0, node_end = staged ? 0u : p.n_nodes, ncache = 0;
-    for (;;) {
-        if (node != node_end) {
-            const float4 lo = __ldg(p.nodes + 2 * node);
-            const float4 hi = __ldg(p.nodes + 2 * node + 1);
-            const bool ov = node_overlaps(lo, hi, R);
-            const int cnt = __float_as_int(hi.w);
-            if (cnt < 0) {
-                node = ov ? node + 1 : uint32_t(__float_as_int(lo.w));
-            } else {
-                if (ov) {
-                    if (ncache == XC_CAP) { ncache = 0xFFFFFFFFu; break; }
-                    p.xc_leaf[size_t(ncache) * p.xc_stride + s] = node;
-                    ++ncache;
-                }
-                node = node + 1;
-            }
-        } else {
-            if (k >= n_top) break;
+    // Phase 1 (staged only): the table walk alone, all lanes in the same loop.  The overlapping entries at the cut (and
+    // leaves above it) are the doors into the full array; they come up in emission order and are kept as 10-bit table
+    // indices packed into one 64-bit register (<= 6; a region that opens more than that -- it covers a good part of the
+    // world -- falls back to the plain walk).  Phase 2: the ranges behind the doors, in order, walked as before.
+    // (Interleaving the two cursors in one loop measured no faster than the plain walk: long-scoreboard stalls per issue
+    // fell from 34 to 19, but lanes in "table" and "array" steps serialised, 16.7 -> 13.1 threads per instruction.)
+    unsigned long long doors = 0ull;
+    uint32_t n_doors = 0, door = 0;
+    uint32_t node = 0, node_end = staged ? 0u : p.n_nodes, ncache = 0;
+    if (staged) {
+        uint32_t k = 0;
+        while (k < n_top) {
             const float4 lo = s_top[2 * k];
             const float4 hi = s_top[2 * k + 1];
             const bool ov = node_overlaps(lo, hi, R);
             const int cnt = __float_as_int(hi.w);
-            const uint32_t link = uint32_t(__float_as_int(lo.w));
             if (cnt == -1) {
-                k = ov ? k + 1 : link;
+                k = ov ? k + 1 : uint32_t(__float_as_int(lo.w));
             } else {
                 if (ov) {
-                    if (cnt == 0) { node = link; node_end = link + 1; }            // a leaf above the cut
-                    else { node = link + 1; node_end = uint32_t(-cnt); }           // subtree below the cut: its root overlaps, go on with the first child
+                    if (n_doors == 6u) { n_doors = 0; node_end = p.n_nodes; break; }      // too many doors: plain walk
+                    doors |= (unsigned long long)k << (10u * n_doors);
+                    ++n_doors;
                 }
                 ++k;
             }
+        }
+    }
+    for (;;) {
+        if (node == node_end) {
+            if (door == n_doors) break;
+            const uint32_t k = uint32_t(doors >> (10u * door)) & 1023u;
+            ++door;
+            const uint32_t g = uint32_t(__float_as_int(s_top[2 * k].w));
+            const int cnt = __float_as_int(s_top[2 * k + 1].w);
+            node = cnt == 0 ? g : g + 1;                 // a leaf above the cut is visited itself; below an overlapping
+            node_end = cnt == 0 ? g + 1 : uint32_t(-cnt); // root at the cut the walk goes on with its first child
+            continue;
+        }
+        const float4 lo = __ldg(p.nodes + 2 * node);
+        const float4 hi = __ldg(p.nodes + 2 * node + 1);
+        const bool ov = node_overlaps(lo, hi, R);
+        const int cnt = __float_as_int(hi.w);
+        if (cnt < 0) {
+            node = ov ? node + 1 : uint32_t(__float_as_int(lo.w));
+        } else {
+            if (ov) {
+                if (ncache == XC_CAP) { ncache = 0xFFFFFFFFu; break; }
+                p.xc_leaf[size_t(ncache) * p.xc_stride + s] = node;
+                ++ncache;
+            }
+            node = node + 1;
         }
     }
     if (ncache == 0xFFFFFFFFu) { p.xc_version[s] = 0u; return; }   // too many leaves for a slot: this character walks per substep

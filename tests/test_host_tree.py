@@ -113,18 +113,35 @@ def test_empty_and_single():
     assert np.allclose(nodes[0, 0:3], -0.05) and np.allclose(nodes[0, 4:7], 1.05)
 
 
-def walk_staged(top, nodes, box):
-    """numpy restatement of k_xc_refresh's walk with the top-of-tree table (k_step_stream.cu): cursor k over the table,
-    [node, node_end) = open range of the full array; returns the emitted NODE indices and the two test counts"""
+def walk_staged(top, nodes, box, max_doors=6):
+    """numpy restatement of k_xc_refresh's walk with the top-of-tree table (k_step_stream.cu): phase 1 runs over the
+    table alone and collects the overlapping entries at the cut ("doors", at most 6, else the plain walk is used),
+    phase 2 walks the ranges of the full array behind the doors in order; returns the emitted NODE indices, the two
+    test counts and whether the walk fell back"""
     tl, tc = top[:, 3].view(np.int32), top[:, 7].view(np.int32)
     nl, nc = nodes[:, 3].view(np.int32), nodes[:, 7].view(np.int32)
 
     def ov(rec):
         lo, hi = rec[0:3], rec[4:7]
         return not (lo[0] > box[3] or hi[0] < box[0] or lo[1] > box[4] or hi[1] < box[1] or lo[2] > box[5] or hi[2] < box[2])
-    out, k, node, node_end, t_top, t_full = [], 0, 0, 0, 0, 0
-    while True:
-        if node != node_end:
+    doors, k, t_top, t_full, fell_back = [], 0, 0, 0, False
+    while k < len(top):
+        t_top += 1
+        o = ov(top[k])
+        if tc[k] == -1:
+            k = k + 1 if o else int(tl[k])
+        else:
+            if o:
+                if len(doors) == max_doors:
+                    fell_back = True
+                    break
+                doors.append(k)
+            k += 1
+    ranges = [(0, len(nodes))] if fell_back else [
+        (int(tl[k]), int(tl[k]) + 1) if tc[k] == 0 else (int(tl[k]) + 1, -int(tc[k])) for k in doors]
+    out = []
+    for node, node_end in ranges:
+        while node != node_end:
             t_full += 1
             o = ov(nodes[node])
             if nc[node] < 0:
@@ -134,21 +151,7 @@ def walk_staged(top, nodes, box):
                     out.append(node)
                 node += 1
             assert node <= node_end
-        else:
-            if k >= len(top):
-                break
-            t_top += 1
-            o = ov(top[k])
-            if tc[k] == -1:
-                k = k + 1 if o else int(tl[k])
-            else:
-                if o:
-                    if tc[k] == 0:
-                        node, node_end = int(tl[k]), int(tl[k]) + 1
-                    else:
-                        node, node_end = int(tl[k]) + 1, -int(tc[k])
-                k += 1
-    return out, t_top, t_full
+    return out, t_top, t_full, fell_back
 
 
 def walk_nodes(nodes, box):
@@ -190,17 +193,22 @@ def test_top_table_walk_equals_plain_walk(cap):
     g = top[:, 3].view(np.int32)
     for k in np.nonzero(tc != -1)[0][:200]:
         assert np.array_equal(top[k, [0, 1, 2, 4, 5, 6]], nodes[g[k], [0, 1, 2, 4, 5, 6]])
+    n_fallback = 0
     for q in range(300):
         c = rng.uniform(0, 96, 3)
         c[1] = rng.uniform(-2, 3)
         e = rng.uniform(0.2, 6.0, 3) if q % 10 else np.array([200.0, 200.0, 200.0])   # every 10th box covers everything
         box = np.concatenate([c - e, c + e]).astype(np.float32)
         plain, tested = walk_nodes(nodes, box)
-        staged, t_top, t_full = walk_staged(top, nodes, box)
+        staged, t_top, t_full, fell_back = walk_staged(top, nodes, box)
         assert staged == plain
+        n_fallback += fell_back
+        if fell_back:
+            continue
         leaf_hits_above_cut = sum(1 for k in range(len(top)) if tc[k] == 0 and not (
             top[k, 0] > box[3] or top[k, 4] < box[0] or top[k, 1] > box[4] or top[k, 5] < box[1] or top[k, 2] > box[5] or top[k, 6] < box[2]))
         assert t_top + t_full == tested + leaf_hits_above_cut
+    assert 30 <= n_fallback < 300          # the all-covering boxes open more than 6 doors; how many of the others do depends on how deep the cut is
 
 
 def test_top_table_small_tree_is_not_staged():
