@@ -43,6 +43,8 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="C4", choices=sorted(WORKLOADS))
+    ap.add_argument("--order", default="canonical", choices=["canonical", "by_id"],
+                    help="candidate order: canonical = the reference-built tree (headline), by_id = PRTC_ORDER_BY_ID, tree built on the device")
     ap.add_argument("--capsules", type=int, default=0, help="override capsules per GPU")
     ap.add_argument("--terrain-n", type=int, default=0, help="override terrain size")
     ap.add_argument("--cpu-sample", type=int, default=16384, help="capsules in the bounded CPU sample")
@@ -72,8 +74,10 @@ def make_capsules(n_caps, n_terrain, rank):
 def describe(args, n_terrain, bx, bz, n_caps, n_tris, world):
     return {
         "workload": "%s: %d capsules/GPU x %d-triangle terrain (%dx%d-cell mesh colliders), 4 substeps/frame, %s, "
-                    "canonical order" % (args.workload, n_caps, n_tris, bx, bz,
-                                         "static + dynamic-vs-dynamic pass (JACOBI, records all-gathered per frame)" if args.workload == "C5" else "static pass"),
+                    "%s" % (args.workload, n_caps, n_tris, bx, bz,
+                            "static + dynamic-vs-dynamic pass (JACOBI, records all-gathered per frame)" if args.workload == "C5" else "static pass",
+                            "candidates in ascending collider id, tree built on the device (PRTC_ORDER_BY_ID; the roofline's node "
+                            "tests are those of that tree, not of the reference's)" if args.order == "by_id" else "canonical order"),
         "capsules_per_gpu": n_caps, "global_capsules": n_caps * world, "triangles": n_tris, "terrain_n": n_terrain,
         "substeps": 4, "dt": DT, "abs_mode": "int", "parallelism": "capsules sharded x%d, static geometry replicated" % world,
         "l2_policy": "inputs larger than L2: nodes+triangles+capsule state touched per step exceed 126 MB at C4; "
@@ -276,7 +280,8 @@ def run_ours(args):
     else:
         pos, vel = make_capsules(n_caps, n_terrain, rank)
 
-    ctx = capi.PhysicsContext(device=local, dyn_mode=capi.DYN_JACOBI if dynamic else capi.DYN_OFF)
+    ctx = capi.PhysicsContext(device=local, dyn_mode=capi.DYN_JACOBI if dynamic else capi.DYN_OFF,
+                              order_mode=capi.ORDER_BY_ID if args.order == "by_id" else capi.ORDER_CANONICAL)
     if dynamic:
         ctx.dyn_configure(first, n_caps * world)
     ctx.add_model_collider(xyz, mf, mc)
@@ -371,7 +376,8 @@ def run_ours(args):
     d_ph.copy_(h_ph)
     ctx.set_option(capi.OPT_FRAME_CACHE, 0)
     if dynamic:                                      # stored boxes carry over between frames: start the replay from a fresh context state
-        ctx2 = capi.PhysicsContext(device=local, dyn_mode=capi.DYN_JACOBI)
+        ctx2 = capi.PhysicsContext(device=local, dyn_mode=capi.DYN_JACOBI,
+                                   order_mode=capi.ORDER_BY_ID if args.order == "by_id" else capi.ORDER_CANONICAL)
         ctx2.add_model_collider(xyz, mf, mc)
         ctx2.add_capsule_collider()
         ctx2.dyn_configure(first, n_caps * world)

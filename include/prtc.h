@@ -46,8 +46,14 @@ enum prtc_abs_mode { PRTC_ABS_INT = 0, PRTC_ABS_FLOAT = 1 };
  *                         capsule neighbours in ascending index order.  Scales to millions of capsules.
  *   PRTC_ORDER_LITERAL    the reference's unified mesh+capsule tree is maintained on the host by the same
  *                         algorithm every frame and re-flattened, and characters keep the reference's
- *                         sequential visibility of one another; for engine-sized scenes. */
-enum prtc_order_mode { PRTC_ORDER_LITERAL = 0, PRTC_ORDER_CANONICAL = 1 };
+ *                         sequential visibility of one another; for engine-sized scenes.
+ *   PRTC_ORDER_BY_ID      like CANONICAL, but the mesh candidates of a query -- the same SET, which depends only on
+ *                         the leaves' stored fat boxes, not on the tree -- are taken in ascending collider id
+ *                         (registration order) instead of the insertion-history order of the reference's tree.  No
+ *                         tree is built on the host: the device puts a left-complete tree over the id sequence
+ *                         together in closed form (commit of 1.25 M leaves in milliseconds instead of seconds; a
+ *                         moved model costs one bottom-up pass).  For streamed / very large levels. */
+enum prtc_order_mode { PRTC_ORDER_LITERAL = 0, PRTC_ORDER_CANONICAL = 1, PRTC_ORDER_BY_ID = 2 };
 
 /* Dynamic-vs-dynamic (capsule-capsule) pass in CANONICAL order:
  *   PRTC_DYN_OFF     capsules do not see one another (static pass only)
@@ -246,6 +252,11 @@ int prtc_query_box(prtc_ctx * ctx, const float aabb6[6], uint32_t * mesh_ids, ui
  * indices in traversal order.  Lets the build / flatten logic be checked on a CPU-only box by the tests. */
 int prtc_host_build_tree(const float * aabbs6, uint32_t n, float margin, uint32_t * leaf_order, float * nodes8,
                          uint32_t nodes_capacity, uint32_t * n_nodes);
+/* Host-only utility: the tree PRTC_ORDER_BY_ID builds on the device, computed by the same index arithmetic
+ * (csrc/balanced_tree.cuh) in plain loops: the left-complete binary tree over n boxes (taken as they are, no margin added)
+ * in the flattened layout above, leaf: link = box index, count = 1.  A front-to-back walk emits overlapping boxes in
+ * ascending index. */
+int prtc_host_balanced_tree(const float * aabbs6, uint32_t n, float * nodes8, uint32_t nodes_capacity, uint32_t * n_nodes);
 /* Host-only utility: the top-of-tree table the device stages in shared memory (PRTC_OPT_TOP_STAGING) for a flattened
  * tree in the layout above: all nodes of depth <= D (D the largest depth whose levels together fit `cap` entries), same
  * preorder, 8 words per entry {lo.xyz, link, hi.xyz, count} with

@@ -17,6 +17,11 @@
 //              frozen), capsule neighbours in ascending index order from the
 //              stored fat AABBs, dynamic pass OFF or JACOBI.  This is the
 //              arrangement the GPU path implements at scale.
+//   BY_ID      CANONICAL, except that the mesh candidates of a query -- the
+//              same SET, which does not depend on the tree's shape -- are
+//              taken in ascending collider id (registration order) instead
+//              of the tree's insertion-history order.  Checker of the
+//              product's PRTC_ORDER_BY_ID (tree built on the device).
 //
 // Arithmetic goes through the same glm stand-in header as L0
 // (oracle/shim/glm/glm.hpp; "parity unpinned" at the glm boundary, see there).
@@ -435,7 +440,7 @@ struct Config {                  // mirrors prtc_config (include/prtc.h)
     float friction = 10.0f;      // physics_system.cpp:307
     float stick = 0.05f;         // physics_system.cpp:280
     uint32_t abs_mode = 0;       // 0: `abs(dist)` -> int abs(int) (libstdc++ build), 1: float fabs (libc++ build)
-    uint32_t order_mode = 0;     // 0 LITERAL (unified tree, sequential), 1 CANONICAL (static-only tree)
+    uint32_t order_mode = 0;     // 0 LITERAL (unified tree, sequential), 1 CANONICAL (static-only tree), 2 BY_ID (as 1, mesh candidates sorted by id)
     uint32_t dyn_mode = 0;       // CANONICAL only: 0 OFF, 2 JACOBI
     uint32_t threads = 1;        // CANONICAL only (std::thread over capsules)
 };
@@ -687,6 +692,9 @@ void collideCharacterWithWorld(World & w, uint32_t ci, Scratch & s, Counters & c
             w.tree.query(ci, eAABB, s.meshIDs, s.capsIDs, s.stack, &nodeTests);
         } else {
             w.tree.query(UINT32_MAX, eAABB, s.meshIDs, s.capsIDs, s.stack, &nodeTests);
+            // BY_ID: the candidate SET of the reference's query (it does not depend on the tree's shape), taken in
+            // ascending collider id = registration order instead of the insertion-history order of the tree
+            if (w.cfg.order_mode == 2) std::sort(s.meshIDs.begin(), s.meshIDs.end());
             if (w.cfg.dyn_mode == 2) {
                 // canonical neighbour rule: ascending capsule index over the stored fat AABBs
                 for (uint32_t j = 0; j < uint32_t(w.capsules.size()); ++j)
@@ -870,6 +878,30 @@ int l1_add_model(void * h, const float * xyz, uint32_t n_idx, const uint32_t * m
     for (size_t k = prevSize; k < prevSize + n_meshes; ++k)
         w.meshTreeIdx[k] = w.tree.insertLeaf(uint32_t(k), SHAPE_MESH, w.meshAABBs[k]);
     return int(modelIndex);
+}
+
+// physics_system.cpp:161-202 for one (tag, transform) pair: world cache and mesh boxes of the model recomputed, then
+// DynamicAABBTree::update over the model's leaves (a leaf keeps its stored fat box while it still contains the new one)
+void l1_update_model(void * h, uint32_t model_index, const float * tform10) {
+    World & w = *static_cast<World *>(h);
+    Transform t;
+    t.position = vec3(tform10[0], tform10[1], tform10[2]);
+    t.rotation = quat(tform10[3], tform10[4], tform10[5], tform10[6]);
+    t.scale = vec3(tform10[7], tform10[8], tform10[9]);
+    World::ModelCol const & col = w.models[model_index];
+    mat4 mat = transformMatrix(t);
+    for (uint32_t m = col.firstMesh; m < col.firstMesh + col.numMeshes; ++m) {
+        MeshCol const & curr = w.meshes[m];
+        vec3 mn = vec3(std::numeric_limits<float>::max());
+        vec3 mx = vec3(std::numeric_limits<float>::lowest());
+        for (uint32_t v = curr.first; v < curr.first + curr.count; ++v) {
+            w.cache[v] = mat * vec4(w.raw[v], 1.0f);
+            mn = glm::min(mn, w.cache[v]);
+            mx = glm::max(mx, w.cache[v]);
+        }
+        w.meshAABBs[m] = {mn, mx};
+    }
+    w.tree.update(&w.meshTreeIdx[col.firstMesh], &w.meshAABBs[col.firstMesh], col.numMeshes);
 }
 
 // physics_system.cpp:22-42 (+ the character that owns the capsule)

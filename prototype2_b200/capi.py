@@ -11,7 +11,7 @@ LIB_PATH = os.path.join(_HERE, os.environ.get("PRTC_LIB", "libprtc.so"))   # PRT
 
 PRTC_OK, PRTC_ERR_INVALID, PRTC_ERR_CUDA, PRTC_ERR_CAPACITY, PRTC_ERR_ALLOC = range(5)
 ABS_INT, ABS_FLOAT = 0, 1
-ORDER_LITERAL, ORDER_CANONICAL = 0, 1
+ORDER_LITERAL, ORDER_CANONICAL, ORDER_BY_ID = 0, 1, 2
 DYN_OFF, DYN_JACOBI = 0, 2
 OPT_FRAME_CACHE, OPT_QUICK_REJECT, OPT_PERSISTENT, OPT_CROSS_FRAME_CACHE, OPT_WARP_KERNEL, OPT_STREAMED_COPY, OPT_TOP_STAGING = 1, 2, 3, 4, 5, 6, 7
 
@@ -21,7 +21,7 @@ SYMBOLS = (
     "prtc_add_model", "prtc_add_capsule", "prtc_update_capsule", "prtc_commit", "prtc_update_models", "prtc_remove_model",
     "prtc_step_characters", "prtc_step_characters_device", "prtc_step_characters_traced", "prtc_raycast", "prtc_sweep_ellipsoids",
     "prtc_set_stream", "prtc_synchronize", "prtc_get_counters", "prtc_set_option", "prtc_dyn_configure", "prtc_dyn_prepare", "prtc_dyn_buffer", "prtc_get_tree_info", "prtc_get_leaf_order",
-    "prtc_get_world_vertices", "prtc_query_box", "prtc_host_build_tree", "prtc_host_top_table",
+    "prtc_get_world_vertices", "prtc_query_box", "prtc_host_build_tree", "prtc_host_top_table", "prtc_host_balanced_tree",
 )
 
 
@@ -330,3 +330,15 @@ def host_top_table(nodes8, cap=1024):
     if rc != PRTC_OK:
         raise PrtcError(rc, (lib().prtc_last_error() or b"").decode())
     return top[:nt.value]
+
+
+def host_balanced_tree(aabbs6):
+    """prtc_host_balanced_tree: the tree PRTC_ORDER_BY_ID builds on the device, by the same index arithmetic.  No device needed."""
+    boxes = np.ascontiguousarray(aabbs6, np.float32).reshape(-1, 6)
+    n = len(boxes)
+    nodes = np.zeros((max(2 * n - 1, 1), 8), np.float32)
+    nn = ctypes.c_uint32()
+    rc = lib().prtc_host_balanced_tree(_vp(boxes), ctypes.c_uint32(n), _vp(nodes), ctypes.c_uint32(len(nodes)), ctypes.byref(nn))
+    if rc != PRTC_OK:
+        raise PrtcError(rc, (lib().prtc_last_error() or b"").decode())
+    return nodes[:nn.value]

@@ -117,6 +117,8 @@ void launch_transform_refit(const float * raw_xyz, float * world_xyz, const Mesh
 // leaf-ordered triangle records with precomputed unit normals
 void launch_tri_setup(const float * world_xyz, const uint32_t * tri_src_vertex, uint32_t n_tris, float4 * tris,
                       cudaStream_t stream);
+// PRTC_ORDER_BY_ID: left-complete tree over n_leaves leaf records (2 float4 each, ascending id) built into nodes (k_tree_build.cu)
+void launch_tree_build(const float4 * leaves, uint32_t n_leaves, float4 * nodes, cudaStream_t stream);
 // K7: batched PhysicsSystem::raycast
 void launch_raycast(const float4 * nodes, uint32_t n_nodes, const float4 * tris, uint32_t n_rays, const float * origins,
                     const float * dirs, const float * maxd, float * hit_xyz, unsigned char * hit_mask, cudaStream_t stream);

@@ -3,6 +3,7 @@
 // The per-frame entry points are in prtc_step.cu.  There is no CPU implementation of the compute path in this
 // library: without a compute-capability-10 device prtc_create fails and nothing else can be called.
 #include "prtc_internal.h"
+#include "balanced_tree.cuh"
 
 using namespace prt;
 using namespace prt::host;
@@ -16,6 +17,8 @@ int fail(int code, const std::string & msg) {
     g_last_error = msg;
     return code;
 }
+
+int build_tree_on_device(prtc_ctx * c, cudaStream_t s);
 
 int commit_impl(prtc_ctx * c) {
     cudaStream_t s = c->stream;
@@ -73,12 +76,28 @@ int commit_impl(prtc_ctx * c) {
         };
         // moved models first (they were registered earlier): DynamicAABBTree::update per model, physics_system.cpp:199-200
         // (LITERAL order has done this in prtc_update_models already, where the reference does it)
+        // BY_ID keeps no host tree, only every leaf's stored fat box, with the reference's rules: a new leaf stores its box
+        // grown by the margin (insertLeaf, aabb_tree.cpp:140-141), a moved one keeps the stored box while it still
+        // contains the new one (update, aabb_tree.cpp:102-111) -- the candidate SET of a query depends on nothing else
+        auto fatten = [&](uint32_t m) {
+            const Box b = box_of(m);
+            const V3 lo = b.lo - c->cfg.leaf_margin, hi = b.hi + c->cfg.leaf_margin;
+            float * f = c->leaf_fat.data() + 6 * size_t(m);
+            f[0] = lo.x; f[1] = lo.y; f[2] = lo.z; f[3] = hi.x; f[4] = hi.y; f[5] = hi.z;
+        };
+        if (c->by_id()) c->leaf_fat.resize(size_t(n_meshes) * 6);
         for (uint32_t model : c->moved_models) {
             if (c->literal()) break;
             ModelHost const & mh = c->models[model];
             for (uint32_t m = mh.first_mesh; m < mh.first_mesh + mh.n_meshes && m < c->meshes_in_tree; ++m) {
                 Box b = box_of(m);
-                c->tree.update(&c->meshes[m].tree_index, &b, 1);
+                if (c->by_id()) {
+                    const float * f = c->leaf_fat.data() + 6 * size_t(m);
+                    Box stored; stored.lo = v3(f[0], f[1], f[2]); stored.hi = v3(f[3], f[4], f[5]);
+                    if (!box_contains(stored, b)) fatten(m);
+                } else {
+                    c->tree.update(&c->meshes[m].tree_index, &b, 1);
+                }
             }
         }
         c->moved_models.clear();
@@ -91,9 +110,11 @@ int commit_impl(prtc_ctx * c) {
                 if (aabbs[6 * size_t(m) + 3 + k] > c->world_hi[k]) c->world_hi[k] = aabbs[6 * size_t(m) + 3 + k];
             }
         // new meshes: DynamicAABBTree::insert in registration order, physics_system.cpp:102
-        for (uint32_t m = c->meshes_in_tree; m < n_meshes; ++m)
-            if (c->models[c->meshes[m].model].n_meshes != 0)      // not removed before its first commit
+        for (uint32_t m = c->meshes_in_tree; m < n_meshes; ++m) {
+            if (c->by_id()) fatten(m);
+            else if (c->models[c->meshes[m].model].n_meshes != 0)      // not removed before its first commit
                 c->meshes[m].tree_index = c->tree.insert_leaf(m, LEAF_MESH, box_of(m));
+        }
         c->meshes_in_tree = n_meshes;
         c->meshes_on_device = n_meshes;
         c->geometry_dirty = false;
@@ -105,7 +126,7 @@ int commit_impl(prtc_ctx * c) {
         // Triangle records are laid out in LEAF order in CANONICAL mode (the tree is built once; neighbours in the
         // traversal are neighbours in memory) and in REGISTRATION order in LITERAL mode, where the tree changes shape
         // whenever a capsule leaves its fat box: there a re-flatten only uploads the nodes, the triangles stay put.
-        const bool by_leaf_order = !c->literal();
+        const bool by_leaf_order = !c->literal() && !c->by_id();
         const bool rebuild_tris = by_leaf_order || c->tri_dirty;
         if (rebuild_tris) {
             c->tri_src.clear();
@@ -120,6 +141,10 @@ int commit_impl(prtc_ctx * c) {
             }
         }
         ++c->tree_version;                       // every cached leaf list refers to node indices of the old layout
+        if (c->by_id()) {
+            int rc = build_tree_on_device(c, s);
+            if (rc) return rc;
+        } else
         c->tree.flatten(c->flat, [&](uint32_t mesh_id, uint32_t & first, uint32_t & count) {
             MeshHost const & mh = c->meshes[mesh_id];
             count = mh.n_vertices / 3;
@@ -137,7 +162,8 @@ int commit_impl(prtc_ctx * c) {
         static_assert(sizeof(FlatNode) == 32, "FlatNode must be two float4");
         if (nn) {
             // pageable sources: the runtime stages them before it returns, so the vectors may be rewritten afterwards
-            PRTC_CUDA(cudaMemcpyAsync(c->d_nodes.ptr, c->flat.nodes.data(), nn * sizeof(FlatNode), cudaMemcpyHostToDevice, s));
+            if (!c->by_id())                     // (BY_ID: the nodes were built where they are)
+                PRTC_CUDA(cudaMemcpyAsync(c->d_nodes.ptr, c->flat.nodes.data(), nn * sizeof(FlatNode), cudaMemcpyHostToDevice, s));
             c->leaf_ids_stale = true;            // only traces and prtc_query_box read them: uploaded on demand
         }
         // top levels as a compact table for k_xc_refresh (the LITERAL tree changes shape every frame and never gets there)
@@ -160,6 +186,43 @@ int commit_impl(prtc_ctx * c) {
         c->tree_dirty = false;
         c->tri_dirty = false;
     }
+    return PRTC_OK;
+}
+
+// PRTC_ORDER_BY_ID: leaf records (stored fat box, triangle range) of the live meshes in ascending id go up, the kernels of
+// k_tree_build.cu put the tree together in d_nodes, and the host takes a copy for what it derives from the node array
+// (top-of-tree table, collider id per node, introspection)
+int build_tree_on_device(prtc_ctx * c, cudaStream_t s) {
+    const uint32_t n_meshes = uint32_t(c->meshes.size());
+    std::vector<FlatNode> leaves;
+    c->flat.leaf_order.clear(); c->flat.capsule_order.clear();
+    for (uint32_t m = 0; m < n_meshes; ++m) {
+        if (c->models[c->meshes[m].model].n_meshes == 0) continue;     // removed
+        const float * f = c->leaf_fat.data() + 6 * size_t(m);
+        FlatNode l;
+        l.lo[0] = f[0]; l.lo[1] = f[1]; l.lo[2] = f[2]; l.hi[0] = f[3]; l.hi[1] = f[4]; l.hi[2] = f[5];
+        l.link = int32_t(c->mesh_tri_first[m]);
+        l.count = int32_t(c->meshes[m].n_vertices / 3);
+        leaves.push_back(l);
+        c->flat.leaf_order.push_back(m);
+    }
+    const uint32_t n_leaves = uint32_t(leaves.size());
+    const size_t nn = n_leaves ? 2 * size_t(n_leaves) - 1 : 0;
+    c->flat.nodes.resize(nn);
+    c->flat.node_leaf_id.assign(nn, 0xFFFFFFFFu);
+    c->flat.node_leaf_kind.assign(nn, uint8_t(LEAF_NONE));
+    c->flat.max_depth = bt_levels(n_leaves);
+    if (!n_leaves) return PRTC_OK;
+    PRTC_CUDA(c->d_leaves.reserve(size_t(n_leaves) * 2));
+    PRTC_CUDA(c->d_nodes.reserve(nn * 2));
+    PRTC_CUDA(cudaMemcpyAsync(c->d_leaves.ptr, leaves.data(), size_t(n_leaves) * sizeof(FlatNode), cudaMemcpyHostToDevice, s));
+    launch_tree_build(c->d_leaves.ptr, n_leaves, c->d_nodes.ptr, s);
+    PRTC_CUDA(cudaGetLastError());
+    PRTC_CUDA(cudaMemcpyAsync(c->flat.nodes.data(), c->d_nodes.ptr, nn * sizeof(FlatNode), cudaMemcpyDeviceToHost, s));
+    PRTC_CUDA(cudaStreamSynchronize(s));
+    uint32_t j = 0;
+    for (size_t i = 0; i < nn; ++i)
+        if (c->flat.nodes[i].count >= 0) { c->flat.node_leaf_id[i] = c->flat.leaf_order[j++]; c->flat.node_leaf_kind[i] = uint8_t(LEAF_MESH); }
     return PRTC_OK;
 }
 
@@ -224,7 +287,7 @@ int check_bad_colliders(prtc_ctx * c, cudaStream_t on) {
 }
 
 int check_mode(prtc_ctx * c, bool device_pointers) {
-    if (c->cfg.order_mode != PRTC_ORDER_CANONICAL && c->cfg.order_mode != PRTC_ORDER_LITERAL)
+    if (c->cfg.order_mode != PRTC_ORDER_CANONICAL && c->cfg.order_mode != PRTC_ORDER_LITERAL && c->cfg.order_mode != PRTC_ORDER_BY_ID)
         return fail(PRTC_ERR_INVALID, "unknown order_mode");
     if (c->literal() && device_pointers)
         return fail(PRTC_ERR_INVALID, "PRTC_ORDER_LITERAL maintains the unified tree on the host every frame and needs the "
@@ -330,7 +393,7 @@ void prtc_destroy(prtc_ctx * c) {
     cudaSetDevice(c->cfg.device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     c->d_raw.release(); c->d_world.release(); c->d_aabbs.release(); c->d_meshes.release(); c->d_xforms.release();
-    c->d_nodes.release(); c->d_top.release(); c->d_tris.release(); c->d_node_leaf_id.release(); c->d_tri_src.release();
+    c->d_nodes.release(); c->d_leaves.release(); c->d_top.release(); c->d_tris.release(); c->d_node_leaf_id.release(); c->d_tri_src.release();
     c->d_capsules.release(); c->d_counters.release(); c->d_work.release(); c->d_ingest.release(); c->stage.release();
     c->d_xc_version.release(); c->d_xc_count.release(); c->d_xc_leaf.release(); c->d_xc_region.release(); c->d_tf.release(); c->d_ph.release();
     c->d_tq.release(); c->d_tmesh.release(); c->d_tcaps.release(); c->d_thits.release();
@@ -472,7 +535,7 @@ int prtc_remove_model(prtc_ctx * c, uint32_t model_id) {
     // DynamicAABBTree::remove over the model's mesh leaves in order (physics_system.cpp:136)
     for (uint32_t m = mh.first_mesh; m < mh.first_mesh + mh.n_meshes; ++m) {
         MeshHost & me = c->meshes[m];
-        if (m < c->meshes_in_tree && me.tree_index >= 0) c->tree.remove(me.tree_index);
+        if (m < c->meshes_in_tree && me.tree_index >= 0) c->tree.remove(me.tree_index);     // (BY_ID never has a tree index)
         me.tree_index = -1;
         me.n_vertices = 0;          // the vertices stay in the registry but are never referenced again
     }
@@ -534,6 +597,36 @@ int prtc_host_build_tree(const float * aabbs6, uint32_t n, float margin, uint32_
     if (nodes8) {
         if (nodes_capacity < flat.nodes.size()) return fail(PRTC_ERR_CAPACITY, "prtc_host_build_tree: node buffer too small");
         std::memcpy(nodes8, flat.nodes.data(), flat.nodes.size() * sizeof(FlatNode));
+    }
+    return PRTC_OK;
+}
+
+int prtc_host_balanced_tree(const float * aabbs6, uint32_t n, float * nodes8, uint32_t nodes_capacity, uint32_t * n_nodes) {
+    if ((n && !aabbs6) || !n_nodes) return fail(PRTC_ERR_INVALID, "prtc_host_balanced_tree: null argument");
+    const uint32_t nn = n ? 2 * n - 1 : 0;
+    *n_nodes = nn;
+    if (!nodes8) return PRTC_OK;
+    if (nodes_capacity < nn) return fail(PRTC_ERR_CAPACITY, "prtc_host_balanced_tree: node buffer too small");
+    FlatNode * nodes = reinterpret_cast<FlatNode *>(nodes8);
+    const uint32_t k = bt_levels(n);
+    // the same passes as k_tree_build.cu, as plain loops
+    for (uint32_t j = 0; j < n; ++j) {
+        FlatNode & l = nodes[bt_index(0, j, k, n)];
+        for (int a = 0; a < 3; ++a) { l.lo[a] = aabbs6[6 * size_t(j) + a]; l.hi[a] = aabbs6[6 * size_t(j) + 3 + a]; }
+        l.link = int32_t(j); l.count = 1;
+    }
+    auto lo_of = [](float a, float b) { return (a != a || b != b) ? NAN : std::fmin(a, b); };
+    auto hi_of = [](float a, float b) { return (a != a || b != b) ? NAN : std::fmax(a, b); };
+    for (uint32_t level = 1; level <= k; ++level) {
+        const uint32_t n_blocks = uint32_t((uint64_t(n) + (1ull << level) - 1) >> level);
+        for (uint32_t j = 0; j < n_blocks; ++j) {
+            if (!bt_is_node(level, j, n)) continue;
+            const uint32_t idx = bt_index(level, j, k, n), c1 = idx + 1, c2 = idx + (1u << level);
+            FlatNode & x = nodes[idx];
+            for (int a = 0; a < 3; ++a) { x.lo[a] = lo_of(nodes[c1].lo[a], nodes[c2].lo[a]); x.hi[a] = hi_of(nodes[c1].hi[a], nodes[c2].hi[a]); }
+            x.link = int32_t(idx + 2u * bt_leaves_of(level, j, n) - 1u);
+            x.count = -int32_t(c2);
+        }
     }
     return PRTC_OK;
 }

@@ -122,6 +122,8 @@ struct prtc_ctx {
     prt::host::DevBuf<prt::MeshDev> d_meshes;
     prt::host::DevBuf<prt::ModelXform> d_xforms;
     prt::host::DevBuf<float4> d_nodes, d_tris;
+    prt::host::DevBuf<float4> d_leaves;     // BY_ID: leaf records handed to the device tree build
+    std::vector<float> leaf_fat;            // BY_ID: stored fat box of every mesh leaf (6 floats), kept with the reference's update rule
     prt::host::DevBuf<float4> d_top;        // top-of-tree table (bvh_builder.h build_top_table), CANONICAL order only
     std::vector<prt::FlatNode> top;
     prt::host::DevBuf<uint32_t> d_node_leaf_id, d_tri_src;
@@ -165,7 +167,8 @@ struct prtc_ctx {
     bool dyn_prepared = false;               // prtc_dyn_prepare ran for the coming step (records may have been exchanged since)
     float world_lo[3] = {0, 0, 0}, world_hi[3] = {0, 0, 0};
     bool literal() const { return cfg.order_mode == PRTC_ORDER_LITERAL; }
-    bool jacobi() const { return cfg.order_mode == PRTC_ORDER_CANONICAL && cfg.dyn_mode == PRTC_DYN_JACOBI; }
+    bool by_id() const { return cfg.order_mode == PRTC_ORDER_BY_ID; }
+    bool jacobi() const { return cfg.order_mode != PRTC_ORDER_LITERAL && cfg.dyn_mode == PRTC_DYN_JACOBI; }
 };
 
 namespace prt {

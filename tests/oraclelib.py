@@ -167,7 +167,7 @@ class L0World(_World):
 
 
 class L1World(_World):
-    """Our CPU restatement.  order: 'literal' | 'canonical'; dyn: 'off' | 'jacobi' (canonical only)."""
+    """Our CPU restatement.  order: 'literal' | 'canonical' | 'by_id' (canonical with the mesh candidates of a query in ascending collider id); dyn: 'off' | 'jacobi' (canonical only)."""
     prefix = "l1_"
 
     def __init__(self, order="literal", dyn="off", abs_mode="int", substeps=4, threads=1, gravity=1.0,
@@ -176,9 +176,12 @@ class L1World(_World):
         lib = ctypes.CDLL(path)
         lib.l1_create.restype = _vp
         cf = np.array([gravity, leaf_margin, ground_dot, friction, stick], np.float32)
-        cu = np.array([substeps, {"int": 0, "float": 1}[abs_mode], {"literal": 0, "canonical": 1}[order],
+        cu = np.array([substeps, {"int": 0, "float": 1}[abs_mode], {"literal": 0, "canonical": 1, "by_id": 2}[order],
                        {"off": 0, "jacobi": 2}[dyn], threads], np.uint32)
         super().__init__(lib, lib.l1_create(_ptr(cf), _ptr(cu)))
+
+    def update_model(self, model_index, transform):
+        self._fn("update_model")(self.h, _u32(model_index), _ptr(_f32(transform)))
 
     def counters(self, reset=False):
         out = np.zeros(5, np.uint64)

@@ -843,3 +843,99 @@ def test_top_staging_does_not_change_results(cross_frame):
     ca, cb = on.counters(), off.counters()
     for k in ("substeps", "tri_tests", "node_tests", "contacts", "launches"):
         assert ca[k] == cb[k], k
+
+
+# ------------------------------------------------------------------------------------------------------------
+# PRTC_ORDER_BY_ID: the tree is built on the device; mesh candidates in ascending collider id.
+# Oracle = L1 "by_id": the reference's own candidate set (its tree, its stored fat boxes), sorted by id.
+# ------------------------------------------------------------------------------------------------------------
+def _tf10(t):
+    from prototype2_b200 import capi
+    g = np.zeros(1, capi.TRANSFORM_DTYPE)
+    g["position"][0] = t[0:3]; g["rotation"][0] = (t[4], t[5], t[6], t[3]); g["scale"][0] = t[7:10]
+    return g
+
+
+@pytest.mark.parametrize("n,dyn", [(500, "off"), (500, "jacobi"), (36000, "off")])
+def test_by_id_order_device_built_tree_bit_exact(n, dyn):
+    """two overlapping models (a terrain and a second, finer one 0.3 above part of it -- characters touch both, so the
+    order of the candidates decides the result), one of them nudged inside its margin (stored fat boxes must survive,
+    aabb_tree.cpp:102-111) and then moved for real; states every frame, traces (candidate ids in ascending order, hit
+    indices, pushes) on some; box queries against brute force over the fat boxes"""
+    from prototype2_b200 import capi
+    scene = H.make_scene(96, 2, 2, n, seed=31)
+    xyz2, mf2, mc2 = H.scenes.terrain(40, 1, 3)
+    t2 = [20.0, 0.3, 25.0, 1.0, 0.0, 0.0, 0.0, 1.0, 1.0, 1.0]
+    kw = dict(order="by_id", dyn=dyn)
+    if n > 1000:
+        kw["threads"] = os.cpu_count() or 1
+    orc = H.build_oracle(scene, "l1", **kw)
+    orc.add_model(xyz2, mf2, mc2, t2)
+    ctx, tf, ph = H.build_gpu(scene, order_mode=capi.ORDER_BY_ID, dyn_mode=capi.DYN_JACOBI if dyn == "jacobi" else capi.DYN_OFF)
+    m2, _ = ctx.add_model_collider(xyz2, mf2, mc2, t2)
+    ctx.commit()
+    n_leaves = len(scene["mesh_first"]) + len(mf2)
+    assert np.array_equal(ctx.leaf_order(), np.arange(n_leaves, dtype=np.uint32))
+    # the device-built tree answers box queries with exactly the leaves whose fat box (tight box -/+ 0.05) overlaps,
+    # in ascending id
+    wv = ctx.world_vertices()
+    first = np.concatenate([scene["mesh_first"], np.asarray(mf2) + len(scene["xyz"])]).astype(np.int64)
+    lo = np.minimum.reduceat(wv, first, axis=0) - np.float32(0.05)
+    hi = np.maximum.reduceat(wv, first, axis=0) + np.float32(0.05)
+    rs = np.random.RandomState(3)
+    for q in range(40):
+        c = rs.uniform(0, 96, 3).astype(np.float32); c[1] = rs.uniform(-1, 2)
+        e = rs.uniform(0.3, 9.0, 3).astype(np.float32)
+        qlo, qhi = c - e, c + e
+        brute = np.nonzero(~((lo > qhi).any(axis=1) | (hi < qlo).any(axis=1)))[0]
+        assert np.array_equal(ctx.query_box(np.concatenate([qlo, qhi])), brute.astype(np.uint32)), "query %d" % q
+    keys = LITERAL_KEYS if dyn == "jacobi" else H.TRACE_KEYS
+    for f in range(8):
+        if f == 3:
+            t2 = [20.01, 0.32, 25.0, 1.0, 0.0, 0.0, 0.0, 1.0, 1.0, 1.0]          # inside the margin
+        if f == 5:
+            t2 = [22.0, 0.1, 24.0, 0.9961947, 0.0, 0.0871557, 0.0, 1.0, 1.2, 1.0]
+        if f in (3, 5):
+            orc.update_model(1, t2)
+            ctx.update_model_colliders([m2], _tf10(t2))
+        if f in (0, 3, 5) and n <= 1000:
+            to = orc.step(DT, trace=True)
+            tg = ctx.update_characters_traced(DT, tf, ph)
+            assert H.trace_diff(to, tg, keys) == [], "frame %d trace" % f
+        else:
+            orc.step(DT)
+            ctx.update_characters(DT, tf, ph)
+        assert H.state_diff(orc.get_state(), H.gpu_state(tf, ph)) == [], "frame %d state" % f
+    co, cg = orc.counters(), ctx.counters()
+    for k in ("substeps", "tri_tests", "contacts") + (("cc_tests",) if dyn == "jacobi" else ()):
+        assert co[k] == cg[k], k
+    # some queries did see both models at once
+    assert co["tri_tests"] > 0
+
+
+def test_by_id_order_removed_model_and_empty_world():
+    """a removed model's leaves drop out of the device-built tree; an empty world steps like the reference (no candidates:
+    `if (meshColIDs.empty()) break;`, physics_system.cpp:391-393)"""
+    from prototype2_b200 import capi
+    scene = H.make_scene(48, 2, 2, 300, seed=12)
+    xyz2, mf2, mc2 = H.scenes.terrain(48, 2, 2)
+    t2 = [0.0, 0.4, 0.0, 1.0, 0.0, 0.0, 0.0, 1.0, 1.0, 1.0]
+    ctx, tf, ph = H.build_gpu(scene, order_mode=capi.ORDER_BY_ID)
+    m2, _ = ctx.add_model_collider(xyz2, mf2, mc2, t2)
+    ctx.update_characters(DT, tf, ph)                          # both present
+    ctx.remove_model_collider(m2)
+    ctx.commit()
+    assert np.array_equal(ctx.leaf_order(), np.arange(len(scene["mesh_first"]), dtype=np.uint32))
+    orc = H.build_oracle(scene, "l1", order="by_id")
+    s = H.gpu_state(tf, ph)
+    orc.set_state(pos=s["pos"], vel=s["vel"], gnormal=s["gnormal"], grounded=s["grounded"])
+    for f in range(4):
+        orc.step(DT)
+        ctx.update_characters(DT, tf, ph)
+        assert H.state_diff(orc.get_state(), H.gpu_state(tf, ph)) == [], "frame %d" % f    # exact: no tree history in this order
+    ctx.remove_model_collider(0)
+    ctx.commit()
+    assert ctx.tree_info()["nodes"] == 0
+    before = tf["position"].copy()
+    ctx.update_characters(DT, tf, ph)
+    assert np.isfinite(tf["position"]).all() and not np.array_equal(before, tf["position"])

@@ -215,3 +215,69 @@ def test_top_table_small_tree_is_not_staged():
     _, nodes = capi.host_build_tree(np.array([[0, 0, 0, 1, 1, 1], [2, 0, 0, 3, 1, 1], [0, 2, 0, 1, 3, 1]], np.float32))
     assert len(capi.host_top_table(nodes, 1024)) == 0
     assert len(capi.host_top_table(np.zeros((0, 8), np.float32), 1024)) == 0
+
+
+def _reference_balanced(boxes):
+    """the left-complete tree over the boxes by plain recursion (first half first): what the closed-form index arithmetic
+    of csrc/balanced_tree.cuh must reproduce"""
+    n = len(boxes)
+    nodes = np.zeros((2 * n - 1, 8), np.float32)
+    ints = nodes.view(np.int32)
+    pos = [0]
+
+    def build(a, b, size):                        # block [a, a + size) clipped to n, size a power of two
+        while size > 1 and a + size // 2 >= b:    # second half empty: collapses into the first half
+            size //= 2
+        idx = pos[0]
+        pos[0] += 1
+        if size == 1:
+            nodes[idx, 0:3], nodes[idx, 4:7] = boxes[a, 0:3], boxes[a, 3:6]
+            ints[idx, 3], ints[idx, 7] = a, 1
+            return idx
+        c1 = build(a, a + size // 2, size // 2)
+        c2 = build(a + size // 2, b, size // 2)
+        nodes[idx, 0:3] = np.minimum(nodes[c1, 0:3], nodes[c2, 0:3])
+        nodes[idx, 4:7] = np.maximum(nodes[c1, 4:7], nodes[c2, 4:7])
+        ints[idx, 3], ints[idx, 7] = pos[0], -c2
+        return idx
+    size = 1
+    while size < n:
+        size *= 2
+    build(0, n, size)
+    assert pos[0] == 2 * n - 1
+    return nodes
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 4, 5, 7, 8, 9, 31, 33, 100, 1000, 1025])
+def test_balanced_tree_layout_equals_recursive_construction(n):
+    """PRTC_ORDER_BY_ID: closed-form preorder indices, skip links, second-child indices and boxes == a recursive build"""
+    rng = np.random.default_rng(n)
+    lo = rng.uniform(-50, 50, (n, 3)).astype(np.float32)
+    boxes = np.concatenate([lo, lo + rng.uniform(0.1, 5, (n, 3)).astype(np.float32)], axis=1)
+    got = capi.host_balanced_tree(boxes)
+    want = _reference_balanced(boxes)
+    assert got.shape == want.shape
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+
+
+def test_balanced_tree_walk_emits_overlapping_boxes_in_ascending_id():
+    rng = np.random.default_rng(5)
+    n = 3001
+    lo = rng.uniform(0, 100, (n, 3)).astype(np.float32)
+    boxes = np.concatenate([lo, lo + rng.uniform(0.1, 3, (n, 3)).astype(np.float32)], axis=1)
+    boxes[17, :] = np.nan                                   # an all-NaN box is a candidate of every query (aabb.cpp:3-10)
+    boxes[1200, 1] = np.nan                                 # one NaN coordinate: that compare never rejects
+    nodes = capi.host_balanced_tree(boxes)
+    for q in range(200):
+        c = rng.uniform(0, 100, 3)
+        e = rng.uniform(0.5, 8, 3)
+        box = np.concatenate([c - e, c + e]).astype(np.float32)
+        got, _ = walk_flat(nodes, box)
+        brute = [i for i in range(n) if not (boxes[i, 0] > box[3] or boxes[i, 3] < box[0] or boxes[i, 1] > box[4] or
+                                             boxes[i, 4] < box[1] or boxes[i, 2] > box[5] or boxes[i, 5] < box[2])]
+        assert list(got) == brute
+        assert 17 in brute
+
+
+def test_balanced_tree_empty():
+    assert len(capi.host_balanced_tree(np.zeros((0, 6), np.float32))) == 0

@@ -168,3 +168,45 @@ def test_sweep_checker_known_answers():
     # 3: never reaches the floor; 4: moves away from it
     assert (r["hit_tri"][2:] == -1).all() and np.allclose(r["pos"][2], [3, 4.9, 1]) and np.allclose(r["pos"][3], [0, 3, 0])
     assert np.all(r["vel"] == 0.0)
+
+
+def test_l1_by_id_is_canonical_with_sorted_candidates():
+    """checker of PRTC_ORDER_BY_ID: on the first frame (same start state) every query of the by_id arrangement has the
+    candidate SET of the canonical one -- the reference's own tree query -- in ascending collider id"""
+    import helpers as H
+    scene = H.make_scene(48, 1, 3, 120, seed=5)
+    a = H.build_oracle(scene, "l1", order="canonical")
+    b = H.build_oracle(scene, "l1", order="by_id")
+    ta, tb = a.step(1.0 / 30.0, trace=True), b.step(1.0 / 30.0, trace=True)
+    assert np.array_equal(ta.q_char, tb.q_char) or len(ta.q_char) > 0
+    # first substep of every character: identical query boxes in both arrangements
+    firsts_a = [i for i in range(len(ta.q_char)) if ta.q_sub[i] == 0]
+    firsts_b = [i for i in range(len(tb.q_char)) if tb.q_sub[i] == 0]
+    assert len(firsts_a) == len(firsts_b) == 120
+    differ = 0
+    for ia, ib in zip(firsts_a, firsts_b):
+        la = ta.mesh_ids[(ta.q_mesh_off[ia - 1] if ia else 0):ta.q_mesh_off[ia]]
+        lb = tb.mesh_ids[(tb.q_mesh_off[ib - 1] if ib else 0):tb.q_mesh_off[ib]]
+        assert list(lb) == sorted(la)
+        differ += list(la) != list(lb)
+    assert differ > 0                      # the tree's own order is not the id order, or this test shows nothing
+
+
+@needs_l0
+def test_l1_update_model_equals_reference():
+    """l1_update_model (physics_system.cpp:161-202): a model nudged inside the leaf margin and then moved for real, in
+    lock step with the reference's own updateModelColliders -- states, traces and tree order stay bit-identical"""
+    scene = H.make_scene(32, 2, 2, 40, seed=104)
+    l0 = H.build_oracle(scene, "l0", variant="traced")
+    l1 = H.build_oracle(scene, "l1", order="literal")
+    for f in range(16):
+        if f in (3, 6, 11):
+            t = {3: [0.01, 0.02, 0.0, 1.0, 0.0, 0.0, 0.0, 1.0, 1.0, 1.0],
+                 6: [0.6, -0.1, 0.3, 0.9961947, 0.0, 0.0871557, 0.0, 1.0, 1.1, 1.0],
+                 11: [0.6, -0.12, 0.31, 0.9961947, 0.0, 0.0871557, 0.0, 1.0, 1.1, 1.0]}[f]
+            l0.update_model(0, t)
+            l1.update_model(0, t)
+        t0, t1 = l0.step(DT, trace=True), l1.step(DT, trace=True)
+        assert H.trace_diff(t0, t1, Trace.FIELDS) == [], "frame %d" % f
+        assert H.state_diff(l0.get_state(), l1.get_state()) == [], "frame %d" % f
+        assert H.same(l0.dump_order()[0], l1.dump_order()[0]), "tree order diverged at frame %d" % f
