@@ -158,15 +158,20 @@ PRT_HD bool capsule_triangle(Pose const & ps, float radius, uint32_t abs_mode, V
     bool inside = dot(c0, n) <= 0 && dot(c1, n) <= 0 && dot(c2, n) <= 0;
 
     float radiussq = radius * radius;
-    V3 point1 = closest_on_segment(pa, pb, center);
+    // the three closestPointOnLineSegment calls (:82-99) with their edge lengths and inverse lengths computed together
+    // (same values as closest_on_segment(a, b, p) computes one edge at a time; see len_inv3)
+    const V3 e1 = pb - pa, e2 = pc - pb, e3 = pa - pc;
+    float s1, s2, s3, i1, i2, i3;
+    len_inv3(dot(e1, e1), dot(e2, e2), dot(e3, e3), s1, s2, s3, i1, i2, i3);
+    V3 point1 = closest_on_segment(pa, pb, e1 * i1, s1, center);
     V3 v1 = center - point1;
     float distsq1 = dot(v1, v1);
     bool intersects = distsq1 < radiussq;
-    V3 point2 = closest_on_segment(pb, pc, center);
+    V3 point2 = closest_on_segment(pb, pc, e2 * i2, s2, center);
     V3 v2 = center - point2;
     float distsq2 = dot(v2, v2);
     intersects |= distsq2 < radiussq;
-    V3 point3 = closest_on_segment(pc, pa, center);
+    V3 point3 = closest_on_segment(pc, pa, e3 * i3, s3, center);
     V3 v3_ = center - point3;
     float distsq3 = dot(v3_, v3_);
     intersects |= distsq3 < radiussq;
