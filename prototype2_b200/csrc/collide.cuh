@@ -71,12 +71,17 @@ PRT_HD void segment_ends(CapsuleFrame const & f, V3 pos, V3 & A, V3 & B) { segme
 PRT_HD Pose make_pose(CapsuleFrame const & f, V3 pos) {
     Pose p;
     segment_ends(f, pos, p.A, p.B);
-    p.cn = normalize(p.A - p.B);
-    p.pointA = p.A - p.cn * f.radius;
+    // collision_system.cpp:47 normalises A - B, closestPointOnLineSegment (physics_util.cpp:125-139) normalises B - A and
+    // takes distance(A, B): the squared length is the same float either way ((-x)(-x) == x x, same order of the sums), so
+    // one square root and one reciprocal serve both -- normalize(v) = v * (1 / sqrt(dot(v, v))) (glm::inversesqrt)
+    V3 ab = p.A - p.B;
     V3 ba = p.B - p.A;
     float dd = dot(ba, ba);
     float s = fsqrt(dd);
-    p.segv = ba * fdiv(1.0f, s);
+    float inv = fdiv(1.0f, s);
+    p.cn = ab * inv;
+    p.pointA = p.A - p.cn * f.radius;
+    p.segv = ba * inv;
     p.segd = s;
     return p;
 }
@@ -113,8 +118,8 @@ PRT_HD V3 closest_on_triangle(V3 a, V3 b, V3 c, V3 p) {
     if (va <= 0.0f && unom >= 0.0f && udenom >= 0.0f) return b + fdiv(unom, unom + udenom) * bc;
     float vb = dot(n, cross(c - p, a - p));
     if (vb <= 0.0f && tnom >= 0.0f && tdenom >= 0.0f) return a + fdiv(tnom, tnom + tdenom) * ac;
-    float u = fdiv(va, (va + vb) + vc);
-    float v = fdiv(vb, (va + vb) + vc);
+    float u, v;
+    div2(va, vb, (va + vb) + vc, u, v);
     float w = (1.0f - u) - v;
     return (u * a + v * b) + w * c;
 }
