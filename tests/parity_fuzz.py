@@ -2,7 +2,7 @@
 shapes, rotations and inputs, run free for many frames in CANONICAL order with and without the JACOBI dynamic pass (vs the L1 port) and in LITERAL order (vs the
 reference's own code when oracle/_ref is there); states compared bit for bit every frame, counters at the end.
 CANONICAL rounds take the mesh candidates in ascending collider id (PRTC_ORDER_BY_ID, tree built on the device) half of the time.
-Usage on the GPU box:  PYTHONPATH=$PWD python tools/parity_fuzz.py [rounds] [seed] [big]
+Usage on the GPU box:  PYTHONPATH=$PWD python tests/parity_fuzz.py [rounds] [seed] [big]
 `big`: crowds of 24 000 - 70 000 characters (persistent kernel, per-slot leaf lists, staged tree top), fewer frames."""
 import os
 import sys

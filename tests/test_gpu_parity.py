@@ -797,13 +797,13 @@ def test_warp_kernel_overflow_and_equivalence_with_the_lock_step_kernel():
 
 
 def test_randomised_long_runs():
-    """tools/parity_fuzz.py: 16 random levels / crowds / capsule shapes / rotations / inputs, 60-200 free-running frames
+    """tests/parity_fuzz.py: 16 random levels / crowds / capsule shapes / rotations / inputs, 60-200 free-running frames
     each, CANONICAL vs the L1 port and LITERAL vs the reference's own code, bit for bit every frame"""
     import subprocess
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     env = dict(os.environ, PYTHONPATH=root + os.pathsep + os.environ.get("PYTHONPATH", ""))
-    r = subprocess.run([sys.executable, os.path.join(root, "tools", "parity_fuzz.py"), "16", "11"], env=env, capture_output=True, text=True,
+    r = subprocess.run([sys.executable, os.path.join(root, "tests", "parity_fuzz.py"), "16", "11"], env=env, capture_output=True, text=True,
                        timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
     assert "16 rounds, 0 failures" in r.stdout
