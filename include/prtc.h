@@ -245,6 +245,13 @@ int prtc_get_world_vertices(prtc_ctx * ctx, float * xyz, uint32_t capacity_verti
 int prtc_query_box(prtc_ctx * ctx, const float aabb6[6], uint32_t * mesh_ids, uint32_t capacity, uint32_t * n_found);
 
 
+/* Device self-test (tests only): the kernels compute some IEEE divisions and square roots through written-out copies of
+ * the fast paths of div.rn.f32 / sqrt.rn.f32 that share a reciprocal or interleave independent chains (csrc/prt_math.cuh).
+ * Runs n_threads x 16 pseudo-random operand sets through them and through __fdiv_rn / __fsqrt_rn and returns how many
+ * results differ in their bits (NaN == NaN).  mode 0: random bit patterns; 1: magnitudes around 1; 2 / 3: magnitudes at the
+ * edges of the fast paths' operand ranges (2^+-60 for the divisions, 2^+-100 for the square roots).  Must return 0. */
+int prtc_selftest_math(prtc_ctx * ctx, uint32_t n_threads, uint64_t seed, int mode, uint64_t * mismatches);
+
 /* Host-only utility (needs no device, performs no collision arithmetic): builds the reference's dynamic AABB
  * tree over n boxes inserted in order (DynamicAABBTree::insert, aabb_tree.cpp:95-100) and returns it in the
  * flattened device layout: nodes8 = 8 x 32-bit words per node {lo.xyz, link, hi.xyz, count} in right-first

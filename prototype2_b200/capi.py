@@ -21,7 +21,7 @@ SYMBOLS = (
     "prtc_add_model", "prtc_add_capsule", "prtc_update_capsule", "prtc_commit", "prtc_update_models", "prtc_remove_model",
     "prtc_step_characters", "prtc_step_characters_device", "prtc_step_characters_traced", "prtc_raycast", "prtc_sweep_ellipsoids",
     "prtc_set_stream", "prtc_synchronize", "prtc_get_counters", "prtc_set_option", "prtc_dyn_configure", "prtc_dyn_prepare", "prtc_dyn_buffer", "prtc_get_tree_info", "prtc_get_leaf_order",
-    "prtc_get_world_vertices", "prtc_query_box", "prtc_host_build_tree", "prtc_host_top_table", "prtc_host_balanced_tree",
+    "prtc_get_world_vertices", "prtc_query_box", "prtc_host_build_tree", "prtc_host_top_table", "prtc_host_balanced_tree", "prtc_selftest_math",
 )
 
 
@@ -297,6 +297,11 @@ class PhysicsContext:
         out = np.zeros((max(n.value, 1), 3), np.float32)
         self._check(self.lib.prtc_get_world_vertices(self.h, _vp(out), ctypes.c_uint32(len(out)), ctypes.byref(n)))
         return out[:n.value]
+
+    def selftest_math(self, n_threads, seed, mode):
+        bad = ctypes.c_uint64()
+        self._check(self.lib.prtc_selftest_math(self.h, ctypes.c_uint32(n_threads), ctypes.c_uint64(seed), ctypes.c_int(mode), ctypes.byref(bad)))
+        return bad.value
 
     def query_box(self, aabb6, capacity=4096):
         box = np.ascontiguousarray(aabb6, np.float32)

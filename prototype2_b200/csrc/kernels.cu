@@ -273,6 +273,54 @@ int launch_step(StepParams const & p_in, bool traced, int mode, cudaStream_t str
     return launches;
 }
 
+// Self-test of the written-out division / square-root fast paths (prt_math.cuh operator/(V3, float), div2, len_inv3)
+// against the library's correctly rounded operations on pseudo-random operands: mode 0 = random bit patterns (every
+// exponent, denormals, infinities, NaNs, zeros), mode 1 = magnitudes around 1 (the range the collision code lives in),
+// mode 2 / 3 = magnitudes at the edges of the fast paths' ranges (2^+-60 for the divisions, 2^+-100 for the square roots).  Counts results whose bits differ (two NaNs count as equal).
+__device__ __forceinline__ uint32_t st_hash(uint64_t & s) {
+    s ^= s << 13; s ^= s >> 7; s ^= s << 17;
+    return uint32_t((s * 0x2545F4914F6CDD1Dull) >> 32);
+}
+__device__ __forceinline__ float st_operand(uint64_t & s, int mode) {
+    const uint32_t h = st_hash(s);
+    if (mode == 0) return __uint_as_float(h);
+    const uint32_t sign = h & 0x80000000u, mant = h & 0x007FFFFFu;
+    int e;
+    if (mode == 1) e = 127 + int((h >> 23) & 15u) - 8;                                   // 2^-8 .. 2^7
+    else { const int edge = mode == 2 ? 60 : 100, k = int((h >> 23) & 7u) - 4; e = ((h >> 27) & 1u) ? 127 + edge + k : 127 - edge + k; }   // around 2^+-60 / 2^+-100
+    return __uint_as_float(sign | (uint32_t(e) << 23) | mant);
+}
+__device__ __forceinline__ bool st_same(float a, float b) {
+    return __float_as_uint(a) == __float_as_uint(b) || (a != a && b != b);
+}
+__global__ void k_selftest_math(uint64_t seed, uint32_t n, int mode, unsigned long long * bad) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint64_t s = seed * 0x9E3779B97F4A7C15ull + (uint64_t(i) + 1) * 0xD1B54A32D192ED03ull;
+    st_hash(s); st_hash(s);
+    uint32_t wrong = 0;
+    for (int round = 0; round < 16; ++round) {
+        const V3 a = v3(st_operand(s, mode), st_operand(s, mode), st_operand(s, mode));
+        const float b = st_operand(s, mode);
+        const V3 q = a / b;
+        wrong += !st_same(q.x, __fdiv_rn(a.x, b)) + !st_same(q.y, __fdiv_rn(a.y, b)) + !st_same(q.z, __fdiv_rn(a.z, b));
+        float u, v;
+        div2(a.x, a.y, b, u, v);
+        wrong += !st_same(u, __fdiv_rn(a.x, b)) + !st_same(v, __fdiv_rn(a.y, b));
+        // squared lengths are sums of squares: non-negative (or NaN / inf)
+        const float d1 = fabsf(a.x), d2 = fabsf(a.y), d3 = fabsf(b);
+        float s1, s2, s3, i1, i2, i3;
+        len_inv3(d1, d2, d3, s1, s2, s3, i1, i2, i3);
+        const float r1 = __fsqrt_rn(d1), r2 = __fsqrt_rn(d2), r3 = __fsqrt_rn(d3);
+        wrong += !st_same(s1, r1) + !st_same(s2, r2) + !st_same(s3, r3);
+        wrong += !st_same(i1, __fdiv_rn(1.0f, r1)) + !st_same(i2, __fdiv_rn(1.0f, r2)) + !st_same(i3, __fdiv_rn(1.0f, r3));
+    }
+    if (wrong) atomicAdd(bad, (unsigned long long)wrong);
+}
+void launch_selftest_math(uint64_t seed, uint32_t n, int mode, unsigned long long * bad, cudaStream_t stream) {
+    k_selftest_math<<<(n + 255) / 256, 256, 0, stream>>>(seed, n, mode, bad);
+}
+
 __global__ void k_fold_counters(unsigned long long * main_counters, unsigned long long * scratch) {
     const unsigned k = threadIdx.x;
     if (k < 6) { if (scratch[k]) atomicAdd(main_counters + k, scratch[k]); scratch[k] = 0ull; }

@@ -107,6 +107,8 @@ void launch_dyn_grid(const float4 * records, uint32_t n, float ox, float oz, flo
 
 // main[k] += scratch[k], scratch[k] = 0 for the device-side work counters (per-frame scratch of the LITERAL fixpoint rounds)
 void launch_fold_counters(unsigned long long * main_counters, unsigned long long * scratch, cudaStream_t stream);
+// device self-test of the written-out IEEE division / square-root fast paths (16 operand sets per thread)
+void launch_selftest_math(uint64_t seed, uint32_t n, int mode, unsigned long long * bad, cudaStream_t stream);
 
 // K8: world-space vertex cache + per-mesh AABB (physics_system.cpp:68-93 / :161-202)
 struct MeshDev { uint32_t first_vertex, n_vertices, model; uint32_t pad; };

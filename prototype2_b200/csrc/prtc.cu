@@ -684,4 +684,19 @@ int prtc_query_box(prtc_ctx * c, const float aabb6[6], uint32_t * mesh_ids, uint
     return PRTC_OK;
 }
 
+int prtc_selftest_math(prtc_ctx * c, uint32_t n_threads, uint64_t seed, int mode, uint64_t * mismatches) {
+    if (!c || !mismatches || mode < 0 || mode > 3) return fail(PRTC_ERR_INVALID, "prtc_selftest_math: bad argument");
+    PRTC_CUDA(cudaSetDevice(c->cfg.device));
+    PRTC_CUDA(c->d_scratch_u.reserve(4));
+    unsigned long long * bad = reinterpret_cast<unsigned long long *>(c->d_scratch_u.ptr);
+    PRTC_CUDA(cudaMemsetAsync(bad, 0, sizeof(unsigned long long), c->stream));
+    launch_selftest_math(seed, n_threads, mode, bad, c->stream);
+    PRTC_CUDA(cudaGetLastError());
+    unsigned long long h = 0;
+    PRTC_CUDA(cudaMemcpyAsync(&h, bad, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+    PRTC_CUDA(cudaStreamSynchronize(c->stream));
+    *mismatches = h;
+    return PRTC_OK;
+}
+
 } // extern "C"
