@@ -1,7 +1,7 @@
 """Fixed cost of one engine-sized host-buffer step (prtc_step_characters, n = 1): a character far above the shipped
 level finds no candidate and leaves the kernel at once, so the call time is launch + synchronisation + the kernel's
 accesses to the staged records (+ ctypes); next to it the same character walking on the level (tests/c1_frame_latency.py
-has the scripted 300 frames).  Usage on the GPU box:  PYTHONPATH=$PWD python tools/small_batch_latency.py"""
+has the scripted 300 frames).  Usage on the GPU box:  PYTHONPATH=$PWD python tests/small_batch_latency.py"""
 import os
 import sys
 import time
