@@ -51,6 +51,8 @@ def parse_args():
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU time of the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--opt", action="append", default=[], metavar="NAME=VALUE",
+                    help="prtc_set_option before the run, e.g. --opt POOL_KERNEL=0 (A/B experiments)")
     return ap.parse_args()
 
 
@@ -284,6 +286,9 @@ def run_ours(args):
                               order_mode=capi.ORDER_BY_ID if args.order == "by_id" else capi.ORDER_CANONICAL)
     if dynamic:
         ctx.dyn_configure(first, n_caps * world)
+    for kv in args.opt:
+        name, val = kv.split("=")
+        ctx.set_option(getattr(capi, "OPT_" + name), int(val))
     ctx.add_model_collider(xyz, mf, mc)
     cid = ctx.add_capsule_collider()                      # one shared collider shape (h=0.5 r=0.5 off=(0,0.5,0))
     t_commit = time.perf_counter()

@@ -230,9 +230,15 @@ int prtc_get_counters(prtc_ctx * ctx, prtc_counters * out, int reset);
  *                          chunks that are copied in, stepped and copied out on a few streams).
  *   PRTC_OPT_TOP_STAGING   (default 1) the kernel that refills the per-slot leaf lists walks the top levels of the tree
  *                          (<= 1024 nodes) out of shared memory, staged per block with one TMA bulk copy (0: every
- *                          node comes from global memory).  CANONICAL order, trees of >= 4096 nodes. */
+ *                          node comes from global memory).  CANONICAL order, trees of >= 4096 nodes.
+ *   PRTC_OPT_POOL_KERNEL   (default 1) persistent launches run the pooled kernel: a warp owns 32 characters and all its lanes
+ *                          work through the pooled candidate triangles of those characters (dense cull, dense exact
+ *                          test, speculative ordered commit); 0: the lane-per-character kernel of round 1.
+ *   PRTC_OPT_TIGHT_REJECT  (default 1) pooled kernel only: a second conservative cull (plane and edge-plane distances of
+ *                          the capsule segment) behind the box cull. */
 enum prtc_option { PRTC_OPT_FRAME_CACHE = 1, PRTC_OPT_QUICK_REJECT = 2, PRTC_OPT_PERSISTENT = 3, PRTC_OPT_CROSS_FRAME_CACHE = 4,
-                   PRTC_OPT_WARP_KERNEL = 5, PRTC_OPT_STREAMED_COPY = 6, PRTC_OPT_TOP_STAGING = 7 };
+                   PRTC_OPT_WARP_KERNEL = 5, PRTC_OPT_STREAMED_COPY = 6, PRTC_OPT_TOP_STAGING = 7, PRTC_OPT_POOL_KERNEL = 8,
+                   PRTC_OPT_TIGHT_REJECT = 9 };
 int prtc_set_option(prtc_ctx * ctx, int option, int value);
 
 /* Introspection for parity tests: the flattened tree.  leaf_mesh_ids receives the mesh-collider ids of all

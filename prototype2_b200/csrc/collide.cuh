@@ -207,6 +207,91 @@ PRT_HD bool capsule_triangle(Pose const & ps, float radius, uint32_t abs_mode, V
     return true;
 }
 
+// Conservative plane / edge-plane pre-cull of the pooled kernel (k_step_pool), on a per-triangle CULL RECORD that
+// k_tri_setup precomputes next to the triangle record (4 float4 = 64 bytes):
+//     pl = (n.xyz, d0 = n . pa)        e_k = (m_k.xyz, d_k = m_k . v_k)   for the three edges, m_k = (e_k x n) / |e_k|
+// (the in-plane unit normal of edge k pointing OUT of the triangle, v_k a vertex on that edge).
+//
+// capsule_triangle() reports a contact only through `inside || intersects` (collision_system.cpp:101), and both put
+// `center` -- a point of the capsule segment AB (closestPointOnLineSegment, :67) -- close to the triangle:
+//   intersects -> a point of an edge lies within `radius` of center                                   (:82-99)
+//   inside     -> the projection of center onto the plane lies inside all three edge planes and the plane distance
+//                 is in [0, dmax)  (back-face and range culls :71-72; dmax = radius, or floor(radius) + 1 in int-abs mode)
+// Every point Q of the triangle has (Q - v_k) . m_k <= 0 and (Q - pa) . n == 0, and both forms are linear along AB, so
+// for every centre P on AB
+//   plane distance      dlo <= (P - pa) . n <= dhi          (dlo/dhi = min/max over the two end points)
+//   |P - Q|^2           >=  max(0, dlo)^2 + max(0, s)^2     (s = max over the edges of min over the end points of
+//                                                            (. - v_k) . m_k)
+// Hence no contact is possible at this pose when
+//   dlo > dmax + eps,   or   dhi < -eps,   or   (s > eps  and  max(0, dlo)^2 + s^2 > (radius + eps)^2)
+// `eps` absorbs the rounding of the exact test's intermediate points and of this test (>= 64 ulp of the largest world
+// coordinate, StepParams::qr_eps).  `slack` makes the answer hold for EVERY pose whose translation differs from the
+// tested one by at most `slack` (in any norm <= the 1-norm): both linear forms move by at most that much, so dlo, dhi
+// and s are widened by it.  The pooled kernel culls a window of triangles once, at the pose the window starts with, and
+// keeps the answers while the pushes applied since then stay inside that budget.
+// The edge-plane argument needs a stored normal that really is perpendicular to the edges, which rounding cannot
+// guarantee for slivers: the record carries edge planes only for triangles whose squared area is at least
+// 2^-4 |ab|^2 |ac|^2 (sine of the angle at pa >= 1/4; the normal of such a triangle is tilted by < 1e-6 rad), all-zero
+// edge entries otherwise (s == 0: never rejected by the edges).  A degenerate triangle (length(n) == 0, skipped by
+// the reference :53) is marked in pl.x.  NaNs anywhere make dA or dB NaN => "not rejected".  MUFU.RSQ / fused
+// multiply-adds are fine here: nothing computed in these functions reaches an output.  Soundness is checked on the CPU
+// by tests/test_precull.py (host build of this header, random poses displaced within the slack).
+PRT_HD float rsq_approx(float x) {
+#ifdef __CUDA_ARCH__
+    return rsqrtf(x);
+#else
+    return 1.0f / sqrtf(x);
+#endif
+}
+PRT_HD float fdot(V3 a, V3 b) { return fmaf(a.x, b.x, fmaf(a.y, b.y, a.z * b.z)); }
+PRT_HD V3 fcross(V3 a, V3 b) {
+    return v3(fmaf(a.y, b.z, -(a.z * b.y)), fmaf(a.z, b.x, -(a.x * b.z)), fmaf(a.x, b.y, -(a.y * b.x)));
+}
+struct CullRec { float pl[4], e0[4], e1[4], e2[4]; };
+PRT_HD CullRec make_cull_record(V3 pa, V3 pb, V3 pc, V3 n, bool degenerate) {
+    CullRec r;
+    for (int k = 0; k < 4; ++k) { r.pl[k] = 0.0f; r.e0[k] = 0.0f; r.e1[k] = 0.0f; r.e2[k] = 0.0f; }
+    if (degenerate) {
+        union { uint32_t u; float f; } mark; mark.u = PRT_DEGENERATE_BITS;
+        r.pl[0] = mark.f;
+        return r;
+    }
+    r.pl[0] = n.x; r.pl[1] = n.y; r.pl[2] = n.z; r.pl[3] = fdot(n, pa);
+    const V3 eab = pb - pa, ebc = pc - pb, eca = pa - pc;
+    const float lab = fdot(eab, eab), lbc = fdot(ebc, ebc), lca = fdot(eca, eca);
+    const V3 mab = fcross(eab, n);
+    // conditioning: |ab x ac|^2 >= 2^-4 |ab|^2 |ac|^2, with ab x ac reconstructed as (mab . ca) n-wards: |mab . eca| is
+    // twice the area when n is the true unit normal, so this also fails for a normal that is not
+    const float twice_area = fdot(mab, eca);
+    if (!(twice_area * twice_area >= 0.0625f * (lab * lca)) || !(twice_area > 0.0f)) return r;
+    const V3 mbc = fcross(ebc, n), mca = fcross(eca, n);
+    const float iab = rsq_approx(lab), ibc = rsq_approx(lbc), ica = rsq_approx(lca);
+    const V3 uab = mab * iab, ubc = mbc * ibc, uca = mca * ica;
+    const float dab = fdot(uab, pa), dbc = fdot(ubc, pb), dca = fdot(uca, pa);
+    const float all = ((uab.x + uab.y) + (uab.z + dab)) + ((ubc.x + ubc.y) + (ubc.z + dbc)) + ((uca.x + uca.y) + (uca.z + dca));
+    if (!(all - all == 0.0f)) return r;                          // something overflowed / is not finite: no edge planes
+    r.e0[0] = uab.x; r.e0[1] = uab.y; r.e0[2] = uab.z; r.e0[3] = dab;
+    r.e1[0] = ubc.x; r.e1[1] = ubc.y; r.e1[2] = ubc.z; r.e1[3] = dbc;
+    r.e2[0] = uca.x; r.e2[1] = uca.y; r.e2[2] = uca.z; r.e2[3] = dca;
+    return r;
+}
+// the record's four rows as they are loaded: (x, y, z, w)
+PRT_HD bool tight_reject_rec(V3 A, V3 B, float radius, float dmax, float eps, float slack,
+                             V3 n, float d0, V3 m0, float d0e, V3 m1, float d1e, V3 m2, float d2e) {
+    const float dA = fdot(A, n) - d0, dB = fdot(B, n) - d0;
+    if (!(dA == dA) || !(dB == dB)) return false;
+    const float dlo = fminf(dA, dB) - slack, dhi = fmaxf(dA, dB) + slack;
+    if (dlo > dmax + eps || dhi < -eps) return true;
+    const float s0 = fminf(fdot(A, m0), fdot(B, m0)) - d0e;
+    const float s1 = fminf(fdot(A, m1), fdot(B, m1)) - d1e;
+    const float s2 = fminf(fdot(A, m2), fdot(B, m2)) - d2e;
+    const float s = fmaxf(fmaxf(s0, s1), s2) - slack;
+    if (!(s > eps)) return false;
+    const float dp = fmaxf(dlo, 0.0f);
+    const float reach = radius + eps;
+    return fmaf(dp, dp, s * s) > reach * reach;
+}
+
 // collision_system.cpp:164-221: capsule A (pose endpoints a_A, a_B) against capsule B (b_A, b_B).
 PRT_HD bool capsule_capsule(V3 a_A, V3 a_B, float radiusA, V3 b_A, V3 b_B, float radiusB, Contact & out) {
     V3 v0 = b_A - a_A;

@@ -43,7 +43,7 @@ __global__ void k_transform_refit(const float * __restrict__ raw, float * __rest
 }
 
 __global__ void k_tri_setup(const float * __restrict__ world, const uint32_t * __restrict__ tri_src_vertex,
-                            uint32_t n_tris, float4 * __restrict__ tris) {
+                            uint32_t n_tris, float4 * __restrict__ tris, float4 * __restrict__ cull) {
     uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n_tris) return;
     size_t o = 3 * size_t(tri_src_vertex[t]);
@@ -56,6 +56,13 @@ __global__ void k_tri_setup(const float * __restrict__ world, const uint32_t * _
     tris[3 * size_t(t)] = make_float4(a.x, a.y, a.z, n.x);
     tris[3 * size_t(t) + 1] = make_float4(b.x, b.y, b.z, n.y);
     tris[3 * size_t(t) + 2] = make_float4(c.x, c.y, c.z, n.z);
+    if (cull) {                                                   // cull record of the pooled kernel (collide.cuh make_cull_record)
+        const CullRec r = make_cull_record(a, b, c, n, !ok);
+        cull[4 * size_t(t)] = make_float4(r.pl[0], r.pl[1], r.pl[2], r.pl[3]);
+        cull[4 * size_t(t) + 1] = make_float4(r.e0[0], r.e0[1], r.e0[2], r.e0[3]);
+        cull[4 * size_t(t) + 2] = make_float4(r.e1[0], r.e1[1], r.e1[2], r.e1[3]);
+        cull[4 * size_t(t) + 3] = make_float4(r.e2[0], r.e2[1], r.e2[2], r.e2[3]);
+    }
 }
 
 __global__ void k_query_box(const float4 * __restrict__ nodes, uint32_t n_nodes, const uint32_t * __restrict__ node_leaf_id,
@@ -244,9 +251,23 @@ int launch_step(StepParams const & p_in, bool traced, int mode, cudaStream_t str
     int launches = 1;
     StepParams p = p_in;
     const uint32_t block = STEP_BLOCK;
+    const bool pooled = p.pool && p.work_counter && !traced && mode != MODE_LITERAL;
     // fewer characters than resident lanes: thin the warps out (1..32 characters per warp)
-    const uint32_t resident_warps = p.persistent_blocks ? p.persistent_blocks : 2368u;
+    const uint32_t resident_warps = pooled ? p.pool_blocks : (p.persistent_blocks ? p.persistent_blocks : 2368u);
     uint32_t lpw = (p.n + resident_warps - 1) / resident_warps;
+    const bool warp_per_character = !traced && lpw <= 1u && mode != MODE_JACOBI && !(p.tune & 2u);
+    if (pooled && !warp_per_character) {
+        // the pooled kernel: 32 characters per warp when the batch fills the machine, else 4 / 8 / 16 so that every
+        // resident warp slot gets work (the pooled cull and exact stages use all 32 lanes whatever the number of owners)
+        uint32_t opw = 4u;
+        while (opw < 32u && (p.n + opw - 1) / opw > p.pool_blocks) opw <<= 1;
+        p.lanes_per_warp = opw;
+        if (p.xc_version != nullptr && !(p.tune & 1u)) { launch_k_xc_refresh(p, stream); ++launches; }
+        else p.xc_version = nullptr;
+        const uint32_t want = (p.n + opw - 1) / opw;
+        launch_k_step_pool(p, want < p.pool_blocks ? want : p.pool_blocks, false, mode, stream);
+        return launches;
+    }
     lpw = lpw < 1u ? 1u : (lpw > 8u ? 32u : lpw);       // measured: thinning pays up to ~8 lanes/warp (C2 0.29 -> 0.11 ms), not at 22 (C3)
     const bool small = lpw < 32u;
     p.lanes_per_warp = lpw;
@@ -260,7 +281,6 @@ int launch_step(StepParams const & p_in, bool traced, int mode, cudaStream_t str
                        ((mode == MODE_STATIC && p.work_counter != nullptr) || (mode == MODE_JACOBI && !small));
     if (!slots) p.xc_version = nullptr;
     if (slots) { launch_k_xc_refresh(p, stream); ++launches; }
-    const bool warp_per_character = !traced && lpw == 1u && mode != MODE_JACOBI && !(p.tune & 2u);
     if (warp_per_character) {
         launch_k_step_warp(p, mode, stream);
     } else if (mode == MODE_STATIC && !traced && p.work_counter) {
@@ -335,7 +355,8 @@ int launch_step_ingest(StepParams const & p_in, cudaStream_t stream) {
     p.lanes_per_warp = 32;
     if (p.tune & 1u) p.xc_version = nullptr;
     const uint32_t want = (p.n + 31) / 32;
-    launch_k_step_stream(p, want < p.persistent_blocks ? want : p.persistent_blocks, true, stream);
+    if (p.pool) launch_k_step_pool(p, want < p.pool_blocks ? want : p.pool_blocks, true, MODE_STATIC, stream);
+    else launch_k_step_stream(p, want < p.persistent_blocks ? want : p.persistent_blocks, true, stream);
     if (!p.xc_version) return 1;
     // the slots cannot be refreshed ahead of the kernel (the input is not there yet): refresh them behind it from the
     // state this frame leaves, which is the next frame's input unless the caller edits it -- and then the per-substep
@@ -366,11 +387,11 @@ void launch_transform_refit(const float * raw_xyz, float * world_xyz, const Mesh
                                                                            n_meshes, xforms, mesh_aabbs);
 }
 
-void launch_tri_setup(const float * world_xyz, const uint32_t * tri_src_vertex, uint32_t n_tris, float4 * tris,
+void launch_tri_setup(const float * world_xyz, const uint32_t * tri_src_vertex, uint32_t n_tris, float4 * tris, float4 * cull,
                       cudaStream_t stream) {
     if (n_tris == 0) return;
     const uint32_t block = 256;
-    k_tri_setup<<<(n_tris + block - 1) / block, block, 0, stream>>>(world_xyz, tri_src_vertex, n_tris, tris);
+    k_tri_setup<<<(n_tris + block - 1) / block, block, 0, stream>>>(world_xyz, tri_src_vertex, n_tris, tris, cull);
 }
 
 void launch_query_box(const float4 * nodes, uint32_t n_nodes, const uint32_t * node_leaf_id, const float * aabb6,

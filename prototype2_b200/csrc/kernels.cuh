@@ -40,6 +40,8 @@ struct StepParams {
     const float4 * nodes;           // 2 float4 per node, right-first preorder (bvh_builder.h FlatNode)
     uint32_t n_nodes;
     const float4 * tris;            // 3 float4 per triangle, leaf order: (a, n.x) (b, n.y) (c, n.z)
+    const float4 * cull;            // 4 float4 per triangle: plane and edge planes of the pooled kernel's pre-cull (collide.cuh)
+    float push_slack;               // k_step_pool: how far pushes may move a capsule before its window of triangles is culled again
     const uint32_t * node_leaf_id;  // mesh-collider id per node (trace only)
     const CapsuleDev * capsules;
     uint32_t n_capsules;
@@ -62,7 +64,8 @@ struct StepParams {
     // constants (prtc_config)
     float dt, gravity, ground_dot, friction, stick;
     uint32_t substeps, abs_mode;
-    // conservative pre-cull (kernels.cu quick_reject): margin and enable, derived from the scene extent at commit
+    // conservative pre-culls: margin and enables (bit 0: box cull quick_reject, step_common.cuh; bit 1: plane/edge cull
+    // tight_reject, collide.cuh, k_step_pool only), derived from the scene extent at commit
     float qr_eps;
     uint32_t qr_enable;
     uint32_t tune;                  // bit 0: frame cache OFF (walk the tree every substep, reference-equivalent counters)
@@ -82,6 +85,9 @@ struct StepParams {
     const float4 * top;             // k_xc_refresh: top-of-tree table staged in shared memory (2 float4 per entry), null => plain walk
     uint32_t n_top;
     uint32_t persistent_blocks;     // k_step_stream: resident blocks to launch
+    uint32_t pool;                  // 1: the pooled kernel k_step_pool runs the persistent launches (PRTC_OPT_POOL_KERNEL)
+    uint32_t pool_blocks;           // k_step_pool: resident blocks to launch
+    uint32_t n_tris;                // triangle records behind `tris`
     // k_step_stream fed by a host->device copy that is still in flight (prtc_step_characters on big host batches):
     const uint32_t * gate;          // characters [0, *gate) have arrived; advanced by the copy-in stream, polled by LOAD
     uint32_t * done_sub;            // finished characters per block of 2^INGEST_SUB_SHIFT characters
@@ -96,6 +102,7 @@ constexpr uint32_t INGEST_CHUNK_SHIFT = 6;     // 64 of those = 65536 characters
 
 enum StepMode { STEP_STATIC = 0, STEP_LITERAL = 1, STEP_JACOBI = 2 };
 int launch_step(StepParams const & p, bool traced, int mode, cudaStream_t stream);   // returns the number of kernels launched
+uint32_t pool_blocks_per_sm();                  // resident one-warp blocks per SM k_step_pool is built for
 // static pass over a batch whose input is still being copied in (gate / done_* set): the persistent kernel alone, then the
 // refresh of the per-slot leaf lists for the NEXT frame from the state it leaves behind; returns the number of launches
 int launch_step_ingest(StepParams const & p, cudaStream_t stream);
@@ -116,8 +123,8 @@ struct ModelXform { Affine m; };
 void launch_transform_refit(const float * raw_xyz, float * world_xyz, const MeshDev * meshes, uint32_t first_mesh,
                             uint32_t n_meshes, const ModelXform * xforms, float * mesh_aabbs /*6 per mesh*/,
                             cudaStream_t stream);
-// leaf-ordered triangle records with precomputed unit normals
-void launch_tri_setup(const float * world_xyz, const uint32_t * tri_src_vertex, uint32_t n_tris, float4 * tris,
+// leaf-ordered triangle records with precomputed unit normals (3 float4 each) and their cull records (4 float4 each)
+void launch_tri_setup(const float * world_xyz, const uint32_t * tri_src_vertex, uint32_t n_tris, float4 * tris, float4 * cull,
                       cudaStream_t stream);
 // PRTC_ORDER_BY_ID: left-complete tree over n_leaves leaf records (2 float4 each, ascending id) built into nodes (k_tree_build.cu)
 void launch_tree_build(const float4 * leaves, uint32_t n_leaves, float4 * nodes, cudaStream_t stream);

@@ -176,9 +176,10 @@ int commit_impl(prtc_ctx * c) {
         if (rebuild_tris) {
             PRTC_CUDA(c->d_tri_src.reserve(nt));
             PRTC_CUDA(c->d_tris.reserve(nt * 3));
+            PRTC_CUDA(c->d_cull.reserve(nt * 4));
             if (nt) {
                 PRTC_CUDA(cudaMemcpyAsync(c->d_tri_src.ptr, c->tri_src.data(), nt * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
-                launch_tri_setup(c->d_world.ptr, c->d_tri_src.ptr, uint32_t(nt), c->d_tris.ptr, s);
+                launch_tri_setup(c->d_world.ptr, c->d_tri_src.ptr, uint32_t(nt), c->d_tris.ptr, c->d_cull.ptr, s);
                 PRTC_CUDA(cudaGetLastError());
             }
             PRTC_CUDA(cudaStreamSynchronize(s));
@@ -231,6 +232,8 @@ int fill_params(prtc_ctx * c, float dt, uint32_t n, prtc_transform * d_tf, prtc_
     p.nodes = c->d_nodes.ptr;
     p.n_nodes = uint32_t(c->flat.nodes.size());
     p.tris = c->d_tris.ptr;
+    p.cull = c->d_cull.ptr;
+    p.push_slack = c->push_slack;
     p.node_leaf_id = c->d_node_leaf_id.ptr;
     p.capsules = c->d_capsules.ptr;
     p.n_capsules = uint32_t(c->capsules.size());
@@ -250,10 +253,13 @@ int fill_params(prtc_ctx * c, float dt, uint32_t n, prtc_transform * d_tf, prtc_
         float m = c->world_max_abs;
         float ulp = std::nextafter(m, INFINITY) - m;
         p.qr_eps = std::max(1e-3f, 64.0f * ulp);
-        p.qr_enable = (c->quick_reject && m < 1.0e6f) ? 1u : 0u;
+        p.qr_enable = (m < 1.0e6f) ? ((c->quick_reject ? 1u : 0u) | (c->tight_reject ? 2u : 0u)) : 0u;
         p.tune = (c->frame_cache ? 0u : 1u) | (c->warp_kernel ? 0u : 2u) | c->tune_hi;
         p.work_counter = c->persistent ? c->d_work.ptr : nullptr;
         p.persistent_blocks = uint32_t(c->sm_count) * 20u;
+        p.pool_blocks = uint32_t(c->sm_count) * pool_blocks_per_sm();
+        p.n_tris = uint32_t(c->tri_src.size());
+        p.pool = (c->pool_kernel && p.n_tris < (1u << 27)) ? 1u : 0u;    // a job word holds 27 bits of triangle index
         p.tree_version = c->tree_version;
         p.xc_margin = c->xc_margin;
         if (c->persistent && n > c->xc_capacity) {
@@ -373,6 +379,7 @@ int prtc_create(const prtc_config * cfg, prtc_ctx ** out) {
     if (const char * e = std::getenv("PRTC_STAGED")) ctx->staged = std::atoi(e);
     if (const char * e = std::getenv("PRTC_XC_MARGIN")) ctx->xc_margin = float(std::atof(e));
     if (const char * e = std::getenv("PRTC_TUNE")) ctx->tune_hi = uint32_t(std::strtoul(e, nullptr, 0)) & 0xFFFFFF00u;
+    if (const char * e = std::getenv("PRTC_PUSH_SLACK")) { const float v = float(std::atof(e)); if (v >= 0.0f && v <= 1.0f) ctx->push_slack = v; }
     ctx->sm_count = prop.multiProcessorCount;
     ctx->tree.set_margin(c.leaf_margin);
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
@@ -393,7 +400,7 @@ void prtc_destroy(prtc_ctx * c) {
     cudaSetDevice(c->cfg.device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     c->d_raw.release(); c->d_world.release(); c->d_aabbs.release(); c->d_meshes.release(); c->d_xforms.release();
-    c->d_nodes.release(); c->d_leaves.release(); c->d_top.release(); c->d_tris.release(); c->d_node_leaf_id.release(); c->d_tri_src.release();
+    c->d_nodes.release(); c->d_leaves.release(); c->d_top.release(); c->d_tris.release(); c->d_cull.release(); c->d_node_leaf_id.release(); c->d_tri_src.release();
     c->d_capsules.release(); c->d_counters.release(); c->d_work.release(); c->d_ingest.release(); c->stage.release();
     c->d_xc_version.release(); c->d_xc_count.release(); c->d_xc_leaf.release(); c->d_xc_region.release(); c->d_tf.release(); c->d_ph.release();
     c->d_tq.release(); c->d_tmesh.release(); c->d_tcaps.release(); c->d_thits.release();
@@ -568,6 +575,8 @@ int prtc_set_option(prtc_ctx * c, int option, int value) {
         case PRTC_OPT_WARP_KERNEL: c->warp_kernel = value != 0; return PRTC_OK;
         case PRTC_OPT_STREAMED_COPY: c->streamed_copy = value != 0; return PRTC_OK;
         case PRTC_OPT_TOP_STAGING: c->top_staging = value != 0; return PRTC_OK;
+        case PRTC_OPT_POOL_KERNEL: c->pool_kernel = value != 0; return PRTC_OK;
+        case PRTC_OPT_TIGHT_REJECT: c->tight_reject = value != 0; return PRTC_OK;
         default: return fail(PRTC_ERR_INVALID, "prtc_set_option: unknown option");
     }
 }

@@ -115,13 +115,16 @@ struct prtc_ctx {
     uint32_t tune_hi = 0;                   // PRTC_TUNE: batch thresholds of k_step_stream (bits 8-15 load, 16-23 substep), experiments
     int sm_count = 148;
     int quick_reject = 1;                   // PRTC_OPT_QUICK_REJECT
+    int tight_reject = 1;                   // PRTC_OPT_TIGHT_REJECT (k_step_pool)
+    float push_slack = 0.0025f;               // k_step_pool: push budget of a culled window (PRTC_PUSH_SLACK)
+    int pool_kernel = 1;                    // PRTC_OPT_POOL_KERNEL: persistent launches run k_step_pool (0: k_step_stream)
     std::vector<uint32_t> moved_models;     // models whose transform changed (prtc_update_models)
 
     // device
     prt::host::DevBuf<float> d_raw, d_world, d_aabbs;
     prt::host::DevBuf<prt::MeshDev> d_meshes;
     prt::host::DevBuf<prt::ModelXform> d_xforms;
-    prt::host::DevBuf<float4> d_nodes, d_tris;
+    prt::host::DevBuf<float4> d_nodes, d_tris, d_cull;
     prt::host::DevBuf<float4> d_leaves;     // BY_ID: leaf records handed to the device tree build
     std::vector<float> leaf_fat;            // BY_ID: stored fat box of every mesh leaf (6 floats), kept with the reference's update rule
     prt::host::DevBuf<float4> d_top;        // top-of-tree table (bvh_builder.h build_top_table), CANONICAL order only

@@ -77,6 +77,7 @@ void launch_k_step(StepParams const & p, bool traced, int mode, uint32_t grid, c
 void launch_k_step_warp(StepParams const & p, int mode, cudaStream_t stream);
 void launch_k_xc_refresh(StepParams const & p, cudaStream_t stream);
 void launch_k_step_stream(StepParams const & p, uint32_t blocks, bool gated, cudaStream_t stream);
+void launch_k_step_pool(StepParams const & p, uint32_t blocks, bool gated, int mode, cudaStream_t stream);
 
 } // namespace prt
 #endif

@@ -1,9 +1,10 @@
 // precull_check.cpp -- TEST program (host build of prototype2_b200/csrc/collide.cuh, no oracle, no GPU).
 //
-// Soundness of the conservative pre-cull the step kernels run in front of the exact capsule-triangle test:
+// Soundness of the two conservative pre-culls the step kernels run in front of the exact capsule-triangle test:
 // whenever capsule_triangle() -- the restatement of collision_system.cpp:56-142 the kernels execute -- reports a
-// contact, the box cull (same formula as quick_reject in step_common.cuh) must not have answered "skip".
-// Two generators:
+// contact, neither the box cull (same formula as quick_reject in step_common.cuh) nor tight_reject_rec on the
+// triangle's precomputed cull record (collide.cuh; what the pooled kernel runs, at a pose displaced within its push
+// budget) may have answered "skip".  Two generators:
 //   sim   a crowd of capsules falling onto / sliding over the synthetic terrain of SURVEY 8d, brute-force candidates
 //         from the cell grid, poses exactly as the step kernels chain them (pose rebuilt after every non-zero push);
 //         also reports how many exact tests each stage leaves
@@ -21,11 +22,9 @@
 using namespace prt;
 
 static bool box_reject(V3 smin, V3 smax, float radius, float dmax, float eps, V3 pa, V3 pb, V3 pc, V3 n) {
-    // PRECULL_MULT < 1 shrinks the reach: the test suite uses it to show that the generators do find an unsound cull
-    static const float mult = getenv("PRECULL_MULT") ? float(atof(getenv("PRECULL_MULT"))) : 1.0f;
-    const float ex = mult * (fmaxf(radius, dmax * fabsf(n.x)) + eps);
-    const float ey = mult * (fmaxf(radius, dmax * fabsf(n.y)) + eps);
-    const float ez = mult * (fmaxf(radius, dmax * fabsf(n.z)) + eps);
+    const float ex = fmaxf(radius, dmax * fabsf(n.x)) + eps;
+    const float ey = fmaxf(radius, dmax * fabsf(n.y)) + eps;
+    const float ez = fmaxf(radius, dmax * fabsf(n.z)) + eps;
     const float lox = fminf(fminf(pa.x, pb.x), pc.x), hix = fmaxf(fmaxf(pa.x, pb.x), pc.x);
     const float loy = fminf(fminf(pa.y, pb.y), pc.y), hiy = fmaxf(fmaxf(pa.y, pb.y), pc.y);
     const float loz = fminf(fminf(pa.z, pb.z), pc.z), hiz = fmaxf(fmaxf(pa.z, pb.z), pc.z);
@@ -38,7 +37,7 @@ static float margin_for(float world_max_abs) {            // prtc.cu make_params
     return std::max(1e-3f, 64.0f * ulp);
 }
 
-struct Stats { unsigned long long tris = 0, after_box = 0, contacts = 0, bad_box = 0; };
+struct Stats { unsigned long long tris = 0, after_box = 0, after_tight = 0, contacts = 0, bad_box = 0, bad_tight = 0; };
 
 static void probe(Pose const & ps, float radius, uint32_t abs_mode, float eps, V3 pa, V3 pb, V3 pc, Stats & st, Contact & ct, bool & hit) {
     V3 n;
@@ -47,13 +46,29 @@ static void probe(Pose const & ps, float radius, uint32_t abs_mode, float eps, V
     const float dmax = abs_mode == 1u ? radius : floorf(radius) + 1.0f;
     ++st.tris;
     const bool rb = box_reject(gmin(ps.A, ps.B), gmax(ps.A, ps.B), radius, dmax, eps, pa, pb, pc, n);
+    static const float mult = getenv("PRECULL_MULT") ? float(atof(getenv("PRECULL_MULT"))) : 1.0f;   // the kernels pass the first stage's margin
+    // the pooled kernel culls at the pose a window STARTED with and keeps the answer while the pushes since then stay
+    // within the budget `slack` (1-norm): test the record at a pose displaced by up to that much from the one the exact
+    // test runs at
+    static std::mt19937 drng(777);
+    std::uniform_real_distribution<float> du(-1.0f, 1.0f);
+    const float slack = (drng() % 3 == 0) ? 0.0f : 0.1f * radius * float(drng() % 4);
+    V3 d = v3(du(drng), du(drng), du(drng));
+    const float l1 = fabsf(d.x) + fabsf(d.y) + fabsf(d.z);
+    d = l1 > 0 ? d * (slack * (0.999f * (drng() % 2 ? 1.0f : du(drng) * du(drng))) / l1) : v3(0.0f);
+    const CullRec rec = make_cull_record(pa, pb, pc, n, false);
+    const bool rt = tight_reject_rec(ps.A + d, ps.B + d, radius, dmax, mult * eps, mult * slack, v3(rec.pl[0], rec.pl[1], rec.pl[2]), rec.pl[3],
+                                     v3(rec.e0[0], rec.e0[1], rec.e0[2]), rec.e0[3], v3(rec.e1[0], rec.e1[1], rec.e1[2]), rec.e1[3],
+                                     v3(rec.e2[0], rec.e2[1], rec.e2[2]), rec.e2[3]);
     if (!rb) ++st.after_box;
+    if (!rb && !rt) ++st.after_tight;
     hit = capsule_triangle(ps, radius, abs_mode, pa, pb, pc, n, ct);
     if (hit) {
         ++st.contacts;
-        if (rb) {
-            ++st.bad_box;
-            if (st.bad_box < 5)
+        if (rb) ++st.bad_box;
+        if (rt) {
+            ++st.bad_tight;
+            if (st.bad_tight < 5)
                 fprintf(stderr, "FALSE REJECT A=(%g %g %g) B=(%g %g %g) r=%g tri=(%g %g %g)(%g %g %g)(%g %g %g)\n", ps.A.x, ps.A.y,
                         ps.A.z, ps.B.x, ps.B.y, ps.B.z, radius, pa.x, pa.y, pa.z, pb.x, pb.y, pb.z, pc.x, pc.y, pc.z);
         }
@@ -128,10 +143,10 @@ static int run_sim(int N, int ncaps, int frames, float shift, uint32_t abs_mode)
             pos[i] = p; vel[i] = v; grounded[i] = g;
         }
     }
-    printf("sim N=%d caps=%d frames=%d shift=%g abs=%u eps=%g: per substep: triangles %.2f, after box cull %.2f, contacts %.3f; "
-           "false rejects: %llu\n", N, ncaps, frames, shift, abs_mode, eps, double(st.tris) / substeps,
-           double(st.after_box) / substeps, double(st.contacts) / substeps, st.bad_box);
-    return st.bad_box ? 1 : 0;
+    printf("sim N=%d caps=%d frames=%d shift=%g abs=%u eps=%g: per substep: triangles %.2f, after box cull %.2f, after tight cull %.2f, contacts %.3f; "
+           "false rejects: box %llu tight %llu\n", N, ncaps, frames, shift, abs_mode, eps, double(st.tris) / substeps,
+           double(st.after_box) / substeps, double(st.after_tight) / substeps, double(st.contacts) / substeps, st.bad_box, st.bad_tight);
+    return (st.bad_box || st.bad_tight) ? 1 : 0;
 }
 
 static int run_fuzz(long cases, unsigned seed) {
@@ -180,9 +195,9 @@ static int run_fuzz(long cases, unsigned seed) {
         Contact ct; bool hit;
         probe(ps, cap.radius, rng() % 2, eps, pa, pb, pc, st, ct, hit);
     }
-    printf("fuzz cases=%ld seed=%u: non-degenerate %llu, after box cull %llu, contacts %llu; false rejects: %llu\n",
-           cases, seed, st.tris, st.after_box, st.contacts, st.bad_box);
-    return st.bad_box ? 1 : 0;
+    printf("fuzz cases=%ld seed=%u: non-degenerate %llu, after box cull %llu, after tight cull %llu, contacts %llu; false rejects: box %llu tight %llu\n",
+           cases, seed, st.tris, st.after_box, st.after_tight, st.contacts, st.bad_box, st.bad_tight);
+    return (st.bad_box || st.bad_tight) ? 1 : 0;
 }
 
 int main(int argc, char ** argv) {

@@ -1,7 +1,7 @@
-"""Soundness of the conservative pre-cull in front of the exact capsule-triangle test (host build of collide.cuh).
+"""Soundness of the conservative pre-culls in front of the exact capsule-triangle test (host build of collide.cuh).
 
-tests/cpp/precull_check.cpp runs the very function the kernels compile -- capsule_triangle (the restatement of
-reference collision_system.cpp:56-142) -- and the box cull's formula on the CPU and counts triangles the cull would
+tests/cpp/precull_check.cpp runs the very functions the kernels compile -- capsule_triangle (the restatement of
+reference collision_system.cpp:56-142), the box cull and tight_reject -- on the CPU and counts triangles a cull would
 have skipped although the exact test reports a contact.  No GPU, no oracle."""
 import os
 import subprocess
@@ -36,6 +36,11 @@ def test_crowd_on_terrain_never_loses_a_contact(checker, shift, abs_mode):
     """capsules landing on and sliding over the SURVEY 8d terrain, near the origin and far from it"""
     rc, out = _run(checker, "sim", 128, 4000, 30, shift, abs_mode)
     assert rc == 0, out
+    # and the second stage earns its keep: it leaves well under half of what the box test lets through
+    f = out.split("after box cull ")[1]
+    after_box, after_tight = float(f.split(",")[0]), float(f.split("after tight cull ")[1].split(",")[0])
+    if abs(shift) <= 2000:                      # (30 000 units out the margin is 0.125, a quarter of the radius)
+        assert after_tight < 0.5 * after_box, out
 
 
 @pytest.mark.parametrize("seed", [1, 2, 3])
@@ -46,6 +51,6 @@ def test_random_triangles_and_capsules_never_lose_a_contact(checker, seed):
 
 
 def test_the_checker_has_teeth(checker):
-    """with the reach of a contact halved the same generator does find false rejects"""
-    rc, out = _run(checker, "fuzz", 1500000, 3, mult=0.5)
+    """with the margin taken away the same generator does find false rejects"""
+    rc, out = _run(checker, "fuzz", 1500000, 3, mult=0)
     assert rc == 1, out
