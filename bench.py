@@ -6,9 +6,12 @@
 
 A "step" is one frame: one call of PhysicsSystem::updateCharacters (reference physics_system.cpp:245-318) over
 the whole batch of capsules = `substeps` swept broadphase queries + narrowphase per capsule.  Workload = C4 of
-BASELINE.json (1M capsules x 10M-triangle terrain) on every GPU: capsules are
-independent units, so ranks hold disjoint capsule sets against replicated static geometry (weak scaling, no
-data-path collective).  Prints ONE JSON line (rank 0).
+BASELINE.json (1M capsules x 10M-triangle terrain): ONE batch of 1M capsules in
+Morton order, rank r of N steps the contiguous slice r against replicated static geometry -- capsules are independent
+units in the static pass, so there is no data-path collective and `scaling` is "strong" (config 4 as BASELINE.json words
+it); the state CRC of all capsules is printed and must not depend on N.  Short extra runs on the same line: a crowd that
+keeps moving, weak scaling (a full batch per GPU) and config 5 (256k capsules with the dynamic-vs-dynamic pass and its
+record exchange).  Prints ONE JSON line (rank 0).
 """
 import argparse
 import json
@@ -26,10 +29,10 @@ from prototype2_b200 import scenes  # noqa: E402
 
 DT = 1.0 / 30.0
 WORKLOADS = {
-    #        terrain N, block x, block z, capsules per GPU
+    #        terrain N, block x, block z, capsules (GLOBAL count with --scaling strong, per GPU with --scaling weak)
     "C4": (2237, 2, 2, 1000000),
     "C3": (708, 4, 2, 64000),
-    "C5": (708, 2, 2, 256000),      # GLOBAL capsule count, partitioned over the ranks; dynamic-vs-dynamic pass on
+    "C5": (708, 2, 2, 256000),      # dynamic-vs-dynamic pass on
     "C2": (224, 1, 1, 1000),
 }
 METRIC = "ellipsoid (capsule) sweep queries/sec"
@@ -51,17 +54,19 @@ def parse_args():
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU time of the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the short extra runs (moving crowd, weak scaling, config 5)")
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
+                    help="strong: ONE global batch split over the GPUs (BASELINE config 4 as written); weak: a full batch per GPU")
     ap.add_argument("--opt", action="append", default=[], metavar="NAME=VALUE",
                     help="prtc_set_option before the run, e.g. --opt POOL_KERNEL=0 (A/B experiments)")
     return ap.parse_args()
 
 
 def workload(args):
+    """(terrain N, block x, block z, GLOBAL capsule count) of the run"""
     n_terrain, bx, bz, n_caps = WORKLOADS[args.workload]
     if args.capsules:
         n_caps = args.capsules
-    if args.workload == "C5":                     # strong scaling: the global batch is split over the ranks
-        n_caps //= max(1, int(os.environ.get("WORLD_SIZE", "1")))
     if args.terrain_n:
         n_terrain = args.terrain_n
     return n_terrain, bx, bz, n_caps
@@ -73,17 +78,22 @@ def make_capsules(n_caps, n_terrain, rank):
     return np.ascontiguousarray(pos[order]), np.ascontiguousarray(vel[order])
 
 
-def describe(args, n_terrain, bx, bz, n_caps, n_tris, world):
+def describe_config(args, name, n, n_global, strong, n_tris, n_terrain, bx, bz, world):
+    """the `config` object of the JSON line (both arms print the same one)"""
+    dynamic = name == "C5"
     return {
-        "workload": "%s: %d capsules/GPU x %d-triangle terrain (%dx%d-cell mesh colliders), 4 substeps/frame, %s, "
-                    "%s" % (args.workload, n_caps, n_tris, bx, bz,
-                            "static + dynamic-vs-dynamic pass (JACOBI, records all-gathered per frame)" if args.workload == "C5" else "static pass",
-                            "candidates in ascending collider id, tree built on the device (PRTC_ORDER_BY_ID; the roofline's node "
-                            "tests are those of that tree, not of the reference's)" if args.order == "by_id" else "canonical order"),
-        "capsules_per_gpu": n_caps, "global_capsules": n_caps * world, "triangles": n_tris, "terrain_n": n_terrain,
-        "substeps": 4, "dt": DT, "abs_mode": "int", "parallelism": "capsules sharded x%d, static geometry replicated" % world,
-        "l2_policy": "inputs larger than L2: nodes+triangles+capsule state touched per step exceed 126 MB at C4; "
-                     "no explicit flush", "seed": 12345,
+        "workload": "%s: %d capsules %s x %d-triangle terrain (%dx%d-cell mesh colliders), 4 substeps/frame, %s, %s" % (
+            name, n_global if strong else n,
+            "in ONE Morton-ordered batch, contiguous slices of %d per GPU" % n if strong else "per GPU",
+            n_tris, bx, bz,
+            "static + dynamic-vs-dynamic pass (JACOBI, records all-gathered per frame)" if dynamic else "static pass",
+            "candidates in ascending collider id, tree built on the device (PRTC_ORDER_BY_ID; the roofline's node tests are "
+            "those of that tree, not of the reference's)" if args.order == "by_id" else "canonical order"),
+        "capsules_per_gpu": n, "global_capsules": n_global, "triangles": n_tris, "terrain_n": n_terrain,
+        "substeps": 4, "dt": DT, "abs_mode": "int",
+        "parallelism": "capsules sharded x%d (%s), static geometry replicated" % (world, "one global batch" if strong else "a batch per GPU"),
+        "l2_policy": "inputs larger than L2: nodes+triangles+capsule state touched per step exceed 126 MB at C4; no explicit flush",
+        "seed": 12345,
     }
 
 
@@ -219,26 +229,34 @@ def host_info():
 
 
 def run_reference(args):
+    """The reference's CPU implementation of the path on the host cores (rank 0 only): the L1 port with all host threads on
+    a BOUNDED SAMPLE of the workload's capsules (every k-th in Morton order) against the full terrain -- a rate, not the
+    whole batch; `reference_fraction` says how much of the batch one step covers."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    n_terrain, bx, bz, n_caps = workload(args)
+    world = max(1, args.gpus)
+    strong = args.scaling == "strong"
+    n_terrain, bx, bz, n_global = workload(args)
     xyz, mf, mc = scenes.terrain(n_terrain, bx, bz)
-    sample = min(args.cpu_sample, n_caps)
-    pos, vel = make_capsules(n_caps, n_terrain, 0)
+    sample = min(args.cpu_sample, n_global)
+    pos, vel = make_capsules(n_global, n_terrain, 0)
     # bounded sample: a contiguous Morton range would be one patch of terrain; take every k-th capsule instead
-    sel = np.linspace(0, n_caps - 1, sample).astype(np.int64)
+    sel = np.linspace(0, n_global - 1, sample).astype(np.int64)
     threads = os.cpu_count() or 1
     r = cpu_run(xyz, mf, mc, pos[sel], vel[sel], args.steps, args.warmup, threads)
     value = r["substeps"] / r["seconds"]
     verbatim = reference_verbatim()
     sample_txt = "%d of the workload's %d capsules (every %d-th in Morton order) against the full terrain, per step" % (
-        sample, n_caps, max(1, n_caps // sample))
+        sample, n_global, max(1, n_global // sample))
+    n_rank = n_global // world if strong else n_global
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": r["steps"],
         "warmup": args.warmup, "ms_per_step": 1e3 * r["seconds"] / max(1, r["steps"]), "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": describe(args, n_terrain, bx, bz, n_caps, len(xyz) // 3, max(1, args.gpus)),
+        "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": describe_config(args, args.workload, n_rank, n_global if strong else n_global * world, strong, len(xyz) // 3, n_terrain, bx, bz, world),
+        "reference_fraction": sample / float(n_global),
+        "reference_sample": sample_txt,
         "tri_tests_per_s": r["tri_tests"] / r["seconds"],
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample_txt, "host": host_info(),
                          "note": "oracle/l1_oracle.cpp (restatement pinned bit-identical to the reference's own sources; "
@@ -252,9 +270,156 @@ def run_reference(args):
 # ----------------------------------------------------------------------------------------------------------
 # our arm
 # ----------------------------------------------------------------------------------------------------------
+class Dist:
+    """barrier / reductions over the ranks (NCCL through torch.distributed; plumbing only)"""
+
+    def __init__(self, torch, dev, world):
+        self.torch, self.dev, self.world, self.d = torch, dev, world, None
+        if world > 1:
+            import torch.distributed as dist
+            self.d = dist
+
+    def barrier(self):
+        if self.d is not None:
+            self.d.barrier()
+        self.torch.cuda.synchronize()
+
+    def max(self, x):
+        if self.d is None:
+            return x
+        t = self.torch.tensor([x], dtype=self.torch.float64, device=self.dev)
+        self.d.all_reduce(t, op=self.d.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum(self, vals):
+        if self.d is None:
+            return list(vals)
+        t = self.torch.tensor(list(vals), dtype=self.torch.float64, device=self.dev)
+        self.d.all_reduce(t, op=self.d.ReduceOp.SUM)
+        return [float(v) for v in t.tolist()]
+
+
+def state_crc(torch, sharding, d_tf, d_ph, n):
+    """CRC32 of the state of ALL characters in global order: must not depend on the number of ranks"""
+    import zlib
+    mine = torch.cat([d_tf.view(n, 40), d_ph.view(n, 44)], dim=1).contiguous()
+    return zlib.crc32(sharding.gather_rows(mine).cpu().numpy().tobytes())
+
+
+class Workload:
+    """One context + one batch of characters on this rank.
+    strong=True : ONE global batch in Morton order, rank r owns the contiguous slice r (BASELINE config 4 as written);
+    strong=False: every rank has its own batch of the full size (weak scaling)."""
+
+    def __init__(self, args, name, torch, capi, sharding, local, rank, world, strong, n_override=0, moving=False, ctx=None, geometry=None):
+        self.args, self.name, self.torch, self.capi, self.sharding = args, name, torch, capi, sharding
+        self.rank, self.world, self.local, self.strong = rank, world, local, strong
+        n_terrain, bx, bz, n_global = WORKLOADS[name]
+        if args.terrain_n and name == args.workload:
+            n_terrain = args.terrain_n
+        if n_override:
+            n_global = n_override
+        self.n_terrain, self.bx, self.bz = n_terrain, bx, bz
+        self.dynamic = name == "C5"
+        if strong:
+            gpos, gvel = make_capsules(n_global, n_terrain, 0)
+            self.first, self.n = sharding.partition(n_global, world, rank)
+            pos, vel = gpos[self.first:self.first + self.n], gvel[self.first:self.first + self.n]
+            self.n_global = n_global
+        else:
+            pos, vel = make_capsules(n_global, n_terrain, rank)
+            self.first, self.n, self.n_global = 0, n_global, n_global * world
+        self.pos, self.vel = pos, vel
+        dev = torch.device("cuda", local)
+        self.t_commit = None
+        if ctx is None:
+            self.xyz, self.mf, self.mc = geometry if geometry is not None else scenes.terrain(n_terrain, bx, bz)
+            ctx = capi.PhysicsContext(device=local, dyn_mode=capi.DYN_JACOBI if self.dynamic else capi.DYN_OFF,
+                                      order_mode=capi.ORDER_BY_ID if args.order == "by_id" else capi.ORDER_CANONICAL)
+            for kv in args.opt:
+                oname, val = kv.split("=")
+                ctx.set_option(getattr(capi, "OPT_" + oname), int(val))
+            if self.dynamic:
+                ctx.dyn_configure(self.first, self.n_global if strong else self.n)
+            ctx.add_model_collider(self.xyz, self.mf, self.mc)
+            self.cid = ctx.add_capsule_collider()          # one shared collider shape (h=0.5 r=0.5 off=(0,0.5,0))
+            t0 = time.perf_counter()
+            ctx.commit()
+            self.t_commit = time.perf_counter() - t0
+        else:
+            self.cid = 0
+        self.ctx = ctx
+        self.n_tris = ctx.tree_info()["triangles"]
+        self.tf0 = capi.make_transforms(pos)
+        move = None
+        if moving:
+            # a crowd that keeps walking: movementVector of 0.1 per frame (half the engine's run speed, character.cpp:99)
+            # in a per-character direction, so the per-slot leaf lists keep being refilled
+            ang = np.random.RandomState(777 + rank).uniform(-np.pi, np.pi, self.n)
+            move = np.stack([0.1 * np.cos(ang), np.zeros(self.n), 0.1 * np.sin(ang)], axis=1).astype(np.float32)
+        self.ph0 = capi.make_physics(vel, movement=move, collider=np.full(self.n, self.cid, np.uint32))
+        self.h_tf = torch.empty(self.n * 40, dtype=torch.uint8).pin_memory()
+        self.h_ph = torch.empty(self.n * 44, dtype=torch.uint8).pin_memory()
+        self.tf_np = self.h_tf.numpy().view(capi.TRANSFORM_DTYPE)
+        self.ph_np = self.h_ph.numpy().view(capi.PHYSICS_DTYPE)
+        self.d_tf = torch.empty(self.n * 40, dtype=torch.uint8, device=dev)
+        self.d_ph = torch.empty(self.n * 44, dtype=torch.uint8, device=dev)
+        self.stream = torch.cuda.current_stream()
+        ctx.set_stream(self.stream.cuda_stream)
+
+    def reset(self):
+        self.tf_np[:] = self.tf0
+        self.ph_np[:] = self.ph0
+        self.d_tf.copy_(self.h_tf)
+        self.d_ph.copy_(self.h_ph)
+
+    def device_step(self):
+        if self.dynamic and self.world > 1 and self.strong:
+            # the one exchange of the path: the records of every character, all-gathered in place over NVLink
+            self.ctx.dyn_prepare(DT, self.n, self.d_tf.data_ptr(), self.d_ph.data_ptr())
+            rec, rfirst = self.sharding.records_tensor(self.ctx)
+            self.sharding.allgather_records(rec, rfirst, self.n)
+        self.ctx.update_characters_device(DT, self.n, self.d_tf.data_ptr(), self.d_ph.data_ptr())
+
+    def timed(self, dist, steps, warmup, sample_clocks=False):
+        """W untimed + K timed frames, device-resident state; CUDA events on the launching stream, max over ranks"""
+        torch = self.torch
+        self.reset()
+        for _ in range(warmup):
+            self.device_step()
+        torch.cuda.synchronize()
+        self.ctx.counters(reset=True)
+        sampler = ClockSampler(self.local) if sample_clocks else None
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+        dist.barrier()
+        if sampler:
+            sampler.start()
+        ev[0].record(self.stream)
+        for k in range(steps):
+            self.device_step()
+            ev[k + 1].record(self.stream)
+        dist.barrier()
+        clocks = sampler.stop() if sampler else None
+        total_ms = ev[0].elapsed_time(ev[steps])
+        per = [ev[k].elapsed_time(ev[k + 1]) for k in range(steps)]
+        cnt = self.ctx.counters(reset=True)
+        el = dist.max(total_ms * 1e-3)
+        sums = dist.sum([cnt["substeps"], cnt["tri_tests"], cnt["node_tests"]])
+        return {"el": el, "total_ms": total_ms, "per": per, "cnt": cnt, "clocks": clocks, "substeps": sums[0], "tri_tests": sums[1],
+                "node_tests": sums[2]}
+
+    def crc(self):
+        if self.strong:
+            return state_crc(self.torch, self.sharding, self.d_tf, self.d_ph, self.n)
+        return None
+
+    def describe(self):
+        return describe_config(self.args, self.name, self.n, self.n_global, self.strong, self.n_tris, self.n_terrain, self.bx, self.bz, self.world)
+
+
 def run_ours(args):
     import torch
-    from prototype2_b200 import capi
+    from prototype2_b200 import capi, sharding
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -262,151 +427,59 @@ def run_ours(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the collision path has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
-    dist = None
     if world > 1:
-        import torch.distributed as dist
+        import torch.distributed as tdist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        tdist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
+    dist = Dist(torch, dev, world)
+    strong = args.scaling == "strong"
 
-    n_terrain, bx, bz, n_caps = workload(args)
-    xyz, mf, mc = scenes.terrain(n_terrain, bx, bz)
-    n_tris = len(xyz) // 3
-    dynamic = args.workload == "C5"
-    if dynamic:
-        # one global batch in Morton order, contiguous slices per rank (ascending-index neighbour order is global)
-        from prototype2_b200 import sharding
-        gpos, gvel = make_capsules(n_caps * world, n_terrain, 0)
-        first, _ = sharding.partition(n_caps * world, world, rank)
-        pos, vel = gpos[first:first + n_caps], gvel[first:first + n_caps]
-    else:
-        pos, vel = make_capsules(n_caps, n_terrain, rank)
-
-    ctx = capi.PhysicsContext(device=local, dyn_mode=capi.DYN_JACOBI if dynamic else capi.DYN_OFF,
-                              order_mode=capi.ORDER_BY_ID if args.order == "by_id" else capi.ORDER_CANONICAL)
-    if dynamic:
-        ctx.dyn_configure(first, n_caps * world)
-    for kv in args.opt:
-        name, val = kv.split("=")
-        ctx.set_option(getattr(capi, "OPT_" + name), int(val))
-    ctx.add_model_collider(xyz, mf, mc)
-    cid = ctx.add_capsule_collider()                      # one shared collider shape (h=0.5 r=0.5 off=(0,0.5,0))
-    t_commit = time.perf_counter()
-    ctx.commit()
-    t_commit = time.perf_counter() - t_commit
+    w = Workload(args, args.workload, torch, capi, sharding, local, rank, world, strong, n_override=args.capsules)
+    ctx, n_caps = w.ctx, w.n
     info = ctx.tree_info()
-
-    tf0 = capi.make_transforms(pos)
-    ph0 = capi.make_physics(vel, collider=np.full(n_caps, cid, np.uint32))
-    h_tf = torch.empty(n_caps * 40, dtype=torch.uint8).pin_memory()
-    h_ph = torch.empty(n_caps * 44, dtype=torch.uint8).pin_memory()
-    tf_np = h_tf.numpy().view(capi.TRANSFORM_DTYPE)
-    ph_np = h_ph.numpy().view(capi.PHYSICS_DTYPE)
-
-    def reset_host():
-        tf_np[:] = tf0
-        ph_np[:] = ph0
-
-    stream = torch.cuda.current_stream()
-    ctx.set_stream(stream.cuda_stream)
-    d_tf = torch.empty(n_caps * 40, dtype=torch.uint8, device=dev)
-    d_ph = torch.empty(n_caps * 44, dtype=torch.uint8, device=dev)
-
-    def barrier():
-        if dist is not None:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def max_over_ranks(x):
-        if dist is None:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
-    def sum_over_ranks(vals):
-        if dist is None:
-            return vals
-        t = torch.tensor(vals, dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        return [float(v) for v in t.tolist()]
-
-    def device_step():
-        if dynamic and world > 1:
-            # the one exchange of the path: 64-byte records of every character, all-gathered in place over NVLink
-            ctx.dyn_prepare(DT, n_caps, d_tf.data_ptr(), d_ph.data_ptr())
-            rec, rfirst = sharding.records_tensor(ctx)
-            sharding.allgather_records(rec, rfirst, n_caps)
-        ctx.update_characters_device(DT, n_caps, d_tf.data_ptr(), d_ph.data_ptr())
+    cfg, commit_s = w.describe(), w.t_commit
 
     # ---- device-resident leg: `value` --------------------------------------------------------------------
-    reset_host()
-    d_tf.copy_(h_tf)
-    d_ph.copy_(h_ph)
-    for _ in range(args.warmup):
-        device_step()
-    torch.cuda.synchronize()
-    ctx.counters(reset=True)
-    sampler = ClockSampler(local)
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
-    barrier()
-    sampler.start()
-    ev[0].record(stream)
-    for k in range(args.steps):
-        device_step()
-        ev[k + 1].record(stream)
-    barrier()
-    clocks = sampler.stop()
-    total_ms = ev[0].elapsed_time(ev[args.steps])
-    kernel_ms = [ev[k].elapsed_time(ev[k + 1]) for k in range(args.steps)]
-    cnt = ctx.counters(reset=True)
-    state_crc = None
-    if dynamic:
-        # one global batch: the state after W+K frames must not depend on the number of ranks -> checksum over all
-        # characters in global order (compare the value printed by an N=1 and an N>1 run)
-        import zlib
-        mine = torch.cat([d_tf.view(n_caps, 40), d_ph.view(n_caps, 44)], dim=1).contiguous()
-        allrows = sharding.gather_rows(mine)
-        state_crc = zlib.crc32(allrows.cpu().numpy().tobytes())
-    el = max_over_ranks(total_ms * 1e-3)
-    substeps, tri_tests, node_tests = sum_over_ranks([cnt["substeps"], cnt["tri_tests"], cnt["node_tests"]])
-    value = substeps / el
+    r = w.timed(dist, args.steps, args.warmup, sample_clocks=True)
+    cnt, el, total_ms, kernel_ms = r["cnt"], r["el"], r["total_ms"], r["per"]
+    value = r["substeps"] / el
+    crc = w.crc()
 
     # Numerators of the roofline: the REFERENCE ALGORITHM's counts over the same K frames.  The timed run uses the
     # frame cache (fewer node tests than DynamicAABBTree::query performs), so the same frames are replayed untimed
     # with PRTC_OPT_FRAME_CACHE=0, where the device walks the tree per substep and counts exactly what the
     # reference would test; substeps and triangle tests must come out identical in both runs.
-    reset_host()
-    d_tf.copy_(h_tf)
-    d_ph.copy_(h_ph)
-    ctx.set_option(capi.OPT_FRAME_CACHE, 0)
-    if dynamic:                                      # stored boxes carry over between frames: start the replay from a fresh context state
-        ctx2 = capi.PhysicsContext(device=local, dyn_mode=capi.DYN_JACOBI,
-                                   order_mode=capi.ORDER_BY_ID if args.order == "by_id" else capi.ORDER_CANONICAL)
-        ctx2.add_model_collider(xyz, mf, mc)
-        ctx2.add_capsule_collider()
-        ctx2.dyn_configure(first, n_caps * world)
-        ctx2.set_stream(stream.cuda_stream)
-        ctx, ctx_timed = ctx2, ctx
-        ctx.set_option(capi.OPT_FRAME_CACHE, 0)
+    if w.dynamic:                                    # stored boxes carry over between frames: replay on a fresh context
+        w2 = Workload(args, args.workload, torch, capi, sharding, local, rank, world, strong, n_override=args.capsules,
+                      geometry=(w.xyz, w.mf, w.mc))
+    else:
+        w2 = w
+    w2.ctx.set_option(capi.OPT_FRAME_CACHE, 0)
+    w2.reset()
     for _ in range(args.warmup):
-        device_step()
+        w2.device_step()
     torch.cuda.synchronize()
-    ctx.counters(reset=True)
+    w2.ctx.counters(reset=True)
     for _ in range(args.steps):
-        device_step()
+        w2.device_step()
     torch.cuda.synchronize()
-    ref_cnt = ctx.counters(reset=True)
-    if dynamic:
-        ctx = ctx_timed
-    ctx.set_option(capi.OPT_FRAME_CACHE, 1)
+    ref_cnt = w2.ctx.counters(reset=True)
+    w2.ctx.set_option(capi.OPT_FRAME_CACHE, 1)
+    if w.dynamic:
+        del w2
     assert ref_cnt["substeps"] == cnt["substeps"] and ref_cnt["tri_tests"] == cnt["tri_tests"], (ref_cnt, cnt)
     gpu_node_tests = cnt["node_tests"]
-    cnt = dict(cnt, node_tests=ref_cnt["node_tests"])
-    (node_tests,) = sum_over_ranks([cnt["node_tests"]])
+    (node_tests,) = dist.sum([ref_cnt["node_tests"]])
 
-    # roofline of the dominant (only) kernel, this rank: algorithmic bytes / measured duration
-    alg_bytes = 96.0 * cnt["substeps"] + 32.0 * cnt["node_tests"] + 36.0 * cnt["tri_tests"] + 64.0 * n_caps * args.steps
+    # roofline of the dominant kernel, this rank.  `achieved` is what the contract defines: ALGORITHMIC bytes (SURVEY.md 8d,
+    # with the node tests the REFERENCE's traversal performs) / measured duration.  Two more fractions beside it say what
+    # the number is made of: the same formula with the node tests the DEVICE performed (its leaf lists are cached across
+    # substeps and frames), and the DRAM bytes ncu measured for one launch -- the working set is cache resident and the
+    # kernel is bound by instruction issue and latency, not by HBM.
+    def alg(nodes):
+        return 96.0 * cnt["substeps"] + 32.0 * nodes + 36.0 * cnt["tri_tests"] + 64.0 * n_caps * args.steps
+    alg_bytes = alg(ref_cnt["node_tests"])
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(peaks_path):
         peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
@@ -422,71 +495,113 @@ def run_ours(args):
                 traffic = tj.get("dram_bytes_per_launch")
         except Exception:
             traffic = None
+    kernel = ("k_step_warp<MODE_STATIC>" if n_caps <= 2368 and not w.dynamic else
+              "k_step_pool<false, %s>" % ("MODE_JACOBI" if w.dynamic else "MODE_STATIC"))          # what launch_step picks
+    avg_ms = float(np.mean(kernel_ms))
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                "kernel": ("k_step<false, MODE_JACOBI>" if args.workload == "C5" else
-                           "k_step_warp<MODE_STATIC>" if n_caps <= 2960 else "k_step_stream<false>"),   # what launch_step picks
-                "peak_source": peak_src,
+                "kernel": kernel, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes / args.steps,
-                "avg_launch_ms": float(np.mean(kernel_ms)), "formula": "96*S + 32*V + 36*T + 64*capsules (SURVEY.md 8d)",
-                "per_query": {"V_q": cnt["node_tests"] / max(1, cnt["substeps"]), "T_q": cnt["tri_tests"] / max(1, cnt["substeps"]),
+                "avg_launch_ms": avg_ms, "formula": "96*S + 32*V + 36*T + 64*capsules (SURVEY.md 8d)",
+                "frac_device_node_tests": alg(gpu_node_tests) / (total_ms * 1e-3) / 1e9 / peak,
+                "frac_dram": (traffic / (avg_ms * 1e-3) / 1e9 / peak) if traffic else None,
+                "note": "frac = reference-equivalent algorithmic bytes (the contract's definition); frac_device_node_tests = same "
+                        "formula with the node tests the device performed; frac_dram = measured DRAM bytes of one launch / time / peak: "
+                        "the kernel is issue- and latency-bound, not HBM-bound",
+                "per_query": {"V_q": ref_cnt["node_tests"] / max(1, cnt["substeps"]), "T_q": cnt["tri_tests"] / max(1, cnt["substeps"]),
                               "gpu_node_tests_per_query": gpu_node_tests / max(1, cnt["substeps"]),
                               "exact_tests_per_query": cnt["exact_tests"] / max(1, cnt["substeps"]),
                               "contacts_per_query": cnt["contacts"] / max(1, cnt["substeps"])}}
 
     # ---- end-to-end leg: host buffers through prtc_step_characters (H2D + kernel + D2H every step) ----------
     e2e = None
-    if not args.no_e2e and not (dynamic and world > 1):       # the host-buffer entry point has no exchange hook
+    if not args.no_e2e and not (w.dynamic and world > 1):       # the host-buffer entry point has no exchange hook
         own = torch.cuda.Stream()
         ctx.set_stream(own.cuda_stream)
-        reset_host()
+        w.tf_np[:] = w.tf0
+        w.ph_np[:] = w.ph0
         for _ in range(min(2, args.warmup)):
-            ctx.update_characters(DT, tf_np, ph_np)
-        reset_host()
+            ctx.update_characters(DT, w.tf_np, w.ph_np)
+        w.tf_np[:] = w.tf0
+        w.ph_np[:] = w.ph0
         ctx.counters(reset=True)
-        barrier()
+        dist.barrier()
         t0 = time.perf_counter()
         for _ in range(args.steps):
-            ctx.update_characters(DT, tf_np, ph_np)
+            ctx.update_characters(DT, w.tf_np, w.ph_np)
         torch.cuda.synchronize()
         el_e = time.perf_counter() - t0
-        if dist is not None:
-            dist.barrier()
-        el_e = max_over_ranks(el_e)
+        dist.barrier()
+        el_e = dist.max(el_e)
         c2 = ctx.counters(reset=True)
-        (sub_e,) = sum_over_ranks([c2["substeps"]])
+        (sub_e,) = dist.sum([c2["substeps"]])
         e2e = {"value": sub_e / el_e, "unit": UNIT, "h2d_bytes_per_step": n_caps * 84, "d2h_bytes_per_step": n_caps * 84,
                "ms_per_step": 1e3 * el_e / args.steps, "api": "prtc_step_characters (host AoS buffers, pinned)"}
-        ctx.set_stream(stream.cuda_stream)
+        ctx.set_stream(w.stream.cuda_stream)
+
+    # ---- extra measurements on the same line (short runs) -----------------------------------------------------
+    extras = {}
+    if args.workload == "C4" and not args.capsules and not args.no_extras:
+        steps_x = max(3, min(args.steps, 10))
+        # a crowd that keeps moving (movement input != 0): the per-slot leaf lists are refilled all the time
+        wm = Workload(args, "C4", torch, capi, sharding, local, rank, world, strong, moving=True, ctx=ctx)
+        rm = wm.timed(dist, steps_x, 3)
+        extras["moving_crowd"] = {"ms_per_step": 1e3 * rm["el"] / steps_x, "value": rm["substeps"] / rm["el"], "unit": UNIT,
+                                  "movement": "0.1 per frame in a per-character direction", "state_crc32": wm.crc()}
+        del wm
+        if world > 1 and strong:
+            # weak scaling beside the strong number: every rank its own 1 M capsules, no exchange -- trivially linear
+            ww = Workload(args, "C4", torch, capi, sharding, local, rank, world, False, ctx=ctx)
+            rw = ww.timed(dist, steps_x, 3)
+            extras["weak"] = {"ms_per_step": 1e3 * rw["el"] / steps_x, "value": rw["substeps"] / rw["el"], "unit": UNIT,
+                              "capsules_per_gpu": ww.n, "scaling": "weak"}
+            del ww
+        # config 5: 256 k moving capsules with the dynamic-vs-dynamic pass, one global batch over the ranks
+        del w
+        torch.cuda.empty_cache()
+        w5 = Workload(args, "C5", torch, capi, sharding, local, rank, world, True)
+        r5 = w5.timed(dist, max(steps_x, 10), 3)
+        k5 = max(steps_x, 10)
+        extras["c5"] = {"workload": w5.describe()["workload"], "ms_per_step": 1e3 * r5["el"] / k5, "value": r5["substeps"] / r5["el"],
+                        "unit": UNIT, "state_crc32": w5.crc(), "scaling": "strong",
+                        "exchange_bytes_per_step": (w5.n_global * 64) if world > 1 else 0,
+                        "exchange": "ncclAllGather of 64-byte records, in place" if world > 1 else "none (one rank)"}
+        del w5
 
     # ---- CPU baseline beside it (rank 0, N=1 only) ----------------------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        n_terrain, bx, bz, _ = WORKLOADS[args.workload]
+        xyz, mf, mc = scenes.terrain(args.terrain_n or n_terrain, bx, bz)
+        pos, vel = make_capsules(n_caps, args.terrain_n or n_terrain, 0)
         sample = min(args.cpu_sample, n_caps)
         sel = np.linspace(0, n_caps - 1, sample).astype(np.int64)
         threads = os.cpu_count() or 1
-        r = cpu_run(xyz, mf, mc, pos[sel], vel[sel], 1000, 1, threads, seconds_cap=args.cpu_seconds)
+        rc = cpu_run(xyz, mf, mc, pos[sel], vel[sel], 1000, 1, threads, seconds_cap=args.cpu_seconds)
         r1 = cpu_run(xyz, mf, mc, pos[sel[::8]], vel[sel[::8]], 1000, 1, 1, seconds_cap=4.0)
-        cpu = {"value": r["substeps"] / r["seconds"], "unit": UNIT, "cores": threads, "kind": "port", "host": host_info(),
+        cpu = {"value": rc["substeps"] / rc["seconds"], "unit": UNIT, "cores": threads, "kind": "port", "host": host_info(),
                "single_thread_value": r1["substeps"] / r1["seconds"],
                "sample": "%d of %d capsules (every %d-th in Morton order) x %d frames against the full terrain, %.1f s" % (
-                   sample, n_caps, max(1, n_caps // sample), r["steps"], r["seconds"]),
-               "tri_tests_per_s": r["tri_tests"] / r["seconds"]}
+                   sample, n_caps, max(1, n_caps // sample), rc["steps"], rc["seconds"]),
+               "tri_tests_per_s": rc["tri_tests"] / rc["seconds"]}
 
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * el / args.steps, "ms_per_step_median": float(np.median(kernel_ms)), "ms_per_step_min": float(np.min(kernel_ms)),
-            "higher_is_better": True, "scaling": "strong" if dynamic else "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic", "config": describe(args, n_terrain, bx, bz, n_caps, n_tris, world),
-            "tri_tests_per_s": tri_tests / el, "node_tests_per_s": node_tests / el,
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(cnt["launches"]), "clocks": clocks,
-            "setup": {"commit_s": t_commit, "nodes": info["nodes"], "leaves": info["leaves"]},
+            "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": cfg,
+            "tri_tests_per_s": r["tri_tests"] / el, "node_tests_per_s": node_tests / el,
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(cnt["launches"]), "clocks": r["clocks"],
+            "setup": {"commit_s": commit_s, "nodes": info["nodes"], "leaves": info["leaves"]},
         }
-        if state_crc is not None:
-            line["state_crc32"] = state_crc
+        if crc is not None:
+            line["state_crc32"] = crc
+        line.update(extras)
         emit(line)
-    if dist is not None:
-        dist.destroy_process_group()
+    if world > 1:
+        import torch.distributed as tdist
+        tdist.destroy_process_group()
+
 
 
 _REAL_STDOUT = None

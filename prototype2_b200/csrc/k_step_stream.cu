@@ -51,6 +51,7 @@ __global__ void __launch_bounds__(XC_BLOCK) k_xc_refresh(StepParams p, int reuse
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     bool walk = i < p.n;
     Box R; R.lo = v3(0.0f); R.hi = v3(0.0f);
+    float ph_vx = 0.0f, ph_vz = 0.0f, ph_mx = 0.0f, ph_mz = 0.0f;
     const size_t s = size_t(p.xc_first) + i;
     if (walk) {
         const prtc_transform * tf = p.transforms + i;
@@ -63,6 +64,7 @@ __global__ void __launch_bounds__(XC_BLOCK) k_xc_refresh(StepParams p, int reuse
         const CapsuleDev cap = p.capsules[cid];
         const CapsuleFrame fr = capsule_frame(cap, rotation_of(q));
         if (ph->grounded) vel = vel + ((-p.stick * p.gravity) * p.dt) * v3(ph->ground_normal[0], ph->ground_normal[1], ph->ground_normal[2]);
+        ph_vx = ph->velocity[0]; ph_vz = ph->velocity[2]; ph_mx = ph->movement[0]; ph_mz = ph->movement[2];
         vel.x = vel.x + ph->movement[0];
         vel.z = vel.z + ph->movement[2];
         V3 a0, b0, eA, eB;
@@ -85,7 +87,21 @@ __global__ void __launch_bounds__(XC_BLOCK) k_xc_refresh(StepParams p, int reuse
         n_top = p.n_top;
     }
     if (!walk) return;
-    if (reuse) { R.lo = R.lo - v3(p.xc_margin); R.hi = R.hi + v3(p.xc_margin); }
+    if (reuse) {
+        // A fresh list should last: grow the region by xc_margin and stretch it along the way the character is going to
+        // coast -- friction leaves velocity.xz * r after this frame, * r^2 after the next, ... (r = 1 / (1 + dt friction),
+        // physics_system.cpp:307), r / (1 - r) of it in total, plus two more frames of the movement input.  Any region
+        // is correct (the list is a function of the region); this one keeps a crowd that was set in motion from refilling
+        // its slots in waves a few frames later.
+        const float r = fdiv(1.0f, 1.0f + p.dt * p.friction);
+        const float coast = r < 0.999f ? fdiv(r, 1.0f - r) : 0.0f;
+        const float dx = coast * ph_vx + 2.0f * ph_mx, dz = coast * ph_vz + 2.0f * ph_mz;
+        if (dx == dx && dz == dz && fabsf(dx) < 4.0f && fabsf(dz) < 4.0f) {
+            R.lo.x = R.lo.x + fminf(dx, 0.0f); R.hi.x = R.hi.x + fmaxf(dx, 0.0f);
+            R.lo.z = R.lo.z + fminf(dz, 0.0f); R.hi.z = R.hi.z + fmaxf(dz, 0.0f);
+        }
+        R.lo = R.lo - v3(p.xc_margin); R.hi = R.hi + v3(p.xc_margin);
+    }
     if (staged) mbar_wait(&s_bar, 0);
     // Phase 1 (staged only): the table walk alone, all lanes in the same loop.  The overlapping entries at the cut (and
     // leaves above it) are the doors into the full array; they come up in emission order and are kept as 10-bit table

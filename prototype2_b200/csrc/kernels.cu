@@ -12,6 +12,8 @@
 //   k_query_box        one box against the flattened tree (introspection)
 //
 // Compile with -fmad=false: results must be bit-identical to the CPU reference (see prt_math.cuh).
+#include <cstdlib>
+
 #include "step_common.cuh"
 
 
@@ -95,11 +97,13 @@ __global__ void k_query_box(const float4 * __restrict__ nodes, uint32_t n_nodes,
 // hysteresis of DynamicAABBTree::update/insertLeaf (aabb_tree.cpp:102-111,140-141) and the start-of-frame segment.
 // Record = 4 float4: (A.xyz, radius) (B.xyz, 0) (stored.lo, 0) (stored.hi, 0) at global index dyn_first + i.
 __global__ void k_dyn_prep(const prtc_transform * __restrict__ tf, const prtc_char_physics * __restrict__ ph,
-                           const CapsuleDev * __restrict__ capsules, uint32_t n, uint32_t first, float4 * __restrict__ records,
-                           float dt, float gravity, float margin, uint32_t init) {
+                           const CapsuleDev * __restrict__ capsules, uint32_t n_capsules, uint32_t n, uint32_t first,
+                           float4 * __restrict__ records, float dt, float gravity, float margin, uint32_t init) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const CapsuleDev cap = capsules[ph[i].collider];
+    uint32_t cid = ph[i].collider;
+    if (cid >= n_capsules) cid = 0;               // unknown capsule id: never dereferenced (the step kernel reports it, counters[6])
+    const CapsuleDev cap = capsules[cid];
     Quat q; q.x = tf[i].rotation[0]; q.y = tf[i].rotation[1]; q.z = tf[i].rotation[2]; q.w = tf[i].rotation[3];
     const Rot3 R = rotation_of(q);
     const CapsuleFrame fr = capsule_frame(cap, R);
@@ -261,6 +265,8 @@ int launch_step(StepParams const & p_in, bool traced, int mode, cudaStream_t str
         // resident warp slot gets work (the pooled cull and exact stages use all 32 lanes whatever the number of owners)
         uint32_t opw = 4u;
         while (opw < 32u && (p.n + opw - 1) / opw > p.pool_blocks) opw <<= 1;
+        static const uint32_t force_opw = [] { const char * e = std::getenv("PRTC_OPW"); return e ? uint32_t(std::atoi(e)) : 0u; }();
+        if (force_opw == 4u || force_opw == 8u || force_opw == 16u || force_opw == 32u) opw = force_opw;   // experiments
         p.lanes_per_warp = opw;
         if (p.xc_version != nullptr && !(p.tune & 1u)) { launch_k_xc_refresh(p, stream); ++launches; }
         else p.xc_version = nullptr;
@@ -367,10 +373,10 @@ int launch_step_ingest(StepParams const & p_in, cudaStream_t stream) {
     return 2;
 }
 
-void launch_dyn_prep(const prtc_transform * tf, const prtc_char_physics * ph, const CapsuleDev * capsules, uint32_t n, uint32_t first,
-                     float4 * records, float dt, float gravity, float margin, bool init, cudaStream_t stream) {
+void launch_dyn_prep(const prtc_transform * tf, const prtc_char_physics * ph, const CapsuleDev * capsules, uint32_t n_capsules, uint32_t n,
+                     uint32_t first, float4 * records, float dt, float gravity, float margin, bool init, cudaStream_t stream) {
     if (n == 0) return;
-    k_dyn_prep<<<(n + 127) / 128, 128, 0, stream>>>(tf, ph, capsules, n, first, records, dt, gravity, margin, init ? 1u : 0u);
+    k_dyn_prep<<<(n + 127) / 128, 128, 0, stream>>>(tf, ph, capsules, n_capsules, n, first, records, dt, gravity, margin, init ? 1u : 0u);
 }
 
 void launch_dyn_grid(const float4 * records, uint32_t n, float ox, float oz, float inv_cell, uint32_t gx, uint32_t gz,

@@ -107,8 +107,8 @@ uint32_t pool_blocks_per_sm();                  // resident one-warp blocks per 
 // refresh of the per-slot leaf lists for the NEXT frame from the state it leaves behind; returns the number of launches
 int launch_step_ingest(StepParams const & p, cudaStream_t stream);
 // dynamic pass, CANONICAL / JACOBI: per-character record (4 float4) and the uniform grid over all stored boxes
-void launch_dyn_prep(const prtc_transform * tf, const prtc_char_physics * ph, const CapsuleDev * capsules, uint32_t n, uint32_t first,
-                     float4 * records, float dt, float gravity, float margin, bool init, cudaStream_t stream);
+void launch_dyn_prep(const prtc_transform * tf, const prtc_char_physics * ph, const CapsuleDev * capsules, uint32_t n_capsules, uint32_t n,
+                     uint32_t first, float4 * records, float dt, float gravity, float margin, bool init, cudaStream_t stream);
 void launch_dyn_grid(const float4 * records, uint32_t n, float ox, float oz, float inv_cell, uint32_t gx, uint32_t gz,
                      uint32_t * cell_count, const uint32_t * cell_start, uint32_t * items, bool fill, cudaStream_t stream);
 

@@ -101,14 +101,18 @@ int commit_impl(prtc_ctx * c) {
             }
         }
         c->moved_models.clear();
+        // extent of the world: meshes without vertices (an empty mesh, a removed model) have the fold's start values
+        // +-FLT_MAX as their box (physics_system.cpp:80-82) and say nothing about where the geometry is
         c->world_max_abs = 0.0f;
-        for (float v : aabbs) { float a = std::fabs(v); if (a > c->world_max_abs) c->world_max_abs = a; }   // NaN never wins
         for (int k = 0; k < 3; ++k) { c->world_lo[k] = 3.0e38f; c->world_hi[k] = -3.0e38f; }
-        for (uint32_t m = 0; m < n_meshes; ++m)
+        for (uint32_t m = 0; m < n_meshes; ++m) {
+            if (c->meshes[m].n_vertices == 0 || c->models[c->meshes[m].model].n_meshes == 0) continue;
+            for (int k = 0; k < 6; ++k) { const float a = std::fabs(aabbs[6 * size_t(m) + k]); if (a > c->world_max_abs) c->world_max_abs = a; }   // NaN never wins
             for (int k = 0; k < 3; ++k) {
                 if (aabbs[6 * size_t(m) + k] < c->world_lo[k]) c->world_lo[k] = aabbs[6 * size_t(m) + k];
                 if (aabbs[6 * size_t(m) + 3 + k] > c->world_hi[k]) c->world_hi[k] = aabbs[6 * size_t(m) + 3 + k];
             }
+        }
         // new meshes: DynamicAABBTree::insert in registration order, physics_system.cpp:102
         for (uint32_t m = c->meshes_in_tree; m < n_meshes; ++m) {
             if (c->by_id()) fatten(m);

@@ -91,8 +91,8 @@ int dyn_prepare(prtc_ctx * c, float dt, uint32_t n, const prtc_transform * d_tf,
         PRTC_CUDA(c->d_dyn_records.reserve(size_t(c->dyn_global) * 4));
         PRTC_CUDA(cudaMemsetAsync(c->d_dyn_records.ptr, 0, size_t(c->dyn_global) * 4 * sizeof(float4), c->stream));
     }
-    launch_dyn_prep(d_tf, d_ph, c->d_capsules.ptr, n, c->dyn_first, c->d_dyn_records.ptr, dt, c->cfg.gravity, c->cfg.leaf_margin,
-                    !c->dyn_initialized, c->stream);
+    launch_dyn_prep(d_tf, d_ph, c->d_capsules.ptr, uint32_t(c->capsules.size()), n, c->dyn_first, c->d_dyn_records.ptr, dt, c->cfg.gravity,
+                    c->cfg.leaf_margin, !c->dyn_initialized, c->stream);
     PRTC_CUDA(cudaGetLastError());
     c->dyn_initialized = true;
     c->dyn_prepared = true;
@@ -169,7 +169,7 @@ int literal_step_staged(prtc_ctx * c, float dt, uint32_t n, prtc_transform * tf,
         flags[0] = 0u; flags[1] = 0u;
         if (round > 0) PRTC_CUDA(cudaMemsetAsync(scratch, 0, 6 * sizeof(unsigned long long), s));       // only the last round counts
         StepParams p;
-        fill_params(c, dt, n, s_tf, s_ph, p);
+        { const int frc = fill_params(c, dt, n, s_tf, s_ph, p); if (frc) return frc; }
         p.cap2char = s_cap2char; p.seg_start = s_seg_start; p.seg_prev = s_seg_prev; p.last_box = s_last_box;
         p.counters = scratch;
         p.host_flags = flags;
@@ -268,7 +268,8 @@ int literal_step(prtc_ctx * c, float dt, uint32_t n, prtc_transform * tf, prtc_c
         PRTC_CUDA(cudaMemcpyAsync(c->d_ph.ptr, ph, size_t(n) * sizeof(prtc_char_physics), cudaMemcpyHostToDevice, s));
         PRTC_CUDA(cudaMemcpyAsync(c->d_seg_prev.ptr, seg_prev.data(), seg_prev.size() * sizeof(float4), cudaMemcpyHostToDevice, s));
         StepParams p;
-        fill_params(c, dt, n, c->d_tf.ptr, c->d_ph.ptr, p);
+        rc = fill_params(c, dt, n, c->d_tf.ptr, c->d_ph.ptr, p);
+        if (rc) return rc;
         p.cap2char = c->d_cap2char.ptr; p.seg_start = c->d_seg_start.ptr; p.seg_prev = c->d_seg_prev.ptr; p.last_box = c->d_last_box.ptr;
         if (tr) { rc = prepare_trace(c, n, p); if (rc) return rc; }
         c->launches += uint64_t(launch_step(p, tr != nullptr, STEP_LITERAL, s));
@@ -325,7 +326,8 @@ int prtc_step_characters_device(prtc_ctx * c, float dt, uint32_t n, prtc_transfo
     if (c->geometry_dirty || c->tree_dirty || c->capsules_dirty) { rc = commit_impl(c); if (rc) return rc; }
     if (c->capsules.empty() && n) return fail(PRTC_ERR_INVALID, "prtc_step_characters: no capsule collider registered");
     StepParams p;
-    fill_params(c, dt, n, d_tf, d_ph, p);
+    rc = fill_params(c, dt, n, d_tf, d_ph, p);
+    if (rc) return rc;
     int mode = STEP_STATIC;
     if (c->jacobi()) {
         if (!c->dyn_prepared) { rc = dyn_prepare(c, dt, n, d_tf, d_ph); if (rc) return rc; }
@@ -400,9 +402,10 @@ int ingest_step(prtc_ctx * c, float dt, uint32_t n, prtc_transform * tf, prtc_ch
     // copy-in pieces: 32 Ki characters first so the kernel starts early, 64 Ki after that.  Measured at C4 (1 M characters):
     // bigger pieces finish the copy sooner (1.7 vs 2.1 ms) but open the gate in coarser steps and the kernel ends later
     // (e2e 3.08 ms at 256 Ki, 3.33 at 1 Mi vs 2.96); smaller ones pay per-operation gaps (3.27 ms at 32 Ki throughout)
-    static const uint32_t in_first = [] { const char * e = std::getenv("PRTC_INGEST_IN_FIRST"); return e ? uint32_t(std::atoi(e)) : 32768u; }();
-    static const uint32_t in_max = [] { const char * e = std::getenv("PRTC_INGEST_IN_MAX"); return e ? uint32_t(std::atoi(e)) : 65536u; }();
-    for (uint32_t first = 0, piece = in_first & ~31u; first < n; first += piece, piece = std::min(2 * piece, in_max & ~31u)) {
+    // (experiment knobs, clamped: a piece is at least 32 characters -- whole lines of both record arrays -- and the pieces never shrink)
+    static const uint32_t in_first = [] { const char * e = std::getenv("PRTC_INGEST_IN_FIRST"); const long v = e ? std::atol(e) : 32768; return uint32_t(std::min(std::max(v, 32L), 1L << 24)); }();
+    static const uint32_t in_max = [] { const char * e = std::getenv("PRTC_INGEST_IN_MAX"); const long v = e ? std::atol(e) : 65536; return uint32_t(std::min(std::max(v, 32L), 1L << 24)); }();
+    for (uint32_t first = 0, piece = in_first & ~31u; first < n; first += piece, piece = std::max(piece, std::min(2 * piece, in_max & ~31u))) {
         const uint32_t cnt = std::min(piece, n - first);
         PRTC_CUDA(cudaMemcpyAsync(c->d_tf.ptr + first, tf + first, size_t(cnt) * sizeof(prtc_transform), cudaMemcpyHostToDevice, in));
         PRTC_CUDA(cudaMemcpyAsync(c->d_ph.ptr + first, ph + first, size_t(cnt) * sizeof(prtc_char_physics), cudaMemcpyHostToDevice, in));
@@ -440,7 +443,7 @@ int prtc_step_characters(prtc_ctx * c, float dt, uint32_t n, prtc_transform * tf
     // Static pass, big batch: characters are independent, so the batch is cut into chunks and the chunks' host->device
     // copies, steps and device->host copies overlap on a few streams (PCIe is full duplex).  Results are identical
     // to one launch -- every character's frame is computed by one thread either way.
-    static const uint32_t kChunk = [] { const char * e = std::getenv("PRTC_CHUNK"); return e ? uint32_t(std::atoi(e)) : 65536u; }();
+    static const uint32_t kChunk = [] { const char * e = std::getenv("PRTC_CHUNK"); const long v = e ? std::atol(e) : 65536; return uint32_t(std::min(std::max(v, 1024L), 1L << 24)); }();
     static const bool kChunkPersistent = [] { const char * e = std::getenv("PRTC_CHUNK_PERSISTENT"); return e ? std::atoi(e) != 0 : false; }();   // chunks overlap: the lock-step kernel has no per-launch drain tail (3.13 vs 3.70 ms)
     if (!c->jacobi() && n >= 4 * kChunk) {
         if (c->geometry_dirty || c->tree_dirty || c->capsules_dirty) { rc = commit_impl(c); if (rc) return rc; }
@@ -460,7 +463,8 @@ int prtc_step_characters(prtc_ctx * c, float dt, uint32_t n, prtc_transform * tf
             PRTC_CUDA(cudaMemcpyAsync(c->d_tf.ptr + first, tf + first, size_t(cnt) * sizeof(prtc_transform), cudaMemcpyHostToDevice, s));
             PRTC_CUDA(cudaMemcpyAsync(c->d_ph.ptr + first, ph + first, size_t(cnt) * sizeof(prtc_char_physics), cudaMemcpyHostToDevice, s));
             StepParams p;
-            fill_params(c, dt, cnt, c->d_tf.ptr + first, c->d_ph.ptr + first, p);
+            rc = fill_params(c, dt, cnt, c->d_tf.ptr + first, c->d_ph.ptr + first, p);
+            if (rc) return rc;
             if (!kChunkPersistent) p.work_counter = nullptr;
             if (p.work_counter) p.work_counter += 1 + k % prtc_ctx::PIPE_STREAMS;     // launches on one stream are ordered
             p.xc_first = first;                               // cache slots are indexed by the character's position in the batch
@@ -523,7 +527,8 @@ int prtc_step_characters_traced(prtc_ctx * c, float dt, uint32_t n, prtc_transfo
     PRTC_CUDA(cudaMemcpyAsync(c->d_tf.ptr, tf, size_t(n) * sizeof(prtc_transform), cudaMemcpyHostToDevice, s));
     PRTC_CUDA(cudaMemcpyAsync(c->d_ph.ptr, ph, size_t(n) * sizeof(prtc_char_physics), cudaMemcpyHostToDevice, s));
     StepParams p;
-    fill_params(c, dt, n, c->d_tf.ptr, c->d_ph.ptr, p);
+    rc = fill_params(c, dt, n, c->d_tf.ptr, c->d_ph.ptr, p);
+    if (rc) return rc;
     rc = prepare_trace(c, n, p);
     if (rc) return rc;
     int mode = STEP_STATIC;

@@ -2,6 +2,8 @@
 on identical inputs.  Bar: BIT-EXACT positions, velocities, ground normals, flags, candidate mesh ids (ordered),
 hit-triangle indices (ordered), push vectors and post-push positions (north_star asks for bit-exact indices
 and 1e-5 relative on floats; this path delivers bit-exact floats too, so the tolerance written here is 0)."""
+import os
+
 import numpy as np
 import pytest
 
@@ -561,47 +563,61 @@ def test_c3_full_size_bit_exact():
         assert co[k] == cg[k], k
 
 
-def test_c4_full_size_properties():
-    """C4 at full size (1 M capsules x 10 M triangles): too big for the CPU oracle to replay in a test, so the
-    size-independent properties of the path are checked instead:
+@pytest.mark.parametrize("order", ["canonical", "by_id"])
+def test_c4_full_size_properties(order):
+    """C4 at full size (1 M capsules x 10 M triangles), CANONICAL order and the device-built BY_ID tree:
+      * a 65 536-character sample replayed by the CPU oracle against the full terrain for 12 frames is bit-identical
+        (the persistent kernel's cross-frame cache is in its steady state by then; characters are independent, so a
+        sample's frames are the full run's);
       * work-saving devices off (walk per substep, no pre-cull) == on, bit for bit, and the counters obey
-        substeps/tri_tests/contacts equal, exact_tests(on) <= tri_tests;
-      * batch independence: stepping two halves separately == stepping the whole batch (characters are independent);
-      * permutation equivariance: permuting the characters permutes the result;
-      * a 4096-character sample replayed by the CPU oracle against the full terrain is bit-identical."""
-    import torch
+        substeps / tri_tests / contacts equal, fewer exact tests with the cull;
+      * batch independence: stepping two halves separately == stepping the whole batch;
+      * permutation equivariance: permuting the characters permutes the result."""
     from prototype2_b200 import capi
-    n = 1000000
+    n, frames = 1000000, 12
     scene = H.make_scene(2237, 2, 2, n, seed=12345)
-    order = H.scenes.morton_order(scene["pos"], 2237)
+    morton = H.scenes.morton_order(scene["pos"], 2237)
     for k in ("pos", "vel", "rot", "move"):
-        scene[k] = np.ascontiguousarray(scene[k][order])
-    ctx = capi.PhysicsContext()
+        scene[k] = np.ascontiguousarray(scene[k][morton])
+    ctx = capi.PhysicsContext(order_mode=capi.ORDER_BY_ID if order == "by_id" else capi.ORDER_CANONICAL)
     ctx.add_model_collider(scene["xyz"], scene["mesh_first"], scene["mesh_count"])
     cid = ctx.add_capsule_collider()
     ctx.commit()
     tf0 = capi.make_transforms(scene["pos"])
     ph0 = capi.make_physics(scene["vel"], collider=np.full(n, cid, np.uint32))
 
-    def run(frames, tf, ph, **opts):
+    def run(nframes, tf, ph, **opts):
         for o, v in opts.items():
             ctx.set_option(getattr(capi, o), v)
         ctx.counters(reset=True)
-        for _ in range(frames):
+        for _ in range(nframes):
             ctx.update_characters(DT, tf, ph)
         c = ctx.counters(reset=True)
         ctx.set_option(capi.OPT_FRAME_CACHE, 1)
         ctx.set_option(capi.OPT_QUICK_REJECT, 1)
+        ctx.set_option(capi.OPT_TIGHT_REJECT, 1)
         return c
+    # oracle on a sample against the full terrain, every frame
+    sel = np.linspace(0, n - 1, 65536).astype(np.int64)
+    sub = dict(scene, pos=scene["pos"][sel], vel=scene["vel"][sel], rot=scene["rot"][sel], move=scene["move"][sel], n=len(sel))
+    orc = H.build_oracle(sub, "l1", order=order, threads=os.cpu_count() or 1)
+    tf_a, ph_a = tf0.copy(), ph0.copy()
+    for f in range(frames):
+        orc.step(DT)
+        ctx.update_characters(DT, tf_a, ph_a)
+        assert H.state_diff(orc.get_state(), H.gpu_state(tf_a[sel], ph_a[sel])) == [], "frame %d" % f
+    # options
     tf_a, ph_a = tf0.copy(), ph0.copy()
     ca = run(3, tf_a, ph_a)
     tf_b, ph_b = tf0.copy(), ph0.copy()
-    cb = run(3, tf_b, ph_b, OPT_FRAME_CACHE=0, OPT_QUICK_REJECT=0)
+    cb = run(3, tf_b, ph_b, OPT_FRAME_CACHE=0, OPT_QUICK_REJECT=0, OPT_TIGHT_REJECT=0)
     assert H.state_diff(H.gpu_state(tf_a, ph_a), H.gpu_state(tf_b, ph_b)) == []
     for k in ("substeps", "tri_tests", "contacts"):
         assert ca[k] == cb[k], k
-    assert ca["exact_tests"] < cb["exact_tests"] <= cb["tri_tests"]
+    assert ca["exact_tests"] < cb["exact_tests"] and ca["exact_tests"] < ca["tri_tests"]
     assert ca["node_tests"] < cb["node_tests"]
+    if order == "by_id":
+        return
     # halves
     tf_c, ph_c = tf0.copy(), ph0.copy()
     for _ in range(3):
@@ -614,28 +630,44 @@ def test_c4_full_size_properties():
     for _ in range(3):
         ctx.update_characters(DT, tf_d, ph_d)
     assert H.state_diff(H.gpu_state(tf_a[perm], ph_a[perm]), H.gpu_state(tf_d, ph_d)) == []
-    # oracle on a sample against the full terrain
-    sel = np.linspace(0, n - 1, 4096).astype(np.int64)
-    sub = dict(scene, pos=scene["pos"][sel], vel=scene["vel"][sel], rot=scene["rot"][sel], move=scene["move"][sel], n=len(sel))
-    orc = H.build_oracle(sub, "l1", order="canonical", threads=os.cpu_count() or 1)
-    for _ in range(3):
-        orc.step(DT)
-    so, sg = orc.get_state(), H.gpu_state(tf_a[sel], ph_a[sel])
-    assert H.state_diff(so, sg) == []
 
 
-def test_unknown_collider_id_is_reported_not_dereferenced():
+@pytest.mark.parametrize("dyn,n", [("off", 64), ("jacobi", 64), ("off", 5000), ("jacobi", 5000)])
+def test_unknown_collider_id_is_reported_not_dereferenced(dyn, n):
+    """a character naming a capsule that was never added: the step returns PRTC_ERR_INVALID, nothing out of range is read
+    (static pass and the dynamic pass's record kernel alike, small and pooled batches), the others are stepped"""
     from prototype2_b200 import capi
-    scene = H.make_scene(24, 2, 2, 64, seed=2)
-    ctx, tf, ph = H.build_gpu(scene)
+    scene = H.make_scene(48, 2, 2, n, seed=2)
+    ctx, tf, ph = H.build_gpu(scene, dyn_mode=capi.DYN_JACOBI if dyn == "jacobi" else capi.DYN_OFF)
     before = tf["position"].copy()
-    ph["collider"][5] = 9999
+    ph["collider"][5] = 0x7FFFFFF0
     with pytest.raises(capi.PrtcError) as e:
         ctx.update_characters(DT, tf, ph)
     assert e.value.code == capi.PRTC_ERR_INVALID and "never added" in str(e.value)
     assert not H.same(tf["position"][6], before[6])                # the others were stepped
     ph["collider"][5] = 5
     ctx.update_characters(DT, tf, ph)                              # and the context keeps working
+
+
+def test_pre_cull_survives_empty_meshes_and_removed_models():
+    """a mesh without vertices (and a removed model) has the fold's +-FLT_MAX start values as its box; that must not be
+    taken for the extent of the world, or the pre-cull switches itself off for good"""
+    from prototype2_b200 import capi
+    scene = H.make_scene(48, 2, 2, 3000, seed=9)
+    mc = scene["mesh_count"].copy()
+    mc[3] = 0                                                      # an empty mesh collider
+    scene["mesh_count"] = mc
+    orc = H.build_oracle(scene, "l1", order="by_id")               # (by-id order: adding and removing a model leaves the others' order alone)
+    ctx, tf, ph = H.build_gpu(scene, order_mode=capi.ORDER_BY_ID)
+    extra = ctx.add_model_collider(scene["xyz"][:36] + np.float32(500.0), np.array([0], np.uint32), np.array([36], np.uint32))
+    ctx.commit()
+    ctx.remove_model_collider(extra[0])
+    for f in range(3):
+        orc.step(DT)
+        ctx.update_characters(DT, tf, ph)
+        assert H.state_diff(orc.get_state(), H.gpu_state(tf, ph)) == [], "frame %d" % f
+    c = ctx.counters()
+    assert c["exact_tests"] < c["tri_tests"] // 2                  # the cull is at work
 
 
 # ------------------------------------------------------------------------------------------------------------
