@@ -355,7 +355,10 @@ class Workload:
         if moving:
             # a crowd that keeps walking: movementVector of 0.1 per frame (half the engine's run speed, character.cpp:99)
             # in a per-character direction, so the per-slot leaf lists keep being refilled
-            ang = np.random.RandomState(777 + rank).uniform(-np.pi, np.pi, self.n)
+            if strong:                         # one global crowd: the state CRC must not depend on the number of ranks
+                ang = np.random.RandomState(777).uniform(-np.pi, np.pi, self.n_global)[self.first:self.first + self.n]
+            else:
+                ang = np.random.RandomState(777 + rank).uniform(-np.pi, np.pi, self.n)
             move = np.stack([0.1 * np.cos(ang), np.zeros(self.n), 0.1 * np.sin(ang)], axis=1).astype(np.float32)
         self.ph0 = capi.make_physics(vel, movement=move, collider=np.full(self.n, self.cid, np.uint32))
         self.h_tf = torch.empty(self.n * 40, dtype=torch.uint8).pin_memory()
@@ -512,11 +515,40 @@ def run_ours(args):
                               "exact_tests_per_query": cnt["exact_tests"] / max(1, cnt["substeps"]),
                               "contacts_per_query": cnt["contacts"] / max(1, cnt["substeps"])}}
 
-    # ---- end-to-end leg: host buffers through prtc_step_characters (H2D + kernel + D2H every step) ----------
-    e2e = None
-    if not args.no_e2e and not (w.dynamic and world > 1):       # the host-buffer entry point has no exchange hook
+    # ---- end-to-end legs: through the public host API, transfers inside the timed region, wall clock ----------
+    # e2e      prtc_resident_step: the records stay on the device (as the engine's caller only gathers / scatters positions
+    #          around updateCharacters, character_system.cpp:55-78); every step the kernels read this frame's movement input
+    #          (12 B per character) from pinned host memory and write position + isGrounded (16 B) back to pinned host
+    #          memory, in place over the bus; the host reads the result array after every step.
+    # e2e_aos  prtc_step_characters: the full AoS records (84 B per character each way) from and to pinned host buffers.
+    e2e = e2e_aos = None
+    if not args.no_e2e and not (w.dynamic and world > 1):       # (config 5 over several ranks has its exchange hook in the device leg)
         own = torch.cuda.Stream()
         ctx.set_stream(own.cuda_stream)
+        ctx.resident_begin(w.tf0, w.ph0)
+        move, result = ctx.resident_io()
+        for _ in range(min(2, args.warmup)):
+            ctx.resident_step(DT)
+        ctx.resident_begin(w.tf0, w.ph0)                         # same start state as the device leg
+        move, result = ctx.resident_io()
+        ctx.counters(reset=True)
+        dist.barrier()
+        t0 = time.perf_counter()
+        seen = 0.0
+        for _ in range(args.steps):
+            ctx.resident_step(DT)
+            seen += float(result[::1024, 1].sum())               # the caller scatters positions back: touch the result
+        el_r = time.perf_counter() - t0
+        dist.barrier()
+        el_r = dist.max(el_r)
+        c3 = ctx.counters(reset=True)
+        (sub_r,) = dist.sum([c3["substeps"]])
+        e2e = {"value": sub_r / el_r, "unit": UNIT, "h2d_bytes_per_step": n_caps * 12, "d2h_bytes_per_step": n_caps * 16,
+               "ms_per_step": 1e3 * el_r / args.steps,
+               "api": "prtc_resident_step (records resident on the device; movement in / position + isGrounded out through mapped "
+                      "pinned host arrays, read and written by the kernels in place, host reads the result every step)",
+               "result_checksum": seen}
+        ctx.resident_end()
         w.tf_np[:] = w.tf0
         w.ph_np[:] = w.ph0
         for _ in range(min(2, args.warmup)):
@@ -534,8 +566,8 @@ def run_ours(args):
         el_e = dist.max(el_e)
         c2 = ctx.counters(reset=True)
         (sub_e,) = dist.sum([c2["substeps"]])
-        e2e = {"value": sub_e / el_e, "unit": UNIT, "h2d_bytes_per_step": n_caps * 84, "d2h_bytes_per_step": n_caps * 84,
-               "ms_per_step": 1e3 * el_e / args.steps, "api": "prtc_step_characters (host AoS buffers, pinned)"}
+        e2e_aos = {"value": sub_e / el_e, "unit": UNIT, "h2d_bytes_per_step": n_caps * 84, "d2h_bytes_per_step": n_caps * 84,
+                   "ms_per_step": 1e3 * el_e / args.steps, "api": "prtc_step_characters (host AoS buffers, pinned)"}
         ctx.set_stream(w.stream.cuda_stream)
 
     # ---- extra measurements on the same line (short runs) -----------------------------------------------------
@@ -591,7 +623,7 @@ def run_ours(args):
             "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "config": cfg,
             "tri_tests_per_s": r["tri_tests"] / el, "node_tests_per_s": node_tests / el,
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(cnt["launches"]), "clocks": r["clocks"],
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "e2e_aos": e2e_aos, "gpu_launches": int(cnt["launches"]), "clocks": r["clocks"],
             "setup": {"commit_s": commit_s, "nodes": info["nodes"], "leaves": info["leaves"]},
         }
         if crc is not None:

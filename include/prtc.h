@@ -172,6 +172,28 @@ int prtc_step_characters_device(prtc_ctx * ctx, float dt, uint32_t n, prtc_trans
 int prtc_step_characters_traced(prtc_ctx * ctx, float dt, uint32_t n, prtc_transform * transforms,
                                 prtc_char_physics * physics, prtc_trace * trace);
 
+/* RESIDENT STATE.  The engine's caller gathers the characters' transforms, calls updateCharacters and scatters the positions
+ * back (CharacterSystem::updatePhysics, character_system.cpp:55-78); between frames it only touches movementVector (input /
+ * AI, character_system.cpp:20-35) and, now and then, a velocity (jump, :92) or a transform (teleport).  With resident state
+ * the records stay on the device:
+ *   prtc_resident_begin   uploads n records once (CANONICAL / BY_ID order; LITERAL keeps its host records)
+ *   prtc_resident_io      two host arrays owned by the context (pinned, mapped into the device's address space):
+ *                         movement[3n]  IN   this frame's movementVector per character -- the caller writes it before a step
+ *                         result[4n]    OUT  position.xyz and isGrounded (0.0f / 1.0f) per character -- valid when a step returns
+ *   prtc_resident_step    one frame (updateCharacters, physics_system.cpp:245-318): the kernels read movement[] and write
+ *                         result[] in place over the bus while they run -- 12 + 16 bytes per character and frame instead of
+ *                         84 + 84, no separate copies; returns after the frame is complete
+ *   prtc_resident_edit    overwrites k records (transform and / or physics; either may be null) -- jumps, teleports, spawns
+ *   prtc_resident_fetch   downloads all records (either pointer may be null)
+ * Same results, bit for bit, as prtc_step_characters on the same records with physics[i].movement = movement[3i..]. */
+int prtc_resident_begin(prtc_ctx * ctx, uint32_t n, const prtc_transform * transforms, const prtc_char_physics * physics);
+int prtc_resident_io(prtc_ctx * ctx, float ** movement, float ** result);
+int prtc_resident_step(prtc_ctx * ctx, float dt);
+int prtc_resident_edit(prtc_ctx * ctx, uint32_t k, const uint32_t * indices, const prtc_transform * transforms,
+                       const prtc_char_physics * physics);
+int prtc_resident_fetch(prtc_ctx * ctx, prtc_transform * transforms, prtc_char_physics * physics);
+int prtc_resident_end(prtc_ctx * ctx);
+
 /* PhysicsSystem::raycast(origin, direction, maxDistance, hit&)  physics_system.cpp:205-242, batched:
  * n rays; hit_xyz[3*i..] is written and hit_mask[i]=1 where ray i hits a mesh collider. */
 int prtc_raycast(prtc_ctx * ctx, uint32_t n, const float * origins, const float * directions,

@@ -23,6 +23,7 @@ SYMBOLS = (
     "prtc_step_characters", "prtc_step_characters_device", "prtc_step_characters_traced", "prtc_raycast", "prtc_sweep_ellipsoids",
     "prtc_set_stream", "prtc_synchronize", "prtc_get_counters", "prtc_set_option", "prtc_dyn_configure", "prtc_dyn_prepare", "prtc_dyn_buffer", "prtc_get_tree_info", "prtc_get_leaf_order",
     "prtc_get_world_vertices", "prtc_query_box", "prtc_host_build_tree", "prtc_host_top_table", "prtc_host_balanced_tree", "prtc_selftest_math",
+    "prtc_resident_begin", "prtc_resident_io", "prtc_resident_step", "prtc_resident_edit", "prtc_resident_fetch", "prtc_resident_end",
 )
 
 
@@ -252,6 +253,36 @@ class PhysicsContext:
                "h_query": arr["h_query"][:nh], "h_poly": arr["h_poly"][:nh], "h_impulse": arr["h_impulse"][:nh],
                "h_normal": arr["h_normal"][:nh], "h_pos": arr["h_pos"][:nh]}
         return out
+
+    # -- resident state (prtc_resident_*) ------------------------------------------------------------------
+    def resident_begin(self, transforms, physics):
+        assert transforms.dtype == TRANSFORM_DTYPE and physics.dtype == PHYSICS_DTYPE and len(transforms) == len(physics)
+        self._check(self.lib.prtc_resident_begin(self.h, ctypes.c_uint32(len(transforms)), _vp(transforms), _vp(physics)))
+        self._resident_n = len(transforms)
+
+    def resident_io(self):
+        """(movement [n,3] float32 IN, result [n,4] float32 OUT): numpy views of the context's mapped pinned arrays"""
+        mv, res = ctypes.POINTER(ctypes.c_float)(), ctypes.POINTER(ctypes.c_float)()
+        self._check(self.lib.prtc_resident_io(self.h, ctypes.byref(mv), ctypes.byref(res)))
+        n = self._resident_n
+        if n == 0:
+            return np.zeros((0, 3), np.float32), np.zeros((0, 4), np.float32)
+        return (np.ctypeslib.as_array(mv, shape=(n, 3)), np.ctypeslib.as_array(res, shape=(n, 4)))
+
+    def resident_step(self, dt):
+        self._check(self.lib.prtc_resident_step(self.h, ctypes.c_float(dt)))
+
+    def resident_edit(self, indices, transforms=None, physics=None):
+        idx = np.ascontiguousarray(indices, dtype=np.uint32)
+        self._check(self.lib.prtc_resident_edit(self.h, ctypes.c_uint32(len(idx)), _vp(idx), _vp(transforms), _vp(physics)))
+
+    def resident_fetch(self):
+        tf, ph = np.zeros(self._resident_n, TRANSFORM_DTYPE), np.zeros(self._resident_n, PHYSICS_DTYPE)
+        self._check(self.lib.prtc_resident_fetch(self.h, _vp(tf), _vp(ph)))
+        return tf, ph
+
+    def resident_end(self):
+        self._check(self.lib.prtc_resident_end(self.h))
 
     def dyn_configure(self, first_global, n_global):
         self._check(self.lib.prtc_dyn_configure(self.h, ctypes.c_uint32(first_global), ctypes.c_uint32(n_global)))

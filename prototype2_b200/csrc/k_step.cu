@@ -51,6 +51,7 @@ __global__ void __launch_bounds__(STEP_BLOCK, 512 / STEP_BLOCK) k_step(StepParam
         uint32_t cid = ph->collider;
         if (cid >= p.n_capsules) {                                // unknown capsule id: never dereferenced; reported, result undefined
             if (p.counters) atomicAdd(p.counters + 6, 1ull);
+            if (p.host_flags) p.host_flags[1] = 1u;
             cid = 0;
         }
         const CapsuleDev cap = p.capsules[cid];

@@ -108,14 +108,21 @@ __global__ void __launch_bounds__(32, 16) k_step_pool(StepParams p) {
         uint32_t cid = ph->collider;
         if (cid >= p.n_capsules) {                                // unknown capsule id: never dereferenced; reported, result undefined
             if (valid && p.counters) atomicAdd(p.counters + 6, 1ull);
+            if (valid && p.host_flags) p.host_flags[1] = 1u;
             cid = 0;
         }
         const CapsuleDev cap = p.capsules[cid];
         const CapsuleFrame fr = capsule_frame(cap, rotation_of(q));
         const float radius = cap.radius;
         if (ph->grounded) vel = vel + ((-p.stick * p.gravity) * p.dt) * gn;
-        vel.x = vel.x + ph->movement[0];
-        vel.z = vel.z + ph->movement[2];
+        float mvx = ph->movement[0], mvz = ph->movement[2];
+        if (p.io_move && valid) {                                 // resident state: this frame's movement input comes from the I/O array
+            const float * mv = p.io_move + 3 * size_t(i);
+            mvx = mv[0]; mvz = mv[2];
+            ph->movement[0] = mvx; ph->movement[1] = mv[1]; ph->movement[2] = mvz;
+        }
+        vel.x = vel.x + mvx;
+        vel.z = vel.z + mvz;
         uint32_t grounded = 0;
         const V3 stepv = vel / fsub;
         V3 prevA, prevB;
@@ -502,6 +509,7 @@ __global__ void __launch_bounds__(32, 16) k_step_pool(StepParams p) {
             ph->velocity[0] = v.x; ph->velocity[1] = v.y; ph->velocity[2] = v.z;
             ph->ground_normal[0] = gn.x; ph->ground_normal[1] = gn.y; ph->ground_normal[2] = gn.z;
             ph->grounded = grounded;
+            if (p.io_result) p.io_result[i] = make_float4(pos.x, pos.y, pos.z, grounded ? 1.0f : 0.0f);
         }
         if (GATED) {
             // every finished character is counted (per 1024, then per 65536) so that the copy-out stream can start on a
@@ -528,6 +536,16 @@ __global__ void __launch_bounds__(32, 16) k_step_pool(StepParams p) {
     c_contact = __reduce_add_sync(FULL, c_contact);
     c_exact = __reduce_add_sync(FULL, c_exact);
     c_cc = __reduce_add_sync(FULL, c_cc);
+    if (p.done_flag && p.io_result) {
+        // resident step: every result this warp wrote is visible to the host before the doorbell can ring
+        __threadfence_system();
+        __syncwarp(FULL);
+        if (lane == 0 && atomicAdd(p.done_count, 1u) + 1u == gridDim.x) {
+            *p.done_count = 0u;
+            __threadfence_system();
+            *reinterpret_cast<volatile uint32_t *>(p.done_flag) = p.done_value;
+        }
+    }
     if (lane == 0 && p.counters) {
         atomicAdd(p.counters + 0, (unsigned long long)c_sub);
         atomicAdd(p.counters + 1, (unsigned long long)c_tri);

@@ -324,6 +324,7 @@ __global__ void __launch_bounds__(32, 20) k_step_stream(StepParams p) {
                     uint32_t cid = ph->collider;
                     if (cid >= p.n_capsules) {                    // unknown capsule id: never dereferenced; reported, result undefined
                         if (p.counters) atomicAdd(p.counters + 6, 1ull);
+                        if (p.host_flags) p.host_flags[1] = 1u;
                         cid = 0;
                     }
                     pos = v3(tf->position[0], tf->position[1], tf->position[2]);

@@ -250,8 +250,48 @@ void launch_raycast(const float4 * nodes, uint32_t n_nodes, const float4 * tris,
     k_raycast<<<(n_rays + block - 1) / block, block, 0, stream>>>(nodes, n_nodes, tris, n_rays, origins, dirs, maxd, hit_xyz, hit_mask);
 }
 
+// resident state, step kernels that do not read / write the I/O arrays themselves: movement in before, results out after
+__global__ void k_resident_in(uint32_t n, const float * __restrict__ io_move, prtc_char_physics * __restrict__ ph) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    ph[i].movement[0] = io_move[3 * size_t(i)]; ph[i].movement[1] = io_move[3 * size_t(i) + 1]; ph[i].movement[2] = io_move[3 * size_t(i) + 2];
+}
+__global__ void k_resident_out(uint32_t n, const prtc_transform * __restrict__ tf, const prtc_char_physics * __restrict__ ph,
+                               float4 * __restrict__ io_result, uint32_t * done_flag, unsigned * done_count, uint32_t done_value) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) io_result[i] = make_float4(tf[i].position[0], tf[i].position[1], tf[i].position[2], ph[i].grounded ? 1.0f : 0.0f);
+    if (done_flag) {                                               // doorbell, see StepParams::done_flag
+        __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x == 0 && atomicAdd(done_count, 1u) + 1u == gridDim.x) {
+            *done_count = 0u;
+            __threadfence_system();
+            *reinterpret_cast<volatile uint32_t *>(done_flag) = done_value;
+        }
+    }
+}
+
+static int launch_step_inner(StepParams const & p_in, bool traced, int mode, cudaStream_t stream);
+
 int launch_step(StepParams const & p_in, bool traced, int mode, cudaStream_t stream) {
     if (p_in.n == 0) return 0;
+    // which kernel will run is decided inside; the pooled kernel reads / writes the resident I/O arrays itself, the others
+    // get the two small kernels around them
+    StepParams p = p_in;
+    const bool pooled_first = p.pool && p.work_counter && !traced && mode != MODE_LITERAL;
+    const uint32_t resident_warps = pooled_first ? p.pool_blocks : (p.persistent_blocks ? p.persistent_blocks : 2368u);
+    const bool wpc = !traced && (p.n + resident_warps - 1) / resident_warps <= 1u && mode != MODE_JACOBI && !(p.tune & 2u);
+    const bool native_io = pooled_first && !wpc;
+    int launches = 0;
+    if (p.io_move && !native_io) { k_resident_in<<<(p.n + 255) / 256, 256, 0, stream>>>(p.n, p.io_move, p.physics); ++launches; }
+    float4 * io_result = p.io_result;
+    if (!native_io) { p.io_move = nullptr; p.io_result = nullptr; }
+    launches += launch_step_inner(p, traced, mode, stream);
+    if (io_result && !native_io) { k_resident_out<<<(p.n + 255) / 256, 256, 0, stream>>>(p.n, p.transforms, p.physics, io_result, p.done_flag, p.done_count, p.done_value); ++launches; }
+    return launches;
+}
+
+static int launch_step_inner(StepParams const & p_in, bool traced, int mode, cudaStream_t stream) {
     int launches = 1;
     StepParams p = p_in;
     const uint32_t block = STEP_BLOCK;
@@ -265,8 +305,16 @@ int launch_step(StepParams const & p_in, bool traced, int mode, cudaStream_t str
         // resident warp slot gets work (the pooled cull and exact stages use all 32 lanes whatever the number of owners)
         uint32_t opw = 4u;
         while (opw < 32u && (p.n + opw - 1) / opw > p.pool_blocks) opw <<= 1;
+        if (opw == 32u) {
+            // a batch of a few rounds of claims: size the claims so that the rounds come out whole (125 000 characters on
+            // 2368 resident warps: 27 per claim = 2 rounds, instead of 32 per claim = 1.65 rounds with a half-empty tail)
+            const uint32_t rounds = (p.n + 32u * p.pool_blocks - 1) / (32u * p.pool_blocks);
+            if (rounds <= 6u) opw = (p.n + rounds * p.pool_blocks - 1) / (rounds * p.pool_blocks);
+            if (opw < 16u) opw = 16u;
+            if (opw > 32u) opw = 32u;
+        }
         static const uint32_t force_opw = [] { const char * e = std::getenv("PRTC_OPW"); return e ? uint32_t(std::atoi(e)) : 0u; }();
-        if (force_opw == 4u || force_opw == 8u || force_opw == 16u || force_opw == 32u) opw = force_opw;   // experiments
+        if (force_opw >= 1u && force_opw <= 32u) opw = force_opw;   // experiments
         p.lanes_per_warp = opw;
         if (p.xc_version != nullptr && !(p.tune & 1u)) { launch_k_xc_refresh(p, stream); ++launches; }
         else p.xc_version = nullptr;

@@ -70,7 +70,7 @@ struct StepParams {
     uint32_t qr_enable;
     uint32_t tune;                  // bit 0: frame cache OFF (walk the tree every substep, reference-equivalent counters)
     unsigned long long * counters;  // prtc_counters layout
-    uint32_t * host_flags;          // k_step_warp, small host-buffer batches: host-mapped words the kernel raises --
+    uint32_t * host_flags;          // host-mapped words the kernels raise (small host-buffer batches, resident steps) --
                                     // [0] a capsule-capsule test ran (LITERAL), [1] a character named an unknown capsule
     unsigned * work_counter;        // k_step_stream: next character to hand out (null => lock-step kernel)
     // k_step_stream: cross-frame leaf cache, one slot per character index (SoA, stride xc_stride); null => off
@@ -93,6 +93,14 @@ struct StepParams {
     uint32_t * done_sub;            // finished characters per block of 2^INGEST_SUB_SHIFT characters
     uint32_t * done_chunk;          // finished blocks per chunk of 2^INGEST_CHUNK_SHIFT blocks: what the copy-out stream waits on
     uint32_t lanes_per_warp;        // k_step: characters per warp (set by launch_step; < 32 for small batches)
+    // resident state (prtc_resident_step): per-frame input / output arrays, host-mapped or device memory; null => the records only
+    const float * io_move;          // 3 floats per character: this frame's movementVector (replaces and updates physics[i].movement)
+    float4 * io_result;             // per character: (position.xyz, isGrounded as 0.0f / 1.0f) after the frame
+    // completion doorbell of a resident step: the last warp / block to finish writes `done_value` to host-mapped `done_flag`
+    // (after a system-wide fence), so the host can spin on a word instead of sleeping in cudaStreamSynchronize
+    uint32_t * done_flag;
+    unsigned * done_count;          // device counter of finished warps / blocks (reset by the one that rings)
+    uint32_t done_value;
     TraceBuffers trace;
 };
 

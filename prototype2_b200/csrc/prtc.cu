@@ -383,6 +383,7 @@ int prtc_create(const prtc_config * cfg, prtc_ctx ** out) {
     if (const char * e = std::getenv("PRTC_STAGED")) ctx->staged = std::atoi(e);
     if (const char * e = std::getenv("PRTC_XC_MARGIN")) ctx->xc_margin = float(std::atof(e));
     if (const char * e = std::getenv("PRTC_TUNE")) ctx->tune_hi = uint32_t(std::strtoul(e, nullptr, 0)) & 0xFFFFFF00u;
+    if (const char * e = std::getenv("PRTC_DOORBELL")) ctx->doorbell = std::atoi(e) != 0;
     if (const char * e = std::getenv("PRTC_PUSH_SLACK")) { const float v = float(std::atof(e)); if (v >= 0.0f && v <= 1.0f) ctx->push_slack = v; }
     ctx->sm_count = prop.multiProcessorCount;
     ctx->tree.set_margin(c.leaf_margin);
@@ -391,7 +392,8 @@ int prtc_create(const prtc_config * cfg, prtc_ctx ** out) {
         return fail(PRTC_ERR_CUDA, "prtc_create: cudaStreamCreate failed");
     }
     ctx->own_stream = true;
-    if (ctx->d_work.reserve(16) != cudaSuccess || ctx->d_counters.reserve(16) != cudaSuccess || cudaMemsetAsync(ctx->d_counters.ptr, 0, 16 * sizeof(unsigned long long), ctx->stream) != cudaSuccess) {
+    if (ctx->d_work.reserve(16) != cudaSuccess || ctx->d_counters.reserve(16) != cudaSuccess || cudaMemsetAsync(ctx->d_counters.ptr, 0, 16 * sizeof(unsigned long long), ctx->stream) != cudaSuccess ||
+        cudaMemsetAsync(ctx->d_work.ptr, 0, 16 * sizeof(unsigned), ctx->stream) != cudaSuccess) {
         prtc_destroy(ctx);
         return fail(PRTC_ERR_CUDA, "prtc_create: counter allocation failed");
     }
@@ -405,7 +407,7 @@ void prtc_destroy(prtc_ctx * c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     c->d_raw.release(); c->d_world.release(); c->d_aabbs.release(); c->d_meshes.release(); c->d_xforms.release();
     c->d_nodes.release(); c->d_leaves.release(); c->d_top.release(); c->d_tris.release(); c->d_cull.release(); c->d_node_leaf_id.release(); c->d_tri_src.release();
-    c->d_capsules.release(); c->d_counters.release(); c->d_work.release(); c->d_ingest.release(); c->stage.release();
+    c->d_capsules.release(); c->d_counters.release(); c->d_work.release(); c->d_ingest.release(); c->stage.release(); c->resident_io.release();
     c->d_xc_version.release(); c->d_xc_count.release(); c->d_xc_leaf.release(); c->d_xc_region.release(); c->d_tf.release(); c->d_ph.release();
     c->d_tq.release(); c->d_tmesh.release(); c->d_tcaps.release(); c->d_thits.release();
     c->d_scratch_f.release(); c->d_scratch_u.release();

@@ -169,6 +169,15 @@ struct prtc_ctx {
     bool dyn_initialized = false;            // stored boxes exist (first prepare creates them at the identity pose)
     bool dyn_prepared = false;               // prtc_dyn_prepare ran for the coming step (records may have been exchanged since)
     float world_lo[3] = {0, 0, 0}, world_hi[3] = {0, 0, 0};
+    // resident state (prtc_resident_*): the records stay in d_tf / d_ph between frames; per-frame I/O through mapped pinned arrays
+    bool resident = false;
+    uint32_t resident_n = 0;
+    prt::host::HostStage resident_io;        // [flags 64 B][movement 3n floats][result 4n floats]
+    float * resident_move = nullptr;
+    float * resident_result = nullptr;
+    uint32_t * resident_flags = nullptr;     // [0] unused, [1] unknown capsule id, [2] completion doorbell
+    uint32_t resident_frame = 0;
+    int doorbell = 1;                        // PRTC_DOORBELL=0: resident steps wait in cudaStreamSynchronize
     bool literal() const { return cfg.order_mode == PRTC_ORDER_LITERAL; }
     bool by_id() const { return cfg.order_mode == PRTC_ORDER_BY_ID; }
     bool jacobi() const { return cfg.order_mode != PRTC_ORDER_LITERAL && cfg.dyn_mode == PRTC_DYN_JACOBI; }

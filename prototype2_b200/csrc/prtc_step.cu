@@ -632,6 +632,137 @@ int prtc_sweep_ellipsoids(prtc_ctx * c, uint32_t n, const float * centers, const
     return PRTC_OK;
 }
 
+// ---- resident state ------------------------------------------------------------------------------------------------
+// What the engine's caller does around updateCharacters is gather -> call -> scatter of positions (character_system.cpp:
+// 55-78); the records themselves need not cross the bus every frame.  With resident state they stay on the device, the
+// caller writes this frame's movementVector into a mapped pinned array the kernel reads in place, and position + isGrounded
+// come back through a second mapped array the kernel writes in place: 12 bytes in and 16 bytes out per character instead
+// of 84 + 84, no separate copies, one launch and one synchronisation per frame.
+int prtc_resident_begin(prtc_ctx * c, uint32_t n, const prtc_transform * tf, const prtc_char_physics * ph) {
+    if (!c || (n && (!tf || !ph))) return fail(PRTC_ERR_INVALID, "prtc_resident_begin: null argument");
+    int rc = check_mode(c, true);                                  // LITERAL order maintains the tree on the host from host records
+    if (rc) return rc;
+    PRTC_CUDA(cudaSetDevice(c->cfg.device));
+    if (c->capsules.empty() && n) return fail(PRTC_ERR_INVALID, "prtc_resident_begin: no capsule collider registered");
+    if (c->geometry_dirty || c->tree_dirty || c->capsules_dirty) { rc = commit_impl(c); if (rc) return rc; }
+    PRTC_CUDA(c->d_tf.reserve(n));
+    PRTC_CUDA(c->d_ph.reserve(n));
+    PRTC_CUDA(c->resident_io.reserve(64 + size_t(n) * 7 * sizeof(float) + 64));
+    c->resident_flags = reinterpret_cast<uint32_t *>(c->resident_io.base);
+    c->resident_move = reinterpret_cast<float *>(c->resident_io.base + 64);
+    c->resident_result = c->resident_move + 3 * size_t(n) + ((4 - (3 * size_t(n)) % 4) % 4);       // float4-aligned
+    c->resident_flags[0] = 0u; c->resident_flags[1] = 0u; c->resident_flags[2] = 0u;
+    c->resident_frame = 0;
+    if (n) {
+        PRTC_CUDA(cudaMemcpyAsync(c->d_tf.ptr, tf, size_t(n) * sizeof(prtc_transform), cudaMemcpyHostToDevice, c->stream));
+        PRTC_CUDA(cudaMemcpyAsync(c->d_ph.ptr, ph, size_t(n) * sizeof(prtc_char_physics), cudaMemcpyHostToDevice, c->stream));
+        PRTC_CUDA(cudaStreamSynchronize(c->stream));
+    }
+    for (uint32_t i = 0; i < n; ++i) {
+        for (int k = 0; k < 3; ++k) c->resident_move[3 * size_t(i) + k] = ph[i].movement[k];
+        c->resident_result[4 * size_t(i)] = tf[i].position[0]; c->resident_result[4 * size_t(i) + 1] = tf[i].position[1];
+        c->resident_result[4 * size_t(i) + 2] = tf[i].position[2]; c->resident_result[4 * size_t(i) + 3] = ph[i].grounded ? 1.0f : 0.0f;
+    }
+    c->resident = true;
+    c->resident_n = n;
+    return PRTC_OK;
+}
+
+int prtc_resident_io(prtc_ctx * c, float ** movement, float ** result) {
+    if (!c || !c->resident) return fail(PRTC_ERR_INVALID, "prtc_resident_io: call prtc_resident_begin first");
+    if (movement) *movement = c->resident_move;
+    if (result) *result = c->resident_result;
+    return PRTC_OK;
+}
+
+int prtc_resident_step(prtc_ctx * c, float dt) {
+    if (!c || !c->resident) return fail(PRTC_ERR_INVALID, "prtc_resident_step: call prtc_resident_begin first");
+    int rc = check_mode(c, true);
+    if (rc) return rc;
+    PRTC_CUDA(cudaSetDevice(c->cfg.device));
+    if (c->geometry_dirty || c->tree_dirty || c->capsules_dirty) { rc = commit_impl(c); if (rc) return rc; }
+    const uint32_t n = c->resident_n;
+    if (n == 0) return PRTC_OK;
+    StepParams p;
+    rc = fill_params(c, dt, n, c->d_tf.ptr, c->d_ph.ptr, p);
+    if (rc) return rc;
+    p.io_move = c->resident_move;
+    p.io_result = reinterpret_cast<float4 *>(c->resident_result);
+    p.host_flags = c->resident_flags;
+    int mode = STEP_STATIC;
+    if (c->jacobi()) {
+        // the records of the dynamic pass are built from the state BEFORE this frame's movement input is applied: movement
+        // only enters the step (physics_system.cpp:281-282), not the predicted box (:263-273)
+        if (!c->dyn_prepared) { rc = dyn_prepare(c, dt, n, c->d_tf.ptr, c->d_ph.ptr); if (rc) return rc; }
+        rc = dyn_build_grid(c, p);
+        if (rc) return rc;
+        c->dyn_prepared = false;
+        mode = STEP_JACOBI;
+    }
+    // completion doorbell: the last warp of the step's last kernel writes the frame number to a host-mapped word; spinning on
+    // it returns a few microseconds after the kernel ends, where cudaStreamSynchronize's wake-up costs 10-20
+    const bool bell = c->doorbell != 0;
+    if (bell) {
+        p.done_flag = c->resident_flags + 2;
+        p.done_count = c->d_work.ptr + 6;
+        p.done_value = ++c->resident_frame;
+        if (p.done_value == 0u) p.done_value = ++c->resident_frame;
+    }
+    c->launches += uint64_t(launch_step(p, false, mode, c->stream));
+    PRTC_CUDA(cudaGetLastError());
+    if (bell) {
+        volatile uint32_t * flag = c->resident_flags + 2;
+        uint32_t spins = 0;
+        while (*flag != p.done_value) {
+            if ((++spins & 0xFFFu) == 0u) {                        // now and then: did the stream die, or finish without ringing?
+                const cudaError_t q = cudaStreamQuery(c->stream);
+                if (q == cudaSuccess) break;
+                if (q != cudaErrorNotReady) return fail(PRTC_ERR_CUDA, std::string("prtc_resident_step: ") + cudaGetErrorString(q));
+            }
+        }
+    } else {
+        PRTC_CUDA(cudaStreamSynchronize(c->stream));
+    }
+    if (c->resident_flags[1]) {
+        c->resident_flags[1] = 0u;
+        return check_bad_colliders(c);
+    }
+    return PRTC_OK;
+}
+
+int prtc_resident_edit(prtc_ctx * c, uint32_t k, const uint32_t * indices, const prtc_transform * tf, const prtc_char_physics * ph) {
+    if (!c || !c->resident || (k && !indices) || (k && !tf && !ph)) return fail(PRTC_ERR_INVALID, "prtc_resident_edit: null argument or no resident state");
+    PRTC_CUDA(cudaSetDevice(c->cfg.device));
+    for (uint32_t j = 0; j < k; ++j) {
+        const uint32_t i = indices[j];
+        if (i >= c->resident_n) return fail(PRTC_ERR_INVALID, "prtc_resident_edit: index out of range");
+        if (tf) PRTC_CUDA(cudaMemcpyAsync(c->d_tf.ptr + i, tf + j, sizeof(prtc_transform), cudaMemcpyHostToDevice, c->stream));
+        if (ph) {
+            PRTC_CUDA(cudaMemcpyAsync(c->d_ph.ptr + i, ph + j, sizeof(prtc_char_physics), cudaMemcpyHostToDevice, c->stream));
+            for (int d = 0; d < 3; ++d) c->resident_move[3 * size_t(i) + d] = ph[j].movement[d];
+        }
+    }
+    PRTC_CUDA(cudaStreamSynchronize(c->stream));
+    return PRTC_OK;
+}
+
+int prtc_resident_fetch(prtc_ctx * c, prtc_transform * tf, prtc_char_physics * ph) {
+    if (!c || !c->resident) return fail(PRTC_ERR_INVALID, "prtc_resident_fetch: no resident state");
+    PRTC_CUDA(cudaSetDevice(c->cfg.device));
+    const uint32_t n = c->resident_n;
+    if (n && tf) PRTC_CUDA(cudaMemcpyAsync(tf, c->d_tf.ptr, size_t(n) * sizeof(prtc_transform), cudaMemcpyDeviceToHost, c->stream));
+    if (n && ph) PRTC_CUDA(cudaMemcpyAsync(ph, c->d_ph.ptr, size_t(n) * sizeof(prtc_char_physics), cudaMemcpyDeviceToHost, c->stream));
+    PRTC_CUDA(cudaStreamSynchronize(c->stream));
+    return PRTC_OK;
+}
+
+int prtc_resident_end(prtc_ctx * c) {
+    if (!c) return fail(PRTC_ERR_INVALID, "prtc_resident_end: null context");
+    c->resident = false;
+    c->resident_n = 0;
+    return PRTC_OK;
+}
+
 int prtc_dyn_configure(prtc_ctx * c, uint32_t first_global, uint32_t n_global) {
     if (!c) return fail(PRTC_ERR_INVALID, "prtc_dyn_configure: null context");
     if (c->dyn_initialized && (n_global != c->dyn_global)) return fail(PRTC_ERR_INVALID, "prtc_dyn_configure: the global count is fixed after the first frame");
@@ -642,6 +773,7 @@ int prtc_dyn_configure(prtc_ctx * c, uint32_t first_global, uint32_t n_global) {
 }
 
 int prtc_dyn_prepare(prtc_ctx * c, float dt, uint32_t n, const prtc_transform * d_tf, const prtc_char_physics * d_ph) {
+    if (c && c->resident && !d_tf && !d_ph) { d_tf = c->d_tf.ptr; d_ph = c->d_ph.ptr; n = c->resident_n; }   // resident state: its own arrays
     if (!c || (n && (!d_tf || !d_ph))) return fail(PRTC_ERR_INVALID, "prtc_dyn_prepare: null argument");
     if (!c->jacobi()) return fail(PRTC_ERR_INVALID, "prtc_dyn_prepare: context is not in PRTC_ORDER_CANONICAL + PRTC_DYN_JACOBI");
     PRTC_CUDA(cudaSetDevice(c->cfg.device));
