@@ -369,6 +369,7 @@ class Workload:
         self.d_ph = torch.empty(self.n * 44, dtype=torch.uint8, device=dev)
         self.stream = torch.cuda.current_stream()
         ctx.set_stream(self.stream.cuda_stream)
+        self._rec = None
 
     def reset(self):
         self.tf_np[:] = self.tf0
@@ -380,8 +381,9 @@ class Workload:
         if self.dynamic and self.world > 1 and self.strong:
             # the one exchange of the path: the records of every character, all-gathered in place over NVLink
             self.ctx.dyn_prepare(DT, self.n, self.d_tf.data_ptr(), self.d_ph.data_ptr())
-            rec, rfirst = self.sharding.records_tensor(self.ctx)
-            self.sharding.allgather_records(rec, rfirst, self.n)
+            if self._rec is None:                          # the record array never moves: wrap it once
+                self._rec = self.sharding.records_tensor(self.ctx)
+            self.sharding.allgather_records(self._rec[0], self._rec[1], self.n)
         self.ctx.update_characters_device(DT, self.n, self.d_tf.data_ptr(), self.d_ph.data_ptr())
 
     def timed(self, dist, steps, warmup, sample_clocks=False):

@@ -194,6 +194,39 @@ int prtc_resident_edit(prtc_ctx * ctx, uint32_t k, const uint32_t * indices, con
 int prtc_resident_fetch(prtc_ctx * ctx, prtc_transform * transforms, prtc_char_physics * physics);
 int prtc_resident_end(prtc_ctx * ctx);
 
+/* SEVERAL GPUs OF ONE NODE BEHIND ONE HANDLE.  One process, one context per device; static geometry and its
+ * tree are replicated (every registration call is repeated on every device, the ids come out the same), the characters of a
+ * call are partitioned into contiguous slices, device k steps slice k on its own stream.  The static pass needs no exchange.
+ * The dynamic-vs-dynamic pass (PRTC_DYN_JACOBI) has one per frame: every device's record kernel stores its characters' records
+ * straight into the other devices' record arrays (peer stores over NVLink; cudaMemcpyPeerAsync where there is no peer access).
+ * Results are byte-identical to one context stepping the whole batch.  PRTC_ORDER_CANONICAL / PRTC_ORDER_BY_ID (LITERAL order
+ * keeps the reference's sequential visibility between characters and does not shard).  `cfg->device` is ignored.
+ * prtc_multi_context() exposes the per-device contexts (options, counters, introspection). */
+typedef struct prtc_multi prtc_multi;
+int prtc_multi_create(const prtc_config * cfg, const int32_t * devices, uint32_t n_devices, prtc_multi ** out);
+void prtc_multi_destroy(prtc_multi * m);
+uint32_t prtc_multi_device_count(const prtc_multi * m);
+prtc_ctx * prtc_multi_context(prtc_multi * m, uint32_t k);
+int prtc_multi_add_model(prtc_multi * m, const float * xyz, uint32_t n_vertices, const uint32_t * mesh_first, const uint32_t * mesh_count,
+                         uint32_t n_meshes, const prtc_transform * transform, uint32_t * out_model_id, uint32_t * out_first_mesh_id);
+int prtc_multi_add_capsule(prtc_multi * m, float height, float radius, const float offset[3], uint32_t * out_id);
+int prtc_multi_update_capsule(prtc_multi * m, uint32_t id, float height, float radius, const float offset[3]);
+int prtc_multi_remove_model(prtc_multi * m, uint32_t model_id);
+int prtc_multi_update_models(prtc_multi * m, const uint32_t * model_ids, const prtc_transform * transforms, uint32_t n);
+int prtc_multi_commit(prtc_multi * m);
+int prtc_multi_set_option(prtc_multi * m, int option, int value);
+int prtc_multi_raycast(prtc_multi * m, uint32_t n, const float * origins, const float * directions, const float * max_distances,
+                       float * hit_xyz, uint8_t * hit_mask);
+int prtc_multi_get_counters(prtc_multi * m, prtc_counters * out, int reset);          /* summed over the devices */
+/* PhysicsSystem::updateCharacters, HOST buffers, over all devices */
+int prtc_multi_step_characters(prtc_multi * m, float dt, uint32_t n, prtc_transform * transforms, prtc_char_physics * physics);
+/* resident state over all devices: ONE movement[3n] and ONE result[4n] host array, slice k read / written by device k */
+int prtc_multi_resident_begin(prtc_multi * m, uint32_t n, const prtc_transform * transforms, const prtc_char_physics * physics);
+int prtc_multi_resident_io(prtc_multi * m, float ** movement, float ** result);
+int prtc_multi_resident_step(prtc_multi * m, float dt);
+int prtc_multi_resident_fetch(prtc_multi * m, prtc_transform * transforms, prtc_char_physics * physics);
+int prtc_multi_resident_end(prtc_multi * m);
+
 /* PhysicsSystem::raycast(origin, direction, maxDistance, hit&)  physics_system.cpp:205-242, batched:
  * n rays; hit_xyz[3*i..] is written and hit_mask[i]=1 where ray i hits a mesh collider. */
 int prtc_raycast(prtc_ctx * ctx, uint32_t n, const float * origins, const float * directions,

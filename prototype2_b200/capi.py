@@ -24,6 +24,10 @@ SYMBOLS = (
     "prtc_set_stream", "prtc_synchronize", "prtc_get_counters", "prtc_set_option", "prtc_dyn_configure", "prtc_dyn_prepare", "prtc_dyn_buffer", "prtc_get_tree_info", "prtc_get_leaf_order",
     "prtc_get_world_vertices", "prtc_query_box", "prtc_host_build_tree", "prtc_host_top_table", "prtc_host_balanced_tree", "prtc_selftest_math",
     "prtc_resident_begin", "prtc_resident_io", "prtc_resident_step", "prtc_resident_edit", "prtc_resident_fetch", "prtc_resident_end",
+    "prtc_multi_create", "prtc_multi_destroy", "prtc_multi_device_count", "prtc_multi_context", "prtc_multi_add_model", "prtc_multi_add_capsule",
+    "prtc_multi_update_capsule", "prtc_multi_remove_model", "prtc_multi_update_models", "prtc_multi_commit", "prtc_multi_set_option",
+    "prtc_multi_raycast", "prtc_multi_get_counters", "prtc_multi_step_characters", "prtc_multi_resident_begin", "prtc_multi_resident_io",
+    "prtc_multi_resident_step", "prtc_multi_resident_fetch", "prtc_multi_resident_end",
 )
 
 
@@ -379,3 +383,90 @@ def host_balanced_tree(aabbs6):
     if rc != PRTC_OK:
         raise PrtcError(rc, (lib().prtc_last_error() or b"").decode())
     return nodes[:nn.value]
+
+
+class MultiContext:
+    """prtc_multi: several devices of one node behind one handle (one process).  Same method names as PhysicsContext."""
+
+    def __init__(self, devices, abs_mode=ABS_INT, order_mode=ORDER_CANONICAL, dyn_mode=DYN_OFF, substeps=4, **kw):
+        self.lib = lib()
+        cfg = Config()
+        self.lib.prtc_default_config(ctypes.byref(cfg))
+        cfg.abs_mode, cfg.order_mode, cfg.dyn_mode, cfg.substeps = abs_mode, order_mode, dyn_mode, substeps
+        for k, v in kw.items():
+            setattr(cfg, k, v)
+        self.cfg = cfg
+        self.devices = list(devices)
+        dev = (ctypes.c_int32 * len(self.devices))(*self.devices)
+        self.h = ctypes.c_void_p()
+        self._check(self.lib.prtc_multi_create(ctypes.byref(cfg), dev, ctypes.c_uint32(len(self.devices)), ctypes.byref(self.h)))
+        self._resident_n = 0
+
+    def _check(self, rc):
+        if rc != PRTC_OK:
+            raise PrtcError(rc, self.lib.prtc_last_error().decode())
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.prtc_multi_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def add_model_collider(self, xyz, mesh_first, mesh_count, transform=None):
+        xyz = np.ascontiguousarray(xyz, dtype=np.float32).reshape(-1, 3)
+        mf = np.ascontiguousarray(mesh_first, dtype=np.uint32)
+        mc = np.ascontiguousarray(mesh_count, dtype=np.uint32)
+        t = make_transforms(np.zeros((1, 3), np.float32))
+        if transform is not None:
+            tr = np.asarray(transform, dtype=np.float32)
+            t["position"][0] = tr[0:3]
+            t["rotation"][0] = (tr[4], tr[5], tr[6], tr[3])
+            t["scale"][0] = tr[7:10]
+        mid, first = ctypes.c_uint32(), ctypes.c_uint32()
+        self._check(self.lib.prtc_multi_add_model(self.h, _vp(xyz), ctypes.c_uint32(xyz.shape[0]), _vp(mf), _vp(mc), ctypes.c_uint32(len(mf)),
+                                                  _vp(t), ctypes.byref(mid), ctypes.byref(first)))
+        return mid.value, first.value
+
+    def add_capsule_collider(self, height=0.5, radius=0.5, offset=(0.0, 0.5, 0.0)):
+        off = (ctypes.c_float * 3)(*offset)
+        cid = ctypes.c_uint32()
+        self._check(self.lib.prtc_multi_add_capsule(self.h, ctypes.c_float(height), ctypes.c_float(radius), off, ctypes.byref(cid)))
+        return cid.value
+
+    def commit(self):
+        self._check(self.lib.prtc_multi_commit(self.h))
+
+    def set_option(self, option, value):
+        self._check(self.lib.prtc_multi_set_option(self.h, ctypes.c_int(option), ctypes.c_int(value)))
+
+    def update_characters(self, dt, transforms, physics):
+        assert transforms.dtype == TRANSFORM_DTYPE and physics.dtype == PHYSICS_DTYPE and len(transforms) == len(physics)
+        self._check(self.lib.prtc_multi_step_characters(self.h, ctypes.c_float(dt), ctypes.c_uint32(len(transforms)), _vp(transforms), _vp(physics)))
+
+    def resident_begin(self, transforms, physics):
+        self._check(self.lib.prtc_multi_resident_begin(self.h, ctypes.c_uint32(len(transforms)), _vp(transforms), _vp(physics)))
+        self._resident_n = len(transforms)
+
+    def resident_io(self):
+        mv, res = ctypes.POINTER(ctypes.c_float)(), ctypes.POINTER(ctypes.c_float)()
+        self._check(self.lib.prtc_multi_resident_io(self.h, ctypes.byref(mv), ctypes.byref(res)))
+        n = self._resident_n
+        return (np.ctypeslib.as_array(mv, shape=(n, 3)), np.ctypeslib.as_array(res, shape=(n, 4)))
+
+    def resident_step(self, dt):
+        self._check(self.lib.prtc_multi_resident_step(self.h, ctypes.c_float(dt)))
+
+    def resident_fetch(self):
+        tf, ph = np.zeros(self._resident_n, TRANSFORM_DTYPE), np.zeros(self._resident_n, PHYSICS_DTYPE)
+        self._check(self.lib.prtc_multi_resident_fetch(self.h, _vp(tf), _vp(ph)))
+        return tf, ph
+
+    def counters(self, reset=False):
+        c = Counters()
+        self._check(self.lib.prtc_multi_get_counters(self.h, ctypes.byref(c), ctypes.c_int(1 if reset else 0)))
+        return {k: int(getattr(c, k)) for k, _ in Counters._fields_}

@@ -159,42 +159,13 @@ __global__ void __launch_bounds__(STEP_BLOCK, 512 / STEP_BLOCK) k_step(StepParam
             // stored boxes are binned in a uniform xz grid; a pair is reported from the one cell that holds the
             // lower corner of the two boxes' common cell range, so nothing is reported twice.
             const uint32_t self = p.dyn_first + i;
-            int cx0 = 0, cx1 = -1, cz0 = 0, cz1 = -1;
-            if (alive) {
-                cx0 = dyn_cell(qb.lo.x, p.dyn_origin_x, p.dyn_inv_cell, p.dyn_gx); cx1 = dyn_cell(qb.hi.x, p.dyn_origin_x, p.dyn_inv_cell, p.dyn_gx);
-                cz0 = dyn_cell(qb.lo.z, p.dyn_origin_z, p.dyn_inv_cell, p.dyn_gz); cz1 = dyn_cell(qb.hi.z, p.dyn_origin_z, p.dyn_inv_cell, p.dyn_gz);
-            }
+            bool searching = alive;
             uint32_t t_caps = 0;
             long long last = -1;                                  // largest neighbour index already processed
             while (true) {
                 uint32_t ncand = 0;
                 bool more = false;
-                for (int cz = cz0; cz <= cz1; ++cz) {
-                    for (int cx = cx0; cx <= cx1; ++cx) {
-                        const uint32_t cell = uint32_t(cz) * p.dyn_gx + uint32_t(cx);
-                        const uint32_t beg = __ldg(p.dyn_cell_start + cell), end = __ldg(p.dyn_cell_start + cell + 1);
-                        for (uint32_t k = beg; k < end; ++k) {
-                            const uint32_t j = __ldg(p.dyn_items + k);
-                            if (j == self || (long long)j <= last) continue;
-                            const float4 blo = __ldg(p.dyn_records + 4 * size_t(j) + 2);
-                            const float4 bhi = __ldg(p.dyn_records + 4 * size_t(j) + 3);
-                            if (!node_overlaps(blo, bhi, qb)) continue;
-                            const int bx0 = dyn_cell(blo.x, p.dyn_origin_x, p.dyn_inv_cell, p.dyn_gx);
-                            const int bz0 = dyn_cell(blo.z, p.dyn_origin_z, p.dyn_inv_cell, p.dyn_gz);
-                            if (max(bx0, cx0) != cx || max(bz0, cz0) != cz) continue;      // reported from another cell
-                            // keep the DYN_CAP smallest indices, sorted
-                            if (ncand == DYN_CAP) {
-                                more = true;
-                                if (j > s_dyn[DYN_CAP - 1][tid]) continue;
-                                --ncand;
-                            }
-                            uint32_t q = ncand;
-                            while (q > 0 && s_dyn[q - 1][tid] > j) { s_dyn[q][tid] = s_dyn[q - 1][tid]; --q; }
-                            s_dyn[q][tid] = j;
-                            ++ncand;
-                        }
-                    }
-                }
+                if (searching) ncand = dyn_collect(dyn_grid_of(p), qb, self, last, &s_dyn[0][tid], more);
                 __syncwarp(FULL);
                 const uint32_t rounds = __reduce_max_sync(FULL, ncand);
                 if (rounds == 0) break;
@@ -231,7 +202,7 @@ __global__ void __launch_bounds__(STEP_BLOCK, 512 / STEP_BLOCK) k_step(StepParam
                     }
                 }
                 if (ncand) last = (long long)s_dyn[ncand - 1][tid];
-                if (!more) { cx1 = cx0 - 1; cz1 = cz0 - 1; }       // this lane is finished: empty cell range
+                if (!more) searching = false;                      // this lane is finished
             }
             if (TRACE && alive) p.trace.queries[slot].n_caps = t_caps;
             ps = make_pose(fr, pos);

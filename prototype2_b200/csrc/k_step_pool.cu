@@ -142,6 +142,20 @@ __global__ void __launch_bounds__(32, 16) k_step_pool(StepParams p) {
             region.hi = v3(p.xc_region[3 * size_t(p.xc_stride) + slot], p.xc_region[4 * size_t(p.xc_stride) + slot], p.xc_region[5 * size_t(p.xc_stride) + slot]);
         }
 
+        // JACOBI: the neighbours of the whole frame -- every other capsule whose stored box overlaps the region the frame can
+        // reach (pose now, pose after the pre-stepped velocity, 0.25 of slack for push-outs) -- collected once, ascending
+        bool dyn_cached = false;
+        uint32_t n_dyn = 0;
+        Box dyn_region; dyn_region.lo = v3(0.0f); dyn_region.hi = v3(0.0f);
+        if (JACOBI && valid && !(p.tune & 1u)) {
+            V3 eA, eB;
+            segment_ends(fr, pos + vel, eA, eB);
+            dyn_region = box_union(capsule_box(prevA, prevB, radius), capsule_box(eA, eB, radius));
+            dyn_region.lo = dyn_region.lo - v3(0.25f); dyn_region.hi = dyn_region.hi + v3(0.25f);
+            bool more = false;
+            n_dyn = dyn_collect(dyn_grid_of(p), dyn_region, p.dyn_first + i, -1, &sh.dyn[0][lane], more);
+            dyn_cached = !more;
+        }
         bool running = valid;
         Box qb; qb.lo = v3(0.0f); qb.hi = v3(0.0f);
         uint32_t node = 0, nleaf = 0, remaining = 0, cur_k = 0, cur_off = 0;
@@ -191,50 +205,33 @@ __global__ void __launch_bounds__(32, 16) k_step_pool(StepParams p) {
                     // box overlaps the query box, ascending global index, seen at its start-of-frame pose; stored boxes
                     // are binned in a uniform xz grid and a pair is reported from the one cell that holds the lower
                     // corner of the common cell range (same rule as k_step<JACOBI>)
+                    // (the frame's neighbours were collected once, at LOAD, for a region covering the whole frame's motion; a
+                    //  substep whose query box lies inside that region re-tests just those stored boxes -- same set, same
+                    //  ascending order -- instead of searching the grid again)
                     const uint32_t self = p.dyn_first + i;
-                    const int cx0 = dyn_cell(qb.lo.x, p.dyn_origin_x, p.dyn_inv_cell, p.dyn_gx), cx1 = dyn_cell(qb.hi.x, p.dyn_origin_x, p.dyn_inv_cell, p.dyn_gx);
-                    const int cz0 = dyn_cell(qb.lo.z, p.dyn_origin_z, p.dyn_inv_cell, p.dyn_gz), cz1 = dyn_cell(qb.hi.z, p.dyn_origin_z, p.dyn_inv_cell, p.dyn_gz);
+                    auto cc_test = [&](uint32_t j) {
+                        const float4 sA = __ldg(p.dyn_records + 4 * size_t(j)), sB = __ldg(p.dyn_records + 4 * size_t(j) + 1);
+                        V3 aA, aB;
+                        segment_ends(fr, pos, aA, aB);
+                        Contact ct;
+                        ++c_cc;
+                        if (capsule_capsule(aA, aB, radius, v3(sA.x, sA.y, sA.z), v3(sB.x, sB.y, sB.z), sA.w, ct)) {
+                            pos = pos + ct.impulse;               // handleCollision (collision_system.cpp:242-252)
+                            ++c_contact;
+                            if (dot(ct.normal, v3(0.0f, 1.0f, 0.0f)) > p.ground_dot) { grounded = 1; gn = ct.normal; }
+                        }
+                    };
+                    // (one loop for both cases, one copy of the capsule-capsule test: the instruction cache is precious here)
+                    const bool from_cache = dyn_cached && box_contains(dyn_region, qb);
+                    if (!from_cache) dyn_cached = false;          // the passes below reuse the buffer
                     long long last = -1;
                     for (;;) {
-                        uint32_t ncand = 0;
                         bool more = false;
-                        for (int cz = cz0; cz <= cz1; ++cz) {
-                            for (int cx = cx0; cx <= cx1; ++cx) {
-                                const uint32_t cell = uint32_t(cz) * p.dyn_gx + uint32_t(cx);
-                                const uint32_t beg = __ldg(p.dyn_cell_start + cell), end = __ldg(p.dyn_cell_start + cell + 1);
-                                for (uint32_t k = beg; k < end; ++k) {
-                                    const uint32_t j = __ldg(p.dyn_items + k);
-                                    if (j == self || (long long)j <= last) continue;
-                                    const float4 blo = __ldg(p.dyn_records + 4 * size_t(j) + 2);
-                                    const float4 bhi = __ldg(p.dyn_records + 4 * size_t(j) + 3);
-                                    if (!node_overlaps(blo, bhi, qb)) continue;
-                                    const int bx0 = dyn_cell(blo.x, p.dyn_origin_x, p.dyn_inv_cell, p.dyn_gx);
-                                    const int bz0 = dyn_cell(blo.z, p.dyn_origin_z, p.dyn_inv_cell, p.dyn_gz);
-                                    if (max(bx0, cx0) != cx || max(bz0, cz0) != cz) continue;      // reported from another cell
-                                    if (ncand == uint32_t(DYN_CAP)) {                               // keep the DYN_CAP smallest, sorted
-                                        more = true;
-                                        if (j > sh.dyn[DYN_CAP - 1][lane]) continue;
-                                        --ncand;
-                                    }
-                                    uint32_t s = ncand;
-                                    while (s > 0 && sh.dyn[s - 1][lane] > j) { sh.dyn[s][lane] = sh.dyn[s - 1][lane]; --s; }
-                                    sh.dyn[s][lane] = j;
-                                    ++ncand;
-                                }
-                            }
-                        }
+                        const uint32_t ncand = from_cache ? n_dyn : dyn_collect(dyn_grid_of(p), qb, self, last, &sh.dyn[0][lane], more);
                         for (uint32_t r = 0; r < ncand; ++r) {
                             const uint32_t j = sh.dyn[r][lane];
-                            const float4 sA = __ldg(p.dyn_records + 4 * size_t(j)), sB = __ldg(p.dyn_records + 4 * size_t(j) + 1);
-                            V3 aA, aB;
-                            segment_ends(fr, pos, aA, aB);
-                            Contact ct;
-                            ++c_cc;
-                            if (capsule_capsule(aA, aB, radius, v3(sA.x, sA.y, sA.z), v3(sB.x, sB.y, sB.z), sA.w, ct)) {
-                                pos = pos + ct.impulse;           // handleCollision (collision_system.cpp:242-252)
-                                ++c_contact;
-                                if (dot(ct.normal, v3(0.0f, 1.0f, 0.0f)) > p.ground_dot) { grounded = 1; gn = ct.normal; }
-                            }
+                            if (from_cache && !node_overlaps(__ldg(p.dyn_records + 4 * size_t(j) + 2), __ldg(p.dyn_records + 4 * size_t(j) + 3), qb)) continue;
+                            cc_test(j);
                         }
                         if (!more) break;
                         last = (long long)sh.dyn[ncand - 1][lane];

@@ -92,67 +92,6 @@ __global__ void k_query_box(const float4 * __restrict__ nodes, uint32_t n_nodes,
     *out_count = found;
 }
 
-// K1 for the dynamic pass: per own character, the phase-1 predicted box (physics_system.cpp:263-273: pose box united
-// with the box after `velocity + gravity*dt`, displacement applied in the capsule's rotated frame), the stored fat box
-// hysteresis of DynamicAABBTree::update/insertLeaf (aabb_tree.cpp:102-111,140-141) and the start-of-frame segment.
-// Record = 4 float4: (A.xyz, radius) (B.xyz, 0) (stored.lo, 0) (stored.hi, 0) at global index dyn_first + i.
-__global__ void k_dyn_prep(const prtc_transform * __restrict__ tf, const prtc_char_physics * __restrict__ ph,
-                           const CapsuleDev * __restrict__ capsules, uint32_t n_capsules, uint32_t n, uint32_t first,
-                           float4 * __restrict__ records, float dt, float gravity, float margin, uint32_t init) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    uint32_t cid = ph[i].collider;
-    if (cid >= n_capsules) cid = 0;               // unknown capsule id: never dereferenced (the step kernel reports it, counters[6])
-    const CapsuleDev cap = capsules[cid];
-    Quat q; q.x = tf[i].rotation[0]; q.y = tf[i].rotation[1]; q.z = tf[i].rotation[2]; q.w = tf[i].rotation[3];
-    const Rot3 R = rotation_of(q);
-    const CapsuleFrame fr = capsule_frame(cap, R);
-    const V3 pos = v3(tf[i].position[0], tf[i].position[1], tf[i].position[2]);
-    V3 A, B;
-    segment_ends(fr, pos, A, B);
-    Box e = capsule_box(A, B, cap.radius);
-    const V3 vel = v3(ph[i].velocity[0], ph[i].velocity[1], ph[i].velocity[2]);
-    const V3 d = vel + (v3(0.0f, -1.0f, 0.0f) * gravity) * dt;
-    const V3 pos2 = ((R.c0 * d.x + R.c1 * d.y) + R.c2 * d.z) + pos;
-    V3 A2, B2;
-    segment_ends(fr, pos, pos2, A2, B2);
-    e = box_union(e, capsule_box(A2, B2, cap.radius));
-    float4 * rec = records + 4 * size_t(first + i);
-    Box stored;
-    if (init) {                                                    // the leaf is created at the identity pose (physics_system.cpp:36-39)
-        Quat qi; qi.x = qi.y = qi.z = 0.0f; qi.w = 1.0f;
-        V3 iA, iB;
-        segment_ends(capsule_frame(cap, rotation_of(qi)), v3(0.0f), iA, iB);
-        const Box ib = capsule_box(iA, iB, cap.radius);
-        stored.lo = ib.lo - margin; stored.hi = ib.hi + margin;
-    } else {
-        const float4 lo = rec[2], hi = rec[3];
-        stored.lo = v3(lo.x, lo.y, lo.z); stored.hi = v3(hi.x, hi.y, hi.z);
-    }
-    if (!box_contains(stored, e)) { stored.lo = e.lo - margin; stored.hi = e.hi + margin; }
-    rec[0] = make_float4(A.x, A.y, A.z, cap.radius);
-    rec[1] = make_float4(B.x, B.y, B.z, 0.0f);
-    rec[2] = make_float4(stored.lo.x, stored.lo.y, stored.lo.z, 0.0f);
-    rec[3] = make_float4(stored.hi.x, stored.hi.y, stored.hi.z, 0.0f);
-}
-
-// counting-sort build of the uniform grid over ALL capsules' stored boxes (pass 0 counts, pass 1 fills)
-__global__ void k_dyn_grid(const float4 * __restrict__ records, uint32_t n, float ox, float oz, float inv_cell, uint32_t gx, uint32_t gz,
-                           uint32_t * __restrict__ cell_count, const uint32_t * __restrict__ cell_start, uint32_t * __restrict__ items, int fill) {
-    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= n) return;
-    const float4 lo = records[4 * size_t(j) + 2], hi = records[4 * size_t(j) + 3];
-    const int x0 = dyn_cell(lo.x, ox, inv_cell, gx), x1 = dyn_cell(hi.x, ox, inv_cell, gx);
-    const int z0 = dyn_cell(lo.z, oz, inv_cell, gz), z1 = dyn_cell(hi.z, oz, inv_cell, gz);
-    // a NaN corner puts the box in every cell it could matter for: (0,0)..(x1,z1) is what dyn_cell yields
-    for (int z = z0; z <= z1; ++z)
-        for (int x = x0; x <= x1; ++x) {
-            const uint32_t cell = uint32_t(z) * gx + uint32_t(x);
-            const uint32_t slot = atomicAdd(cell_count + cell, 1u);
-            if (fill) items[cell_start[cell] + slot] = j;
-        }
-}
-
 // PhysicsSystem::raycast (physics_system.cpp:205-242): one thread per ray.  DynamicAABBTree::queryRaycast
 // (aabb_tree.cpp:70-93) with AABB::intersectRay (aabb.cpp:13-48, Ericson's slab test), then
 // intersectLineSegmentTriangle (physics_util.cpp:181-216) on every triangle of every mesh leaf hit; the result is
@@ -419,18 +358,6 @@ int launch_step_ingest(StepParams const & p_in, cudaStream_t stream) {
     r.gate = nullptr;
     launch_k_xc_refresh(r, stream);
     return 2;
-}
-
-void launch_dyn_prep(const prtc_transform * tf, const prtc_char_physics * ph, const CapsuleDev * capsules, uint32_t n_capsules, uint32_t n,
-                     uint32_t first, float4 * records, float dt, float gravity, float margin, bool init, cudaStream_t stream) {
-    if (n == 0) return;
-    k_dyn_prep<<<(n + 127) / 128, 128, 0, stream>>>(tf, ph, capsules, n_capsules, n, first, records, dt, gravity, margin, init ? 1u : 0u);
-}
-
-void launch_dyn_grid(const float4 * records, uint32_t n, float ox, float oz, float inv_cell, uint32_t gx, uint32_t gz,
-                     uint32_t * cell_count, const uint32_t * cell_start, uint32_t * items, bool fill, cudaStream_t stream) {
-    if (n == 0) return;
-    k_dyn_grid<<<(n + 127) / 128, 128, 0, stream>>>(records, n, ox, oz, inv_cell, gx, gz, cell_count, cell_start, items, fill ? 1 : 0);
 }
 
 void launch_transform_refit(const float * raw_xyz, float * world_xyz, const MeshDev * meshes, uint32_t first_mesh,

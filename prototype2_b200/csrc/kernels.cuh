@@ -57,7 +57,8 @@ struct StepParams {
     // CANONICAL order, JACOBI dynamic pass: records of ALL characters (4 float4 each) + uniform xz grid over their stored boxes
     const float4 * dyn_records;
     const uint32_t * dyn_cell_start;  // [gx*gz + 1]
-    const uint32_t * dyn_items;
+    const uint32_t * dyn_items;       // [n_global] record indices, cell by cell (every record in the cell of its stored box's lower corner)
+    const uint32_t * dyn_reach;       // [2] how many cells (x, z) a stored box reaches beyond its own, maximum over all records this frame
     uint32_t dyn_first;             // global index of this launch's character 0
     uint32_t dyn_gx, dyn_gz;
     float dyn_origin_x, dyn_origin_z, dyn_inv_cell;
@@ -114,11 +115,13 @@ uint32_t pool_blocks_per_sm();                  // resident one-warp blocks per 
 // static pass over a batch whose input is still being copied in (gate / done_* set): the persistent kernel alone, then the
 // refresh of the per-slot leaf lists for the NEXT frame from the state it leaves behind; returns the number of launches
 int launch_step_ingest(StepParams const & p, cudaStream_t stream);
-// dynamic pass, CANONICAL / JACOBI: per-character record (4 float4) and the uniform grid over all stored boxes
+// dynamic pass, CANONICAL / JACOBI: per-character record (4 float4) and the uniform grid over all stored boxes (k_dyn.cu)
+struct DynPeers { float4 * records[15]; uint32_t n; };      // record arrays of the other devices of a prtc_multi (peer-mapped)
 void launch_dyn_prep(const prtc_transform * tf, const prtc_char_physics * ph, const CapsuleDev * capsules, uint32_t n_capsules, uint32_t n,
-                     uint32_t first, float4 * records, float dt, float gravity, float margin, bool init, cudaStream_t stream);
-void launch_dyn_grid(const float4 * records, uint32_t n, float ox, float oz, float inv_cell, uint32_t gx, uint32_t gz,
-                     uint32_t * cell_count, const uint32_t * cell_start, uint32_t * items, bool fill, cudaStream_t stream);
+                     uint32_t first, float4 * records, DynPeers const & peers, float dt, float gravity, float margin, bool init, cudaStream_t stream);
+// counting sort of all n stored boxes into the uniform xz grid (one cell per box) + the per-frame reach; returns kernels launched
+int launch_dyn_grid_build(const float4 * records, uint32_t n, float ox, float oz, float inv_cell, uint32_t gx, uint32_t gz,
+                          uint32_t * cell_count, uint32_t * cell_start, uint32_t * items, uint32_t * reach, cudaStream_t stream);
 
 // main[k] += scratch[k], scratch[k] = 0 for the device-side work counters (per-frame scratch of the LITERAL fixpoint rounds)
 void launch_fold_counters(unsigned long long * main_counters, unsigned long long * scratch, cudaStream_t stream);

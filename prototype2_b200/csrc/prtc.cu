@@ -412,7 +412,7 @@ void prtc_destroy(prtc_ctx * c) {
     c->d_tq.release(); c->d_tmesh.release(); c->d_tcaps.release(); c->d_thits.release();
     c->d_scratch_f.release(); c->d_scratch_u.release();
     c->d_cap2char.release(); c->d_seg_start.release(); c->d_seg_prev.release(); c->d_last_box.release();
-    c->d_dyn_records.release(); c->d_dyn_count.release(); c->d_dyn_start.release(); c->d_dyn_items.release(); c->d_cub_temp.release();
+    c->d_dyn_records.release(); c->d_dyn_count.release(); c->d_dyn_start.release(); c->d_dyn_items.release(); c->d_dyn_reach.release();
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
     for (int k = 0; k < prtc_ctx::PIPE_STREAMS; ++k) if (c->pipe[k]) cudaStreamDestroy(c->pipe[k]);
     if (c->pipe_ready) cudaEventDestroy(c->pipe_ready);

@@ -162,12 +162,12 @@ struct prtc_ctx {
     prt::host::DevBuf<float> d_last_box;
     // CANONICAL order, JACOBI dynamic pass
     prt::host::DevBuf<float4> d_dyn_records;
-    prt::host::DevBuf<uint32_t> d_dyn_count, d_dyn_start, d_dyn_items;
-    prt::host::DevBuf<unsigned char> d_cub_temp;
+    prt::host::DevBuf<uint32_t> d_dyn_count, d_dyn_start, d_dyn_items, d_dyn_reach;
     uint32_t dyn_first = 0, dyn_global = 0;  // this context's slice [dyn_first, dyn_first + n) of dyn_global characters
     bool dyn_configured = false;             // prtc_dyn_configure called (multi-rank); otherwise the slice is the whole batch
     bool dyn_initialized = false;            // stored boxes exist (first prepare creates them at the identity pose)
     bool dyn_prepared = false;               // prtc_dyn_prepare ran for the coming step (records may have been exchanged since)
+    prt::DynPeers dyn_peers = {};            // prtc_multi: the other devices' record arrays, written by this device's k_dyn_prep
     float world_lo[3] = {0, 0, 0}, world_hi[3] = {0, 0, 0};
     // resident state (prtc_resident_*): the records stay in d_tf / d_ph between frames; per-frame I/O through mapped pinned arrays
     bool resident = false;
@@ -177,6 +177,7 @@ struct prtc_ctx {
     float * resident_result = nullptr;
     uint32_t * resident_flags = nullptr;     // [0] unused, [1] unknown capsule id, [2] completion doorbell
     uint32_t resident_frame = 0;
+    uint32_t resident_pending = 0;           // doorbell value of the frame in flight (0: wait with cudaStreamSynchronize)
     int doorbell = 1;                        // PRTC_DOORBELL=0: resident steps wait in cudaStreamSynchronize
     bool literal() const { return cfg.order_mode == PRTC_ORDER_LITERAL; }
     bool by_id() const { return cfg.order_mode == PRTC_ORDER_BY_ID; }
@@ -192,6 +193,15 @@ int fill_params(prtc_ctx * c, float dt, uint32_t n, prtc_transform * d_tf, prtc_
 int check_bad_colliders(prtc_ctx * c, cudaStream_t on = nullptr);
 int check_mode(prtc_ctx * c, bool device_pointers);
 int upload_leaf_ids(prtc_ctx * c);               // collider id per node, for traced kernels and prtc_query_box
+// ---- prtc_step.cu ----------------------------------------------------------------------------------------------
+int dyn_reserve(prtc_ctx * c, uint32_t n);       // allocates the record array of the JACOBI pass (dyn_first / dyn_global set)
+int dyn_prepare(prtc_ctx * c, float dt, uint32_t n, const prtc_transform * d_tf, const prtc_char_physics * d_ph);
+// resident state, in pieces (prtc_multi drives several contexts through them): `io` = caller-provided mapped pinned memory
+// ([flags 64 B] / movement / result) or null for the context's own
+int resident_begin_impl(prtc_ctx * c, uint32_t n, const prtc_transform * tf, const prtc_char_physics * ph, uint32_t * io_flags, float * io_move, float * io_result);
+int resident_launch(prtc_ctx * c, float dt);     // enqueues one frame
+int resident_wait(prtc_ctx * c);                 // returns when it is complete
+int dyn_build_grid_for(prtc_ctx * c, StepParams & p);   // grid over the (exchanged) records, wired into the launch parameters
 
 } // namespace host
 } // namespace prt

@@ -1,8 +1,6 @@
 // prtc_step.cu -- host side of the C-ABI declared in include/prtc.h, part 2: the per-frame entry points
 // (prtc_step_characters*, the LITERAL fixpoint, the staged and the streamed host-buffer steps, the dynamic pass plumbing,
 // prtc_raycast, prtc_sweep_ellipsoids) and the trace read-back.
-#include <cub/device/device_scan.cuh>
-
 #include "prtc_internal.h"
 
 using namespace prt;
@@ -82,8 +80,12 @@ int prepare_trace(prtc_ctx * c, uint32_t n, StepParams & p) {
     return PRTC_OK;
 }
 
-// JACOBI dynamic pass: records of this context's characters (phase-1 box, stored-box hysteresis, start-of-frame segment)
-int dyn_prepare(prtc_ctx * c, float dt, uint32_t n, const prtc_transform * d_tf, const prtc_char_physics * d_ph) {
+} // namespace
+
+namespace prt {
+namespace host {
+
+int dyn_reserve(prtc_ctx * c, uint32_t n) {
     if (!c->dyn_configured) { c->dyn_first = 0; c->dyn_global = n; }
     if (uint64_t(c->dyn_first) + n > c->dyn_global) return fail(PRTC_ERR_INVALID, "prtc_dyn_prepare: slice exceeds the configured global count");
     if (c->d_dyn_records.cap < size_t(c->dyn_global) * 4) {
@@ -91,13 +93,25 @@ int dyn_prepare(prtc_ctx * c, float dt, uint32_t n, const prtc_transform * d_tf,
         PRTC_CUDA(c->d_dyn_records.reserve(size_t(c->dyn_global) * 4));
         PRTC_CUDA(cudaMemsetAsync(c->d_dyn_records.ptr, 0, size_t(c->dyn_global) * 4 * sizeof(float4), c->stream));
     }
-    launch_dyn_prep(d_tf, d_ph, c->d_capsules.ptr, uint32_t(c->capsules.size()), n, c->dyn_first, c->d_dyn_records.ptr, dt, c->cfg.gravity,
-                    c->cfg.leaf_margin, !c->dyn_initialized, c->stream);
+    return PRTC_OK;
+}
+
+// JACOBI dynamic pass: records of this context's characters (phase-1 box, stored-box hysteresis, start-of-frame segment)
+int dyn_prepare(prtc_ctx * c, float dt, uint32_t n, const prtc_transform * d_tf, const prtc_char_physics * d_ph) {
+    int rc = dyn_reserve(c, n);
+    if (rc) return rc;
+    launch_dyn_prep(d_tf, d_ph, c->d_capsules.ptr, uint32_t(c->capsules.size()), n, c->dyn_first, c->d_dyn_records.ptr, c->dyn_peers, dt,
+                    c->cfg.gravity, c->cfg.leaf_margin, !c->dyn_initialized, c->stream);
     PRTC_CUDA(cudaGetLastError());
     c->dyn_initialized = true;
     c->dyn_prepared = true;
     return PRTC_OK;
 }
+
+} // namespace host
+} // namespace prt
+
+namespace {
 
 // uniform xz grid over the stored boxes of ALL characters (counting sort), wired into the launch parameters
 int dyn_build_grid(prtc_ctx * c, StepParams & p) {
@@ -110,24 +124,18 @@ int dyn_build_grid(prtc_ctx * c, StepParams & p) {
     const uint32_t gx = std::max(1u, uint32_t(std::ceil((hix - lox) / cell))), gz = std::max(1u, uint32_t(std::ceil((hiz - loz) / cell)));
     const size_t cells = size_t(gx) * gz;
     const uint32_t ng = c->dyn_global;
+    // every stored box is binned in exactly one cell, so the item array has ng entries: nothing here depends on a device count
     PRTC_CUDA(c->d_dyn_count.reserve(cells + 1));
     PRTC_CUDA(c->d_dyn_start.reserve(cells + 1));
-    PRTC_CUDA(cudaMemsetAsync(c->d_dyn_count.ptr, 0, (cells + 1) * sizeof(uint32_t), s));
-    launch_dyn_grid(c->d_dyn_records.ptr, ng, lox, loz, 1.0f / cell, gx, gz, c->d_dyn_count.ptr, nullptr, nullptr, false, s);
-    size_t temp_bytes = 0;
-    cub::DeviceScan::ExclusiveSum(nullptr, temp_bytes, c->d_dyn_count.ptr, c->d_dyn_start.ptr, int(cells + 1), s);
-    PRTC_CUDA(c->d_cub_temp.reserve(temp_bytes));
-    PRTC_CUDA(cub::DeviceScan::ExclusiveSum(c->d_cub_temp.ptr, temp_bytes, c->d_dyn_count.ptr, c->d_dyn_start.ptr, int(cells + 1), s));
-    uint32_t total = 0;
-    PRTC_CUDA(cudaMemcpyAsync(&total, c->d_dyn_start.ptr + cells, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
-    PRTC_CUDA(cudaStreamSynchronize(s));
-    PRTC_CUDA(c->d_dyn_items.reserve(size_t(total) + 1));
-    PRTC_CUDA(cudaMemsetAsync(c->d_dyn_count.ptr, 0, (cells + 1) * sizeof(uint32_t), s));
-    launch_dyn_grid(c->d_dyn_records.ptr, ng, lox, loz, 1.0f / cell, gx, gz, c->d_dyn_count.ptr, c->d_dyn_start.ptr, c->d_dyn_items.ptr, true, s);
+    PRTC_CUDA(c->d_dyn_items.reserve(size_t(ng) + 1));
+    PRTC_CUDA(c->d_dyn_reach.reserve(2));
+    c->launches += uint64_t(launch_dyn_grid_build(c->d_dyn_records.ptr, ng, lox, loz, 1.0f / cell, gx, gz, c->d_dyn_count.ptr, c->d_dyn_start.ptr,
+                                                  c->d_dyn_items.ptr, c->d_dyn_reach.ptr, s));
     PRTC_CUDA(cudaGetLastError());
     p.dyn_records = c->d_dyn_records.ptr;
     p.dyn_cell_start = c->d_dyn_start.ptr;
     p.dyn_items = c->d_dyn_items.ptr;
+    p.dyn_reach = c->d_dyn_reach.ptr;
     p.dyn_first = c->dyn_first;
     p.dyn_gx = gx; p.dyn_gz = gz;
     p.dyn_origin_x = lox; p.dyn_origin_z = loz; p.dyn_inv_cell = 1.0f / cell;
@@ -337,7 +345,7 @@ int prtc_step_characters_device(prtc_ctx * c, float dt, uint32_t n, prtc_transfo
         mode = STEP_JACOBI;
     }
     c->launches += uint64_t(launch_step(p, false, mode, c->stream));
-    if (mode == STEP_JACOBI) c->launches += 3;                // k_dyn_prep + two k_dyn_grid passes (+ cub scan)
+    if (mode == STEP_JACOBI) c->launches += 1;                // k_dyn_prep (the grid build counts its own)
     PRTC_CUDA(cudaGetLastError());
     return PRTC_OK;
 }
@@ -632,13 +640,15 @@ int prtc_sweep_ellipsoids(prtc_ctx * c, uint32_t n, const float * centers, const
     return PRTC_OK;
 }
 
-// ---- resident state ------------------------------------------------------------------------------------------------
-// What the engine's caller does around updateCharacters is gather -> call -> scatter of positions (character_system.cpp:
-// 55-78); the records themselves need not cross the bus every frame.  With resident state they stay on the device, the
-// caller writes this frame's movementVector into a mapped pinned array the kernel reads in place, and position + isGrounded
-// come back through a second mapped array the kernel writes in place: 12 bytes in and 16 bytes out per character instead
-// of 84 + 84, no separate copies, one launch and one synchronisation per frame.
-int prtc_resident_begin(prtc_ctx * c, uint32_t n, const prtc_transform * tf, const prtc_char_physics * ph) {
+} // extern "C"
+
+namespace prt {
+namespace host {
+
+int dyn_build_grid_for(prtc_ctx * c, StepParams & p) { return dyn_build_grid(c, p); }
+
+int resident_begin_impl(prtc_ctx * c, uint32_t n, const prtc_transform * tf, const prtc_char_physics * ph, uint32_t * io_flags, float * io_move,
+                        float * io_result) {
     if (!c || (n && (!tf || !ph))) return fail(PRTC_ERR_INVALID, "prtc_resident_begin: null argument");
     int rc = check_mode(c, true);                                  // LITERAL order maintains the tree on the host from host records
     if (rc) return rc;
@@ -647,10 +657,14 @@ int prtc_resident_begin(prtc_ctx * c, uint32_t n, const prtc_transform * tf, con
     if (c->geometry_dirty || c->tree_dirty || c->capsules_dirty) { rc = commit_impl(c); if (rc) return rc; }
     PRTC_CUDA(c->d_tf.reserve(n));
     PRTC_CUDA(c->d_ph.reserve(n));
-    PRTC_CUDA(c->resident_io.reserve(64 + size_t(n) * 7 * sizeof(float) + 64));
-    c->resident_flags = reinterpret_cast<uint32_t *>(c->resident_io.base);
-    c->resident_move = reinterpret_cast<float *>(c->resident_io.base + 64);
-    c->resident_result = c->resident_move + 3 * size_t(n) + ((4 - (3 * size_t(n)) % 4) % 4);       // float4-aligned
+    if (io_flags) {
+        c->resident_flags = io_flags; c->resident_move = io_move; c->resident_result = io_result;
+    } else {
+        PRTC_CUDA(c->resident_io.reserve(64 + size_t(n) * 7 * sizeof(float) + 64));
+        c->resident_flags = reinterpret_cast<uint32_t *>(c->resident_io.base);
+        c->resident_move = reinterpret_cast<float *>(c->resident_io.base + 64);
+        c->resident_result = c->resident_move + 3 * size_t(n) + ((4 - (3 * size_t(n)) % 4) % 4);       // float4-aligned
+    }
     c->resident_flags[0] = 0u; c->resident_flags[1] = 0u; c->resident_flags[2] = 0u;
     c->resident_frame = 0;
     if (n) {
@@ -668,20 +682,14 @@ int prtc_resident_begin(prtc_ctx * c, uint32_t n, const prtc_transform * tf, con
     return PRTC_OK;
 }
 
-int prtc_resident_io(prtc_ctx * c, float ** movement, float ** result) {
-    if (!c || !c->resident) return fail(PRTC_ERR_INVALID, "prtc_resident_io: call prtc_resident_begin first");
-    if (movement) *movement = c->resident_move;
-    if (result) *result = c->resident_result;
-    return PRTC_OK;
-}
-
-int prtc_resident_step(prtc_ctx * c, float dt) {
+int resident_launch(prtc_ctx * c, float dt) {
     if (!c || !c->resident) return fail(PRTC_ERR_INVALID, "prtc_resident_step: call prtc_resident_begin first");
     int rc = check_mode(c, true);
     if (rc) return rc;
     PRTC_CUDA(cudaSetDevice(c->cfg.device));
     if (c->geometry_dirty || c->tree_dirty || c->capsules_dirty) { rc = commit_impl(c); if (rc) return rc; }
     const uint32_t n = c->resident_n;
+    c->resident_pending = 0u;
     if (n == 0) return PRTC_OK;
     StepParams p;
     rc = fill_params(c, dt, n, c->d_tf.ptr, c->d_ph.ptr, p);
@@ -694,32 +702,40 @@ int prtc_resident_step(prtc_ctx * c, float dt) {
         // the records of the dynamic pass are built from the state BEFORE this frame's movement input is applied: movement
         // only enters the step (physics_system.cpp:281-282), not the predicted box (:263-273)
         if (!c->dyn_prepared) { rc = dyn_prepare(c, dt, n, c->d_tf.ptr, c->d_ph.ptr); if (rc) return rc; }
-        rc = dyn_build_grid(c, p);
+        rc = dyn_build_grid_for(c, p);
         if (rc) return rc;
         c->dyn_prepared = false;
         mode = STEP_JACOBI;
     }
     // completion doorbell: the last warp of the step's last kernel writes the frame number to a host-mapped word; spinning on
     // it returns a few microseconds after the kernel ends, where cudaStreamSynchronize's wake-up costs 10-20
-    const bool bell = c->doorbell != 0;
-    if (bell) {
+    if (c->doorbell) {
         p.done_flag = c->resident_flags + 2;
         p.done_count = c->d_work.ptr + 6;
         p.done_value = ++c->resident_frame;
         if (p.done_value == 0u) p.done_value = ++c->resident_frame;
+        c->resident_pending = p.done_value;
     }
     c->launches += uint64_t(launch_step(p, false, mode, c->stream));
     PRTC_CUDA(cudaGetLastError());
-    if (bell) {
+    return PRTC_OK;
+}
+
+int resident_wait(prtc_ctx * c) {
+    if (!c || !c->resident) return fail(PRTC_ERR_INVALID, "prtc_resident_step: call prtc_resident_begin first");
+    if (c->resident_n == 0) return PRTC_OK;
+    PRTC_CUDA(cudaSetDevice(c->cfg.device));
+    if (c->resident_pending) {
         volatile uint32_t * flag = c->resident_flags + 2;
         uint32_t spins = 0;
-        while (*flag != p.done_value) {
+        while (*flag != c->resident_pending) {
             if ((++spins & 0xFFFu) == 0u) {                        // now and then: did the stream die, or finish without ringing?
                 const cudaError_t q = cudaStreamQuery(c->stream);
                 if (q == cudaSuccess) break;
                 if (q != cudaErrorNotReady) return fail(PRTC_ERR_CUDA, std::string("prtc_resident_step: ") + cudaGetErrorString(q));
             }
         }
+        c->resident_pending = 0u;
     } else {
         PRTC_CUDA(cudaStreamSynchronize(c->stream));
     }
@@ -728,6 +744,33 @@ int prtc_resident_step(prtc_ctx * c, float dt) {
         return check_bad_colliders(c);
     }
     return PRTC_OK;
+}
+
+} // namespace host
+} // namespace prt
+
+extern "C" {
+
+// ---- resident state ------------------------------------------------------------------------------------------------
+// What the engine's caller does around updateCharacters is gather -> call -> scatter of positions (character_system.cpp:
+// 55-78); the records themselves need not cross the bus every frame.  With resident state they stay on the device, the
+// caller writes this frame's movementVector into a mapped pinned array the kernel reads in place, and position + isGrounded
+// come back through a second mapped array the kernel writes in place: 12 bytes in and 16 bytes out per character instead
+// of 84 + 84, no separate copies, one launch and one synchronisation per frame.
+int prtc_resident_begin(prtc_ctx * c, uint32_t n, const prtc_transform * tf, const prtc_char_physics * ph) {
+    return resident_begin_impl(c, n, tf, ph, nullptr, nullptr, nullptr);
+}
+
+int prtc_resident_io(prtc_ctx * c, float ** movement, float ** result) {
+    if (!c || !c->resident) return fail(PRTC_ERR_INVALID, "prtc_resident_io: call prtc_resident_begin first");
+    if (movement) *movement = c->resident_move;
+    if (result) *result = c->resident_result;
+    return PRTC_OK;
+}
+
+int prtc_resident_step(prtc_ctx * c, float dt) {
+    const int rc = resident_launch(c, dt);
+    return rc ? rc : resident_wait(c);
 }
 
 int prtc_resident_edit(prtc_ctx * c, uint32_t k, const uint32_t * indices, const prtc_transform * tf, const prtc_char_physics * ph) {

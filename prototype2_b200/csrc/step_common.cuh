@@ -29,6 +29,55 @@ __device__ __forceinline__ int dyn_cell(float v, float origin, float inv_cell, u
     return c;
 }
 
+constexpr int DYN_CAP = 16;      // capsule neighbours buffered per lane and pass of the JACOBI pass
+
+// JACOBI pass: the (at most DYN_CAP) smallest record indices > `last` of the characters other than `self` whose STORED fat
+// box overlaps `b`, ascending, into col[0], col[32], col[64], ... (one column of a [DYN_CAP][32] shared array); `more` says
+// that there are further ones (call again with last = the largest returned).  Every record lives in the cell of its stored
+// box's lower corner, so the cells to look at are those of `b` and `reach` cells before them.
+struct DynGrid {
+    const float4 * dyn_records; const uint32_t * dyn_cell_start, * dyn_items, * dyn_reach;
+    uint32_t dyn_gx, dyn_gz; float dyn_origin_x, dyn_origin_z, dyn_inv_cell;
+};
+__device__ __forceinline__ DynGrid dyn_grid_of(StepParams const & q) {
+    DynGrid g;
+    g.dyn_records = q.dyn_records; g.dyn_cell_start = q.dyn_cell_start; g.dyn_items = q.dyn_items; g.dyn_reach = q.dyn_reach;
+    g.dyn_gx = q.dyn_gx; g.dyn_gz = q.dyn_gz; g.dyn_origin_x = q.dyn_origin_x; g.dyn_origin_z = q.dyn_origin_z; g.dyn_inv_cell = q.dyn_inv_cell;
+    return g;
+}
+// (not inlined: it is called from two places of the pooled kernel, whose instruction footprint matters)
+static __device__ __noinline__ uint32_t dyn_collect(DynGrid p, Box b, uint32_t self, long long last, uint32_t * col, bool & more) {
+    const int rx = int(__ldg(p.dyn_reach)), rz = int(__ldg(p.dyn_reach + 1));
+    int cx0 = dyn_cell(b.lo.x, p.dyn_origin_x, p.dyn_inv_cell, p.dyn_gx) - rx, cz0 = dyn_cell(b.lo.z, p.dyn_origin_z, p.dyn_inv_cell, p.dyn_gz) - rz;
+    const int cx1 = dyn_cell(b.hi.x, p.dyn_origin_x, p.dyn_inv_cell, p.dyn_gx), cz1 = dyn_cell(b.hi.z, p.dyn_origin_z, p.dyn_inv_cell, p.dyn_gz);
+    if (cx0 < 0) cx0 = 0;
+    if (cz0 < 0) cz0 = 0;
+    uint32_t ncand = 0;
+    more = false;
+    for (int cz = cz0; cz <= cz1; ++cz) {
+        // the cells of one grid row are contiguous in the item array
+        const uint32_t beg = __ldg(p.dyn_cell_start + uint32_t(cz) * p.dyn_gx + uint32_t(cx0));
+        const uint32_t end = __ldg(p.dyn_cell_start + uint32_t(cz) * p.dyn_gx + uint32_t(cx1) + 1);
+        for (uint32_t k = beg; k < end; ++k) {
+            const uint32_t j = __ldg(p.dyn_items + k);
+            if (j == self || (long long)j <= last) continue;
+            const float4 blo = __ldg(p.dyn_records + 4 * size_t(j) + 2);
+            const float4 bhi = __ldg(p.dyn_records + 4 * size_t(j) + 3);
+            if (!node_overlaps(blo, bhi, b)) continue;
+            if (ncand == uint32_t(DYN_CAP)) {                     // keep the DYN_CAP smallest, sorted
+                more = true;
+                if (j > col[32 * (DYN_CAP - 1)]) continue;
+                --ncand;
+            }
+            uint32_t s = ncand;
+            while (s > 0 && col[32 * (s - 1)] > j) { col[32 * s] = col[32 * (s - 1)]; --s; }
+            col[32 * s] = j;
+            ++ncand;
+        }
+    }
+    return ncand;
+}
+
 // Conservative per-triangle pre-cull.  A contact needs `inside || intersects` (collision_system.cpp:101):
 //   intersects -> a point of the triangle lies within `radius` of `center`, and `center` lies on the segment AB;
 //   inside     -> point0 = center - n*dist lies in the triangle with 0 <= dist < dmax (the range cull :71-72), so
@@ -67,7 +116,6 @@ struct Parked {
 
 constexpr int STEP_BLOCK = 32;      // one warp per block: a finished warp frees its slot at once (2.79 -> 2.71 ms at C4 vs 128)
 constexpr int MODE_STATIC = 0, MODE_LITERAL = 1, MODE_JACOBI = 2;
-constexpr int DYN_CAP = 16;      // capsule neighbours buffered per lane and pass of the JACOBI pass
 constexpr int XC_CAP = 12;       // leaves per cached region slot (k_xc_refresh / k_step_stream)
 constexpr int TRI_RING = 2;      // triangles in flight per lane (cp.async ring in shared memory)
 constexpr int LEAF_CAP = 8;      // candidate leaves buffered per lane and pass (more => another pass)
