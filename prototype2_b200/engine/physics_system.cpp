@@ -29,10 +29,27 @@ PhysicsSystem::PhysicsSystem() {
     cfg.order_mode = PRTC_ORDER_LITERAL;
     if (char const * e = std::getenv("PRTC_ABS_MODE")) cfg.abs_mode = unsigned(std::atoi(e));   // see prtc_abs_mode
     if (char const * e = std::getenv("PRTC_DEVICE")) cfg.device = std::atoi(e);
+    if (char const * e = std::getenv("PRTC_ORDER")) cfg.order_mode = unsigned(std::atoi(e));     // see prtc_order_mode
+    if (char const * e = std::getenv("PRTC_DYN")) cfg.dyn_mode = unsigned(std::atoi(e));         // see prtc_dyn_mode
+    // PRTC_DEVICES=0,1,...: crowd-sized scenes over several GPUs of the node behind the same class surface (include/prtc.h
+    // prtc_multi_*): geometry replicated, characters partitioned.  CANONICAL / BY_ID order only (LITERAL does not shard).
+    if (char const * e = std::getenv("PRTC_DEVICES")) {
+        std::vector<int32_t> devices;
+        for (char const * p = e; *p;) {
+            devices.push_back(int32_t(std::strtol(p, const_cast<char **>(&p), 10)));
+            while (*p == ',' || *p == ' ') ++p;
+        }
+        if (cfg.order_mode == PRTC_ORDER_LITERAL) cfg.order_mode = PRTC_ORDER_CANONICAL;
+        check(prtc_multi_create(&cfg, devices.data(), uint32_t(devices.size()), &m_multi), "PhysicsSystem");
+        return;
+    }
     check(prtc_create(&cfg, &m_ctx), "PhysicsSystem");
 }
 
-PhysicsSystem::~PhysicsSystem() { prtc_destroy(m_ctx); }
+PhysicsSystem::~PhysicsSystem() {
+    if (m_multi) prtc_multi_destroy(m_multi);
+    else prtc_destroy(m_ctx);
+}
 
 // CollisionSystem::newFrame only rotates the collision-event sets, which nothing reads and which this
 // implementation does not produce.
@@ -42,7 +59,7 @@ ColliderTag PhysicsSystem::addCapsuleCollider(float height, float radius, glm::v
     assert(m_capsules.size() < 65535 && "Too many capsule colliders!");
     float const off[3] = {offset.x, offset.y, offset.z};
     uint32_t id = 0;
-    check(prtc_add_capsule(m_ctx, height, radius, off, &id), "addCapsuleCollider");
+    check(m_multi ? prtc_multi_add_capsule(m_multi, height, radius, off, &id) : prtc_add_capsule(m_ctx, height, radius, off, &id), "addCapsuleCollider");
     CapsuleCollider c;
     c.height = height; c.radius = radius; c.offset = offset;
     m_capsules.push_back(c);
@@ -69,7 +86,8 @@ ColliderTag PhysicsSystem::addModelCollider(Model const & model, Transform const
     prtc_transform t;
     std::memcpy(&t, &transform, sizeof(t));
     uint32_t modelId = 0;
-    check(prtc_add_model(m_ctx, xyz.data(), uint32_t(xyz.size() / 3), first.data(), count.data(), uint32_t(first.size()),
+    check(m_multi ? prtc_multi_add_model(m_multi, xyz.data(), uint32_t(xyz.size() / 3), first.data(), count.data(), uint32_t(first.size()),
+                         &t, &modelId, nullptr) : prtc_add_model(m_ctx, xyz.data(), uint32_t(xyz.size() / 3), first.data(), count.data(), uint32_t(first.size()),
                          &t, &modelId, nullptr), "addModelCollider");
     ColliderTag tag;
     tag.index = uint16_t(modelId);
@@ -80,7 +98,7 @@ ColliderTag PhysicsSystem::addModelCollider(Model const & model, Transform const
 void PhysicsSystem::removeCollider(ColliderTag const & tag) {
     switch (tag.shape) {
         case COLLIDER_SHAPE_MODEL:
-            check(prtc_remove_model(m_ctx, tag.index), "removeCollider");
+            check(m_multi ? prtc_multi_remove_model(m_multi, tag.index) : prtc_remove_model(m_ctx, tag.index), "removeCollider");
             break;
         case COLLIDER_SHAPE_CAPSULE:
             assert(false && "Not yet implemeneted!");            // as in the reference (physics_system.cpp:113-115)
@@ -110,14 +128,14 @@ void PhysicsSystem::updateModelColliders(ColliderTag const * tags, Transform con
         ids[i] = tags[i].index;
         std::memcpy(&tf[i], &transforms[i], sizeof(prtc_transform));
     }
-    check(prtc_update_models(m_ctx, ids.data(), tf.data(), uint32_t(count)), "updateModelColliders");
+    check(m_multi ? prtc_multi_update_models(m_multi, ids.data(), tf.data(), uint32_t(count)) : prtc_update_models(m_ctx, ids.data(), tf.data(), uint32_t(count)), "updateModelColliders");
 }
 
 bool PhysicsSystem::raycast(glm::vec3 const & origin, glm::vec3 const & direction, float maxDistance, glm::vec3 & hit) {
     float const o[3] = {origin.x, origin.y, origin.z}, d[3] = {direction.x, direction.y, direction.z};
     float h[3] = {0.0f, 0.0f, 0.0f};
     uint8_t mask = 0;
-    check(prtc_raycast(m_ctx, 1, o, d, &maxDistance, h, &mask), "raycast");
+    check(m_multi ? prtc_multi_raycast(m_multi, 1, o, d, &maxDistance, h, &mask) : prtc_raycast(m_ctx, 1, o, d, &maxDistance, h, &mask), "raycast");
     if (mask) hit = glm::vec3(h[0], h[1], h[2]);
     return mask != 0;
 }
@@ -132,7 +150,7 @@ void PhysicsSystem::updateCharacters(float deltaTime, Scene & scene, Transform *
         CapsuleCollider & b = m_uploaded[i];
         if (a.height != b.height || a.radius != b.radius || a.offset.x != b.offset.x || a.offset.y != b.offset.y || a.offset.z != b.offset.z) {
             float const off[3] = {a.offset.x, a.offset.y, a.offset.z};
-            check(prtc_update_capsule(m_ctx, uint32_t(i), a.height, a.radius, off), "updateCharacters");
+            check(m_multi ? prtc_multi_update_capsule(m_multi, uint32_t(i), a.height, a.radius, off) : prtc_update_capsule(m_ctx, uint32_t(i), a.height, a.radius, off), "updateCharacters");
             b = a;
         }
     }
@@ -151,7 +169,7 @@ void PhysicsSystem::updateCharacters(float deltaTime, Scene & scene, Transform *
         q.grounded = p.isGrounded ? 1u : 0u;
     }
 
-    check(prtc_step_characters(m_ctx, deltaTime, uint32_t(n), m_tf.data(), m_ph.data()), "updateCharacters");
+    check(m_multi ? prtc_multi_step_characters(m_multi, deltaTime, uint32_t(n), m_tf.data(), m_ph.data()) : prtc_step_characters(m_ctx, deltaTime, uint32_t(n), m_tf.data(), m_ph.data()), "updateCharacters");
 
     // scatter: position is the only Transform field the reference writes (collision_system.cpp:242, physics_system.cpp:350,437)
     for (size_t i = 0; i < n; ++i) {

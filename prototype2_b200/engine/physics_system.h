@@ -21,6 +21,7 @@
 
 class Scene;
 struct prtc_ctx;
+struct prtc_multi;
 struct prtc_transform;
 struct prtc_char_physics;
 
@@ -48,6 +49,7 @@ public:
 
 private:
     prtc_ctx * m_ctx = nullptr;
+    prtc_multi * m_multi = nullptr;          // PRTC_DEVICES=...: several GPUs behind the same surface (include/prtc.h prtc_multi_*)
     std::vector<CapsuleCollider> m_capsules;      // what getCapsuleCollider hands out by reference ...
     std::vector<CapsuleCollider> m_uploaded;      // ... and what the device currently has (re-synced every frame)
     std::vector<prtc_transform> m_tf;

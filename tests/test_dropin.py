@@ -50,3 +50,25 @@ def test_same_caller_same_bytes(args, tmp_path):
     a, b = open(ref, "rb").read(), open(dro, "rb").read()
     assert len(a) == len(b) and len(a) > 1000
     assert a == b, "first difference at byte %d" % next(i for i in range(len(a)) if a[i] != b[i])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("args", [("32", "100", "120"), ("24", "60", "200", "4")])
+def test_drop_in_over_several_devices_same_bytes(args, tmp_path):
+    """PRTC_DEVICES: the same engine-side caller through the same class surface, the characters partitioned over several
+    contexts (two on cuda:0; one per GPU when the box has more than one) -- byte-identical to one context in the same
+    (canonical) order, with and without the dynamic-vs-dynamic pass"""
+    from prototype2_b200 import capi
+    for dyn in ("0", "2"):
+        env = dict(os.environ, PRTC_ORDER="1", PRTC_DYN=dyn)
+        env.pop("PRTC_DEVICES", None)
+        one = str(tmp_path / ("one%s.bin" % dyn))
+        subprocess.run([os.path.join(BIN, "driver_dropin"), *args[:3], one, *args[3:]], check=True, env=env)
+        a = open(one, "rb").read()
+        sets = ["0,0", "0,0,0"] + ([",".join(str(k) for k in range(min(8, capi.device_count())))] if capi.device_count() >= 2 else [])
+        for devs in sets:
+            out = str(tmp_path / "multi.bin")
+            subprocess.run([os.path.join(BIN, "driver_dropin"), *args[:3], out, *args[3:]], check=True, env=dict(env, PRTC_DEVICES=devs))
+            b = open(out, "rb").read()
+            assert len(a) == len(b) and len(a) > 1000
+            assert a == b, "PRTC_DEVICES=%s dyn=%s: first difference at byte %d" % (devs, dyn, next(i for i in range(len(a)) if a[i] != b[i]))
