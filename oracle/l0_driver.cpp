@@ -152,6 +152,19 @@ int l0_add_model(void * h, const float * xyz, uint32_t n_idx,
     return int(tag.index);
 }
 
+// PhysicsSystem::removeCollider for a MODEL tag (physics_system.cpp:108-149).  Only well defined in the reference when the
+// model is the most recently added one AND its first mesh index equals its model index (e.g. every model has one mesh):
+// later meshes keep stale indices in the tree after the arrays are compacted (:141-146), and geometries[] is cleared at
+// the MESH start index (:148, trap T19).  The tests stay inside that envelope.
+void l0_remove_model(void * h, uint32_t model_index) {
+    World * w = static_cast<World *>(h);
+    ColliderTag tag;
+    tag.index = ColliderIndex(model_index);
+    tag.shape = COLLIDER_SHAPE_MODEL;
+    tag.type = COLLIDER_TYPE_COLLIDE;
+    w->ps.removeCollider(tag);
+}
+
 // adds the capsule collider AND the character that owns it (character i <-> capsule i)
 int l0_add_capsule(void * h, float height, float radius, const float * off3) {
     World * w = static_cast<World *>(h);

@@ -904,6 +904,22 @@ void l1_update_model(void * h, uint32_t model_index, const float * tform10) {
     w.tree.update(&w.meshTreeIdx[col.firstMesh], &w.meshAABBs[col.firstMesh], col.numMeshes);
 }
 
+// PhysicsSystem::removeCollider for a MODEL tag (physics_system.cpp:108-149): the model's mesh leaves leave the tree, in
+// mesh order (aabb_tree.cpp: remove per leaf).  The widened restatement keeps the ids of the other colliders stable -- the
+// reference compacts its mesh arrays but leaves the tree's tags stale (:141-146), which only works out when the removed
+// model is the last one (the envelope in which L0 and this function are compared, tests/test_oracle_pinning.py); the
+// follow-up tree.update of the later leaves (:137-140) is a no-op (their boxes have not changed).
+void l1_remove_model(void * h, uint32_t model_index) {
+    World & w = *static_cast<World *>(h);
+    World::ModelCol & col = w.models[model_index];
+    for (uint32_t m = col.firstMesh; m < col.firstMesh + col.numMeshes; ++m) {
+        if (w.meshTreeIdx[m] >= 0) w.tree.remove(w.meshTreeIdx[m]);
+        w.meshTreeIdx[m] = -1;
+        w.meshes[m].count = 0;
+    }
+    col.numMeshes = 0;
+}
+
 // physics_system.cpp:22-42 (+ the character that owns the capsule)
 int l1_add_capsule(void * h, float height, float radius, const float * off3) {
     World & w = *static_cast<World *>(h);

@@ -90,7 +90,14 @@ ColliderTag PhysicsSystem::addModelCollider(Model const & model, Transform const
                          &t, &modelId, nullptr) : prtc_add_model(m_ctx, xyz.data(), uint32_t(xyz.size() / 3), first.data(), count.data(), uint32_t(first.size()),
                          &t, &modelId, nullptr), "addModelCollider");
     ColliderTag tag;
-    tag.index = uint16_t(modelId);
+    if (!m_modelFree.empty()) {                                   // physics_system.cpp:49-56: the last freed index first
+        tag.index = m_modelFree.back();
+        m_modelFree.pop_back();
+        m_modelSlots[tag.index] = modelId;
+    } else {
+        tag.index = uint16_t(m_modelSlots.size());
+        m_modelSlots.push_back(modelId);
+    }
     tag.shape = COLLIDER_SHAPE_MODEL;
     return tag;
 }
@@ -98,7 +105,9 @@ ColliderTag PhysicsSystem::addModelCollider(Model const & model, Transform const
 void PhysicsSystem::removeCollider(ColliderTag const & tag) {
     switch (tag.shape) {
         case COLLIDER_SHAPE_MODEL:
-            check(m_multi ? prtc_multi_remove_model(m_multi, tag.index) : prtc_remove_model(m_ctx, tag.index), "removeCollider");
+            assert(tag.index < m_modelSlots.size());
+            check(m_multi ? prtc_multi_remove_model(m_multi, m_modelSlots[tag.index]) : prtc_remove_model(m_ctx, m_modelSlots[tag.index]), "removeCollider");
+            m_modelFree.push_back(tag.index);                     // physics_system.cpp:123
             break;
         case COLLIDER_SHAPE_CAPSULE:
             assert(false && "Not yet implemeneted!");            // as in the reference (physics_system.cpp:113-115)
@@ -125,7 +134,8 @@ void PhysicsSystem::updateModelColliders(ColliderTag const * tags, Transform con
     std::vector<prtc_transform> tf(count);
     for (size_t i = 0; i < count; ++i) {
         assert(tags[i].shape == COLLIDER_SHAPE_MODEL);
-        ids[i] = tags[i].index;
+        assert(tags[i].index < m_modelSlots.size());
+        ids[i] = m_modelSlots[tags[i].index];
         std::memcpy(&tf[i], &transforms[i], sizeof(prtc_transform));
     }
     check(m_multi ? prtc_multi_update_models(m_multi, ids.data(), tf.data(), uint32_t(count)) : prtc_update_models(m_ctx, ids.data(), tf.data(), uint32_t(count)), "updateModelColliders");

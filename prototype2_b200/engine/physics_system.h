@@ -52,6 +52,10 @@ private:
     prtc_multi * m_multi = nullptr;          // PRTC_DEVICES=...: several GPUs behind the same surface (include/prtc.h prtc_multi_*)
     std::vector<CapsuleCollider> m_capsules;      // what getCapsuleCollider hands out by reference ...
     std::vector<CapsuleCollider> m_uploaded;      // ... and what the device currently has (re-synced every frame)
+    // the reference hands out model indices from a LIFO free list (physics_system.cpp:49-56,122-123): the tag index is the
+    // slot, the slot holds the C-ABI's (never reused) model id
+    std::vector<uint32_t> m_modelSlots;
+    std::vector<uint16_t> m_modelFree;
     std::vector<prtc_transform> m_tf;
     std::vector<prtc_char_physics> m_ph;
     float m_gravity = 1.0f;                       // physics_system.h:122

@@ -36,16 +36,22 @@ int main(int argc, char ** argv) {
     int const frames = argc > 3 ? std::atoi(argv[3]) : 40;
     char const * outPath = argc > 4 ? argv[4] : "dump.bin";
     if (argc > 5) rng_state = uint32_t(std::strtoul(argv[5], nullptr, 10));   // another crowd on the same level
+    // "props": the map is ONE mesh and two one-mesh platforms stand on it, which are removed and re-added during the run
+    // (Scene::loadModel, scene.cpp:354-359: removeCollider + addModelCollider).  One mesh per model and last-added-first
+    // removal is the envelope in which the reference's removeModelCollider is well defined (physics_system.cpp:141-148:
+    // stale tree tags after the arrays are compacted, geometries[] cleared at the MESH start index).
+    bool const props = argc > 6 && std::strcmp(argv[6], "props") == 0;
 
     PhysicsSystem physics;
     Scene scene;
 
     // a terrain model with one mesh per 2x2 cells, registered like SceneSerialization does for a MODEL collider
     Model model;
-    for (int bx = 0; bx < N; bx += 2) for (int bz = 0; bz < N; bz += 2) {
+    int const block = props ? N : 2;
+    for (int bx = 0; bx < N; bx += block) for (int bz = 0; bz < N; bz += block) {
         Model::Mesh mesh;
         mesh.startIndex = model.indexBuffer.size();
-        for (int x = bx; x < bx + 2 && x < N; ++x) for (int z = bz; z < bz + 2 && z < N; ++z) {
+        for (int x = bx; x < bx + block && x < N; ++x) for (int z = bz; z < bz + block && z < N; ++z) {
             float const xs[4] = {float(x), float(x), float(x + 1), float(x + 1)};
             float const zs[4] = {float(z), float(z + 1), float(z + 1), float(z)};
             int const order[6] = {0, 1, 2, 0, 2, 3};
@@ -62,6 +68,36 @@ int main(int argc, char ** argv) {
     Transform mapTransform;
     mapTransform.scale = glm::vec3(1.5f, 1.0f, 1.5f);
     ColliderTag mapTag = physics.addModelCollider(model, mapTransform);
+
+    // the platforms: a 4x4-cell slab, one mesh each
+    auto slab = [](float y) {
+        Model m;
+        Model::Mesh mesh;
+        mesh.startIndex = 0;
+        for (int x = 0; x < 4; ++x) for (int z = 0; z < 4; ++z) {
+            float const xs[4] = {float(x), float(x), float(x + 1), float(x + 1)};
+            float const zs[4] = {float(z), float(z + 1), float(z + 1), float(z)};
+            int const order[6] = {0, 1, 2, 0, 2, 3};
+            for (int k = 0; k < 6; ++k) {
+                Model::Vertex v;
+                v.pos = glm::vec3(xs[order[k]], y, zs[order[k]]);
+                m.indexBuffer.push_back(uint32_t(m.vertexBuffer.size()));
+                m.vertexBuffer.push_back(v);
+            }
+        }
+        mesh.numIndices = m.indexBuffer.size();
+        m.meshes.push_back(mesh);
+        return m;
+    };
+    Model const slabModel = slab(1.2f);
+    ColliderTag propTag[2];
+    Transform propTransform[2];
+    std::vector<uint8_t> dump;
+    if (props) {
+        propTransform[0].position = glm::vec3(4.0f, 0.0f, 4.0f);
+        propTransform[1].position = glm::vec3(0.4f * 1.5f * float(N), 0.3f, 0.5f * 1.5f * float(N));
+        for (int k = 0; k < 2; ++k) { propTag[k] = physics.addModelCollider(slabModel, propTransform[k]); put(dump, &propTag[k].index, sizeof(propTag[k].index)); }
+    }
 
     // characters with capsule colliders (cavern.prt:9 values), some of them overlapping each other
     std::vector<Transform> transforms{static_cast<size_t>(nChars)};
@@ -88,7 +124,6 @@ int main(int argc, char ** argv) {
         }
         if (FILE * fi = std::fopen(initPath, "wb")) { std::fwrite(init.data(), 1, init.size(), fi); std::fclose(fi); }
     }
-    std::vector<uint8_t> dump;
     std::vector<double> stepTimes, rayTimes;             // native cost of the two per-frame entry points, microseconds
     typedef std::chrono::steady_clock Clock;
     for (int f = 0; f < frames; ++f) {
@@ -100,6 +135,22 @@ int main(int argc, char ** argv) {
         if (f == 20) {                                   // the editor moves the map (editor.cpp:40 -> scene.cpp:190-211)
             mapTransform.position = glm::vec3(0.25f, -0.1f, 0.0f);
             physics.updateModelColliders(&mapTag, &mapTransform, 1);
+        }
+        if (props) {                                     // Scene::loadModel: removeCollider + addModelCollider (scene.cpp:354-359)
+            if (f == 30) physics.removeCollider(propTag[1]);
+            if (f == 45) {
+                propTransform[1].position = propTransform[1].position + glm::vec3(1.0f, 0.4f, -1.0f);
+                propTag[1] = physics.addModelCollider(slabModel, propTransform[1]);
+                put(dump, &propTag[1].index, sizeof(propTag[1].index));          // the freed index comes back (physics_system.cpp:49-51)
+            }
+            if (f == 60) { physics.removeCollider(propTag[1]); physics.removeCollider(propTag[0]); }
+            if (f == 70) {
+                for (int k = 0; k < 2; ++k) {
+                    propTransform[k].position = propTransform[k].position + glm::vec3(-0.5f, -0.2f, 0.5f);
+                    propTag[k] = physics.addModelCollider(slabModel, propTransform[k]);
+                    put(dump, &propTag[k].index, sizeof(propTag[k].index));
+                }
+            }
         }
         if (f == 25 && nChars > 2)                       // the editor edits a capsule (editor_gui.cpp:293-301)
             physics.updateCapsuleCollider(scene.getCharacterSystem().getCharacter(2).physics.colliderTag, 0.8f, 0.4f, glm::vec3(0.0f, 0.4f, 0.0f));

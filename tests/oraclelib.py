@@ -146,6 +146,10 @@ class L0World(_World):
     def update_capsule(self, capsule_index, height, radius, offset):
         self._fn("update_capsule")(self.h, _u32(capsule_index), _f(height), _f(radius), _ptr(_f32(offset)))
 
+    def remove_model(self, model_index):
+        """PhysicsSystem::removeCollider(MODEL tag); see the envelope note at l0_remove_model"""
+        self._fn("remove_model")(self.h, _u32(model_index))
+
     def dump_order(self):
         m = np.zeros(70000, np.uint16)
         c = np.zeros(70000, np.uint16)
@@ -182,6 +186,9 @@ class L1World(_World):
 
     def update_model(self, model_index, transform):
         self._fn("update_model")(self.h, _u32(model_index), _ptr(_f32(transform)))
+
+    def remove_model(self, model_index):
+        self._fn("remove_model")(self.h, _u32(model_index))
 
     def counters(self, reset=False):
         out = np.zeros(5, np.uint64)

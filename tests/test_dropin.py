@@ -41,8 +41,10 @@ def test_drop_in_keeps_the_reference_class_surface():
 # the long runs matter: the map is moved at frame 20 and a wrong ORDER of tree operations (mesh leaves re-inserted after
 # instead of before the capsule leaves of that frame) only showed as a different candidate order at frame 63 and as a
 # 1-ulp position difference at frame 84
+# ("props": the map as one mesh plus two one-mesh platforms that are removed and re-added mid-run, tag indices in the dump)
 @pytest.mark.parametrize("args", [("24", "12", "40"), ("40", "60", "30"), ("16", "1", "60"), ("24", "12", "300"), ("48", "100", "300"),
-                                  ("32", "100", "150"), ("12", "30", "300", "3"), ("10", "100", "200", "5")])
+                                  ("32", "100", "150"), ("12", "30", "300", "3"), ("10", "100", "200", "5"),
+                                  ("12", "40", "120", "7", "props"), ("10", "80", "200", "9", "props")])
 def test_same_caller_same_bytes(args, tmp_path):
     ref, dro = str(tmp_path / "ref.bin"), str(tmp_path / "dropin.bin")
     subprocess.run([os.path.join(BIN, "driver_reference"), *args[:3], ref, *args[3:]], check=True)      # [3] = seed of the crowd

@@ -210,3 +210,47 @@ def test_l1_update_model_equals_reference():
         assert H.trace_diff(t0, t1, Trace.FIELDS) == [], "frame %d" % f
         assert H.state_diff(l0.get_state(), l1.get_state()) == [], "frame %d" % f
         assert H.same(l0.dump_order()[0], l1.dump_order()[0]), "tree order diverged at frame %d" % f
+
+
+@pytest.mark.skipif(not L0World.available("plain"), reason="oracle/_ref not built")
+def test_l1_remove_and_re_add_equals_the_reference():
+    """removeCollider + addModelCollider (physics_system.cpp:108-149, 44-106): the restatement goes through the same tree
+    removals and insertions as the reference's own code; one-mesh models removed last-first (the envelope in which the
+    reference is well defined, see oracle/l0_driver.cpp l0_remove_model)"""
+    def patch(x0, z0, y, n=6):
+        xyz, mf, mc = H.scenes.terrain(n, n, n)
+        xyz = xyz.copy()
+        xyz[:, 1] = np.float32(y); xyz[:, 0] += np.float32(x0); xyz[:, 2] += np.float32(z0)
+        return xyz, mf, mc
+    l0, l1 = L0World("plain"), L1World("literal")
+    ids = []
+    for pch in (patch(0, 0, 0.0), patch(6, 0, 0.25), patch(0, 6, -0.25)):
+        assert l0.add_model(*pch) == len(ids)
+        ids.append(l1.add_model(*pch))
+    n = 50
+    rs = np.random.RandomState(11)
+    pos = np.stack([rs.uniform(0.8, 11.2, n), rs.uniform(0.8, 1.6, n), rs.uniform(0.8, 11.2, n)], axis=1).astype(np.float32)
+    vel = rs.uniform(-0.05, 0.05, (n, 3)).astype(np.float32)
+    for w in (l0, l1):
+        for _ in range(n):
+            w.add_capsule()
+        w.set_state(pos=pos, vel=vel)
+
+    def frames(k, what):
+        for f in range(k):
+            l0.step(1.0 / 30.0)
+            l1.step(1.0 / 30.0)
+            assert H.state_diff(l0.get_state(), l1.get_state()) == [], "%s, frame %d" % (what, f)
+            assert np.array_equal(l0.dump_order()[1], l1.dump_order()[1]), what      # capsule leaves in the same DFS order
+    frames(5, "three models")
+    l0.remove_model(2); l1.remove_model(ids[2])
+    frames(5, "last removed")
+    lower = patch(0, 6, -0.75)
+    assert l0.add_model(*lower) == 2
+    ids[2] = l1.add_model(*lower)
+    frames(5, "re-added")
+    l0.remove_model(2); l1.remove_model(ids[2]); l0.remove_model(1); l1.remove_model(ids[1])
+    frames(4, "two removed")
+    assert l0.add_model(*patch(6, 0, -0.5)) == 1
+    ids[1] = l1.add_model(*patch(6, 0, -0.5))
+    frames(6, "one re-added")
