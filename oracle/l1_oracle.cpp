@@ -29,6 +29,7 @@
 #include <algorithm>
 #include <climits>
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <vector>
@@ -517,6 +518,15 @@ struct World {
     Tree tree;
     Trace trace;
     Counters counters;
+    // JACOBI neighbour search at scale: uniform xz grid over the stored fat boxes, rebuilt once per frame (the stored boxes
+    // are fixed within a frame).  Pure acceleration: a query collects the boxes binned in the cells it touches, de-duplicates,
+    // keeps those that pass the same box_intersect as the brute-force loop, ascending.  Boxes or queries with a non-finite
+    // coordinate (box_intersect is true for NaN, aabb.cpp:3-10) bypass the grid.
+    struct DynGrid {
+        float ox = 0, oz = 0, inv = 0; int gx = 0, gz = 0;
+        std::vector<uint32_t> start, items, always;
+        bool valid = false;
+    } dyn_grid;
 };
 
 struct Scratch {
@@ -697,8 +707,26 @@ void collideCharacterWithWorld(World & w, uint32_t ci, Scratch & s, Counters & c
             if (w.cfg.order_mode == 2) std::sort(s.meshIDs.begin(), s.meshIDs.end());
             if (w.cfg.dyn_mode == 2) {
                 // canonical neighbour rule: ascending capsule index over the stored fat AABBs
-                for (uint32_t j = 0; j < uint32_t(w.capsules.size()); ++j)
-                    if (j != ci && box_intersect(w.capsuleStored[j], eAABB)) s.capsIDs.push_back(j);
+                World::DynGrid const & g = w.dyn_grid;
+                const float fin = (eAABB.lo.x + eAABB.lo.z) + (eAABB.hi.x + eAABB.hi.z);
+                if (!g.valid || !(fin - fin == 0.0f)) {
+                    for (uint32_t j = 0; j < uint32_t(w.capsules.size()); ++j)
+                        if (j != ci && box_intersect(w.capsuleStored[j], eAABB)) s.capsIDs.push_back(j);
+                } else {
+                    auto cell = [&](float v, float o, int n) { int c = int(std::floor((v - o) * g.inv)); return c < 0 ? 0 : (c >= n ? n - 1 : c); };
+                    const int x0 = cell(eAABB.lo.x, g.ox, g.gx), x1 = cell(eAABB.hi.x, g.ox, g.gx);
+                    const int z0 = cell(eAABB.lo.z, g.oz, g.gz), z1 = cell(eAABB.hi.z, g.oz, g.gz);
+                    for (int z = z0; z <= z1; ++z)
+                        for (int x = x0; x <= x1; ++x)
+                            for (uint32_t k = g.start[size_t(z) * g.gx + x]; k < g.start[size_t(z) * g.gx + x + 1]; ++k) s.capsIDs.push_back(g.items[k]);
+                    for (uint32_t j : g.always) s.capsIDs.push_back(j);
+                    std::sort(s.capsIDs.begin(), s.capsIDs.end());
+                    s.capsIDs.erase(std::unique(s.capsIDs.begin(), s.capsIDs.end()), s.capsIDs.end());
+                    size_t keep = 0;
+                    for (uint32_t j : s.capsIDs)
+                        if (j != ci && box_intersect(w.capsuleStored[j], eAABB)) s.capsIDs[keep++] = j;
+                    s.capsIDs.resize(keep);
+                }
             }
         }
         ++cnt.substeps;
@@ -818,8 +846,69 @@ void updateCharacters(World & w, float deltaTime) {
         } else {
             // JACOBI (frame-level snapshot): every capsule collides against the start-of-frame pose of the others
             std::vector<Transform> snapshot(w.transforms);
-            Scratch s;
-            for (uint32_t i = 0; i < n; ++i) collideCharacterWithWorld(w, i, s, w.counters, &snapshot);
+            {   // the grid over this frame's stored boxes (every box in every cell it touches)
+                World::DynGrid & g = w.dyn_grid;
+                g.valid = false; g.always.clear();
+                float lox = 3e38f, loz = 3e38f, hix = -3e38f, hiz = -3e38f;
+                std::vector<uint8_t> finite(n);
+                for (uint32_t i = 0; i < n; ++i) {
+                    Box const & b = w.capsuleStored[i];
+                    const float f = (b.lo.x + b.lo.z) + (b.hi.x + b.hi.z);
+                    finite[i] = (f - f == 0.0f) && std::fabs(b.lo.x) < 1e7f && std::fabs(b.hi.x) < 1e7f && std::fabs(b.lo.z) < 1e7f && std::fabs(b.hi.z) < 1e7f;
+                    if (!finite[i]) { g.always.push_back(i); continue; }
+                    lox = std::min(lox, b.lo.x); loz = std::min(loz, b.lo.z); hix = std::max(hix, b.hi.x); hiz = std::max(hiz, b.hi.z);
+                }
+                if (n >= 2048 && hix > lox && hiz > loz && !std::getenv("PRT_L1_NO_GRID")) {     // (the switch lets the tests compare with the plain loop)
+                    const float cellsz = std::max(4.0f, std::max(hix - lox, hiz - loz) / 1024.0f);
+                    g.ox = lox; g.oz = loz; g.inv = 1.0f / cellsz;
+                    g.gx = std::max(1, int(std::ceil((hix - lox) * g.inv)) + 1); g.gz = std::max(1, int(std::ceil((hiz - loz) * g.inv)) + 1);
+                    auto cell = [&](float v, float o, int m) { int c = int(std::floor((v - o) * g.inv)); return c < 0 ? 0 : (c >= m ? m - 1 : c); };
+                    g.start.assign(size_t(g.gx) * g.gz + 1, 0u);
+                    for (int pass = 0; pass < 2; ++pass) {
+                        std::vector<uint32_t> fill(pass ? g.start : std::vector<uint32_t>());
+                        for (uint32_t i = 0; i < n; ++i) {
+                            if (!finite[i]) continue;
+                            Box const & b = w.capsuleStored[i];
+                            for (int z = cell(b.lo.z, g.oz, g.gz); z <= cell(b.hi.z, g.oz, g.gz); ++z)
+                                for (int x = cell(b.lo.x, g.ox, g.gx); x <= cell(b.hi.x, g.ox, g.gx); ++x) {
+                                    if (!pass) ++g.start[size_t(z) * g.gx + x + 1];
+                                    else g.items[fill[size_t(z) * g.gx + x]++] = i;
+                                }
+                        }
+                        if (!pass) {
+                            for (size_t c = 1; c < g.start.size(); ++c) g.start[c] += g.start[c - 1];
+                            g.items.assign(g.start.back(), 0u);
+                        }
+                    }
+                    g.valid = true;
+                }
+            }
+            // every capsule reads the snapshot and its own state only: independent units, like the static pass
+            int threads = w.trace.on ? 1 : int(std::max(1u, w.cfg.threads));
+            std::vector<Counters> tc{static_cast<size_t>(threads)};
+            std::atomic<uint32_t> next{0};
+            auto worker = [&](int tid) {
+                Scratch s;
+                Counters & c = tc[size_t(tid)];
+                for (;;) {
+                    uint32_t begin = next.fetch_add(256u);
+                    if (begin >= n) break;
+                    uint32_t end = std::min(n, begin + 256u);
+                    for (uint32_t i = begin; i < end; ++i) collideCharacterWithWorld(w, i, s, c, &snapshot);
+                }
+            };
+            if (threads == 1) {
+                worker(0);
+            } else {
+                std::vector<std::thread> pool;
+                for (int t = 0; t < threads; ++t) pool.emplace_back(worker, t);
+                for (auto & th : pool) th.join();
+            }
+            for (auto & c : tc) {
+                w.counters.substeps += c.substeps; w.counters.tri_tests += c.tri_tests;
+                w.counters.node_tests += c.node_tests; w.counters.contacts += c.contacts; w.counters.cc_tests += c.cc_tests;
+            }
+            w.dyn_grid.valid = false;
         }
     }
     for (uint32_t i = 0; i < n; ++i) phase3(w, i, deltaTime, prevVelocities[i]);

@@ -542,6 +542,42 @@ def test_jacobi_rotated_capsules_and_no_static_geometry():
     assert ctx.counters()["cc_tests"] > 0
 
 
+def test_c5_full_size_jacobi_against_the_oracle():
+    """config 5 at full size: 256 000 capsules x 1 002 528 triangles with the dynamic-vs-dynamic pass, 4 frames, every
+    character compared with the CPU oracle (grid-accelerated, all host threads) bit for bit, counters included; the same
+    batch split over two contexts behind prtc_multi gives the same bytes"""
+    from prototype2_b200 import capi
+    n = 256000
+    scene = H.make_scene(708, 2, 2, n, seed=12345)
+    morton = H.scenes.morton_order(scene["pos"], 708)
+    for k in ("pos", "vel", "rot", "move"):
+        scene[k] = np.ascontiguousarray(scene[k][morton])
+    orc = H.L1World("canonical", dyn="jacobi", threads=os.cpu_count() or 1)
+    orc.add_model(scene["xyz"], scene["mesh_first"], scene["mesh_count"], None)
+    ctx = capi.PhysicsContext(dyn_mode=capi.DYN_JACOBI)
+    ctx.add_model_collider(scene["xyz"], scene["mesh_first"], scene["mesh_count"])
+    multi = capi.MultiContext([0, 0], dyn_mode=capi.DYN_JACOBI)
+    multi.add_model_collider(scene["xyz"], scene["mesh_first"], scene["mesh_count"])
+    cid = ctx.add_capsule_collider()
+    multi.add_capsule_collider()
+    for _ in range(n):
+        orc.add_capsule()
+    orc.set_state(pos=scene["pos"], vel=scene["vel"])
+    tf = capi.make_transforms(scene["pos"])
+    ph = capi.make_physics(scene["vel"], collider=np.full(n, cid, np.uint32))
+    tf2, ph2 = tf.copy(), ph.copy()
+    for f in range(4):
+        orc.step(DT)
+        ctx.update_characters(DT, tf, ph)
+        multi.update_characters(DT, tf2, ph2)
+        assert H.state_diff(orc.get_state(), H.gpu_state(tf, ph)) == [], "frame %d" % f
+        assert H.state_diff(H.gpu_state(tf, ph), H.gpu_state(tf2, ph2)) == [], "frame %d, two contexts" % f
+    co, cg = orc.counters(), ctx.counters()
+    for k in ("substeps", "tri_tests", "contacts", "cc_tests"):
+        assert co[k] == cg[k], k
+    assert cg["cc_tests"] > 100000
+
+
 def test_jacobi_two_ranks_emulated_on_one_gpu_equal_one_rank():
     """multi-rank dynamic pass without a second GPU: two contexts on cuda:0 each own half of the characters, prepare
     their records, exchange them (device copies standing in for the NCCL all-gather), step -- and the concatenated

@@ -254,3 +254,27 @@ def test_l1_remove_and_re_add_equals_the_reference():
     assert l0.add_model(*patch(6, 0, -0.5)) == 1
     ids[1] = l1.add_model(*patch(6, 0, -0.5))
     frames(6, "one re-added")
+
+
+def test_l1_jacobi_grid_and_threads_equal_the_plain_loop(monkeypatch):
+    """the restatement's JACOBI neighbour search uses a uniform grid and host threads from 2048 capsules on (so that config
+    5 can be checked at full size); both are pure acceleration: states, counters and the ordered capsule-candidate lists
+    of the trace equal the single-threaded loop over all pairs -- crowded scene, NaN and far-away capsules included"""
+    scene = H.make_scene(48, 2, 2, 2600, seed=21)
+    scene["pos"][7] = np.nan
+    scene["pos"][11, 0] = np.float32(3.0e8)
+    scene["vel"][13, 2] = np.inf
+    monkeypatch.setenv("PRT_L1_NO_GRID", "1")
+    plain = H.build_oracle(scene, "l1", order="canonical", dyn="jacobi", threads=1)
+    st, tr = [], []
+    for f in range(4):
+        tr.append(plain.step(1.0 / 30.0, trace=(f == 2)))
+        st.append(plain.get_state())
+    monkeypatch.delenv("PRT_L1_NO_GRID")
+    fast = H.build_oracle(scene, "l1", order="canonical", dyn="jacobi", threads=4)
+    for f in range(4):
+        t = fast.step(1.0 / 30.0, trace=(f == 2))
+        assert H.state_diff(st[f], fast.get_state()) == [], "frame %d" % f
+        if f == 2:
+            assert H.trace_diff(tr[f], t, keys=H.TRACE_KEYS + ("q_caps_off", "caps_ids")) == []
+    assert plain.counters() == fast.counters() and plain.counters()["cc_tests"] > 1000
