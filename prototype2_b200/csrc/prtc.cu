@@ -380,6 +380,8 @@ int prtc_create(const prtc_config * cfg, prtc_ctx ** out) {
     if (const char * e = std::getenv("PRTC_WARP_KERNEL")) ctx->warp_kernel = std::atoi(e);
     if (const char * e = std::getenv("PRTC_STREAMED_COPY")) ctx->streamed_copy = std::atoi(e);
     if (const char * e = std::getenv("PRTC_TOP_STAGING")) ctx->top_staging = std::atoi(e);
+    if (const char * e = std::getenv("PRTC_POOL_KERNEL")) ctx->pool_kernel = std::atoi(e);
+    if (const char * e = std::getenv("PRTC_TIGHT_REJECT")) ctx->tight_reject = std::atoi(e);
     if (const char * e = std::getenv("PRTC_STAGED")) ctx->staged = std::atoi(e);
     if (const char * e = std::getenv("PRTC_XC_MARGIN")) ctx->xc_margin = float(std::atof(e));
     if (const char * e = std::getenv("PRTC_TUNE")) ctx->tune_hi = uint32_t(std::strtoul(e, nullptr, 0)) & 0xFFFFFF00u;
