@@ -300,6 +300,10 @@ int prtc_set_option(prtc_ctx * ctx, int option, int value);
  * leaves in traversal (= reference DFS) order. */
 int prtc_get_tree_info(prtc_ctx * ctx, uint32_t * n_nodes, uint32_t * n_leaves, uint32_t * n_triangles);
 int prtc_get_leaf_order(prtc_ctx * ctx, uint32_t * leaf_mesh_ids, uint32_t capacity);
+/* How the commits since prtc_create were done: `incremental` = moved models only (their transforms, vertices, boxes and
+ * triangle records; the tree is left alone or, in BY_ID order, put together again on the device), `full` = the tree was
+ * re-flattened / rebuilt and uploaded. */
+int prtc_get_commit_stats(prtc_ctx * ctx, uint32_t * incremental, uint32_t * full);
 /* world-space vertex cache as the device computed it (physics_system.cpp:86), 3 floats per vertex */
 int prtc_get_world_vertices(prtc_ctx * ctx, float * xyz, uint32_t capacity_vertices, uint32_t * n_vertices);
 /* candidate mesh colliders of one box, in test order (DynamicAABBTree::query, aabb_tree.cpp:34-68), on the device */

@@ -27,7 +27,7 @@ SYMBOLS = (
     "prtc_multi_create", "prtc_multi_destroy", "prtc_multi_device_count", "prtc_multi_context", "prtc_multi_add_model", "prtc_multi_add_capsule",
     "prtc_multi_update_capsule", "prtc_multi_remove_model", "prtc_multi_update_models", "prtc_multi_commit", "prtc_multi_set_option",
     "prtc_multi_raycast", "prtc_multi_get_counters", "prtc_multi_step_characters", "prtc_multi_resident_begin", "prtc_multi_resident_io",
-    "prtc_multi_resident_step", "prtc_multi_resident_fetch", "prtc_multi_resident_end",
+    "prtc_multi_resident_step", "prtc_multi_resident_fetch", "prtc_multi_resident_end", "prtc_get_commit_stats",
 )
 
 
@@ -315,6 +315,11 @@ class PhysicsContext:
         c = Counters()
         self._check(self.lib.prtc_get_counters(self.h, ctypes.byref(c), ctypes.c_int(1 if reset else 0)))
         return {k: int(getattr(c, k)) for k, _ in Counters._fields_}
+
+    def commit_stats(self):
+        a, b = ctypes.c_uint32(), ctypes.c_uint32()
+        self._check(self.lib.prtc_get_commit_stats(self.h, ctypes.byref(a), ctypes.byref(b)))
+        return {"incremental": a.value, "full": b.value}
 
     def tree_info(self):
         a, b, c = ctypes.c_uint32(), ctypes.c_uint32(), ctypes.c_uint32()

@@ -11,7 +11,9 @@
 #ifndef PRT_BVH_BUILDER_H
 #define PRT_BVH_BUILDER_H
 
+#include <atomic>
 #include <cstdint>
+#include <thread>
 #include <vector>
 
 #include "prt_math.cuh"
@@ -60,6 +62,10 @@ public:
     // (leaf-ordered) device triangle array -- filled by the caller through `assign`.
     template <class LeafRange>
     void flatten(FlatTree & out, LeafRange && leaf_range) const;
+    // the same arrays, written by several host threads (mesh-only trees; `leaf_range` must be safe to call concurrently):
+    // the top levels are laid out by one thread, the subtrees below them are counted and then written in parallel
+    template <class LeafRange>
+    void flatten_parallel(FlatTree & out, LeafRange && leaf_range, unsigned threads) const;
 
 private:
     static constexpr int32_t NIL = -1;
@@ -143,6 +149,132 @@ void RefTree::flatten(FlatTree & out, LeafRange && leaf_range) const {
     }
 }
 
+template <class LeafRange>
+void RefTree::flatten_parallel(FlatTree & out, LeafRange && leaf_range, unsigned threads) const {
+    constexpr uint32_t CUT = 9;                                   // subtrees rooted at this depth (or leaves above it) are the parallel tasks
+    if (root_ == NIL || size_ < 8192 || threads < 2) { flatten(out, leaf_range); return; }
+    struct Ref { bool task; uint32_t idx; };
+    struct Top { int32_t node; Ref r, l; uint32_t size, leaves; size_t flat, leaf_base; };
+    struct Task { int32_t root; uint32_t size, leaves, depth; size_t flat, leaf_base; };
+    std::vector<Top> tops;
+    std::vector<Task> tasks;
+    // 1. the top part, right-first preorder (aabb_tree.cpp:63-64: left pushed first, right popped first)
+    struct Frame { int32_t node; uint32_t depth; int parent; bool second; };
+    std::vector<Frame> stack;
+    stack.push_back({root_, 0, -1, false});
+    Ref root_ref{false, 0};
+    while (!stack.empty()) {
+        const Frame f = stack.back();
+        stack.pop_back();
+        Node const & n = nodes_[size_t(f.node)];
+        Ref me;
+        if (n.right == NIL || f.depth >= CUT) { me = Ref{true, uint32_t(tasks.size())}; tasks.push_back(Task{f.node, 0, 0, 0, 0, 0}); }
+        else {
+            me = Ref{false, uint32_t(tops.size())};
+            tops.push_back(Top{f.node, Ref{true, 0}, Ref{true, 0}, 0, 0, 0, 0});
+            stack.push_back({n.left, f.depth + 1, int(me.idx), true});
+            stack.push_back({n.right, f.depth + 1, int(me.idx), false});
+        }
+        if (f.parent < 0) root_ref = me;
+        else if (f.second) tops[size_t(f.parent)].l = me;
+        else tops[size_t(f.parent)].r = me;
+    }
+    auto run = [&](auto && body) {
+        std::atomic<size_t> next{0};
+        auto worker = [&]() { for (;;) { const size_t k = next.fetch_add(1); if (k >= tasks.size()) break; body(tasks[k]); } };
+        const unsigned nt = unsigned(std::min<size_t>(threads, tasks.size()));
+        std::vector<std::thread> pool;
+        for (unsigned t = 1; t < nt; ++t) pool.emplace_back(worker);
+        worker();
+        for (auto & th : pool) th.join();
+    };
+    // 2. sizes of the subtrees, in parallel
+    run([&](Task & t) {
+        std::vector<std::pair<int32_t, uint32_t>> st;
+        st.push_back({t.root, 0u});
+        uint32_t size = 0, leaves = 0, depth = 0;
+        while (!st.empty()) {
+            const auto it = st.back();
+            st.pop_back();
+            Node const & n = nodes_[size_t(it.first)];
+            ++size;
+            if (it.second > depth) depth = it.second;
+            if (n.right == NIL) { if (n.kind == LEAF_MESH) ++leaves; }
+            else { st.push_back({n.left, it.second + 1}); st.push_back({n.right, it.second + 1}); }
+        }
+        t.size = size; t.leaves = leaves; t.depth = depth;
+    });
+    // 3. sizes of the top nodes (children follow their parents in the list), then every node's place
+    auto size_of = [&](Ref r) { return r.task ? tasks[r.idx].size : tops[r.idx].size; };
+    auto leaves_of = [&](Ref r) { return r.task ? tasks[r.idx].leaves : tops[r.idx].leaves; };
+    for (size_t k = tops.size(); k-- > 0;) {
+        tops[k].size = 1u + size_of(tops[k].r) + size_of(tops[k].l);
+        tops[k].leaves = leaves_of(tops[k].r) + leaves_of(tops[k].l);
+    }
+    const size_t nn = size_of(root_ref), nl = leaves_of(root_ref);
+    out.nodes.resize(nn); out.node_leaf_id.resize(nn); out.node_leaf_kind.resize(nn);
+    out.leaf_order.resize(nl); out.capsule_order.clear();
+    struct Place { Ref r; size_t flat, leaf_base; };
+    std::vector<Place> todo;
+    todo.push_back({root_ref, 0, 0});
+    uint32_t max_depth = 0;
+    while (!todo.empty()) {
+        const Place pl = todo.back();
+        todo.pop_back();
+        if (pl.r.task) { tasks[pl.r.idx].flat = pl.flat; tasks[pl.r.idx].leaf_base = pl.leaf_base; continue; }
+        Top & t = tops[pl.r.idx];
+        t.flat = pl.flat; t.leaf_base = pl.leaf_base;
+        Node const & n = nodes_[size_t(t.node)];
+        FlatNode f;
+        f.lo[0] = n.box.lo.x; f.lo[1] = n.box.lo.y; f.lo[2] = n.box.lo.z;
+        f.hi[0] = n.box.hi.x; f.hi[1] = n.box.hi.y; f.hi[2] = n.box.hi.z;
+        f.link = int32_t(pl.flat + t.size);                        // skip: the node after this subtree
+        f.count = -int32_t(pl.flat + 1 + size_of(t.r));            // second child (the left one)
+        out.nodes[pl.flat] = f;
+        out.node_leaf_id[pl.flat] = 0xFFFFFFFFu;
+        out.node_leaf_kind[pl.flat] = uint8_t(LEAF_NONE);
+        todo.push_back({t.r, pl.flat + 1, pl.leaf_base});
+        todo.push_back({t.l, pl.flat + 1 + size_of(t.r), pl.leaf_base + leaves_of(t.r)});
+    }
+    for (Task const & t : tasks) if (t.depth + CUT > max_depth) max_depth = t.depth + CUT;
+    out.max_depth = max_depth;
+    // 4. the subtrees, in parallel: the serial algorithm with the subtree's base added
+    run([&](Task & t) {
+        struct Item { int32_t node; int64_t flat_parent; };
+        std::vector<Item> st;
+        std::vector<std::pair<size_t, uint32_t>> pending;
+        st.push_back({t.root, -1});
+        size_t at = t.flat, leaf_at = t.leaf_base;
+        while (!st.empty()) {
+            const Item it = st.back();
+            st.pop_back();
+            while (!pending.empty() && pending.back().second > st.size()) { out.nodes[pending.back().first].link = int32_t(at); pending.pop_back(); }
+            Node const & n = nodes_[size_t(it.node)];
+            FlatNode f;
+            f.lo[0] = n.box.lo.x; f.lo[1] = n.box.lo.y; f.lo[2] = n.box.lo.z;
+            f.hi[0] = n.box.hi.x; f.hi[1] = n.box.hi.y; f.hi[2] = n.box.hi.z;
+            if (it.flat_parent >= 0) out.nodes[size_t(it.flat_parent)].count = -int32_t(at);
+            if (n.right == NIL) {
+                uint32_t first = 0, count = 0;
+                if (n.kind == LEAF_MESH) { leaf_range(n.id, first, count); out.leaf_order[leaf_at++] = n.id; }
+                f.link = int32_t(first); f.count = int32_t(count);
+                out.node_leaf_id[at] = n.id;
+                out.node_leaf_kind[at] = uint8_t(n.kind);
+            } else {
+                f.link = -1; f.count = -1;
+                out.node_leaf_id[at] = 0xFFFFFFFFu;
+                out.node_leaf_kind[at] = uint8_t(LEAF_NONE);
+                pending.push_back({at, uint32_t(st.size())});
+                st.push_back({n.left, int64_t(at)});
+                st.push_back({n.right, -1});
+            }
+            out.nodes[at] = f;
+            ++at;
+        }
+        while (!pending.empty()) { out.nodes[pending.back().first].link = int32_t(at); pending.pop_back(); }
+    });
+}
+
 // Top of the flattened tree as a compact table for staging in shared memory (k_xc_refresh): every node of depth <= D,
 // D the largest depth whose levels together fit `cap` entries, in the same right-first preorder -- so a walk that runs
 // over the table and drops into the full array below it visits nodes in the order of the plain walk and emits the same
@@ -152,40 +284,53 @@ void RefTree::flatten(FlatTree & out, LeafRange && leaf_range) const {
 //                          in the full array over [g + 1, skip)
 //   leaf:                  link = its index g in the full array, count = 0: on overlap the walk visits [g, g + 1)
 // Returns an empty table when the whole tree is not bigger than a few tables (nothing to gain).
-inline void build_top_table(std::vector<FlatNode> const & nodes, uint32_t cap, std::vector<FlatNode> & top) {
+inline void build_top_table(std::vector<FlatNode> const & nodes, uint32_t cap, std::vector<FlatNode> & top, std::vector<uint32_t> * src = nullptr) {
     top.clear();
+    if (src) src->clear();
     const size_t n = nodes.size();
     if (n < size_t(cap) * 4) return;
-    std::vector<uint8_t> depth(n, 0);
-    std::vector<uint32_t> per_depth;
-    for (size_t i = 0; i < n; ++i) {
-        const uint32_t d = depth[i];
-        if (d >= per_depth.size()) per_depth.resize(d + 1, 0);
-        ++per_depth[d];
-        if (nodes[i].count < 0) {
-            const uint8_t dc = uint8_t(d < 255 ? d + 1 : 255);
-            depth[i + 1] = dc;
-            depth[size_t(-nodes[i].count)] = dc;
+    // level by level from the root until the next level no longer fits: only the table's own nodes are touched
+    std::vector<uint32_t> level{0u}, next;
+    uint32_t D = 0, kept = 1;
+    for (;;) {
+        next.clear();
+        for (uint32_t i : level)
+            if (nodes[i].count < 0) { next.push_back(i + 1); next.push_back(uint32_t(-nodes[i].count)); }
+        if (next.empty() || kept + next.size() > cap || D + 1 >= 255) break;
+        ++D; kept += uint32_t(next.size());
+        level.swap(next);
+    }
+    if (D == 0) return;
+    // the kept nodes in preorder (= ascending index) with their depths
+    struct It { uint32_t node, depth; };
+    std::vector<It> order, st;
+    st.push_back({0u, 0u});
+    while (!st.empty()) {
+        const It it = st.back();
+        st.pop_back();
+        order.push_back(it);
+        if (nodes[it.node].count < 0 && it.depth < D) {
+            st.push_back({uint32_t(-nodes[it.node].count), it.depth + 1});      // second child later
+            st.push_back({it.node + 1, it.depth + 1});
         }
     }
-    uint32_t D = 0, kept = per_depth[0];
-    while (D + 1 < per_depth.size() && D + 1 < 255 && kept + per_depth[D + 1] <= cap) { ++D; kept += per_depth[D]; }
-    if (D == 0) return;
-    std::vector<int32_t> table_index(n + 1, -1);
-    int32_t k = 0;
-    for (size_t i = 0; i < n; ++i) if (depth[i] <= D) table_index[i] = k++;
-    table_index[n] = k;
-    top.reserve(size_t(k));
-    for (size_t i = 0; i < n; ++i) {
-        if (depth[i] > D) continue;
-        FlatNode f = nodes[i];
-        if (nodes[i].count < 0) {
-            if (depth[i] < D) { f.link = table_index[size_t(nodes[i].link)]; f.count = -1; }   // the node after a subtree is never deeper than its root
-            else { f.link = int32_t(i); f.count = -nodes[i].link; }
+    // table index of the first kept node at or after a full-array index (for the table skip links)
+    auto table_index_of = [&](uint32_t full) {
+        size_t lo = 0, hi = order.size();
+        while (lo < hi) { const size_t mid = (lo + hi) / 2; if (order[mid].node < full) lo = mid + 1; else hi = mid; }
+        return int32_t(lo);
+    };
+    top.reserve(order.size());
+    for (It const & it : order) {
+        FlatNode f = nodes[it.node];
+        if (nodes[it.node].count < 0) {
+            if (it.depth < D) { f.link = table_index_of(uint32_t(nodes[it.node].link)); f.count = -1; }   // the node after a subtree is never deeper than its root
+            else { f.link = int32_t(it.node); f.count = -nodes[it.node].link; }
         } else {
-            f.link = int32_t(i); f.count = 0;
+            f.link = int32_t(it.node); f.count = 0;
         }
         top.push_back(f);
+        if (src) src->push_back(it.node);
     }
 }
 

@@ -67,6 +67,17 @@ __global__ void k_tri_setup(const float * __restrict__ world, const uint32_t * _
     }
 }
 
+// the staged top-of-tree table after the node boxes changed but the topology did not (PRTC_ORDER_BY_ID, a moved model):
+// every entry takes its box from the node it mirrors, the two integer words (table links) stay
+__global__ void k_top_refresh(const float4 * __restrict__ nodes, float4 * __restrict__ top, const uint32_t * __restrict__ src, uint32_t n_top) {
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n_top) return;
+    const float4 lo = nodes[2 * size_t(src[k])], hi = nodes[2 * size_t(src[k]) + 1];
+    float4 tlo = top[2 * size_t(k)], thi = top[2 * size_t(k) + 1];
+    tlo.x = lo.x; tlo.y = lo.y; tlo.z = lo.z; thi.x = hi.x; thi.y = hi.y; thi.z = hi.z;
+    top[2 * size_t(k)] = tlo; top[2 * size_t(k) + 1] = thi;
+}
+
 __global__ void k_query_box(const float4 * __restrict__ nodes, uint32_t n_nodes, const uint32_t * __restrict__ node_leaf_id,
                             const float * __restrict__ aabb6, uint32_t * out_ids, uint32_t capacity, uint32_t * out_count) {
     if (blockIdx.x != 0 || threadIdx.x != 0) return;
@@ -373,6 +384,10 @@ void launch_tri_setup(const float * world_xyz, const uint32_t * tri_src_vertex, 
     if (n_tris == 0) return;
     const uint32_t block = 256;
     k_tri_setup<<<(n_tris + block - 1) / block, block, 0, stream>>>(world_xyz, tri_src_vertex, n_tris, tris, cull);
+}
+
+void launch_top_refresh(const float4 * nodes, float4 * top, const uint32_t * src, uint32_t n_top, cudaStream_t stream) {
+    if (n_top) k_top_refresh<<<(n_top + 255) / 256, 256, 0, stream>>>(nodes, top, src, n_top);
 }
 
 void launch_query_box(const float4 * nodes, uint32_t n_nodes, const uint32_t * node_leaf_id, const float * aabb6,

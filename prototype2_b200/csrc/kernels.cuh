@@ -155,6 +155,8 @@ struct SweepParams {
     unsigned long long * counters;
 };
 void launch_sweep(SweepParams const & p, cudaStream_t stream);
+// boxes of the staged top-of-tree table re-read from the node array (topology unchanged)
+void launch_top_refresh(const float4 * nodes, float4 * top, const uint32_t * src, uint32_t n_top, cudaStream_t stream);
 // single box query (introspection / tests)
 void launch_query_box(const float4 * nodes, uint32_t n_nodes, const uint32_t * node_leaf_id, const float * aabb6,
                       uint32_t * out_ids, uint32_t capacity, uint32_t * out_count, cudaStream_t stream);

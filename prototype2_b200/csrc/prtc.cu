@@ -33,6 +33,111 @@ int commit_impl(prtc_ctx * c) {
         c->capsules_dirty = false;
     }
 
+    // ---- moved models only (prtc_update_models since the last commit, nothing added or removed): INCREMENTAL -------------
+    // Only those models' transforms go up, only their meshes are re-transformed (K8) and only their boxes come back.  If every
+    // new box still lies inside its leaf's stored fat box (DynamicAABBTree::update keeps the leaf then, aabb_tree.cpp:102-111)
+    // the tree is untouched: the triangle / cull records of just those meshes are rebuilt and that is all -- no re-flatten, no
+    // upload of the level, the per-slot leaf lists stay valid.  Otherwise: CANONICAL order re-inserts the leaves in the
+    // host tree and re-flattens (the shape -- hence the candidate order -- changed; the vertices are not uploaded again);
+    // BY_ID order uploads the changed leaf records and lets the device put the tree together again (same topology: the staged
+    // top-of-tree table only refreshes its boxes).
+    if (c->geometry_dirty && !c->registry_dirty && !c->literal() && !c->moved_models.empty() && c->meshes_on_device == n_meshes &&
+        c->h_aabbs.size() == size_t(n_meshes) * 6 && !c->tree_dirty) {
+        std::sort(c->moved_models.begin(), c->moved_models.end());
+        c->moved_models.erase(std::unique(c->moved_models.begin(), c->moved_models.end()), c->moved_models.end());
+        size_t moved_meshes = 0;
+        for (uint32_t model : c->moved_models) moved_meshes += c->models[model].n_meshes;
+        if (moved_meshes <= 8192) {
+            std::vector<ModelXform> xf(c->moved_models.size());
+            for (size_t k = 0; k < c->moved_models.size(); ++k) {
+                const uint32_t model = c->moved_models[k];
+                ModelHost const & mh = c->models[model];
+                xf[k].m = affine_from(mh.transform);
+                PRTC_CUDA(cudaMemcpyAsync(c->d_xforms.ptr + model, &xf[k], sizeof(ModelXform), cudaMemcpyHostToDevice, s));
+                if (!mh.n_meshes) continue;
+                launch_transform_refit(c->d_raw.ptr, c->d_world.ptr, c->d_meshes.ptr, mh.first_mesh, mh.n_meshes, c->d_xforms.ptr, c->d_aabbs.ptr, s);
+                PRTC_CUDA(cudaMemcpyAsync(c->h_aabbs.data() + 6 * size_t(mh.first_mesh), c->d_aabbs.ptr + 6 * size_t(mh.first_mesh),
+                                          size_t(mh.n_meshes) * 6 * sizeof(float), cudaMemcpyDeviceToHost, s));
+            }
+            PRTC_CUDA(cudaGetLastError());
+            PRTC_CUDA(cudaStreamSynchronize(s));
+            bool changed = false;
+            std::vector<uint32_t> refit;                           // BY_ID: meshes whose stored fat box changed
+            for (uint32_t model : c->moved_models) {
+                ModelHost const & mh = c->models[model];
+                for (uint32_t m = mh.first_mesh; m < mh.first_mesh + mh.n_meshes; ++m) {
+                    const float * a = c->h_aabbs.data() + 6 * size_t(m);
+                    Box b; b.lo = v3(a[0], a[1], a[2]); b.hi = v3(a[3], a[4], a[5]);
+                    if (c->meshes[m].n_vertices) {
+                        for (int k = 0; k < 6; ++k) { const float v = std::fabs(a[k]); if (v > c->world_max_abs) c->world_max_abs = v; }
+                        for (int k = 0; k < 3; ++k) { if (a[k] < c->world_lo[k]) c->world_lo[k] = a[k]; if (a[3 + k] > c->world_hi[k]) c->world_hi[k] = a[3 + k]; }
+                    }
+                    if (c->by_id()) {
+                        float * f = c->leaf_fat.data() + 6 * size_t(m);
+                        Box stored; stored.lo = v3(f[0], f[1], f[2]); stored.hi = v3(f[3], f[4], f[5]);
+                        if (!box_contains(stored, b)) {
+                            const V3 lo = b.lo - c->cfg.leaf_margin, hi = b.hi + c->cfg.leaf_margin;
+                            f[0] = lo.x; f[1] = lo.y; f[2] = lo.z; f[3] = hi.x; f[4] = hi.y; f[5] = hi.z;
+                            refit.push_back(m);
+                            changed = true;
+                        }
+                    } else if (c->tree.update(&c->meshes[m].tree_index, &b, 1) != 0) {
+                        changed = true;
+                    }
+                }
+            }
+            // triangle + cull records of the moved meshes (their layout does not change unless the CANONICAL tree does)
+            auto rebuild_records = [&]() -> int {
+                for (uint32_t model : c->moved_models) {
+                    ModelHost const & mh = c->models[model];
+                    for (uint32_t m = mh.first_mesh; m < mh.first_mesh + mh.n_meshes; ++m) {
+                        const uint32_t cnt = c->meshes[m].n_vertices / 3, first = c->mesh_tri_first[m];
+                        if (cnt) launch_tri_setup(c->d_world.ptr, c->d_tri_src.ptr + first, cnt, c->d_tris.ptr + 3 * size_t(first), c->d_cull.ptr + 4 * size_t(first), s);
+                    }
+                }
+                PRTC_CUDA(cudaGetLastError());
+                return PRTC_OK;
+            };
+            if (!changed) {
+                int rc = rebuild_records();
+                if (rc) return rc;
+                c->moved_models.clear();
+                c->geometry_dirty = false;
+                ++c->incremental_commits;
+                return PRTC_OK;
+            }
+            if (c->by_id() && c->leaf_slot.size() == n_meshes) {
+                for (uint32_t m : refit) {
+                    const float * f = c->leaf_fat.data() + 6 * size_t(m);
+                    FlatNode l;
+                    l.lo[0] = f[0]; l.lo[1] = f[1]; l.lo[2] = f[2]; l.hi[0] = f[3]; l.hi[1] = f[4]; l.hi[2] = f[5];
+                    l.link = int32_t(c->mesh_tri_first[m]);
+                    l.count = int32_t(c->meshes[m].n_vertices / 3);
+                    PRTC_CUDA(cudaMemcpyAsync(c->d_leaves.ptr + 2 * size_t(c->leaf_slot[m]), &l, sizeof(FlatNode), cudaMemcpyHostToDevice, s));
+                }
+                launch_tree_build(c->d_leaves.ptr, uint32_t(c->flat.leaf_order.size()), c->d_nodes.ptr, s);
+                if (!c->top.empty()) launch_top_refresh(c->d_nodes.ptr, c->d_top.ptr, c->d_top_src.ptr, uint32_t(c->top.size()), s);
+                int rc = rebuild_records();
+                if (rc) return rc;
+                PRTC_CUDA(cudaStreamSynchronize(s));               // the staged leaf records are stack-owned
+                ++c->tree_version;                                 // leaf boxes changed: every cached leaf list is stale
+                c->moved_models.clear();
+                c->geometry_dirty = false;
+                ++c->incremental_commits;
+                return PRTC_OK;
+            }
+            // CANONICAL: the host tree changed shape -> re-flatten below; the triangle records keep their (registration-order)
+            // places, only the moved meshes' records are rebuilt -- unless the leaf-ordered layout is in use (A/B switch)
+            static const bool leaf_layout = [] { const char * e = std::getenv("PRTC_LEAF_ORDER"); return e && std::atoi(e) != 0; }();
+            if (leaf_layout) c->tri_dirty = true;
+            else { int rc = rebuild_records(); if (rc) return rc; }
+            c->moved_models.clear();
+            c->geometry_dirty = false;
+            c->tree_dirty = true;
+            ++c->incremental_commits;
+        }
+    }
+
     if (c->geometry_dirty) {
         // (re)upload the registry.  The world cache and AABBs of meshes that are already in the tree stay valid
         // unless a device buffer has to grow, in which case everything is re-derived (simple and rare).
@@ -68,6 +173,8 @@ int commit_impl(prtc_ctx * c) {
         if (n_meshes) PRTC_CUDA(cudaMemcpyAsync(aabbs.data(), c->d_aabbs.ptr, aabbs.size() * sizeof(float), cudaMemcpyDeviceToHost, s));
         PRTC_CUDA(cudaStreamSynchronize(s));
 
+        c->h_aabbs = aabbs;
+        c->registry_dirty = false;
         auto box_of = [&](uint32_t m) {
             Box b;
             b.lo = v3(aabbs[6 * size_t(m)], aabbs[6 * size_t(m) + 1], aabbs[6 * size_t(m) + 2]);
@@ -130,7 +237,11 @@ int commit_impl(prtc_ctx * c) {
         // Triangle records are laid out in LEAF order in CANONICAL mode (the tree is built once; neighbours in the
         // traversal are neighbours in memory) and in REGISTRATION order in LITERAL mode, where the tree changes shape
         // whenever a capsule leaves its fat box: there a re-flatten only uploads the nodes, the triangles stay put.
-        const bool by_leaf_order = !c->literal() && !c->by_id();
+        // (round 2: CANONICAL order keeps the triangle records in REGISTRATION order as well -- a moved model that re-inserts a
+        //  leaf then re-flattens the nodes only; measured frame time at C4 is the same, the level is registered block by block.
+        //  PRTC_LEAF_ORDER=1 restores the leaf-ordered layout for A/B.)
+        static const bool leaf_layout = [] { const char * e = std::getenv("PRTC_LEAF_ORDER"); return e && std::atoi(e) != 0; }();
+        const bool by_leaf_order = leaf_layout && !c->literal() && !c->by_id();
         const bool rebuild_tris = by_leaf_order || c->tri_dirty;
         if (rebuild_tris) {
             c->tri_src.clear();
@@ -145,20 +256,27 @@ int commit_impl(prtc_ctx * c) {
             }
         }
         ++c->tree_version;                       // every cached leaf list refers to node indices of the old layout
+        ++c->full_commits;
+        if (by_leaf_order) c->mesh_tri_first.assign(n_meshes, 0u);
         if (c->by_id()) {
             int rc = build_tree_on_device(c, s);
             if (rc) return rc;
-        } else
-        c->tree.flatten(c->flat, [&](uint32_t mesh_id, uint32_t & first, uint32_t & count) {
-            MeshHost const & mh = c->meshes[mesh_id];
-            count = mh.n_vertices / 3;
-            if (by_leaf_order) {
-                first = uint32_t(c->tri_src.size());
-                for (uint32_t k = 0; k < count; ++k) c->tri_src.push_back(mh.first_vertex + 3 * k);
-            } else {
-                first = c->mesh_tri_first[mesh_id];
-            }
-        });
+        } else {
+            auto leaf_range = [&](uint32_t mesh_id, uint32_t & first, uint32_t & count) {
+                MeshHost const & mh = c->meshes[mesh_id];
+                count = mh.n_vertices / 3;
+                if (by_leaf_order) {
+                    first = uint32_t(c->tri_src.size());
+                    c->mesh_tri_first[mesh_id] = first;
+                    for (uint32_t k = 0; k < count; ++k) c->tri_src.push_back(mh.first_vertex + 3 * k);
+                } else {
+                    first = c->mesh_tri_first[mesh_id];
+                }
+            };
+            // a big mesh-only tree is laid out by several host threads (a moved model that re-inserts a leaf re-flattens the level)
+            if (!c->literal() && !by_leaf_order) c->tree.flatten_parallel(c->flat, leaf_range, std::min(16u, std::max(1u, std::thread::hardware_concurrency())));
+            else c->tree.flatten(c->flat, leaf_range);
+        }
         const size_t nn = c->flat.nodes.size();
         const size_t nt = c->tri_src.size();
         PRTC_CUDA(c->d_nodes.reserve(nn * 2));
@@ -166,14 +284,28 @@ int commit_impl(prtc_ctx * c) {
         static_assert(sizeof(FlatNode) == 32, "FlatNode must be two float4");
         if (nn) {
             // pageable sources: the runtime stages them before it returns, so the vectors may be rewritten afterwards
-            if (!c->by_id())                     // (BY_ID: the nodes were built where they are)
+            if (!c->by_id()) {                   // (BY_ID: the nodes were built where they are)
+                // a big node array is page-locked where it lies (once, as long as the vector keeps its storage): the upload
+                // then runs at the link's speed instead of through the runtime's staging buffer
+                void * base = c->flat.nodes.data();
+                const size_t bytes = c->flat.nodes.capacity() * sizeof(FlatNode);
+                if (bytes >= (size_t(8) << 20) && (base != c->flat_pinned || bytes != c->flat_pinned_bytes)) {
+                    if (c->flat_pinned) cudaHostUnregister(c->flat_pinned);
+                    c->flat_pinned = nullptr; c->flat_pinned_bytes = 0;
+                    if (cudaHostRegister(base, bytes, cudaHostRegisterDefault) == cudaSuccess) { c->flat_pinned = base; c->flat_pinned_bytes = bytes; }
+                    (void)cudaGetLastError();
+                }
                 PRTC_CUDA(cudaMemcpyAsync(c->d_nodes.ptr, c->flat.nodes.data(), nn * sizeof(FlatNode), cudaMemcpyHostToDevice, s));
+                if (c->flat_pinned) PRTC_CUDA(cudaStreamSynchronize(s));         // (a pinned source must not be rewritten under the copy)
+            }
             c->leaf_ids_stale = true;            // only traces and prtc_query_box read them: uploaded on demand
         }
         // top levels as a compact table for k_xc_refresh (the LITERAL tree changes shape every frame and never gets there)
         c->top.clear();
-        if (!c->literal()) build_top_table(c->flat.nodes, TOP_CAP, c->top);
+        if (!c->literal()) build_top_table(c->flat.nodes, TOP_CAP, c->top, &c->top_src);
         if (!c->top.empty()) {
+            PRTC_CUDA(c->d_top_src.reserve(c->top_src.size()));
+            PRTC_CUDA(cudaMemcpyAsync(c->d_top_src.ptr, c->top_src.data(), c->top_src.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
             PRTC_CUDA(c->d_top.reserve(c->top.size() * 2));
             PRTC_CUDA(cudaMemcpyAsync(c->d_top.ptr, c->top.data(), c->top.size() * sizeof(FlatNode), cudaMemcpyHostToDevice, s));
         }
@@ -201,8 +333,10 @@ int build_tree_on_device(prtc_ctx * c, cudaStream_t s) {
     const uint32_t n_meshes = uint32_t(c->meshes.size());
     std::vector<FlatNode> leaves;
     c->flat.leaf_order.clear(); c->flat.capsule_order.clear();
+    c->leaf_slot.assign(n_meshes, 0xFFFFFFFFu);
     for (uint32_t m = 0; m < n_meshes; ++m) {
         if (c->models[c->meshes[m].model].n_meshes == 0) continue;     // removed
+        c->leaf_slot[m] = uint32_t(leaves.size());
         const float * f = c->leaf_fat.data() + 6 * size_t(m);
         FlatNode l;
         l.lo[0] = f[0]; l.lo[1] = f[1]; l.lo[2] = f[2]; l.hi[0] = f[3]; l.hi[1] = f[4]; l.hi[2] = f[5];
@@ -408,7 +542,8 @@ void prtc_destroy(prtc_ctx * c) {
     cudaSetDevice(c->cfg.device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     c->d_raw.release(); c->d_world.release(); c->d_aabbs.release(); c->d_meshes.release(); c->d_xforms.release();
-    c->d_nodes.release(); c->d_leaves.release(); c->d_top.release(); c->d_tris.release(); c->d_cull.release(); c->d_node_leaf_id.release(); c->d_tri_src.release();
+    c->d_nodes.release(); c->d_leaves.release(); c->d_top.release(); c->d_top_src.release();
+    if (c->flat_pinned) { cudaHostUnregister(c->flat_pinned); c->flat_pinned = nullptr; } c->d_tris.release(); c->d_cull.release(); c->d_node_leaf_id.release(); c->d_tri_src.release();
     c->d_capsules.release(); c->d_counters.release(); c->d_work.release(); c->d_ingest.release(); c->stage.release(); c->resident_io.release();
     c->d_xc_version.release(); c->d_xc_count.release(); c->d_xc_leaf.release(); c->d_xc_region.release(); c->d_tf.release(); c->d_ph.release();
     c->d_tq.release(); c->d_tmesh.release(); c->d_tcaps.release(); c->d_thits.release();
@@ -463,6 +598,7 @@ int prtc_add_model(prtc_ctx * c, const float * xyz, uint32_t n_vertices, const u
     }
     c->models.push_back(mh);
     c->geometry_dirty = true;
+    c->registry_dirty = true;
     if (c->literal()) {
         // the reference inserts the mesh leaves right here (physics_system.cpp:102), interleaved with capsule leaves
         // in call order, and the tree's shape depends on that order: derive the AABBs on the host with the same
@@ -556,6 +692,7 @@ int prtc_remove_model(prtc_ctx * c, uint32_t model_id) {
     }
     mh.n_meshes = 0;
     c->geometry_dirty = true;
+    c->registry_dirty = true;
     c->tree_dirty = true;
     return PRTC_OK;
 }
@@ -589,6 +726,13 @@ int prtc_set_option(prtc_ctx * c, int option, int value) {
     }
 }
 
+int prtc_get_commit_stats(prtc_ctx * c, uint32_t * incremental, uint32_t * full) {
+    if (!c) return fail(PRTC_ERR_INVALID, "prtc_get_commit_stats: null context");
+    if (incremental) *incremental = c->incremental_commits;
+    if (full) *full = c->full_commits;
+    return PRTC_OK;
+}
+
 int prtc_get_tree_info(prtc_ctx * c, uint32_t * n_nodes, uint32_t * n_leaves, uint32_t * n_triangles) {
     if (!c) return fail(PRTC_ERR_INVALID, "prtc_get_tree_info: null context");
     if (n_nodes) *n_nodes = uint32_t(c->flat.nodes.size());
@@ -608,7 +752,10 @@ int prtc_host_build_tree(const float * aabbs6, uint32_t n, float margin, uint32_
         tree.insert_leaf(i, LEAF_MESH, b);
     }
     FlatTree flat;
-    tree.flatten(flat, [&](uint32_t id, uint32_t & first, uint32_t & count) { first = id; count = 1; });
+    // (PRTC_HOST_FLATTEN_THREADS: lay the tree out with that many host threads, as a commit of a big level does -- for the tests)
+    const char * ft = std::getenv("PRTC_HOST_FLATTEN_THREADS");
+    if (ft && std::atoi(ft) > 1) tree.flatten_parallel(flat, [&](uint32_t id, uint32_t & first, uint32_t & count) { first = id; count = 1; }, unsigned(std::atoi(ft)));
+    else tree.flatten(flat, [&](uint32_t id, uint32_t & first, uint32_t & count) { first = id; count = 1; });
     *n_nodes = uint32_t(flat.nodes.size());
     if (leaf_order) std::copy(flat.leaf_order.begin(), flat.leaf_order.end(), leaf_order);
     if (nodes8) {

@@ -97,6 +97,8 @@ struct prtc_ctx {
     std::vector<prt::CapsuleDev> capsules;
     prt::RefTree tree;
     prt::FlatTree flat;
+    void * flat_pinned = nullptr;           // flat.nodes' storage when it is page-locked (cudaHostRegister)
+    size_t flat_pinned_bytes = 0;
     std::vector<uint32_t> tri_src;          // per leaf-ordered triangle: index of its first vertex in `raw`/`world`
     uint32_t meshes_in_tree = 0;            // meshes that have a leaf in `tree`
     uint32_t meshes_on_device = 0;          // meshes whose world cache / AABB the device has computed
@@ -104,6 +106,8 @@ struct prtc_ctx {
     std::vector<int32_t> capsule_tree_index;
     std::vector<prt::Box> capsule_aabbs;         // m_aabbData.capsuleAABBs
     bool geometry_dirty = false;            // raw / meshes / xforms changed since the last upload
+    bool registry_dirty = false;            // a model was added or removed since the last commit (a moved model alone takes the incremental path)
+    uint32_t incremental_commits = 0, full_commits = 0;     // statistics (prtc_get_commit_stats)
     bool tree_dirty = false;                // tree changed since the last flatten
     bool leaf_ids_stale = true;             // d_node_leaf_id lags behind flat.node_leaf_id (upload_leaf_ids)
     bool tri_dirty = true;                  // triangle records (layout or world positions) must be rebuilt
@@ -119,6 +123,7 @@ struct prtc_ctx {
     float push_slack = 0.0025f;               // k_step_pool: push budget of a culled window (PRTC_PUSH_SLACK)
     int pool_kernel = 1;                    // PRTC_OPT_POOL_KERNEL: persistent launches run k_step_pool (0: k_step_stream)
     std::vector<uint32_t> moved_models;     // models whose transform changed (prtc_update_models)
+    std::vector<float> h_aabbs;             // host copy of the mesh AABBs the device computed (6 floats per mesh)
 
     // device
     prt::host::DevBuf<float> d_raw, d_world, d_aabbs;
@@ -129,6 +134,9 @@ struct prtc_ctx {
     std::vector<float> leaf_fat;            // BY_ID: stored fat box of every mesh leaf (6 floats), kept with the reference's update rule
     prt::host::DevBuf<float4> d_top;        // top-of-tree table (bvh_builder.h build_top_table), CANONICAL order only
     std::vector<prt::FlatNode> top;
+    std::vector<uint32_t> top_src;          // node index behind every table entry
+    prt::host::DevBuf<uint32_t> d_top_src;
+    std::vector<uint32_t> leaf_slot;        // BY_ID: position of every mesh in the device's leaf-record array (-1: removed)
     prt::host::DevBuf<uint32_t> d_node_leaf_id, d_tri_src;
     prt::host::DevBuf<prt::CapsuleDev> d_capsules;
     prt::host::DevBuf<unsigned long long> d_counters;

@@ -407,6 +407,48 @@ def _patch(x0, z0, y, n=6):
     return xyz, mf, mc
 
 
+@pytest.mark.parametrize("order", ["canonical", "by_id"])
+def test_moved_models_take_the_incremental_commit(order):
+    """a level plus two small platforms that are moved every frame (updateModelColliders, physics_system.cpp:161-202) --
+    sometimes inside their leaves' fat boxes (the tree is untouched: only the moved meshes are re-transformed and their
+    triangle records rebuilt), sometimes beyond (CANONICAL: the host tree re-inserts and is re-flattened; BY_ID: the device
+    rebuilds the tree from the changed leaf records) -- bit-identical to the oracle every frame, and the commit statistics
+    show that the level was not rebuilt for the small moves"""
+    from prototype2_b200 import capi
+    scene = H.make_scene(64, 2, 2, 3000, seed=91)
+    px, pmf, pmc = H.scenes.terrain(6, 2, 2)                      # a 6x6-cell platform of nine meshes
+    px = px.copy(); px[:, 1] = np.float32(0.9)
+    orc = H.build_oracle(scene, "l1", order=order)
+    ctx, tf, ph = H.build_gpu(scene, order_mode=capi.ORDER_BY_ID if order == "by_id" else capi.ORDER_CANONICAL)
+    plats = []
+    for k, at in enumerate(((10.0, 0.0, 12.0), (40.0, 0.2, 30.0))):
+        t0 = [at[0], at[1], at[2], 1, 0, 0, 0, 1, 1, 1]
+        plats.append((orc.add_model(px, pmf, pmc, t0), ctx.add_model_collider(px, pmf, pmc, t0)[0], list(at)))
+    ctx.set_option(capi.OPT_WARP_KERNEL, 0)
+    full_before = None
+    for f in range(24):
+        if f > 0:
+            step = 0.004 if f % 6 else 0.3                        # mostly inside the 0.05 margin, now and then beyond it
+            ids, tfs = [], np.zeros(len(plats), capi.TRANSFORM_DTYPE)
+            for k, (oid, gid, at) in enumerate(plats):
+                at[0] += step; at[1] += 0.5 * step * (1 if k else -1)
+                orc.update_model(oid, [at[0], at[1], at[2], 1, 0, 0, 0, 1, 1, 1])
+                ids.append(gid)
+                tfs["position"][k] = at; tfs["rotation"][k] = (0, 0, 0, 1); tfs["scale"][k] = (1, 1, 1)
+            ctx.update_model_colliders(np.array(ids, np.uint32), tfs)
+        orc.step(DT)
+        ctx.update_characters(DT, tf, ph)
+        assert H.state_diff(orc.get_state(), H.gpu_state(tf, ph)) == [], "frame %d" % f
+        if f == 1:
+            full_before = ctx.commit_stats()["full"]
+    st = ctx.commit_stats()
+    assert st["incremental"] >= 15, st                            # the small moves (and, by id, the big ones too)
+    if order == "by_id":
+        assert st["full"] == full_before, st                       # the level's tree is never rebuilt on the host
+    else:
+        assert st["full"] - full_before <= 5, st                   # only the moves that re-insert a leaf re-flatten
+
+
 class _L1Slots:
     """L1 canonical world behind the reference's model-index reuse (LIFO free list, physics_system.cpp:49-56,122-123)"""
 

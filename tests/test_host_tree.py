@@ -281,3 +281,19 @@ def test_balanced_tree_walk_emits_overlapping_boxes_in_ascending_id():
 
 def test_balanced_tree_empty():
     assert len(capi.host_balanced_tree(np.zeros((0, 6), np.float32))) == 0
+
+
+def test_parallel_flatten_equals_serial_flatten(monkeypatch):
+    """a commit of a big level lays the reference-built tree out with several host threads (top levels by one thread, the
+    subtrees below counted and written in parallel): node for node and leaf for leaf the serial right-first preorder"""
+    rs = np.random.RandomState(42)
+    for n in (9000, 60000):
+        lo = rs.uniform(0, 300, (n, 3)).astype(np.float32)
+        boxes = np.concatenate([lo, lo + rs.uniform(0.1, 3.0, (n, 3)).astype(np.float32)], axis=1)
+        monkeypatch.delenv("PRTC_HOST_FLATTEN_THREADS", raising=False)
+        order_a, nodes_a = capi.host_build_tree(boxes)
+        for threads in ("2", "7", "16"):
+            monkeypatch.setenv("PRTC_HOST_FLATTEN_THREADS", threads)
+            order_b, nodes_b = capi.host_build_tree(boxes)
+            assert np.array_equal(order_a, order_b)
+            assert np.array_equal(nodes_a.view(np.uint32), nodes_b.view(np.uint32))
