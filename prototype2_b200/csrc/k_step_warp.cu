@@ -358,6 +358,15 @@ __global__ void __launch_bounds__(32) k_step_warp(StepParams p) {
         }
         if (LITERAL && p.host_flags && c_cc) p.host_flags[0] = 1u;
     }
+    if (p.done_flag) {                                             // completion doorbell (StepParams::done_flag): the records are host-mapped
+        __threadfence_system();
+        __syncwarp(FULL);
+        if (lane == 0 && atomicAdd(p.done_count, 1u) + 1u == gridDim.x) {
+            *p.done_count = 0u;
+            __threadfence_system();
+            *reinterpret_cast<volatile uint32_t *>(p.done_flag) = p.done_value;
+        }
+    }
 }
 
 } // namespace

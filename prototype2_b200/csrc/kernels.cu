@@ -193,12 +193,84 @@ __global__ void k_raycast(const float4 * __restrict__ nodes, uint32_t n_nodes, c
 
 } // namespace
 
+// Engine-sized trees (the shipped level has 345 nodes): ONE WARP PER RAY.  The result is the minimum t over every triangle of
+// every mesh leaf the reference's traversal reaches, and a leaf is reached exactly when its own box passes the slab test --
+// its ancestors' boxes contain it and the test is monotone in the box (correctly rounded subtractions and multiplications
+// are monotone) -- so the hierarchy is not needed for the answer: the lanes test all nodes 32 at a time (a handful of
+// independent round trips instead of one dependent load per tree level and per triangle), the triangles of the hit leaves
+// are spread over the lanes, and the minimum is reduced with shuffles (min of floats is order independent).
+__global__ void __launch_bounds__(32) k_raycast_warp(const float4 * __restrict__ nodes, uint32_t n_nodes, const float4 * __restrict__ tris, uint32_t n_rays,
+                                                     const float * __restrict__ origins, const float * __restrict__ dirs, const float * __restrict__ maxd,
+                                                     float * __restrict__ hit_xyz, unsigned char * __restrict__ hit_mask, uint32_t * done_flag,
+                                                     unsigned * done_count, uint32_t done_value) {
+    constexpr unsigned FULL = 0xffffffffu;
+    const uint32_t r = blockIdx.x, lane = threadIdx.x;
+    if (r < n_rays) {
+        const V3 o = v3(origins[3 * r], origins[3 * r + 1], origins[3 * r + 2]);
+        const V3 d = v3(dirs[3 * r], dirs[3 * r + 1], dirs[3 * r + 2]);
+        const float md = maxd[r];
+        const V3 end = o + d * md;
+        float best = 3.402823466e+38f;                            // std::numeric_limits<float>::max()
+        bool any = false;
+        for (uint32_t base = 0; base < n_nodes; base += 32) {
+            const uint32_t k = base + lane;
+            bool hit_leaf = false;
+            float4 lo = make_float4(0, 0, 0, 0), hi = lo;
+            if (k < n_nodes) {
+                lo = __ldg(nodes + 2 * k); hi = __ldg(nodes + 2 * k + 1);
+                const int cnt = __float_as_int(hi.w);
+                hit_leaf = cnt >= 0 && !(cnt & PRT_CAPSULE_LEAF) && ray_box(lo, hi, o, d, md);
+            }
+            unsigned m = __ballot_sync(FULL, hit_leaf);
+            while (m) {
+                const int src = __ffs(m) - 1;
+                m &= m - 1;
+                const uint32_t first = uint32_t(__float_as_int(__shfl_sync(FULL, lo.w, src)));
+                const uint32_t count = uint32_t(__float_as_int(__shfl_sync(FULL, hi.w, src)));
+                for (uint32_t t = first + lane; t < first + count; t += 32) {
+                    const float4 t0 = __ldg(tris + 3 * size_t(t)), t1 = __ldg(tris + 3 * size_t(t) + 1), t2 = __ldg(tris + 3 * size_t(t) + 2);
+                    float tt;
+                    if (segment_triangle(o, end, v3(t0.x, t0.y, t0.z), v3(t1.x, t1.y, t1.z), v3(t2.x, t2.y, t2.z), tt)) {
+                        any = true;
+                        best = (tt < best) ? tt : best;           // std::min(intersectionTime, t)
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int sft = 16; sft > 0; sft >>= 1) { const float other = __shfl_xor_sync(FULL, best, sft); best = (other < best) ? other : best; }
+        any = __any_sync(FULL, any);
+        if (lane == 0) {
+            hit_mask[r] = any ? 1 : 0;
+            if (any) {
+                const V3 h = o + (d * best) * md;                 // origin + direction * intersectionTime * maxDistance
+                hit_xyz[3 * r] = h.x; hit_xyz[3 * r + 1] = h.y; hit_xyz[3 * r + 2] = h.z;
+            }
+        }
+    }
+    if (done_flag) {                                               // completion doorbell (StepParams::done_flag)
+        __threadfence_system();
+        __syncwarp(FULL);
+        if (lane == 0 && atomicAdd(done_count, 1u) + 1u == gridDim.x) {
+            *done_count = 0u;
+            __threadfence_system();
+            *reinterpret_cast<volatile uint32_t *>(done_flag) = done_value;
+        }
+    }
+}
+
 void launch_raycast(const float4 * nodes, uint32_t n_nodes, const float4 * tris, uint32_t n_rays, const float * origins,
-                    const float * dirs, const float * maxd, float * hit_xyz, unsigned char * hit_mask, cudaStream_t stream) {
+                    const float * dirs, const float * maxd, float * hit_xyz, unsigned char * hit_mask, cudaStream_t stream,
+                    uint32_t * done_flag, unsigned * done_count, uint32_t done_value) {
     if (n_rays == 0) return;
+    if (n_nodes <= 4096u && n_rays <= 65535u) {
+        k_raycast_warp<<<n_rays, 32, 0, stream>>>(nodes, n_nodes, tris, n_rays, origins, dirs, maxd, hit_xyz, hit_mask, done_flag, done_count, done_value);
+        return;
+    }
     const uint32_t block = 64;
     k_raycast<<<(n_rays + block - 1) / block, block, 0, stream>>>(nodes, n_nodes, tris, n_rays, origins, dirs, maxd, hit_xyz, hit_mask);
 }
+bool raycast_rings_doorbell(uint32_t n_nodes, uint32_t n_rays) { return n_nodes <= 4096u && n_rays <= 65535u && n_rays > 0; }
 
 // resident state, step kernels that do not read / write the I/O arrays themselves: movement in before, results out after
 __global__ void k_resident_in(uint32_t n, const float * __restrict__ io_move, prtc_char_physics * __restrict__ ph) {
@@ -235,9 +307,11 @@ int launch_step(StepParams const & p_in, bool traced, int mode, cudaStream_t str
     int launches = 0;
     if (p.io_move && !native_io) { k_resident_in<<<(p.n + 255) / 256, 256, 0, stream>>>(p.n, p.io_move, p.physics); ++launches; }
     float4 * io_result = p.io_result;
+    uint32_t * const bell = p.done_flag;
     if (!native_io) { p.io_move = nullptr; p.io_result = nullptr; }
+    if (io_result && !native_io) p.done_flag = nullptr;     // the kernel behind the step writes the results: it rings the doorbell
     launches += launch_step_inner(p, traced, mode, stream);
-    if (io_result && !native_io) { k_resident_out<<<(p.n + 255) / 256, 256, 0, stream>>>(p.n, p.transforms, p.physics, io_result, p.done_flag, p.done_count, p.done_value); ++launches; }
+    if (io_result && !native_io) { k_resident_out<<<(p.n + 255) / 256, 256, 0, stream>>>(p.n, p.transforms, p.physics, io_result, bell, p.done_count, p.done_value); ++launches; }
     return launches;
 }
 

@@ -141,7 +141,9 @@ void launch_tri_setup(const float * world_xyz, const uint32_t * tri_src_vertex, 
 void launch_tree_build(const float4 * leaves, uint32_t n_leaves, float4 * nodes, cudaStream_t stream);
 // K7: batched PhysicsSystem::raycast
 void launch_raycast(const float4 * nodes, uint32_t n_nodes, const float4 * tris, uint32_t n_rays, const float * origins,
-                    const float * dirs, const float * maxd, float * hit_xyz, unsigned char * hit_mask, cudaStream_t stream);
+                    const float * dirs, const float * maxd, float * hit_xyz, unsigned char * hit_mask, cudaStream_t stream,
+                    uint32_t * done_flag = nullptr, unsigned * done_count = nullptr, uint32_t done_value = 0);
+bool raycast_rings_doorbell(uint32_t n_nodes, uint32_t n_rays);      // the launch above will write done_flag when it finishes
 // TIER B (parity unpinned, see k_sweep.cu): swept ellipsoids with collide-and-slide, one warp per ellipsoid
 struct SweepParams {
     const float4 * nodes; uint32_t n_nodes;

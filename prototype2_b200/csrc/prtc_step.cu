@@ -8,6 +8,31 @@ using namespace prt::host;
 
 namespace {
 
+// Completion doorbell of the staged (mapped pinned memory) engine-sized paths: the kernel's last warp writes a sequence number
+// to a word of the staging block, the host spins on it -- a few microseconds after the kernel ends instead of the wake-up
+// of cudaStreamSynchronize.  Every few thousand spins the stream is asked whether it finished (or died) without ringing.
+uint32_t arm_bell(prtc_ctx * c, StepParams & p, uint32_t * word) {
+    if (!c->doorbell) return 0u;
+    *word = 0u;
+    uint32_t v = ++c->resident_frame;
+    if (v == 0u) v = ++c->resident_frame;
+    p.done_flag = word; p.done_count = c->d_work.ptr + 6; p.done_value = v;
+    return v;
+}
+int wait_bell(prtc_ctx * c, const uint32_t * word, uint32_t value) {
+    if (!value) { PRTC_CUDA(cudaStreamSynchronize(c->stream)); return PRTC_OK; }
+    const volatile uint32_t * flag = word;
+    uint32_t spins = 0;
+    while (*flag != value) {
+        if ((++spins & 0xFFFu) == 0u) {
+            const cudaError_t q = cudaStreamQuery(c->stream);
+            if (q == cudaSuccess) break;
+            if (q != cudaErrorNotReady) return fail(PRTC_ERR_CUDA, std::string("stream failed: ") + cudaGetErrorString(q));
+        }
+    }
+    return PRTC_OK;
+}
+
 // copies the device-side trace slots of one traced launch into the caller's prtc_trace
 int gather_trace(prtc_ctx * c, uint32_t n, uint32_t cap_cand, uint32_t cap_hits, prtc_trace * tr) {
     cudaStream_t s = c->stream;
@@ -181,9 +206,10 @@ int literal_step_staged(prtc_ctx * c, float dt, uint32_t n, prtc_transform * tf,
         p.cap2char = s_cap2char; p.seg_start = s_seg_start; p.seg_prev = s_seg_prev; p.last_box = s_last_box;
         p.counters = scratch;
         p.host_flags = flags;
+        const uint32_t bell = arm_bell(c, p, flags + 2);
         c->launches += uint64_t(launch_step(p, false, STEP_LITERAL, s));
         PRTC_CUDA(cudaGetLastError());
-        PRTC_CUDA(cudaStreamSynchronize(s));
+        { const int wrc = wait_bell(c, flags + 2, bell); if (wrc) return wrc; }
         const bool any_capsule_test = flags[0] != 0u;
         const bool settled = !prev_tf.empty() && std::memcmp(prev_tf.data(), s_tf, size_t(n) * sizeof(prtc_transform)) == 0;
         if (!any_capsule_test || settled) break;
@@ -499,9 +525,11 @@ int prtc_step_characters(prtc_ctx * c, float dt, uint32_t n, prtc_transform * tf
         rc = fill_params(c, dt, n, s_tf, s_ph, p);
         if (rc) return rc;
         p.host_flags = flags;
+        const uint32_t bell = arm_bell(c, p, flags + 2);
         c->launches += uint64_t(launch_step(p, false, STEP_STATIC, c->stream));
         PRTC_CUDA(cudaGetLastError());
-        PRTC_CUDA(cudaStreamSynchronize(c->stream));
+        rc = wait_bell(c, flags + 2, bell);
+        if (rc) return rc;
         std::memcpy(tf, s_tf, size_t(n) * sizeof(prtc_transform));
         std::memcpy(ph, s_ph, size_t(n) * sizeof(prtc_char_physics));
         return flags[1] ? check_bad_colliders(c) : PRTC_OK;
@@ -565,7 +593,7 @@ int prtc_raycast(prtc_ctx * c, uint32_t n, const float * origins, const float * 
     if (n <= kSmallBatch && c->staged) {
         // the engine casts four rays per frame, one call each (scene.cpp:248-255): rays and answers live in mapped pinned
         // memory, the call is one launch and one synchronisation instead of four uploads, a launch and two downloads
-        PRTC_CUDA(c->stage.reserve(size_t(n) * 11 * sizeof(float) + 6 * 64));
+        PRTC_CUDA(c->stage.reserve(size_t(n) * 11 * sizeof(float) + 8 * 64));
         StageCursor cur{c->stage.base};
         float * s_o = cur.take<float>(3 * size_t(n)), * s_d = cur.take<float>(3 * size_t(n)), * s_m = cur.take<float>(n);
         float * s_h = cur.take<float>(3 * size_t(n));
@@ -574,9 +602,13 @@ int prtc_raycast(prtc_ctx * c, uint32_t n, const float * origins, const float * 
         std::memcpy(s_d, directions, size_t(n) * 3 * sizeof(float));
         std::memcpy(s_m, max_distances, size_t(n) * sizeof(float));
         std::memset(s_h, 0, size_t(n) * 3 * sizeof(float));
-        launch_raycast(c->d_nodes.ptr, uint32_t(c->flat.nodes.size()), c->d_tris.ptr, n, s_o, s_d, s_m, s_h, s_mask, s);
+        uint32_t * bell_word = cur.take<uint32_t>(16);
+        StepParams bp;
+        std::memset(&bp, 0, sizeof(bp));
+        const uint32_t bell = raycast_rings_doorbell(uint32_t(c->flat.nodes.size()), n) ? arm_bell(c, bp, bell_word) : 0u;
+        launch_raycast(c->d_nodes.ptr, uint32_t(c->flat.nodes.size()), c->d_tris.ptr, n, s_o, s_d, s_m, s_h, s_mask, s, bp.done_flag, bp.done_count, bp.done_value);
         PRTC_CUDA(cudaGetLastError());
-        PRTC_CUDA(cudaStreamSynchronize(s));
+        { const int wrc = wait_bell(c, bell_word, bell); if (wrc) return wrc; }
         std::memcpy(hit_mask, s_mask, n);
         for (uint32_t i = 0; i < n; ++i)
             if (hit_mask[i]) { hit_xyz[3 * i] = s_h[3 * size_t(i)]; hit_xyz[3 * i + 1] = s_h[3 * size_t(i) + 1]; hit_xyz[3 * i + 2] = s_h[3 * size_t(i) + 2]; }
