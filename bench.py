@@ -341,6 +341,11 @@ class Workload:
                 ctx.set_option(getattr(capi, "OPT_" + oname), int(val))
             if self.dynamic:
                 ctx.dyn_configure(self.first, self.n_global if strong else self.n)
+                # the records of the dynamic pass travel by peer stores from the kernel that computes them (CUDA IPC handles
+                # swapped once); PRTC_BENCH_EXCHANGE=nccl keeps the all-gather of round 1 for A/B
+                self.ipc = False
+                if strong and world > 1 and os.environ.get("PRTC_BENCH_EXCHANGE", "ipc") == "ipc":
+                    self.ipc = sharding.ipc_connect(ctx, rank, world)
             ctx.add_model_collider(self.xyz, self.mf, self.mc)
             self.cid = ctx.add_capsule_collider()          # one shared collider shape (h=0.5 r=0.5 off=(0,0.5,0))
             t0 = time.perf_counter()
@@ -378,8 +383,8 @@ class Workload:
         self.d_ph.copy_(self.h_ph)
 
     def device_step(self):
-        if self.dynamic and self.world > 1 and self.strong:
-            # the one exchange of the path: the records of every character, all-gathered in place over NVLink
+        if self.dynamic and self.world > 1 and self.strong and not getattr(self, "ipc", False):
+            # the one exchange of the path, collective flavour: the records of every character, all-gathered in place over NVLink
             self.ctx.dyn_prepare(DT, self.n, self.d_tf.data_ptr(), self.d_ph.data_ptr())
             if self._rec is None:                          # the record array never moves: wrap it once
                 self._rec = self.sharding.records_tensor(self.ctx)
@@ -598,7 +603,9 @@ def run_ours(args):
         extras["c5"] = {"workload": w5.describe()["workload"], "ms_per_step": 1e3 * r5["el"] / k5, "value": r5["substeps"] / r5["el"],
                         "unit": UNIT, "state_crc32": w5.crc(), "scaling": "strong",
                         "exchange_bytes_per_step": (w5.n_global * 64) if world > 1 else 0,
-                        "exchange": "ncclAllGather of 64-byte records, in place" if world > 1 else "none (one rank)"}
+                        "exchange": ("none (one rank)" if world == 1 else
+                                     "peer stores of the 64-byte records from k_dyn_prep into every rank's array (CUDA IPC), arrival words in device memory"
+                                     if getattr(w5, "ipc", False) else "ncclAllGather of 64-byte records, in place")}
         del w5
 
     # ---- CPU baseline beside it (rank 0, N=1 only) ----------------------------------------------------------

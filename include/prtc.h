@@ -257,6 +257,16 @@ int prtc_sweep_ellipsoids(prtc_ctx * ctx, uint32_t n, const float * centers, con
 int prtc_dyn_configure(prtc_ctx * ctx, uint32_t first_global, uint32_t n_global);
 int prtc_dyn_prepare(prtc_ctx * ctx, float dt, uint32_t n, const prtc_transform * d_transforms, const prtc_char_physics * d_physics);
 int prtc_dyn_buffer(prtc_ctx * ctx, void ** d_records, size_t * record_bytes, uint32_t * first_global, uint32_t * n_global);
+/* The same exchange ACROSS PROCESSES without a collective: every rank exports CUDA IPC handles of its record array and of
+ * its arrival table (PRTC_IPC_HANDLE_BYTES bytes), the caller distributes them (any transport), every rank imports all of
+ * them in rank order.  From then on prtc_dyn_prepare stores this rank's records straight into every peer's array (peer
+ * stores over NVLink from the kernel that computes them; the array is double-buffered) and its last block writes the frame
+ * number into the peers' arrival tables; prtc_step_characters_device waits on the device until every rank has arrived
+ * (a rank that does not arrive within a few seconds makes the step fail with PRTC_ERR_CUDA instead of hanging the GPU).
+ * No all-gather, no host involvement per frame.  Call export after prtc_dyn_configure and before the first frame. */
+#define PRTC_IPC_HANDLE_BYTES 128
+int prtc_dyn_ipc_export(prtc_ctx * ctx, uint32_t rank, uint32_t world, void * handle /* PRTC_IPC_HANDLE_BYTES */);
+int prtc_dyn_ipc_import(prtc_ctx * ctx, const void * handles /* world x PRTC_IPC_HANDLE_BYTES, rank order */);
 
 /* stream control for callers that own device memory (bench / multi-GPU drivers) */
 int prtc_set_stream(prtc_ctx * ctx, void * cuda_stream);

@@ -28,6 +28,7 @@ SYMBOLS = (
     "prtc_multi_update_capsule", "prtc_multi_remove_model", "prtc_multi_update_models", "prtc_multi_commit", "prtc_multi_set_option",
     "prtc_multi_raycast", "prtc_multi_get_counters", "prtc_multi_step_characters", "prtc_multi_resident_begin", "prtc_multi_resident_io",
     "prtc_multi_resident_step", "prtc_multi_resident_fetch", "prtc_multi_resident_end", "prtc_get_commit_stats",
+    "prtc_dyn_ipc_export", "prtc_dyn_ipc_import",
 )
 
 
@@ -300,6 +301,17 @@ class PhysicsContext:
         ptr, rb, first, ng = ctypes.c_void_p(), ctypes.c_size_t(), ctypes.c_uint32(), ctypes.c_uint32()
         self._check(self.lib.prtc_dyn_buffer(self.h, ctypes.byref(ptr), ctypes.byref(rb), ctypes.byref(first), ctypes.byref(ng)))
         return ptr.value, rb.value, first.value, ng.value
+
+    def dyn_ipc_export(self, rank, world):
+        """128 bytes of CUDA IPC handles (record array + arrival table) for the other ranks"""
+        buf = ctypes.create_string_buffer(128)
+        self._check(self.lib.prtc_dyn_ipc_export(self.h, ctypes.c_uint32(rank), ctypes.c_uint32(world), buf))
+        return buf.raw
+
+    def dyn_ipc_import(self, handles):
+        """handles: list of the ranks' 128-byte blobs in rank order (own slot is ignored)"""
+        blob = b"".join(handles)
+        self._check(self.lib.prtc_dyn_ipc_import(self.h, ctypes.c_char_p(blob)))
 
     def set_option(self, option, value):
         self._check(self.lib.prtc_set_option(self.h, ctypes.c_int(option), ctypes.c_int(value)))

@@ -10,6 +10,8 @@
 //                 device-side maximum (`reach`), and a query simply starts that many cells earlier (step_common.cuh dyn_collect)
 //   k_dyn_scan    exclusive prefix sum of the cell counts, one block (the grid has at most 2^20 cells; 81 k at C5)
 // Everything runs on the context's stream without the host looking at any of it.
+#include <algorithm>
+
 #include "step_common.cuh"
 
 namespace prt {
@@ -18,9 +20,9 @@ namespace {
 
 __global__ void k_dyn_prep(const prtc_transform * __restrict__ tf, const prtc_char_physics * __restrict__ ph,
                            const CapsuleDev * __restrict__ capsules, uint32_t n_capsules, uint32_t n, uint32_t first,
-                           float4 * __restrict__ records, DynPeers peers, float dt, float gravity, float margin, uint32_t init) {
+                           const float4 * prev_records, float4 * records, DynPeers peers, float dt, float gravity, float margin, uint32_t init) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+    if (i < n) {
     uint32_t cid = ph[i].collider;
     if (cid >= n_capsules) cid = 0;               // unknown capsule id: never dereferenced (the step kernel reports it, counters[6])
     const CapsuleDev cap = capsules[cid];
@@ -45,8 +47,8 @@ __global__ void k_dyn_prep(const prtc_transform * __restrict__ tf, const prtc_ch
         segment_ends(capsule_frame(cap, rotation_of(qi)), v3(0.0f), iA, iB);
         const Box ib = capsule_box(iA, iB, cap.radius);
         stored.lo = ib.lo - margin; stored.hi = ib.hi + margin;
-    } else {
-        const float4 lo = rec[2], hi = rec[3];
+    } else {                                                       // last frame's stored box (the other buffer when the records are double-buffered)
+        const float4 lo = prev_records[4 * size_t(first + i) + 2], hi = prev_records[4 * size_t(first + i) + 3];
         stored.lo = v3(lo.x, lo.y, lo.z); stored.hi = v3(hi.x, hi.y, hi.z);
     }
     if (!box_contains(stored, e)) { stored.lo = e.lo - margin; stored.hi = e.hi + margin; }
@@ -55,10 +57,57 @@ __global__ void k_dyn_prep(const prtc_transform * __restrict__ tf, const prtc_ch
     rec[0] = r0; rec[1] = r1; rec[2] = r2; rec[3] = r3;
     // several devices in one process (prtc_multi): the record goes straight into the other devices' arrays too -- peer stores
     // over NVLink from the kernel that computes it, instead of a collective behind it
-    for (uint32_t k = 0; k < peers.n; ++k) {
+    for (uint32_t k = 0; k < (peers.push_separately ? 0u : peers.n); ++k) {
         float4 * dst = peers.records[k] + 4 * size_t(first + i);
         dst[0] = r0; dst[1] = r1; dst[2] = r2; dst[3] = r3;
     }
+    }
+    if (peers.n_flags && !peers.push_separately) {
+        // arrival: every block's stores are out (system-wide fence) before it counts itself; the last one tells everybody
+        __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x == 0 && atomicAdd(peers.block_count, 1u) + 1u == gridDim.x) {
+            *peers.block_count = 0u;
+            __threadfence_system();
+            for (uint32_t k = 0; k < peers.n_flags; ++k) *reinterpret_cast<volatile uint32_t *>(peers.flags[k]) = peers.flag_value;
+            __threadfence_system();
+        }
+    }
+}
+
+// The exchange across processes: one thread per (destination, float4 of this rank's slice) -- eight times the threads of
+// k_dyn_prep, every one with a single 16-byte peer store in flight -- then the arrival words, written by the last block.
+__global__ void k_dyn_push(const float4 * __restrict__ records, uint32_t first, uint32_t n, DynPeers peers) {
+    const size_t per = 4 * size_t(n);
+    const size_t t = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (t < per * peers.n) {
+        const uint32_t k = uint32_t(t / per);
+        const size_t e = 4 * size_t(first) + t % per;
+        peers.records[k][e] = records[e];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0 && atomicAdd(peers.block_count, 1u) + 1u == gridDim.x) {
+        *peers.block_count = 0u;
+        __threadfence_system();
+        for (uint32_t k = 0; k < peers.n_flags; ++k) *reinterpret_cast<volatile uint32_t *>(peers.flags[k]) = peers.flag_value;
+        __threadfence_system();
+    }
+}
+
+__global__ void k_dyn_wait(const uint32_t * flags, uint32_t n_ranks, uint32_t value, unsigned long long * counters) {
+    const uint32_t r = threadIdx.x;
+    if (r >= n_ranks) return;
+    unsigned long long t0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    // (frame numbers only grow; a rank that is AHEAD has a larger number)
+    while (int32_t(*reinterpret_cast<const volatile uint32_t *>(flags + r) - value) < 0) {
+        __nanosleep(100);
+        unsigned long long t1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+        if (t1 - t0 > 4000000000ull) { if (counters) atomicAdd(counters + 7, 1ull); break; }     // 4 s: a peer is gone; never hang the GPU
+    }
+    __threadfence_system();
 }
 
 // pass 0 counts (and tracks the reach), pass 1 fills; `cell_count` is zero before either pass
@@ -114,9 +163,19 @@ __global__ void __launch_bounds__(1024) k_dyn_scan(const uint32_t * __restrict__
 } // namespace
 
 void launch_dyn_prep(const prtc_transform * tf, const prtc_char_physics * ph, const CapsuleDev * capsules, uint32_t n_capsules, uint32_t n,
-                     uint32_t first, float4 * records, DynPeers const & peers, float dt, float gravity, float margin, bool init, cudaStream_t stream) {
-    if (n == 0) return;
-    k_dyn_prep<<<(n + 127) / 128, 128, 0, stream>>>(tf, ph, capsules, n_capsules, n, first, records, peers, dt, gravity, margin, init ? 1u : 0u);
+                     uint32_t first, const float4 * prev_records, float4 * records, DynPeers const & peers, float dt, float gravity, float margin,
+                     bool init, cudaStream_t stream) {
+    if (n == 0 && !peers.n_flags) return;
+    const uint32_t blocks = n ? (n + 127) / 128 : 1u;             // (a rank without characters still has to arrive)
+    k_dyn_prep<<<blocks, 128, 0, stream>>>(tf, ph, capsules, n_capsules, n, first, prev_records, records, peers, dt, gravity, margin, init ? 1u : 0u);
+    if (peers.push_separately) {
+        const size_t threads = std::max<size_t>(1, 4 * size_t(n) * peers.n);
+        k_dyn_push<<<unsigned((threads + 255) / 256), 256, 0, stream>>>(records, first, n, peers);
+    }
+}
+
+void launch_dyn_wait(const uint32_t * flags, uint32_t n_ranks, uint32_t value, unsigned long long * counters, cudaStream_t stream) {
+    k_dyn_wait<<<1, 32, 0, stream>>>(flags, n_ranks, value, counters);
 }
 
 int launch_dyn_grid_build(const float4 * records, uint32_t n, float ox, float oz, float inv_cell, uint32_t gx, uint32_t gz,

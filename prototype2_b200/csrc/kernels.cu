@@ -295,6 +295,14 @@ __global__ void k_resident_out(uint32_t n, const prtc_transform * __restrict__ t
 
 static int launch_step_inner(StepParams const & p_in, bool traced, int mode, cudaStream_t stream);
 
+// only the pooled path reads slots that a caller may have refreshed ahead of time
+bool launch_slot_refresh(StepParams const & p, int mode, cudaStream_t stream) {
+    if (p.n == 0 || !(p.pool && p.work_counter && mode != MODE_LITERAL) || p.xc_version == nullptr || (p.tune & 1u)) return false;
+    launch_k_xc_refresh(p, stream);
+    return true;
+}
+
+
 int launch_step(StepParams const & p_in, bool traced, int mode, cudaStream_t stream) {
     if (p_in.n == 0) return 0;
     // which kernel will run is decided inside; the pooled kernel reads / writes the resident I/O arrays itself, the others
@@ -340,7 +348,7 @@ static int launch_step_inner(StepParams const & p_in, bool traced, int mode, cud
         static const uint32_t force_opw = [] { const char * e = std::getenv("PRTC_OPW"); return e ? uint32_t(std::atoi(e)) : 0u; }();
         if (force_opw >= 1u && force_opw <= 32u) opw = force_opw;   // experiments
         p.lanes_per_warp = opw;
-        if (p.xc_version != nullptr && !(p.tune & 1u)) { launch_k_xc_refresh(p, stream); ++launches; }
+        if (p.xc_version != nullptr && !(p.tune & 1u)) { if (!p.xc_fresh) { launch_k_xc_refresh(p, stream); ++launches; } }
         else p.xc_version = nullptr;
         const uint32_t want = (p.n + opw - 1) / opw;
         launch_k_step_pool(p, want < p.pool_blocks ? want : p.pool_blocks, false, mode, stream);

@@ -86,6 +86,7 @@ struct StepParams {
     const float4 * top;             // k_xc_refresh: top-of-tree table staged in shared memory (2 float4 per entry), null => plain walk
     uint32_t n_top;
     uint32_t persistent_blocks;     // k_step_stream: resident blocks to launch
+    uint32_t xc_fresh;              // 1: the per-slot leaf lists were brought up to date by the caller (launch_step does not launch k_xc_refresh)
     uint32_t pool;                  // 1: the pooled kernel k_step_pool runs the persistent launches (PRTC_OPT_POOL_KERNEL)
     uint32_t pool_blocks;           // k_step_pool: resident blocks to launch
     uint32_t n_tris;                // triangle records behind `tris`
@@ -115,10 +116,26 @@ uint32_t pool_blocks_per_sm();                  // resident one-warp blocks per 
 // static pass over a batch whose input is still being copied in (gate / done_* set): the persistent kernel alone, then the
 // refresh of the per-slot leaf lists for the NEXT frame from the state it leaves behind; returns the number of launches
 int launch_step_ingest(StepParams const & p, cudaStream_t stream);
+// the refresh of the per-slot leaf lists on its own (callers that want it ahead of something else set xc_fresh afterwards)
+bool launch_slot_refresh(StepParams const & p, int mode, cudaStream_t stream);
 // dynamic pass, CANONICAL / JACOBI: per-character record (4 float4) and the uniform grid over all stored boxes (k_dyn.cu)
-struct DynPeers { float4 * records[15]; uint32_t n; };      // record arrays of the other devices of a prtc_multi (peer-mapped)
+// Where k_dyn_prep stores a record besides the device's own array, and how it tells the others that it is done:
+//   records[k]   the other devices' record arrays (peer-mapped: cudaDeviceEnablePeerAccess inside one process, CUDA IPC across
+//                processes)
+//   flags[k]     (IPC exchange only) one word per destination -- this rank's slot in that device's arrival table; the LAST
+//                block of the kernel writes `flag_value` (the frame number) into all of them behind a system-wide fence, and
+//                the consumer's k_dyn_wait spins on its own table until every rank's word has reached the frame number
+struct DynPeers {
+    float4 * records[15]; uint32_t n;
+    uint32_t * flags[16]; uint32_t n_flags; uint32_t flag_value; unsigned * block_count;
+    uint32_t push_separately;       // 1: the records go out in a kernel of their own (k_dyn_push) behind k_dyn_prep
+};
 void launch_dyn_prep(const prtc_transform * tf, const prtc_char_physics * ph, const CapsuleDev * capsules, uint32_t n_capsules, uint32_t n,
-                     uint32_t first, float4 * records, DynPeers const & peers, float dt, float gravity, float margin, bool init, cudaStream_t stream);
+                     uint32_t first, const float4 * prev_records, float4 * records, DynPeers const & peers, float dt, float gravity, float margin,
+                     bool init, cudaStream_t stream);
+// IPC exchange: wait (on the device, stream-ordered) until every rank's arrival word has reached `value`; gives up after a
+// few seconds and raises counters[7] instead of hanging the GPU
+void launch_dyn_wait(const uint32_t * flags, uint32_t n_ranks, uint32_t value, unsigned long long * counters, cudaStream_t stream);
 // counting sort of all n stored boxes into the uniform xz grid (one cell per box) + the per-frame reach; returns kernels launched
 int launch_dyn_grid_build(const float4 * records, uint32_t n, float ox, float oz, float inv_cell, uint32_t gx, uint32_t gz,
                           uint32_t * cell_count, uint32_t * cell_start, uint32_t * items, uint32_t * reach, cudaStream_t stream);

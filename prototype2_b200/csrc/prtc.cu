@@ -420,9 +420,14 @@ int fill_params(prtc_ctx * c, float dt, uint32_t n, prtc_transform * d_tf, prtc_
 // characters whose collider id names no registered capsule are skipped by the kernels and counted in slot 6
 int check_bad_colliders(prtc_ctx * c, cudaStream_t on) {
     cudaStream_t s = on ? on : c->stream;
-    unsigned long long bad = 0;
-    PRTC_CUDA(cudaMemcpyAsync(&bad, c->d_counters.ptr + 6, sizeof(bad), cudaMemcpyDeviceToHost, s));
+    unsigned long long both[2] = {0, 0};
+    PRTC_CUDA(cudaMemcpyAsync(both, c->d_counters.ptr + 6, sizeof(both), cudaMemcpyDeviceToHost, s));
     PRTC_CUDA(cudaStreamSynchronize(s));
+    if (both[1]) {
+        PRTC_CUDA(cudaMemsetAsync(c->d_counters.ptr + 7, 0, sizeof(unsigned long long), s));
+        return fail(PRTC_ERR_CUDA, "the record exchange of the dynamic pass timed out waiting for a peer rank (prtc_dyn_ipc_*)");
+    }
+    const unsigned long long bad = both[0];
     if (bad) {
         PRTC_CUDA(cudaMemsetAsync(c->d_counters.ptr + 6, 0, sizeof(bad), s));
         return fail(PRTC_ERR_INVALID, "prtc_step_characters: " + std::to_string(bad) + " character(s) name a capsule collider that was never added; their results are undefined");
@@ -549,6 +554,8 @@ void prtc_destroy(prtc_ctx * c) {
     c->d_tq.release(); c->d_tmesh.release(); c->d_tcaps.release(); c->d_thits.release();
     c->d_scratch_f.release(); c->d_scratch_u.release();
     c->d_cap2char.release(); c->d_seg_start.release(); c->d_seg_prev.release(); c->d_last_box.release();
+    for (void * q : c->dyn_ipc.opened) cudaIpcCloseMemHandle(q);
+    c->dyn_ipc.opened.clear(); c->dyn_ipc.flags.release();
     c->d_dyn_records.release(); c->d_dyn_count.release(); c->d_dyn_start.release(); c->d_dyn_items.release(); c->d_dyn_reach.release();
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
     for (int k = 0; k < prtc_ctx::PIPE_STREAMS; ++k) if (c->pipe[k]) cudaStreamDestroy(c->pipe[k]);

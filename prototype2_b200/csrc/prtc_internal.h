@@ -176,6 +176,17 @@ struct prtc_ctx {
     bool dyn_initialized = false;            // stored boxes exist (first prepare creates them at the identity pose)
     bool dyn_prepared = false;               // prtc_dyn_prepare ran for the coming step (records may have been exchanged since)
     prt::DynPeers dyn_peers = {};            // prtc_multi: the other devices' record arrays, written by this device's k_dyn_prep
+    // exchange of the records ACROSS PROCESSES (prtc_dyn_ipc_*): the record array is double-buffered (a fast rank writes
+    // frame f+1's records into its peers while they still step frame f) and every rank's arrival is a word in device memory
+    struct DynIpc {
+        bool on = false;
+        uint32_t rank = 0, world = 0, frame = 0;
+        prt::host::DevBuf<uint32_t> flags;           // [32] arrival table (frame numbers) + block counter at [31]
+        float4 * peer_records[15] = {};              // base of the peers' (2 x n_global records) arrays
+        uint32_t * peer_flags[15] = {};
+        uint32_t n_peers = 0;
+        std::vector<void *> opened;
+    } dyn_ipc;
     float world_lo[3] = {0, 0, 0}, world_hi[3] = {0, 0, 0};
     // resident state (prtc_resident_*): the records stay in d_tf / d_ph between frames; per-frame I/O through mapped pinned arrays
     bool resident = false;

@@ -113,10 +113,12 @@ namespace host {
 int dyn_reserve(prtc_ctx * c, uint32_t n) {
     if (!c->dyn_configured) { c->dyn_first = 0; c->dyn_global = n; }
     if (uint64_t(c->dyn_first) + n > c->dyn_global) return fail(PRTC_ERR_INVALID, "prtc_dyn_prepare: slice exceeds the configured global count");
-    if (c->d_dyn_records.cap < size_t(c->dyn_global) * 4) {
+    // (two buffers when the records are exchanged across processes, see prtc_ctx::DynIpc)
+    const size_t want = size_t(c->dyn_global) * 4 * (c->dyn_ipc.world ? 2 : 1);
+    if (c->d_dyn_records.cap < want) {
         if (c->dyn_initialized) return fail(PRTC_ERR_INVALID, "prtc_dyn_prepare: the global character count may not grow after the first frame");
-        PRTC_CUDA(c->d_dyn_records.reserve(size_t(c->dyn_global) * 4));
-        PRTC_CUDA(cudaMemsetAsync(c->d_dyn_records.ptr, 0, size_t(c->dyn_global) * 4 * sizeof(float4), c->stream));
+        PRTC_CUDA(c->d_dyn_records.reserve(want));
+        PRTC_CUDA(cudaMemsetAsync(c->d_dyn_records.ptr, 0, want * sizeof(float4), c->stream));
     }
     return PRTC_OK;
 }
@@ -125,8 +127,24 @@ int dyn_reserve(prtc_ctx * c, uint32_t n) {
 int dyn_prepare(prtc_ctx * c, float dt, uint32_t n, const prtc_transform * d_tf, const prtc_char_physics * d_ph) {
     int rc = dyn_reserve(c, n);
     if (rc) return rc;
-    launch_dyn_prep(d_tf, d_ph, c->d_capsules.ptr, uint32_t(c->capsules.size()), n, c->dyn_first, c->d_dyn_records.ptr, c->dyn_peers, dt,
-                    c->cfg.gravity, c->cfg.leaf_margin, !c->dyn_initialized, c->stream);
+    if (c->dyn_ipc.on) {
+        // this frame's buffer: own and peers'; the stored boxes of the last frame are in the other one; the kernel's last block
+        // writes the frame number into this rank's word of everybody's arrival table
+        prtc_ctx::DynIpc & x = c->dyn_ipc;
+        const size_t half = size_t(c->dyn_global) * 4;
+        const uint32_t b = x.frame & 1u;
+        DynPeers peers = {};
+        for (uint32_t k = 0; k < x.n_peers; ++k) { peers.records[peers.n++] = x.peer_records[k] + b * half; peers.flags[peers.n_flags++] = x.peer_flags[k] + x.rank; }
+        peers.flags[peers.n_flags++] = x.flags.ptr + x.rank;
+        peers.flag_value = x.frame + 1u;
+        peers.block_count = x.flags.ptr + 31;
+        peers.push_separately = 1u;
+        launch_dyn_prep(d_tf, d_ph, c->d_capsules.ptr, uint32_t(c->capsules.size()), n, c->dyn_first, c->d_dyn_records.ptr + (b ^ 1u) * half,
+                        c->d_dyn_records.ptr + b * half, peers, dt, c->cfg.gravity, c->cfg.leaf_margin, !c->dyn_initialized, c->stream);
+    } else {
+        launch_dyn_prep(d_tf, d_ph, c->d_capsules.ptr, uint32_t(c->capsules.size()), n, c->dyn_first, c->d_dyn_records.ptr, c->d_dyn_records.ptr,
+                        c->dyn_peers, dt, c->cfg.gravity, c->cfg.leaf_margin, !c->dyn_initialized, c->stream);
+    }
     PRTC_CUDA(cudaGetLastError());
     c->dyn_initialized = true;
     c->dyn_prepared = true;
@@ -154,10 +172,19 @@ int dyn_build_grid(prtc_ctx * c, StepParams & p) {
     PRTC_CUDA(c->d_dyn_start.reserve(cells + 1));
     PRTC_CUDA(c->d_dyn_items.reserve(size_t(ng) + 1));
     PRTC_CUDA(c->d_dyn_reach.reserve(2));
-    c->launches += uint64_t(launch_dyn_grid_build(c->d_dyn_records.ptr, ng, lox, loz, 1.0f / cell, gx, gz, c->d_dyn_count.ptr, c->d_dyn_start.ptr,
+    const float4 * records = c->d_dyn_records.ptr;
+    if (c->dyn_ipc.on) {
+        // every rank's records of this frame must have landed in this device's buffer: wait for the arrival words, on the device
+        prtc_ctx::DynIpc & x = c->dyn_ipc;
+        launch_dyn_wait(x.flags.ptr, x.world, x.frame + 1u, c->d_counters.ptr, s);
+        records = c->d_dyn_records.ptr + (x.frame & 1u) * size_t(c->dyn_global) * 4;
+        ++x.frame;
+        c->launches += 1;
+    }
+    c->launches += uint64_t(launch_dyn_grid_build(records, ng, lox, loz, 1.0f / cell, gx, gz, c->d_dyn_count.ptr, c->d_dyn_start.ptr,
                                                   c->d_dyn_items.ptr, c->d_dyn_reach.ptr, s));
     PRTC_CUDA(cudaGetLastError());
-    p.dyn_records = c->d_dyn_records.ptr;
+    p.dyn_records = records;
     p.dyn_cell_start = c->d_dyn_start.ptr;
     p.dyn_items = c->d_dyn_items.ptr;
     p.dyn_reach = c->d_dyn_reach.ptr;
@@ -365,6 +392,8 @@ int prtc_step_characters_device(prtc_ctx * c, float dt, uint32_t n, prtc_transfo
     int mode = STEP_STATIC;
     if (c->jacobi()) {
         if (!c->dyn_prepared) { rc = dyn_prepare(c, dt, n, d_tf, d_ph); if (rc) return rc; }
+        // (the records are on their way to the peers: bring the per-slot leaf lists up to date meanwhile, they do not depend on them)
+        if (c->dyn_ipc.on && launch_slot_refresh(p, STEP_JACOBI, c->stream)) { p.xc_fresh = 1u; c->launches += 1; }
         rc = dyn_build_grid(c, p);
         if (rc) return rc;
         c->dyn_prepared = false;
@@ -856,10 +885,54 @@ int prtc_dyn_prepare(prtc_ctx * c, float dt, uint32_t n, const prtc_transform * 
     return dyn_prepare(c, dt, n, d_tf, d_ph);
 }
 
+int prtc_dyn_ipc_export(prtc_ctx * c, uint32_t rank, uint32_t world, void * handle) {
+    if (!c || !handle || world < 2 || world > 16 || rank >= world) return fail(PRTC_ERR_INVALID, "prtc_dyn_ipc_export: bad argument (2..16 ranks)");
+    if (!c->jacobi() || !c->dyn_configured) return fail(PRTC_ERR_INVALID, "prtc_dyn_ipc_export: needs PRTC_DYN_JACOBI and prtc_dyn_configure first");
+    if (c->dyn_initialized) return fail(PRTC_ERR_INVALID, "prtc_dyn_ipc_export: call it before the first frame");
+    PRTC_CUDA(cudaSetDevice(c->cfg.device));
+    prtc_ctx::DynIpc & x = c->dyn_ipc;
+    x.rank = rank; x.world = world; x.frame = 0;
+    int rc = dyn_reserve(c, 0);
+    if (rc) return rc;
+    PRTC_CUDA(x.flags.reserve(32));
+    PRTC_CUDA(cudaMemsetAsync(x.flags.ptr, 0, 32 * sizeof(uint32_t), c->stream));
+    PRTC_CUDA(cudaStreamSynchronize(c->stream));
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle layout");
+    cudaIpcMemHandle_t h[2];
+    PRTC_CUDA(cudaIpcGetMemHandle(&h[0], c->d_dyn_records.ptr));
+    PRTC_CUDA(cudaIpcGetMemHandle(&h[1], x.flags.ptr));
+    std::memcpy(handle, h, sizeof(h));
+    return PRTC_OK;
+}
+
+int prtc_dyn_ipc_import(prtc_ctx * c, const void * handles) {
+    if (!c || !handles) return fail(PRTC_ERR_INVALID, "prtc_dyn_ipc_import: null argument");
+    prtc_ctx::DynIpc & x = c->dyn_ipc;
+    if (!x.world || !x.flags.ptr) return fail(PRTC_ERR_INVALID, "prtc_dyn_ipc_import: call prtc_dyn_ipc_export first");
+    PRTC_CUDA(cudaSetDevice(c->cfg.device));
+    const unsigned char * hb = static_cast<const unsigned char *>(handles);
+    x.n_peers = 0;
+    for (uint32_t r = 0; r < x.world; ++r) {
+        if (r == x.rank) continue;
+        cudaIpcMemHandle_t h[2];
+        std::memcpy(h, hb + size_t(r) * sizeof(h), sizeof(h));
+        void * rec = nullptr, * flg = nullptr;
+        PRTC_CUDA(cudaIpcOpenMemHandle(&rec, h[0], cudaIpcMemLazyEnablePeerAccess));
+        x.opened.push_back(rec);
+        PRTC_CUDA(cudaIpcOpenMemHandle(&flg, h[1], cudaIpcMemLazyEnablePeerAccess));
+        x.opened.push_back(flg);
+        x.peer_records[x.n_peers] = static_cast<float4 *>(rec);
+        x.peer_flags[x.n_peers] = static_cast<uint32_t *>(flg);
+        ++x.n_peers;
+    }
+    x.on = true;
+    return PRTC_OK;
+}
+
 int prtc_dyn_buffer(prtc_ctx * c, void ** d_records, size_t * record_bytes, uint32_t * first_global, uint32_t * n_global) {
     if (!c || !d_records) return fail(PRTC_ERR_INVALID, "prtc_dyn_buffer: null argument");
     if (!c->d_dyn_records.ptr) return fail(PRTC_ERR_INVALID, "prtc_dyn_buffer: call prtc_dyn_prepare first");
-    *d_records = c->d_dyn_records.ptr;
+    *d_records = c->d_dyn_records.ptr + (c->dyn_ipc.on ? (c->dyn_ipc.frame & 1u) * size_t(c->dyn_global) * 4 : 0);
     if (record_bytes) *record_bytes = 4 * sizeof(float4);
     if (first_global) *first_global = c->dyn_first;
     if (n_global) *n_global = c->dyn_global;

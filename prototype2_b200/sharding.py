@@ -2,8 +2,12 @@
 
 Static pass: characters are independent units -> contiguous index ranges per rank, no collective.
 Dynamic pass (PRTC_DYN_JACOBI): one exchange per frame -- every rank's 64-byte character records (start-of-frame
-capsule segment + stored fat box) are all-gathered IN PLACE into the record array each context owns
-(prtc_dyn_buffer), NCCL over NVLink on GPUs, gloo on CPU tensors in the tests.
+capsule segment + stored fat box).  Two ways:
+  * ipc_connect(): the ranks swap CUDA IPC handles once; from then on the kernel that computes the records stores them
+    straight into every peer's array (peer stores over NVLink) and a device-side arrival table orders the frames -- no
+    collective and no host call per frame (prtc_dyn_ipc_*);
+  * allgather_records(): the records are all-gathered IN PLACE into the record array each context owns (prtc_dyn_buffer),
+    NCCL over NVLink on GPUs, gloo on CPU tensors in the tests.
 """
 import numpy as np
 
@@ -53,3 +57,23 @@ def gather_rows(local_rows, group=None):
     out = [torch.empty_like(local_rows) for _ in range(dist.get_world_size(group))]
     dist.all_gather(out, local_rows, group=group)
     return torch.cat(out, dim=0)
+
+
+def ipc_connect(ctx, rank, world, group=None):
+    """One-time set-up of the collective-free record exchange: every rank exports its handles, all ranks import all of them.
+    Returns False (and leaves the context on the all-gather path) when the devices cannot map each other's memory."""
+    import torch.distributed as dist
+    from . import capi
+    mine = ctx.dyn_ipc_export(rank, world)
+    blobs = [None] * world
+    dist.all_gather_object(blobs, mine, group=group)
+    try:
+        ctx.dyn_ipc_import(blobs)
+        ok = True
+    except capi.PrtcError:
+        ok = False
+    flags = [None] * world
+    dist.all_gather_object(flags, ok, group=group)
+    if not all(flags):
+        raise RuntimeError("CUDA IPC import failed on some rank; use the all-gather path (PRTC_BENCH_EXCHANGE=nccl)")
+    return True
