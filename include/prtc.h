@@ -266,7 +266,7 @@ int prtc_dyn_buffer(prtc_ctx * ctx, void ** d_records, size_t * record_bytes, ui
  * No all-gather, no host involvement per frame.  Call export after prtc_dyn_configure and before the first frame. */
 #define PRTC_IPC_HANDLE_BYTES 128
 int prtc_dyn_ipc_export(prtc_ctx * ctx, uint32_t rank, uint32_t world, void * handle /* PRTC_IPC_HANDLE_BYTES */);
-int prtc_dyn_ipc_import(prtc_ctx * ctx, const void * handles /* world x PRTC_IPC_HANDLE_BYTES, rank order */);
+int prtc_dyn_ipc_import(prtc_ctx * ctx, const void * handles /* world x PRTC_IPC_HANDLE_BYTES, rank order; NULL: give the exchange up again */);
 
 /* stream control for callers that own device memory (bench / multi-GPU drivers) */
 int prtc_set_stream(prtc_ctx * ctx, void * cuda_stream);

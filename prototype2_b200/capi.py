@@ -310,6 +310,9 @@ class PhysicsContext:
 
     def dyn_ipc_import(self, handles):
         """handles: list of the ranks' 128-byte blobs in rank order (own slot is ignored)"""
+        if handles is None:                                        # give the exchange up again
+            self._check(self.lib.prtc_dyn_ipc_import(self.h, None))
+            return
         blob = b"".join(handles)
         self._check(self.lib.prtc_dyn_ipc_import(self.h, ctypes.c_char_p(blob)))
 

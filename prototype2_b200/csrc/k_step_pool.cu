@@ -228,10 +228,25 @@ __global__ void __launch_bounds__(32, 16) k_step_pool(StepParams p) {
                     for (;;) {
                         bool more = false;
                         const uint32_t ncand = from_cache ? n_dyn : dyn_collect(dyn_grid_of(p), qb, self, last, &sh.dyn[0][lane], more);
-                        for (uint32_t r = 0; r < ncand; ++r) {
-                            const uint32_t j = sh.dyn[r][lane];
-                            if (from_cache && !node_overlaps(__ldg(p.dyn_records + 4 * size_t(j) + 2), __ldg(p.dyn_records + 4 * size_t(j) + 3), qb)) continue;
-                            cc_test(j);
+                        // the frame's neighbours against this substep's box, four stored boxes in flight at a time; the tests
+                        // themselves stay in ascending order (every one sees the position the previous one left)
+                        uint32_t live = from_cache ? 0u : ((ncand >= 32u) ? 0xFFFFFFFFu : ((1u << ncand) - 1u));
+                        if (from_cache) {
+                            for (uint32_t r4 = 0; r4 < ncand; r4 += 4) {
+                                float4 blo[4], bhi[4];
+#pragma unroll
+                                for (int u = 0; u < 4; ++u) {
+                                    const uint32_t j = sh.dyn[r4 + u < ncand ? r4 + u : r4][lane];
+                                    blo[u] = __ldg(p.dyn_records + 4 * size_t(j) + 2); bhi[u] = __ldg(p.dyn_records + 4 * size_t(j) + 3);
+                                }
+#pragma unroll
+                                for (int u = 0; u < 4; ++u) if (r4 + u < ncand && node_overlaps(blo[u], bhi[u], qb)) live |= 1u << (r4 + u);
+                            }
+                        }
+                        while (live) {
+                            const uint32_t r = uint32_t(__ffs(live) - 1);
+                            live &= live - 1u;
+                            cc_test(sh.dyn[r][lane]);
                         }
                         if (!more) break;
                         last = (long long)sh.dyn[ncand - 1][lane];

@@ -906,8 +906,16 @@ int prtc_dyn_ipc_export(prtc_ctx * c, uint32_t rank, uint32_t world, void * hand
 }
 
 int prtc_dyn_ipc_import(prtc_ctx * c, const void * handles) {
-    if (!c || !handles) return fail(PRTC_ERR_INVALID, "prtc_dyn_ipc_import: null argument");
+    if (!c) return fail(PRTC_ERR_INVALID, "prtc_dyn_ipc_import: null context");
     prtc_ctx::DynIpc & x = c->dyn_ipc;
+    if (!handles) {                                                // null: give the exchange up again (some rank could not map its peers)
+        for (void * q : x.opened) cudaIpcCloseMemHandle(q);
+        x.opened.clear();
+        x.n_peers = 0;
+        x.on = false;
+        (void)cudaGetLastError();
+        return PRTC_OK;
+    }
     if (!x.world || !x.flags.ptr) return fail(PRTC_ERR_INVALID, "prtc_dyn_ipc_import: call prtc_dyn_ipc_export first");
     PRTC_CUDA(cudaSetDevice(c->cfg.device));
     const unsigned char * hb = static_cast<const unsigned char *>(handles);

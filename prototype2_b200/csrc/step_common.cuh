@@ -58,21 +58,30 @@ static __device__ __noinline__ uint32_t dyn_collect(DynGrid p, Box b, uint32_t s
         // the cells of one grid row are contiguous in the item array
         const uint32_t beg = __ldg(p.dyn_cell_start + uint32_t(cz) * p.dyn_gx + uint32_t(cx0));
         const uint32_t end = __ldg(p.dyn_cell_start + uint32_t(cz) * p.dyn_gx + uint32_t(cx1) + 1);
-        for (uint32_t k = beg; k < end; ++k) {
-            const uint32_t j = __ldg(p.dyn_items + k);
-            if (j == self || (long long)j <= last) continue;
-            const float4 blo = __ldg(p.dyn_records + 4 * size_t(j) + 2);
-            const float4 bhi = __ldg(p.dyn_records + 4 * size_t(j) + 3);
-            if (!node_overlaps(blo, bhi, b)) continue;
-            if (ncand == uint32_t(DYN_CAP)) {                     // keep the DYN_CAP smallest, sorted
-                more = true;
-                if (j > col[32 * (DYN_CAP - 1)]) continue;
-                --ncand;
+        // four items per trip: their indices, then their stored boxes, are independent loads in flight (one dependent load
+        // after the other made this search a good part of a batch's latency)
+        for (uint32_t k4 = beg; k4 < end; k4 += 4) {
+            uint32_t jj[4];
+            float4 blo[4], bhi[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) jj[u] = __ldg(p.dyn_items + (k4 + u < end ? k4 + u : k4));
+#pragma unroll
+            for (int u = 0; u < 4; ++u) { blo[u] = __ldg(p.dyn_records + 4 * size_t(jj[u]) + 2); bhi[u] = __ldg(p.dyn_records + 4 * size_t(jj[u]) + 3); }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const uint32_t j = jj[u];
+                if (k4 + u >= end || j == self || (long long)j <= last) continue;
+                if (!node_overlaps(blo[u], bhi[u], b)) continue;
+                if (ncand == uint32_t(DYN_CAP)) {                 // keep the DYN_CAP smallest, sorted
+                    more = true;
+                    if (j > col[32 * (DYN_CAP - 1)]) continue;
+                    --ncand;
+                }
+                uint32_t s = ncand;
+                while (s > 0 && col[32 * (s - 1)] > j) { col[32 * s] = col[32 * (s - 1)]; --s; }
+                col[32 * s] = j;
+                ++ncand;
             }
-            uint32_t s = ncand;
-            while (s > 0 && col[32 * (s - 1)] > j) { col[32 * s] = col[32 * (s - 1)]; --s; }
-            col[32 * s] = j;
-            ++ncand;
         }
     }
     return ncand;
