@@ -76,6 +76,7 @@ __global__ void __launch_bounds__(32, 16) k_step_pool(StepParams p) {
     const bool use_qr = (p.qr_enable & 1u) != 0u, use_tq = (p.qr_enable & 2u) != 0u;
     const bool use_cache = !(p.tune & 1u) && p.xc_version != nullptr;
     const uint32_t wmax = ((p.tune >> 8) & 0xFFu) ? ((p.tune >> 8) & 0xFFu) : 32u;   // largest window (jobs per owner and round)
+    if (p.work_next && blockIdx.x == 0 && lane == 0) *p.work_next = 0u;      // the NEXT launch's work counter (see StepParams::work_pair)
     const float fsub = float(p.substeps);
     // characters per warp: 32 when the batch fills the machine; fewer owners (lanes [0, opw)) spread a smaller batch over
     // more warps -- the pooled work is executed by all 32 lanes either way
@@ -573,8 +574,17 @@ __global__ void __launch_bounds__(32, 16) k_step_pool(StepParams p) {
 // occupancy the launch bounds aim for (registers: 128 per thread, shared memory: ~10 KB per one-warp block)
 uint32_t pool_blocks_per_sm() { return 16u; }
 
-void launch_k_step_pool(StepParams const & p, uint32_t blocks, bool gated, int mode, cudaStream_t stream) {
-    cudaMemsetAsync(p.work_counter, 0, sizeof(unsigned), stream);
+void launch_k_step_pool(StepParams const & p_in, uint32_t blocks, bool gated, int mode, cudaStream_t stream) {
+    StepParams p = p_in;
+    if (p.work_flip && p.work_pair && !gated) {
+        const uint32_t k = *p.work_flip & 1u;                      // this launch's counter was zeroed by the previous one (or at creation)
+        p.work_counter = p.work_pair + k;
+        p.work_next = p.work_pair + (k ^ 1u);
+        *p.work_flip = k ^ 1u;
+    } else {
+        p.work_next = nullptr;
+        cudaMemsetAsync(p.work_counter, 0, sizeof(unsigned), stream);
+    }
     if (mode == MODE_JACOBI) k_step_pool<false, MODE_JACOBI><<<blocks, 32, 0, stream>>>(p);
     else if (gated) k_step_pool<true, MODE_STATIC><<<blocks, 32, 0, stream>>>(p);
     else k_step_pool<false, MODE_STATIC><<<blocks, 32, 0, stream>>>(p);

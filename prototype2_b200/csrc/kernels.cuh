@@ -73,7 +73,12 @@ struct StepParams {
     unsigned long long * counters;  // prtc_counters layout
     uint32_t * host_flags;          // host-mapped words the kernels raise (small host-buffer batches, resident steps) --
                                     // [0] a capsule-capsule test ran (LITERAL), [1] a character named an unknown capsule
-    unsigned * work_counter;        // k_step_stream: next character to hand out (null => lock-step kernel)
+    unsigned * work_counter;        // k_step_stream / k_step_pool: next character to hand out (null => lock-step kernel)
+    // k_step_pool: two work counters used alternately -- a launch hands characters out of one and zeroes the OTHER for the
+    // next launch (stream order makes that safe), so no memset is queued in front of every frame
+    unsigned * work_pair;           // device: the two counters
+    uint32_t * work_flip;           // HOST: which one the next launch uses (toggled by the launcher); null => memset + work_counter
+    unsigned * work_next;           // device: the counter this launch zeroes (set by the launcher)
     // k_step_stream: cross-frame leaf cache, one slot per character index (SoA, stride xc_stride); null => off
     uint32_t * xc_version;          // tree version the slot was built for (0 = empty)
     float * xc_region;              // [6][stride] region the leaf list is complete for

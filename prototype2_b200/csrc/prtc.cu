@@ -394,6 +394,8 @@ int fill_params(prtc_ctx * c, float dt, uint32_t n, prtc_transform * d_tf, prtc_
         p.qr_enable = (m < 1.0e6f) ? ((c->quick_reject ? 1u : 0u) | (c->tight_reject ? 2u : 0u)) : 0u;
         p.tune = (c->frame_cache ? 0u : 1u) | (c->warp_kernel ? 0u : 2u) | c->tune_hi;
         p.work_counter = c->persistent ? c->d_work.ptr : nullptr;
+        p.work_pair = c->d_work.ptr + 8;
+        p.work_flip = &c->work_flip;
         p.persistent_blocks = uint32_t(c->sm_count) * 20u;
         p.pool_blocks = uint32_t(c->sm_count) * pool_blocks_per_sm();
         p.n_tris = uint32_t(c->tri_src.size());

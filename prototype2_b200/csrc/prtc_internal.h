@@ -151,7 +151,8 @@ struct prtc_ctx {
     int streamed_copy = 1;                  // PRTC_OPT_STREAMED_COPY: big host-buffer batches feed one persistent launch while it runs
     int warp_kernel = 1;                    // small batches: one warp per character (k_step_warp); 0 = thinned lock-step kernel
     float xc_margin = 0.5f;
-    prt::host::DevBuf<unsigned> d_work;                // work counters of the persistent kernel, one per concurrently running launch
+    prt::host::DevBuf<unsigned> d_work;                // work counters of the persistent kernel, one per concurrently running launch ([8], [9]: the pooled kernel's alternating pair)
+    uint32_t work_flip = 0;                            // which of the pair the next pooled launch uses
     prt::host::HostStage stage;                        // small host-buffer batches: records staged in mapped pinned memory
     int staged = 1;                         // PRTC_STAGED=0: small batches take the copy path too (A/B)
     prt::host::DevBuf<uint32_t> d_ingest;              // streamed host-buffer step: [0] arrival gate, then per-chunk and per-block completion counters
@@ -196,6 +197,7 @@ struct prtc_ctx {
     float * resident_result = nullptr;
     uint32_t * resident_flags = nullptr;     // [0] unused, [1] unknown capsule id, [2] completion doorbell
     uint32_t resident_frame = 0;
+    uint32_t resident_prefresh = 0;          // tree version the per-slot leaf lists were refreshed for BEHIND the last resident frame (0: not)
     uint32_t resident_pending = 0;           // doorbell value of the frame in flight (0: wait with cudaStreamSynchronize)
     int doorbell = 1;                        // PRTC_DOORBELL=0: resident steps wait in cudaStreamSynchronize
     bool literal() const { return cfg.order_mode == PRTC_ORDER_LITERAL; }

@@ -528,6 +528,7 @@ int prtc_step_characters(prtc_ctx * c, float dt, uint32_t n, prtc_transform * tf
             StepParams p;
             rc = fill_params(c, dt, cnt, c->d_tf.ptr + first, c->d_ph.ptr + first, p);
             if (rc) return rc;
+            p.work_flip = nullptr;                             // concurrent launches on several streams: a counter each, zeroed by a memset
             if (!kChunkPersistent) p.work_counter = nullptr;
             if (p.work_counter) p.work_counter += 1 + k % prtc_ctx::PIPE_STREAMS;     // launches on one stream are ordered
             p.xc_first = first;                               // cache slots are indexed by the character's position in the batch
@@ -728,6 +729,7 @@ int resident_begin_impl(prtc_ctx * c, uint32_t n, const prtc_transform * tf, con
     }
     c->resident_flags[0] = 0u; c->resident_flags[1] = 0u; c->resident_flags[2] = 0u;
     c->resident_frame = 0;
+    c->resident_prefresh = 0u;
     if (n) {
         PRTC_CUDA(cudaMemcpyAsync(c->d_tf.ptr, tf, size_t(n) * sizeof(prtc_transform), cudaMemcpyHostToDevice, c->stream));
         PRTC_CUDA(cudaMemcpyAsync(c->d_ph.ptr, ph, size_t(n) * sizeof(prtc_char_physics), cudaMemcpyHostToDevice, c->stream));
@@ -777,8 +779,20 @@ int resident_launch(prtc_ctx * c, float dt) {
         if (p.done_value == 0u) p.done_value = ++c->resident_frame;
         c->resident_pending = p.done_value;
     }
+    // the per-slot leaf lists for THIS frame were refreshed behind the previous one (below) unless something intervened
+    if (mode == STEP_STATIC && c->resident_prefresh == c->tree_version && c->resident_prefresh != 0u) p.xc_fresh = 1u;
     c->launches += uint64_t(launch_step(p, false, mode, c->stream));
     PRTC_CUDA(cudaGetLastError());
+    // ... and the lists for the NEXT frame are refreshed right behind this one, from the state it leaves (with this frame's
+    // movement input as the guess for the next): the doorbell has rung by then, the host is already back with the caller.
+    // A wrong guess costs a tree walk inside the step, never a result (the step checks "query box inside region" per substep).
+    c->resident_prefresh = 0u;
+    if (mode == STEP_STATIC) {
+        StepParams r = p;
+        r.done_flag = nullptr; r.io_move = nullptr; r.io_result = nullptr;
+        if (launch_slot_refresh(r, STEP_STATIC, c->stream)) { c->resident_prefresh = c->tree_version; c->launches += 1; }
+        PRTC_CUDA(cudaGetLastError());
+    }
     return PRTC_OK;
 }
 
@@ -840,7 +854,7 @@ int prtc_resident_edit(prtc_ctx * c, uint32_t k, const uint32_t * indices, const
     for (uint32_t j = 0; j < k; ++j) {
         const uint32_t i = indices[j];
         if (i >= c->resident_n) return fail(PRTC_ERR_INVALID, "prtc_resident_edit: index out of range");
-        if (tf) PRTC_CUDA(cudaMemcpyAsync(c->d_tf.ptr + i, tf + j, sizeof(prtc_transform), cudaMemcpyHostToDevice, c->stream));
+        if (tf) { PRTC_CUDA(cudaMemcpyAsync(c->d_tf.ptr + i, tf + j, sizeof(prtc_transform), cudaMemcpyHostToDevice, c->stream)); c->resident_prefresh = 0u; }   // (moved: refresh the leaf lists in front of the next frame)
         if (ph) {
             PRTC_CUDA(cudaMemcpyAsync(c->d_ph.ptr + i, ph + j, sizeof(prtc_char_physics), cudaMemcpyHostToDevice, c->stream));
             for (int d = 0; d < 3; ++d) c->resident_move[3 * size_t(i) + d] = ph[j].movement[d];
