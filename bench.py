@@ -86,7 +86,7 @@ def describe_config(args, name, n, n_global, strong, n_tris, n_terrain, bx, bz, 
             name, n_global if strong else n,
             "in ONE Morton-ordered batch, contiguous slices of %d per GPU" % n if strong else "per GPU",
             n_tris, bx, bz,
-            "static + dynamic-vs-dynamic pass (JACOBI, records all-gathered per frame)" if dynamic else "static pass",
+            "static + dynamic-vs-dynamic pass (JACOBI, records of all characters exchanged per frame)" if dynamic else "static pass",
             "candidates in ascending collider id, tree built on the device (PRTC_ORDER_BY_ID; the roofline's node tests are "
             "those of that tree, not of the reference's)" if args.order == "by_id" else "canonical order"),
         "capsules_per_gpu": n, "global_capsules": n_global, "triangles": n_tris, "terrain_n": n_terrain,
