@@ -39,7 +39,7 @@ METRIC = "ellipsoid (capsule) sweep queries/sec"
 UNIT = "queries/s"
 
 
-def parse_args():
+def parse_args(argv=None):
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=60)
@@ -55,11 +55,12 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the short extra runs (moving crowd, weak scaling, config 5)")
+    ap.add_argument("--trace", default="", help="directory for a per-kernel duration table of every rank (diagnostic)")
     ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
                     help="strong: ONE global batch split over the GPUs (BASELINE config 4 as written); weak: a full batch per GPU")
     ap.add_argument("--opt", action="append", default=[], metavar="NAME=VALUE",
                     help="prtc_set_option before the run, e.g. --opt POOL_KERNEL=0 (A/B experiments)")
-    return ap.parse_args()
+    return ap.parse_args(argv)
 
 
 def workload(args):
@@ -291,6 +292,15 @@ class Dist:
         self.d.all_reduce(t, op=self.d.ReduceOp.MAX)
         return float(t.item())
 
+    def per_rank(self, x):
+        """x of every rank, in rank order"""
+        if self.d is None:
+            return [x]
+        t = self.torch.zeros(self.world, dtype=self.torch.float64, device=self.dev)
+        t[self.d.get_rank()] = x
+        self.d.all_reduce(t, op=self.d.ReduceOp.SUM)
+        return [float(v) for v in t.tolist()]
+
     def sum(self, vals):
         if self.d is None:
             return list(vals)
@@ -324,11 +334,17 @@ class Workload:
         if strong:
             gpos, gvel = make_capsules(n_global, n_terrain, 0)
             self.first, self.n = sharding.partition(n_global, world, rank)
+            # diagnostic (one GPU): step the slice rank 0 of a W-rank job would own, next to the frozen records of the others
+            self.fake = int(os.environ.get("PRTC_BENCH_FAKE_WORLD", "0")) if world == 1 else 0
+            if self.fake:
+                self.first, self.n = sharding.partition(n_global, self.fake, 0)
+                self.gpos, self.gvel = gpos, gvel
             pos, vel = gpos[self.first:self.first + self.n], gvel[self.first:self.first + self.n]
             self.n_global = n_global
         else:
             pos, vel = make_capsules(n_global, n_terrain, rank)
             self.first, self.n, self.n_global = 0, n_global, n_global * world
+            self.fake = 0
         self.pos, self.vel = pos, vel
         dev = torch.device("cuda", local)
         self.t_commit = None
@@ -375,6 +391,11 @@ class Workload:
         self.stream = torch.cuda.current_stream()
         ctx.set_stream(self.stream.cuda_stream)
         self._rec = None
+        if strong and self.fake and self.dynamic:
+            full_tf = torch.from_numpy(capi.make_transforms(self.gpos).view(np.uint8).reshape(-1)).to(dev)
+            full_ph = torch.from_numpy(capi.make_physics(self.gvel, collider=np.full(self.n_global, self.cid, np.uint32)).view(np.uint8).reshape(-1)).to(dev)
+            self.full_tf, self.full_ph = full_tf, full_ph
+            self.d_tf, self.d_ph = full_tf[:self.n * 40], full_ph[:self.n * 44]
 
     def reset(self):
         self.tf_np[:] = self.tf0
@@ -383,6 +404,8 @@ class Workload:
         self.d_ph.copy_(self.h_ph)
 
     def device_step(self):
+        if self.dynamic and self.strong and self.fake:
+            self.ctx.dyn_prepare(DT, self.n_global, self.full_tf.data_ptr(), self.full_ph.data_ptr())
         if self.dynamic and self.world > 1 and self.strong and not getattr(self, "ipc", False):
             # the one exchange of the path, collective flavour: the records of every character, all-gathered in place over NVLink
             self.ctx.dyn_prepare(DT, self.n, self.d_tf.data_ptr(), self.d_ph.data_ptr())
@@ -414,12 +437,40 @@ class Workload:
         per = [ev[k].elapsed_time(ev[k + 1]) for k in range(steps)]
         cnt = self.ctx.counters(reset=True)
         el = dist.max(total_ms * 1e-3)
+        self.rank_ms = [v / steps for v in dist.per_rank(total_ms)]
         sums = dist.sum([cnt["substeps"], cnt["tri_tests"], cnt["node_tests"]])
         return {"el": el, "total_ms": total_ms, "per": per, "cnt": cnt, "clocks": clocks, "substeps": sums[0], "tri_tests": sums[1],
                 "node_tests": sums[2]}
 
+    def trace(self, steps, path):
+        """kernel-by-kernel durations of `steps` more frames (CUPTI through torch.profiler; a diagnostic, never a bench value)"""
+        from torch.profiler import profile, ProfilerActivity
+        torch = self.torch
+        torch.cuda.synchronize()
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            for _ in range(steps):
+                self.device_step()
+            torch.cuda.synchronize()
+        rows = {}
+        t_first, t_last = None, 0
+        for e in prof.events():
+            if getattr(e.device_type, "name", "") != "CUDA":
+                continue
+            r = rows.setdefault(e.name, [0, 0.0])
+            r[0] += 1
+            r[1] += float(getattr(e, "device_time", None) or getattr(e, "cuda_time", 0.0) or (e.time_range.end - e.time_range.start))
+            t0 = e.time_range.start
+            t_first = t0 if t_first is None else min(t_first, t0)
+            t_last = max(t_last, e.time_range.end)
+        out = {"rank": self.rank, "steps": steps, "span_us_per_step": (t_last - (t_first or 0)) / steps,
+               "kernels": {k: {"launches_per_step": v[0] / steps, "us_per_step": v[1] / steps} for k, v in
+                           sorted(rows.items(), key=lambda kv: -kv[1][1])}}
+        os.makedirs(os.path.dirname(path) or ".", exist_ok=True)
+        with open(path, "w") as f:
+            json.dump(out, f, indent=1)
+
     def crc(self):
-        if self.strong:
+        if self.strong and not self.fake:
             return state_crc(self.torch, self.sharding, self.d_tf, self.d_ph, self.n)
         return None
 
@@ -455,6 +506,9 @@ def run_ours(args):
     cnt, el, total_ms, kernel_ms = r["cnt"], r["el"], r["total_ms"], r["per"]
     value = r["substeps"] / el
     crc = w.crc()
+    rank_ms = w.rank_ms
+    if args.trace:
+        w.trace(args.steps, os.path.join(args.trace, "trace_%s_n%d_rank%d.json" % (args.workload, world, rank)))
 
     # Numerators of the roofline: the REFERENCE ALGORITHM's counts over the same K frames.  The timed run uses the
     # frame cache (fewer node tests than DynamicAABBTree::query performs), so the same frames are replayed untimed
@@ -600,8 +654,10 @@ def run_ours(args):
         w5 = Workload(args, "C5", torch, capi, sharding, local, rank, world, True)
         r5 = w5.timed(dist, max(steps_x, 10), 3)
         k5 = max(steps_x, 10)
+        if args.trace:
+            w5.trace(k5, os.path.join(args.trace, "trace_C5_n%d_rank%d.json" % (world, rank)))
         extras["c5"] = {"workload": w5.describe()["workload"], "ms_per_step": 1e3 * r5["el"] / k5, "value": r5["substeps"] / r5["el"],
-                        "unit": UNIT, "state_crc32": w5.crc(), "scaling": "strong",
+                        "unit": UNIT, "state_crc32": w5.crc(), "scaling": "strong", "ms_per_step_by_rank": w5.rank_ms,
                         "exchange_bytes_per_step": (w5.n_global * 64) if world > 1 else 0,
                         "exchange": ("none (one rank)" if world == 1 else
                                      "peer stores of the 64-byte records from k_dyn_prep into every rank's array (CUDA IPC), arrival words in device memory"
@@ -629,6 +685,7 @@ def run_ours(args):
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * el / args.steps, "ms_per_step_median": float(np.median(kernel_ms)), "ms_per_step_min": float(np.min(kernel_ms)),
+            "ms_per_step_by_rank": rank_ms,
             "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "config": cfg,
             "tri_tests_per_s": r["tri_tests"] / el, "node_tests_per_s": node_tests / el,

@@ -27,7 +27,7 @@ SYMBOLS = (
     "prtc_multi_create", "prtc_multi_destroy", "prtc_multi_device_count", "prtc_multi_context", "prtc_multi_add_model", "prtc_multi_add_capsule",
     "prtc_multi_update_capsule", "prtc_multi_remove_model", "prtc_multi_update_models", "prtc_multi_commit", "prtc_multi_set_option",
     "prtc_multi_raycast", "prtc_multi_get_counters", "prtc_multi_step_characters", "prtc_multi_resident_begin", "prtc_multi_resident_io",
-    "prtc_multi_resident_step", "prtc_multi_resident_fetch", "prtc_multi_resident_end", "prtc_get_commit_stats",
+    "prtc_multi_resident_step", "prtc_multi_resident_fetch", "prtc_multi_resident_end", "prtc_get_commit_stats", "prtc_debug_timeline",
     "prtc_dyn_ipc_export", "prtc_dyn_ipc_import",
 )
 
@@ -330,6 +330,15 @@ class PhysicsContext:
         c = Counters()
         self._check(self.lib.prtc_get_counters(self.h, ctypes.byref(c), ctypes.c_int(1 if reset else 0)))
         return {k: int(getattr(c, k)) for k, _ in Counters._fields_}
+
+    def debug_timeline(self):
+        """(claims, 3) uint64 {start ns, end ns, SM} of the last pooled launch (PRTC_TIMELINE=1), rows of unused claims are zero"""
+        nw = ctypes.c_size_t(0)
+        self._check(self.lib.prtc_debug_timeline(self.h, None, 0, ctypes.byref(nw)))
+        out = np.zeros(nw.value, np.uint64)
+        if nw.value:
+            self._check(self.lib.prtc_debug_timeline(self.h, out.ctypes.data_as(ctypes.c_void_p), nw.value, ctypes.byref(nw)))
+        return out[: (len(out) // 3) * 3].reshape(-1, 3)
 
     def commit_stats(self):
         a, b = ctypes.c_uint32(), ctypes.c_uint32()

@@ -88,6 +88,13 @@ __global__ void __launch_bounds__(32, 16) k_step_pool(StepParams p) {
         if (lane == 0) base = atomicAdd(p.work_counter, opw);
         base = __shfl_sync(FULL, base, 0);
         if (base >= p.n) break;
+        if (p.timeline && lane == 0) {                            // diagnostic (PRTC_TIMELINE): when and where this claim started
+            unsigned long long t; uint32_t sm;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+            asm volatile("mov.u32 %0, %%smid;" : "=r"(sm));
+            p.timeline[3 * size_t(base / opw) + 0] = t;
+            p.timeline[3 * size_t(base / opw) + 2] = sm;
+        }
         if (GATED) {
             // the batch is still arriving over PCIe: wait until this warp's records have landed (chunk boundaries are
             // multiples of 32 characters = whole 128-byte lines of both record arrays)
@@ -541,6 +548,11 @@ __global__ void __launch_bounds__(32, 16) k_step_pool(StepParams p) {
             }
         }
         __syncwarp(FULL);
+        if (p.timeline && lane == 0) {
+            unsigned long long t;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+            p.timeline[3 * size_t(base / opw) + 1] = t;
+        }
     }
 
     c_sub = __reduce_add_sync(FULL, c_sub);

@@ -77,6 +77,7 @@ struct StepParams {
     // k_step_pool: two work counters used alternately -- a launch hands characters out of one and zeroes the OTHER for the
     // next launch (stream order makes that safe), so no memset is queued in front of every frame
     unsigned * work_pair;           // device: the two counters
+    unsigned long long * timeline;  // diagnostic (PRTC_TIMELINE=1): per claim of k_step_pool {start ns, end ns, SM}; null otherwise
     uint32_t * work_flip;           // HOST: which one the next launch uses (toggled by the launcher); null => memset + work_counter
     unsigned * work_next;           // device: the counter this launch zeroes (set by the launcher)
     // k_step_stream: cross-frame leaf cache, one slot per character index (SoA, stride xc_stride); null => off
@@ -137,13 +138,17 @@ struct DynPeers {
 };
 void launch_dyn_prep(const prtc_transform * tf, const prtc_char_physics * ph, const CapsuleDev * capsules, uint32_t n_capsules, uint32_t n,
                      uint32_t first, const float4 * prev_records, float4 * records, DynPeers const & peers, float dt, float gravity, float margin,
-                     bool init, cudaStream_t stream);
+                     bool init, uint32_t * reach, cudaStream_t stream);
+// IPC exchange: this rank's slice into every peer's array, then the arrival words (k_dyn_push)
+void launch_dyn_push(const float4 * records, uint32_t first, uint32_t n, DynPeers const & peers, cudaStream_t stream);
 // IPC exchange: wait (on the device, stream-ordered) until every rank's arrival word has reached `value`; gives up after a
 // few seconds and raises counters[7] instead of hanging the GPU
 void launch_dyn_wait(const uint32_t * flags, uint32_t n_ranks, uint32_t value, unsigned long long * counters, cudaStream_t stream);
 // counting sort of all n stored boxes into the uniform xz grid (one cell per box) + the per-frame reach; returns kernels launched
 int launch_dyn_grid_build(const float4 * records, uint32_t n, float ox, float oz, float inv_cell, uint32_t gx, uint32_t gz,
-                          uint32_t * cell_count, uint32_t * cell_start, uint32_t * items, uint32_t * reach, cudaStream_t stream);
+                          uint32_t * cell_count, uint32_t * cell_start, uint32_t * cursor, uint32_t * items, uint32_t * reach,
+                          unsigned long long * scan_state, uint32_t & scan_tickets, uint32_t & scan_launches, cudaStream_t stream);
+constexpr uint32_t DYN_SCAN_WORDS = 1024;           // look-back words of k_dyn_scan (2^20 cells / 2048 per tile + 1, rounded up); the ticket follows
 
 // main[k] += scratch[k], scratch[k] = 0 for the device-side work counters (per-frame scratch of the LITERAL fixpoint rounds)
 void launch_fold_counters(unsigned long long * main_counters, unsigned long long * scratch, cudaStream_t stream);

@@ -396,6 +396,12 @@ int fill_params(prtc_ctx * c, float dt, uint32_t n, prtc_transform * d_tf, prtc_
         p.work_counter = c->persistent ? c->d_work.ptr : nullptr;
         p.work_pair = c->d_work.ptr + 8;
         p.work_flip = &c->work_flip;
+        if (c->timeline && n) {                                    // diagnostic: room for one entry per claim, whatever the claim size
+            if (c->d_timeline.reserve(3 * (size_t(n) + 1)) == cudaSuccess) {
+                cudaMemsetAsync(c->d_timeline.ptr, 0, 3 * (size_t(n) + 1) * sizeof(unsigned long long), c->stream);
+                p.timeline = c->d_timeline.ptr;
+            }
+        }
         p.persistent_blocks = uint32_t(c->sm_count) * 20u;
         p.pool_blocks = uint32_t(c->sm_count) * pool_blocks_per_sm();
         p.n_tris = uint32_t(c->tri_src.size());
@@ -527,6 +533,7 @@ int prtc_create(const prtc_config * cfg, prtc_ctx ** out) {
     if (const char * e = std::getenv("PRTC_XC_MARGIN")) ctx->xc_margin = float(std::atof(e));
     if (const char * e = std::getenv("PRTC_TUNE")) ctx->tune_hi = uint32_t(std::strtoul(e, nullptr, 0)) & 0xFFFFFF00u;
     if (const char * e = std::getenv("PRTC_DOORBELL")) ctx->doorbell = std::atoi(e) != 0;
+    if (const char * e = std::getenv("PRTC_TIMELINE")) ctx->timeline = std::atoi(e) != 0;
     if (const char * e = std::getenv("PRTC_PUSH_SLACK")) { const float v = float(std::atof(e)); if (v >= 0.0f && v <= 1.0f) ctx->push_slack = v; }
     ctx->sm_count = prop.multiProcessorCount;
     ctx->tree.set_margin(c.leaf_margin);
@@ -558,9 +565,11 @@ void prtc_destroy(prtc_ctx * c) {
     c->d_cap2char.release(); c->d_seg_start.release(); c->d_seg_prev.release(); c->d_last_box.release();
     for (void * q : c->dyn_ipc.opened) cudaIpcCloseMemHandle(q);
     c->dyn_ipc.opened.clear(); c->dyn_ipc.flags.release();
-    c->d_dyn_records.release(); c->d_dyn_count.release(); c->d_dyn_start.release(); c->d_dyn_items.release(); c->d_dyn_reach.release();
+    c->d_dyn_records.release(); c->d_dyn_count.release(); c->d_dyn_start.release(); c->d_dyn_items.release(); c->d_dyn_reach.release(); c->d_dyn_cursor.release(); c->d_dyn_scan.release(); c->d_timeline.release();
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
     for (int k = 0; k < prtc_ctx::PIPE_STREAMS; ++k) if (c->pipe[k]) cudaStreamDestroy(c->pipe[k]);
+    if (c->dyn_ipc.push_stream) cudaStreamDestroy(c->dyn_ipc.push_stream);
+    if (c->dyn_ipc.prep_done) cudaEventDestroy(c->dyn_ipc.prep_done);
     if (c->pipe_ready) cudaEventDestroy(c->pipe_ready);
     if (c->ingest_reset) cudaEventDestroy(c->ingest_reset);
     delete c;
@@ -739,6 +748,16 @@ int prtc_get_commit_stats(prtc_ctx * c, uint32_t * incremental, uint32_t * full)
     if (!c) return fail(PRTC_ERR_INVALID, "prtc_get_commit_stats: null context");
     if (incremental) *incremental = c->incremental_commits;
     if (full) *full = c->full_commits;
+    return PRTC_OK;
+}
+
+int prtc_debug_timeline(prtc_ctx * c, unsigned long long * out, size_t capacity_words, size_t * n_words) {
+    if (!c || !n_words) return fail(PRTC_ERR_INVALID, "prtc_debug_timeline: null argument");
+    *n_words = c->d_timeline.ptr ? c->d_timeline.cap : 0;
+    if (!out || !c->d_timeline.ptr) return PRTC_OK;
+    PRTC_CUDA(cudaSetDevice(c->cfg.device));
+    PRTC_CUDA(cudaStreamSynchronize(c->stream));
+    PRTC_CUDA(cudaMemcpy(out, c->d_timeline.ptr, std::min(capacity_words, c->d_timeline.cap) * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
     return PRTC_OK;
 }
 

@@ -171,7 +171,11 @@ struct prtc_ctx {
     prt::host::DevBuf<float> d_last_box;
     // CANONICAL order, JACOBI dynamic pass
     prt::host::DevBuf<float4> d_dyn_records;
-    prt::host::DevBuf<uint32_t> d_dyn_count, d_dyn_start, d_dyn_items, d_dyn_reach;
+    prt::host::DevBuf<uint32_t> d_dyn_count, d_dyn_start, d_dyn_items, d_dyn_reach, d_dyn_cursor;
+    prt::host::DevBuf<unsigned long long> d_dyn_scan;      // look-back words of k_dyn_scan + its ticket counter
+    uint32_t dyn_scan_tickets = 0, dyn_scan_launches = 0;
+    prt::host::DevBuf<unsigned long long> d_timeline;      // PRTC_TIMELINE=1 (diagnostic): claim timeline of the last pooled launch
+    int timeline = 0;
     uint32_t dyn_first = 0, dyn_global = 0;  // this context's slice [dyn_first, dyn_first + n) of dyn_global characters
     bool dyn_configured = false;             // prtc_dyn_configure called (multi-rank); otherwise the slice is the whole batch
     bool dyn_initialized = false;            // stored boxes exist (first prepare creates them at the identity pose)
@@ -187,6 +191,8 @@ struct prtc_ctx {
         uint32_t * peer_flags[15] = {};
         uint32_t n_peers = 0;
         std::vector<void *> opened;
+        cudaStream_t push_stream = nullptr;          // the peer stores run beside the slot refresh of the context's stream
+        cudaEvent_t prep_done = nullptr;
     } dyn_ipc;
     float world_lo[3] = {0, 0, 0}, world_hi[3] = {0, 0, 0};
     // resident state (prtc_resident_*): the records stay in d_tf / d_ph between frames; per-frame I/O through mapped pinned arrays

@@ -120,6 +120,10 @@ int dyn_reserve(prtc_ctx * c, uint32_t n) {
         PRTC_CUDA(c->d_dyn_records.reserve(want));
         PRTC_CUDA(cudaMemsetAsync(c->d_dyn_records.ptr, 0, want * sizeof(float4), c->stream));
     }
+    if (!c->d_dyn_reach.ptr) {
+        PRTC_CUDA(c->d_dyn_reach.reserve(2));
+        PRTC_CUDA(cudaMemsetAsync(c->d_dyn_reach.ptr, 0, c->d_dyn_reach.cap * sizeof(uint32_t), c->stream));
+    }
     return PRTC_OK;
 }
 
@@ -140,10 +144,15 @@ int dyn_prepare(prtc_ctx * c, float dt, uint32_t n, const prtc_transform * d_tf,
         peers.block_count = x.flags.ptr + 31;
         peers.push_separately = 1u;
         launch_dyn_prep(d_tf, d_ph, c->d_capsules.ptr, uint32_t(c->capsules.size()), n, c->dyn_first, c->d_dyn_records.ptr + (b ^ 1u) * half,
-                        c->d_dyn_records.ptr + b * half, peers, dt, c->cfg.gravity, c->cfg.leaf_margin, !c->dyn_initialized, c->stream);
+                        c->d_dyn_records.ptr + b * half, peers, dt, c->cfg.gravity, c->cfg.leaf_margin, !c->dyn_initialized, c->d_dyn_reach.ptr, c->stream);
+        // the peer stores leave on a stream of their own, so the slot refresh that follows on the context's stream runs beside
+        // them; the context's stream meets them again in k_dyn_wait (this rank's own arrival word is written by the same kernel)
+        PRTC_CUDA(cudaEventRecord(x.prep_done, c->stream));
+        PRTC_CUDA(cudaStreamWaitEvent(x.push_stream, x.prep_done, 0));
+        launch_dyn_push(c->d_dyn_records.ptr + b * half, c->dyn_first, n, peers, x.push_stream);
     } else {
         launch_dyn_prep(d_tf, d_ph, c->d_capsules.ptr, uint32_t(c->capsules.size()), n, c->dyn_first, c->d_dyn_records.ptr, c->d_dyn_records.ptr,
-                        c->dyn_peers, dt, c->cfg.gravity, c->cfg.leaf_margin, !c->dyn_initialized, c->stream);
+                        c->dyn_peers, dt, c->cfg.gravity, c->cfg.leaf_margin, !c->dyn_initialized, c->d_dyn_reach.ptr, c->stream);
     }
     PRTC_CUDA(cudaGetLastError());
     c->dyn_initialized = true;
@@ -168,10 +177,19 @@ int dyn_build_grid(prtc_ctx * c, StepParams & p) {
     const size_t cells = size_t(gx) * gz;
     const uint32_t ng = c->dyn_global;
     // every stored box is binned in exactly one cell, so the item array has ng entries: nothing here depends on a device count
-    PRTC_CUDA(c->d_dyn_count.reserve(cells + 1));
-    PRTC_CUDA(c->d_dyn_start.reserve(cells + 1));
+    // (cell_count is all zero between frames: zeroed when allocated, k_dyn_scan zeroes what a frame counted)
+    if (c->d_dyn_count.cap < cells + 8) {
+        PRTC_CUDA(c->d_dyn_count.reserve(cells + 8));
+        PRTC_CUDA(cudaMemsetAsync(c->d_dyn_count.ptr, 0, c->d_dyn_count.cap * sizeof(uint32_t), s));
+    }
+    if (!c->d_dyn_scan.ptr) {
+        PRTC_CUDA(c->d_dyn_scan.reserve(DYN_SCAN_WORDS + 2));
+        PRTC_CUDA(cudaMemsetAsync(c->d_dyn_scan.ptr, 0, c->d_dyn_scan.cap * sizeof(unsigned long long), s));
+        c->dyn_scan_tickets = 0; c->dyn_scan_launches = 0;
+    }
+    PRTC_CUDA(c->d_dyn_start.reserve(cells + 8));
+    PRTC_CUDA(c->d_dyn_cursor.reserve(cells + 8));
     PRTC_CUDA(c->d_dyn_items.reserve(size_t(ng) + 1));
-    PRTC_CUDA(c->d_dyn_reach.reserve(2));
     const float4 * records = c->d_dyn_records.ptr;
     if (c->dyn_ipc.on) {
         // every rank's records of this frame must have landed in this device's buffer: wait for the arrival words, on the device
@@ -182,7 +200,8 @@ int dyn_build_grid(prtc_ctx * c, StepParams & p) {
         c->launches += 1;
     }
     c->launches += uint64_t(launch_dyn_grid_build(records, ng, lox, loz, 1.0f / cell, gx, gz, c->d_dyn_count.ptr, c->d_dyn_start.ptr,
-                                                  c->d_dyn_items.ptr, c->d_dyn_reach.ptr, s));
+                                                  c->d_dyn_cursor.ptr, c->d_dyn_items.ptr, c->d_dyn_reach.ptr, c->d_dyn_scan.ptr,
+                                                  c->dyn_scan_tickets, c->dyn_scan_launches, s));
     PRTC_CUDA(cudaGetLastError());
     p.dyn_records = records;
     p.dyn_cell_start = c->d_dyn_start.ptr;
@@ -947,6 +966,8 @@ int prtc_dyn_ipc_import(prtc_ctx * c, const void * handles) {
         x.peer_flags[x.n_peers] = static_cast<uint32_t *>(flg);
         ++x.n_peers;
     }
+    if (!x.push_stream) PRTC_CUDA(cudaStreamCreateWithFlags(&x.push_stream, cudaStreamNonBlocking));
+    if (!x.prep_done) PRTC_CUDA(cudaEventCreateWithFlags(&x.prep_done, cudaEventDisableTiming));
     x.on = true;
     return PRTC_OK;
 }
