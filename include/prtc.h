@@ -314,7 +314,7 @@ int prtc_get_leaf_order(prtc_ctx * ctx, uint32_t * leaf_mesh_ids, uint32_t capac
  * triangle records; the tree is left alone or, in BY_ID order, put together again on the device), `full` = the tree was
  * re-flattened / rebuilt and uploaded. */
 int prtc_get_commit_stats(prtc_ctx * ctx, uint32_t * incremental, uint32_t * full);
-/* Diagnostic, only with PRTC_TIMELINE=1 in the environment at prtc_create: per claim (a warp's group of characters) of the
+/* Diagnostic, only in the diagnostic build of the library (make timeline) with PRTC_TIMELINE=1 in the environment at prtc_create: per claim (a warp's group of characters) of the
  * last k_step_pool launch three 64-bit words {start ns, end ns, SM} (%globaltimer), zero where no claim was made.
  * `*n_words` = words available; `out` may be null to ask for the size. */
 int prtc_debug_timeline(prtc_ctx * ctx, unsigned long long * out, size_t capacity_words, size_t * n_words);

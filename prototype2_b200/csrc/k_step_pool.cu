@@ -31,6 +31,10 @@
 // Results, counters (substeps, triangle tests, contacts) and candidate order are those of k_step / k_step_stream.
 #include "step_common.cuh"
 
+#ifndef PRTC_WITH_TIMELINE
+#define PRTC_WITH_TIMELINE 0          // 1: k_step_pool records a claim timeline when StepParams::timeline is set (tools/claim_timeline.py)
+#endif
+
 namespace prt {
 
 namespace {
@@ -88,6 +92,7 @@ __global__ void __launch_bounds__(32, 16) k_step_pool(StepParams p) {
         if (lane == 0) base = atomicAdd(p.work_counter, opw);
         base = __shfl_sync(FULL, base, 0);
         if (base >= p.n) break;
+#if PRTC_WITH_TIMELINE
         if (p.timeline && lane == 0) {                            // diagnostic (PRTC_TIMELINE): when and where this claim started
             unsigned long long t; uint32_t sm;
             asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -95,6 +100,7 @@ __global__ void __launch_bounds__(32, 16) k_step_pool(StepParams p) {
             p.timeline[3 * size_t(base / opw) + 0] = t;
             p.timeline[3 * size_t(base / opw) + 2] = sm;
         }
+#endif
         if (GATED) {
             // the batch is still arriving over PCIe: wait until this warp's records have landed (chunk boundaries are
             // multiples of 32 characters = whole 128-byte lines of both record arrays)
@@ -548,11 +554,13 @@ __global__ void __launch_bounds__(32, 16) k_step_pool(StepParams p) {
             }
         }
         __syncwarp(FULL);
+#if PRTC_WITH_TIMELINE
         if (p.timeline && lane == 0) {
             unsigned long long t;
             asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
             p.timeline[3 * size_t(base / opw) + 1] = t;
         }
+#endif
     }
 
     c_sub = __reduce_add_sync(FULL, c_sub);

@@ -561,6 +561,22 @@ def test_jacobi_dynamic_pass_more_neighbours_than_the_buffer():
     assert _run_jacobi(scene, 5) > 50
 
 
+def test_jacobi_grid_of_a_million_cells():
+    """a stray triangle 3 km away stretches the world, so the uniform grid of the dynamic pass has ~10^6 cells: the prefix
+    sum over the cell counts runs over several hundred tiles (look-back over more than one window of 32) with a ragged last
+    tile; some capsules stand next to the stray triangle, i.e. in the last cells"""
+    scene = H.make_scene(48, 2, 2, 600, seed=58)
+    far = np.array([[3001.0, 0.0, 2777.0], [3001.0, 0.0, 2779.0], [3003.0, 0.0, 2779.0]], np.float32)
+    scene["xyz"] = np.concatenate([scene["xyz"], far])
+    scene["mesh_first"] = np.concatenate([scene["mesh_first"], [len(scene["xyz"]) - 3]]).astype(np.uint32)
+    scene["mesh_count"] = np.concatenate([scene["mesh_count"], [3]]).astype(np.uint32)
+    rs = np.random.RandomState(4)
+    scene["pos"][:40, 0] = 3000.5 + rs.uniform(0, 2.5, 40).astype(np.float32)
+    scene["pos"][:40, 2] = 2776.5 + rs.uniform(0, 2.5, 40).astype(np.float32)
+    scene["pos"][:40, 1] = rs.uniform(0.0, 1.0, 40).astype(np.float32)
+    assert _run_jacobi(scene, 6, trace_frames=(0, 3)) > 0
+
+
 def test_jacobi_rotated_capsules_and_no_static_geometry():
     from prototype2_b200 import capi
     scene = H.make_scene(40, 2, 2, 300, seed=57)

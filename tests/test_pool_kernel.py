@@ -173,3 +173,32 @@ def test_pooled_kernel_by_id_order():
     from prototype2_b200 import capi
     scene = H.make_scene(96, 2, 2, 8000, seed=71)
     _run(scene, 4, dict(order="by_id"), dict(order_mode=capi.ORDER_BY_ID))
+
+
+def test_records_edited_between_frames():
+    """the per-slot leaf lists are kept across frames for the region a character was last seen in; the caller may edit the
+    records in between: a third of a walking crowd is teleported (and turned around) after frame 2 and again after frame 4,
+    so their slots' regions are wrong and the refresh / the per-substep region check must catch it"""
+    scene = H.make_scene(96, 2, 2, 9000, seed=21)
+    rs = np.random.RandomState(5)
+    ang = rs.uniform(-np.pi, np.pi, scene["n"])
+    scene["move"] = np.stack([0.08 * np.cos(ang), np.zeros(scene["n"]), 0.08 * np.sin(ang)], axis=1).astype(np.float32)
+    orc = H.build_oracle(scene, "l1", order="canonical")
+    ctx, tf, ph = _pooled_ctx(scene)
+    for f in range(7):
+        if f in (3, 5):
+            st = orc.get_state()
+            who = rs.choice(scene["n"], scene["n"] // 3, replace=False)
+            dst = np.roll(who, 17)
+            pos, vel = st["pos"].copy(), st["vel"].copy()
+            pos[who] = st["pos"][dst] + np.float32(0.3)
+            vel[who] = -st["vel"][dst]
+            orc.set_state(pos=pos, vel=vel)
+            tf["position"][:] = pos
+            ph["velocity"][:] = vel
+        orc.step(DT)
+        ctx.update_characters(DT, tf, ph)
+        assert H.state_diff(orc.get_state(), H.gpu_state(tf, ph)) == [], "frame %d" % f
+    co, cg = orc.counters(), ctx.counters()
+    for k in ("substeps", "tri_tests", "contacts"):
+        assert co[k] == cg[k], k

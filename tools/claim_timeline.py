@@ -1,6 +1,7 @@
 #!/usr/bin/env python
 """Diagnostic: when every claim (a warp's group of characters) of one k_step_pool launch started and ended, and on which SM.
-Needs PRTC_TIMELINE=1 (set below before libprtc is loaded).  GPU box.
+Needs the diagnostic twin of the library (`make -C prototype2_b200/csrc timeline` -> libprtc_timeline.so) and
+PRTC_TIMELINE=1; both are arranged below before the library is loaded.  GPU box.
 
   python tools/claim_timeline.py [--world W] [--workload C4] [--frames 8]
 steps rank 0's slice of a W-rank job of the bench workload and prints what the launch's time is made of."""
@@ -10,6 +11,7 @@ import os
 import sys
 
 os.environ["PRTC_TIMELINE"] = "1"
+os.environ.setdefault("PRTC_LIB", "libprtc_timeline.so")
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import numpy as np  # noqa: E402
