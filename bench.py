@@ -55,6 +55,8 @@ def parse_args(argv=None):
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the short extra runs (moving crowd, weak scaling, config 5)")
+    ap.add_argument("--chain", type=int, default=1,
+                    help="1: PRTC_OPT_CHAIN_FRAMES for the device-resident leg (consecutive frames overlap on the device); 0: off")
     ap.add_argument("--trace", default="", help="directory for a per-kernel duration table of every rank (diagnostic)")
     ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
                     help="strong: ONE global batch split over the GPUs (BASELINE config 4 as written); weak: a full batch per GPU")
@@ -355,6 +357,8 @@ class Workload:
             for kv in args.opt:
                 oname, val = kv.split("=")
                 ctx.set_option(getattr(capi, "OPT_" + oname), int(val))
+            if args.chain and not self.dynamic:
+                ctx.set_option(capi.OPT_CHAIN_FRAMES, 1)
             if self.dynamic:
                 ctx.dyn_configure(self.first, self.n_global if strong else self.n)
                 # the records of the dynamic pass travel by peer stores from the kernel that computes them (CUDA IPC handles
@@ -414,7 +418,7 @@ class Workload:
             self.sharding.allgather_records(self._rec[0], self._rec[1], self.n)
         self.ctx.update_characters_device(DT, self.n, self.d_tf.data_ptr(), self.d_ph.data_ptr())
 
-    def timed(self, dist, steps, warmup, sample_clocks=False):
+    def timed(self, dist, steps, warmup, sample_clocks=False, per_frame_events=False):
         """W untimed + K timed frames, device-resident state; CUDA events on the launching stream, max over ranks"""
         torch = self.torch
         self.reset()
@@ -427,14 +431,17 @@ class Workload:
         dist.barrier()
         if sampler:
             sampler.start()
+        # (chained frames overlap on the device: an event between two of them would serialise them again, so only the ends are marked)
+        chained = bool(self.args.chain) and not self.dynamic and not per_frame_events
         ev[0].record(self.stream)
         for k in range(steps):
             self.device_step()
-            ev[k + 1].record(self.stream)
+            if not chained or k == steps - 1:
+                ev[k + 1].record(self.stream)
         dist.barrier()
         clocks = sampler.stop() if sampler else None
         total_ms = ev[0].elapsed_time(ev[steps])
-        per = [ev[k].elapsed_time(ev[k + 1]) for k in range(steps)]
+        per = [total_ms / steps] * steps if chained else [ev[k].elapsed_time(ev[k + 1]) for k in range(steps)]
         cnt = self.ctx.counters(reset=True)
         el = dist.max(total_ms * 1e-3)
         self.rank_ms = [v / steps for v in dist.per_rank(total_ms)]
@@ -507,6 +514,15 @@ def run_ours(args):
     value = r["substeps"] / el
     crc = w.crc()
     rank_ms = w.rank_ms
+    unchained = None
+    if args.chain and not w.dynamic:
+        # the same frames one launch after the other (option off), with an event per frame
+        ctx.set_option(capi.OPT_CHAIN_FRAMES, 0)
+        ru = w.timed(dist, args.steps, args.warmup, per_frame_events=True)
+        ctx.set_option(capi.OPT_CHAIN_FRAMES, 1)
+        assert w.crc() == crc, "chained and unchained frames must leave the same state"
+        unchained = {"value": ru["substeps"] / ru["el"], "ms_per_step": 1e3 * ru["el"] / args.steps,
+                     "ms_per_step_median": float(np.median(ru["per"])), "ms_per_step_min": float(np.min(ru["per"]))}
     if args.trace:
         w.trace(args.steps, os.path.join(args.trace, "trace_%s_n%d_rank%d.json" % (args.workload, world, rank)))
 
@@ -686,6 +702,11 @@ def run_ours(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * el / args.steps, "ms_per_step_median": float(np.median(kernel_ms)), "ms_per_step_min": float(np.min(kernel_ms)),
             "ms_per_step_by_rank": rank_ms,
+            "frames": ("chained: consecutive frames overlap on the device (PRTC_OPT_CHAIN_FRAMES; per-claim ordering, same bytes)"
+                       if (args.chain and unchained is not None and int(cnt["launches"]) == args.steps) else
+                       "one launch after the other (the library chains batches of up to 6 rounds of claims; this one has more)"
+                       if (args.chain and unchained is not None) else "one launch after the other"),
+            "unchained": unchained,
             "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "config": cfg,
             "tri_tests_per_s": r["tri_tests"] / el, "node_tests_per_s": node_tests / el,

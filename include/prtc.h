@@ -300,10 +300,18 @@ int prtc_get_counters(prtc_ctx * ctx, prtc_counters * out, int reset);
  *                          work through the pooled candidate triangles of those characters (dense cull, dense exact
  *                          test, speculative ordered commit); 0: the lane-per-character kernel of round 1.
  *   PRTC_OPT_TIGHT_REJECT  (default 1) pooled kernel only: a second conservative cull (plane and edge-plane distances of
- *                          the capsule segment) behind the box cull. */
+ *                          the capsule segment) behind the box cull.
+ *   PRTC_OPT_CHAIN_FRAMES  (default 0) prtc_step_characters_device, static pass, batches that fill the GPU: consecutive
+ *                          calls with the same arguments may OVERLAP on the device -- the next frame's thread blocks are
+ *                          scheduled as the current frame's finish (programmatic dependent launch) and a character's next
+ *                          frame starts when its own current frame has been stored, so the idle tail of one frame is filled
+ *                          with the head of the next.  Results are the same bytes; every call still completes in stream
+ *                          order for anything the caller enqueues AFTER it.  Contract: between two chained calls the caller
+ *                          must not enqueue work on the context's stream that WRITES the records (reads are fine, and so is
+ *                          any host-side synchronisation); any other libprtc call breaks the chain by itself. */
 enum prtc_option { PRTC_OPT_FRAME_CACHE = 1, PRTC_OPT_QUICK_REJECT = 2, PRTC_OPT_PERSISTENT = 3, PRTC_OPT_CROSS_FRAME_CACHE = 4,
                    PRTC_OPT_WARP_KERNEL = 5, PRTC_OPT_STREAMED_COPY = 6, PRTC_OPT_TOP_STAGING = 7, PRTC_OPT_POOL_KERNEL = 8,
-                   PRTC_OPT_TIGHT_REJECT = 9 };
+                   PRTC_OPT_TIGHT_REJECT = 9, PRTC_OPT_CHAIN_FRAMES = 10 };
 int prtc_set_option(prtc_ctx * ctx, int option, int value);
 
 /* Introspection for parity tests: the flattened tree.  leaf_mesh_ids receives the mesh-collider ids of all

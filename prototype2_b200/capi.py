@@ -14,7 +14,7 @@ ABS_INT, ABS_FLOAT = 0, 1
 ORDER_LITERAL, ORDER_CANONICAL, ORDER_BY_ID = 0, 1, 2
 DYN_OFF, DYN_JACOBI = 0, 2
 OPT_FRAME_CACHE, OPT_QUICK_REJECT, OPT_PERSISTENT, OPT_CROSS_FRAME_CACHE, OPT_WARP_KERNEL, OPT_STREAMED_COPY, OPT_TOP_STAGING = 1, 2, 3, 4, 5, 6, 7
-OPT_POOL_KERNEL, OPT_TIGHT_REJECT = 8, 9
+OPT_POOL_KERNEL, OPT_TIGHT_REJECT, OPT_CHAIN_FRAMES = 8, 9, 10
 
 # every symbol include/prtc.h declares (tests check the library exports exactly these)
 SYMBOLS = (

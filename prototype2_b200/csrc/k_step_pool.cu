@@ -70,7 +70,15 @@ struct PoolShared {
 __device__ __forceinline__ V3 ld3(const float (*a)[32], int f, uint32_t o) { return v3(a[f][o], a[f + 1][o], a[f + 2][o]); }
 __device__ __forceinline__ void st3(float (*a)[32], int f, uint32_t o, V3 v) { a[f][o] = v.x; a[f + 1][o] = v.y; a[f + 2][o] = v.z; }
 
-template <bool GATED, int MODE>
+// CHAINED (static pass, a batch that fills the machine, PRTC_OPT_CHAIN_FRAMES): consecutive frames of the same batch overlap on
+// the device.  The launch carries the programmatic-stream-serialization attribute and every block lets the next launch in
+// as soon as it runs, so the next frame's blocks take the warp slots this frame's tail leaves empty; what orders the
+// frames is a word per claim: claim g of frame f+1 starts when claim g of frame f (the same characters) has stored its
+// results (StepParams::chain_done).  Nothing may sit between the two step kernels, so this variant brings the per-slot leaf
+// lists up to date itself at LOAD (the check and, rarely, the walk of k_xc_refresh).  What another frame wrote -- the records,
+// the slot arrays -- is read with plain loads behind an acquire of the claim's word (the other side: release store behind
+// the warp barrier), which is what the memory model asks for; reading them past the L1 instead (ld.global.cg) cost 6 %.
+template <bool GATED, int MODE, bool CHAINED>
 __global__ void __launch_bounds__(32, 16) k_step_pool(StepParams p) {
     constexpr bool JACOBI = MODE == MODE_JACOBI;
     __shared__ PoolShared<JACOBI> sh;
@@ -81,6 +89,13 @@ __global__ void __launch_bounds__(32, 16) k_step_pool(StepParams p) {
     const bool use_cache = !(p.tune & 1u) && p.xc_version != nullptr;
     const uint32_t wmax = ((p.tune >> 8) & 0xFFu) ? ((p.tune >> 8) & 0xFFu) : 32u;   // largest window (jobs per owner and round)
     if (p.work_next && blockIdx.x == 0 && lane == 0) *p.work_next = 0u;      // the NEXT launch's work counter (see StepParams::work_pair)
+    if (CHAINED) {
+        // (the next frame's counter is zero before any of its blocks can run: they start only after EVERY block of this
+        //  launch has passed this point)
+        __threadfence();
+        __syncwarp(FULL);
+        asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    }
     const float fsub = float(p.substeps);
     // characters per warp: 32 when the batch fills the machine; fewer owners (lanes [0, opw)) spread a smaller batch over
     // more warps -- the pooled work is executed by all 32 lanes either way
@@ -101,6 +116,18 @@ __global__ void __launch_bounds__(32, 16) k_step_pool(StepParams p) {
             p.timeline[3 * size_t(base / opw) + 2] = sm;
         }
 #endif
+        if (CHAINED && p.chain_prev) {
+            // the same characters' claim of the previous frame must have stored its results: poll, then one acquire load -- what
+            // it orders (through the warp barrier, for all lanes) are the plain loads of the records and the slot arrays below
+            if (lane == 0) {
+                const uint32_t * done = p.chain_done + base / opw;
+                while (*reinterpret_cast<const volatile uint32_t *>(done) != p.chain_prev) __nanosleep(64);
+                uint32_t seen;
+                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(done) : "memory");
+                (void)seen;
+            }
+            __syncwarp(FULL);
+        }
         if (GATED) {
             // the batch is still arriving over PCIe: wait until this warp's records have landed (chunk boundaries are
             // multiples of 32 characters = whole 128-byte lines of both record arrays)
@@ -147,13 +174,60 @@ __global__ void __launch_bounds__(32, 16) k_step_pool(StepParams p) {
         sh.pose[PF_EPS][lane] = p.qr_eps + 1e-5f * (fabsf(cap.radius) + fabsf(cap.height) + fabsf(cap.ox) + fabsf(cap.oy) + fabsf(cap.oz));
         // per-slot leaf list kept valid by k_xc_refresh: read per substep straight from device memory (coalesced: SoA)
         const size_t slot = size_t(p.xc_first) + i;
-        const bool cache_ok = valid && use_cache && p.xc_version[slot] == p.tree_version;
+        bool cache_ok = valid && use_cache && p.xc_version[slot] == p.tree_version;
         Box region; region.lo = v3(0.0f); region.hi = v3(0.0f);
         uint32_t ncache = 0;
         if (cache_ok) {
             ncache = p.xc_count[slot];
             region.lo = v3(p.xc_region[0 * size_t(p.xc_stride) + slot], p.xc_region[1 * size_t(p.xc_stride) + slot], p.xc_region[2 * size_t(p.xc_stride) + slot]);
             region.hi = v3(p.xc_region[3 * size_t(p.xc_stride) + slot], p.xc_region[4 * size_t(p.xc_stride) + slot], p.xc_region[5 * size_t(p.xc_stride) + slot]);
+        }
+        if (CHAINED && use_cache) {
+            // k_xc_refresh's job, done here: does the slot's region cover what this frame can need?  If not, one walk with the
+            // need grown by the margin and stretched along the coasting motion (see k_xc_refresh) rewrites the slot.
+            V3 eA, eB;
+            segment_ends(fr, pos + vel, eA, eB);
+            Box R = box_union(capsule_box(prevA, prevB, radius), capsule_box(eA, eB, radius));
+            R.lo = R.lo - v3(0.25f); R.hi = R.hi + v3(0.25f);
+            if (valid && !(cache_ok && box_contains(region, R))) {
+                if (p.xc_reuse) {
+                    const float r = fdiv(1.0f, 1.0f + p.dt * p.friction);
+                    const float coast = r < 0.999f ? fdiv(r, 1.0f - r) : 0.0f;
+                    const float dx = coast * ph->velocity[0] + 2.0f * mvx, dz = coast * ph->velocity[2] + 2.0f * mvz;
+                    if (dx == dx && dz == dz && fabsf(dx) < 4.0f && fabsf(dz) < 4.0f) {
+                        R.lo.x = R.lo.x + fminf(dx, 0.0f); R.hi.x = R.hi.x + fmaxf(dx, 0.0f);
+                        R.lo.z = R.lo.z + fminf(dz, 0.0f); R.hi.z = R.hi.z + fmaxf(dz, 0.0f);
+                    }
+                    R.lo = R.lo - v3(p.xc_margin); R.hi = R.hi + v3(p.xc_margin);
+                }
+                uint32_t nd = 0, nl = 0;
+                while (nd < p.n_nodes) {
+                    const float4 lo = __ldg(p.nodes + 2 * nd);
+                    const float4 hi = __ldg(p.nodes + 2 * nd + 1);
+                    const bool ov = node_overlaps(lo, hi, R);
+                    const int cnt = __float_as_int(hi.w);
+                    if (cnt < 0) {
+                        nd = ov ? nd + 1 : uint32_t(__float_as_int(lo.w));
+                    } else {
+                        if (ov) {
+                            if (nl == uint32_t(XC_CAP)) { nl = 0xFFFFFFFFu; break; }
+                            p.xc_leaf[size_t(nl) * p.xc_stride + slot] = nd;
+                            ++nl;
+                        }
+                        nd = nd + 1;
+                    }
+                }
+                if (nl == 0xFFFFFFFFu) { p.xc_version[slot] = 0u; cache_ok = false; }     // too many leaves for a slot: walk per substep
+                else {
+                    p.xc_region[0 * size_t(p.xc_stride) + slot] = R.lo.x; p.xc_region[1 * size_t(p.xc_stride) + slot] = R.lo.y;
+                    p.xc_region[2 * size_t(p.xc_stride) + slot] = R.lo.z; p.xc_region[3 * size_t(p.xc_stride) + slot] = R.hi.x;
+                    p.xc_region[4 * size_t(p.xc_stride) + slot] = R.hi.y; p.xc_region[5 * size_t(p.xc_stride) + slot] = R.hi.z;
+                    p.xc_count[slot] = nl;
+                    p.xc_version[slot] = p.tree_version;
+                    region = R; ncache = nl; cache_ok = true;
+                }
+            }
+            __syncwarp(FULL);
         }
 
         // JACOBI: the neighbours of the whole frame -- every other capsule whose stored box overlaps the region the frame can
@@ -277,7 +351,7 @@ __global__ void __launch_bounds__(32, 16) k_step_pool(StepParams p) {
                         uint32_t leaf[4];
                         float4 lo[4], hi[4];
 #pragma unroll
-                        for (int u = 0; u < 4; ++u) leaf[u] = p.xc_leaf[size_t(j4 + u < ncache ? j4 + u : j4) * p.xc_stride + slot];
+                        for (int u = 0; u < 4; ++u) leaf[u] = *(p.xc_leaf + size_t(j4 + u < ncache ? j4 + u : j4) * p.xc_stride + slot);
 #pragma unroll
                         for (int u = 0; u < 4; ++u) { lo[u] = __ldg(p.nodes + 2 * leaf[u]); hi[u] = __ldg(p.nodes + 2 * leaf[u] + 1); }
 #pragma unroll
@@ -537,6 +611,12 @@ __global__ void __launch_bounds__(32, 16) k_step_pool(StepParams p) {
             ph->grounded = grounded;
             if (p.io_result) p.io_result[i] = make_float4(pos.x, pos.y, pos.z, grounded ? 1.0f : 0.0f);
         }
+        if (CHAINED) {
+            // this claim's results are out: the next frame's claim of the same characters may start
+            // (the lanes' stores happen before the warp barrier, the release store after it is cumulative)
+            __syncwarp(FULL);
+            if (lane == 0) asm volatile("st.release.gpu.global.u32 [%0], %1;" :: "l"(p.chain_done + base / opw), "r"(p.chain_serial) : "memory");
+        }
         if (GATED) {
             // every finished character is counted (per 1024, then per 65536) so that the copy-out stream can start on a
             // chunk the moment its last character is written
@@ -596,6 +676,19 @@ uint32_t pool_blocks_per_sm() { return 16u; }
 
 void launch_k_step_pool(StepParams const & p_in, uint32_t blocks, bool gated, int mode, cudaStream_t stream) {
     StepParams p = p_in;
+    if (p.chain_done && !gated && mode == MODE_STATIC) {
+        // a chained frame: its work counter (one of a ring of four) was zeroed by the launch before it or by the caller; the
+        // attribute lets its blocks in before the previous launch has drained
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(blocks); cfg.blockDim = dim3(32); cfg.dynamicSmemBytes = 0; cfg.stream = stream;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = at; cfg.numAttrs = p.chain_prev ? 1 : 0;
+        cudaLaunchKernelEx(&cfg, k_step_pool<false, MODE_STATIC, true>, p);
+        return;
+    }
+    p.chain_done = nullptr;
     if (p.work_flip && p.work_pair && !gated) {
         const uint32_t k = *p.work_flip & 1u;                      // this launch's counter was zeroed by the previous one (or at creation)
         p.work_counter = p.work_pair + k;
@@ -605,9 +698,9 @@ void launch_k_step_pool(StepParams const & p_in, uint32_t blocks, bool gated, in
         p.work_next = nullptr;
         cudaMemsetAsync(p.work_counter, 0, sizeof(unsigned), stream);
     }
-    if (mode == MODE_JACOBI) k_step_pool<false, MODE_JACOBI><<<blocks, 32, 0, stream>>>(p);
-    else if (gated) k_step_pool<true, MODE_STATIC><<<blocks, 32, 0, stream>>>(p);
-    else k_step_pool<false, MODE_STATIC><<<blocks, 32, 0, stream>>>(p);
+    if (mode == MODE_JACOBI) k_step_pool<false, MODE_JACOBI, false><<<blocks, 32, 0, stream>>>(p);
+    else if (gated) k_step_pool<true, MODE_STATIC, false><<<blocks, 32, 0, stream>>>(p);
+    else k_step_pool<false, MODE_STATIC, false><<<blocks, 32, 0, stream>>>(p);
 }
 
 } // namespace prt

@@ -12,6 +12,7 @@
 //   k_query_box        one box against the flattened tree (introspection)
 //
 // Compile with -fmad=false: results must be bit-identical to the CPU reference (see prt_math.cuh).
+#include <cstring>
 #include <cstdlib>
 
 #include "step_common.cuh"
@@ -348,9 +349,37 @@ static int launch_step_inner(StepParams const & p_in, bool traced, int mode, cud
         static const uint32_t force_opw = [] { const char * e = std::getenv("PRTC_OPW"); return e ? uint32_t(std::atoi(e)) : 0u; }();
         if (force_opw >= 1u && force_opw <= 32u) opw = force_opw;   // experiments
         p.lanes_per_warp = opw;
-        if (p.xc_version != nullptr && !(p.tune & 1u)) { if (!p.xc_fresh) { launch_k_xc_refresh(p, stream); ++launches; } }
-        else p.xc_version = nullptr;
         const uint32_t want = (p.n + opw - 1) / opw;
+        // chained frames: the static pass of a batch that fills the machine, nothing of the resident I/O in it
+        bool chained = false;
+        // ... and of few rounds of claims: the chained kernel is ~4 % slower per claim (slot refresh and claim words inside it), which
+        // pays when the tail it fills is a larger share of the frame than that (a 125 k shard: 2 rounds; the full 1 M batch: 13)
+        static const uint32_t chain_max_rounds = [] { const char * e = std::getenv("PRTC_CHAIN_MAX_ROUNDS"); return e ? uint32_t(std::atoi(e)) : 6u; }();
+        if (p.chain && p.chain_done && p.chain_ring && mode == MODE_STATIC && want >= p.pool_blocks && want <= chain_max_rounds * p.pool_blocks && p.xc_version != nullptr &&
+            !(p.tune & 1u) && !p.io_move && !p.io_result && !p.done_flag && !p.host_flags) {
+            ChainState & cs = *p.chain;
+            const unsigned long long sig[6] = {p.n, opw, (unsigned long long)(uintptr_t)p.transforms, (unsigned long long)(uintptr_t)p.physics,
+                                               (unsigned long long)(uintptr_t)stream, p.tree_version};
+            static const bool no_follow = std::getenv("PRTC_CHAIN_NOFOLLOW") != nullptr;     // experiments: the chained kernel, launch after launch
+            const bool follow = cs.armed && std::memcmp(sig, cs.sig, sizeof(sig)) == 0 && !no_follow;
+            if (!follow) { cudaMemsetAsync(p.chain_ring, 0, 4 * sizeof(unsigned), stream); cs.ring = 0; }
+            const uint32_t k = cs.ring & 3u;
+            ++cs.ring;
+            p.work_counter = p.chain_ring + k;
+            p.work_next = p.chain_ring + ((k + 1u) & 3u);
+            p.chain_prev = follow ? cs.serial : 0u;
+            if (++cs.serial == 0u) cs.serial = 1u;
+            p.chain_serial = cs.serial;
+            std::memcpy(cs.sig, sig, sizeof(sig));
+            cs.armed = true;
+            chained = true;
+        } else {
+            if (p.chain) p.chain->armed = false;
+            p.chain_done = nullptr;
+        }
+        if (p.xc_version != nullptr && !(p.tune & 1u)) { static const bool keep_refresh = std::getenv("PRTC_CHAIN_KEEP_REFRESH") != nullptr;   // experiments
+            if (!p.xc_fresh && (!chained || keep_refresh)) { launch_k_xc_refresh(p, stream); ++launches; } }
+        else p.xc_version = nullptr;
         launch_k_step_pool(p, want < p.pool_blocks ? want : p.pool_blocks, false, mode, stream);
         return launches;
     }

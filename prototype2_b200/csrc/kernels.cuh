@@ -77,6 +77,11 @@ struct StepParams {
     // k_step_pool: two work counters used alternately -- a launch hands characters out of one and zeroes the OTHER for the
     // next launch (stream order makes that safe), so no memset is queued in front of every frame
     unsigned * work_pair;           // device: the two counters
+    // chained frames (k_step_pool<CHAINED>, PRTC_OPT_CHAIN_FRAMES): a word per claim; this launch writes `chain_serial` into the
+    // word of every claim it finishes and starts a claim only when its word holds `chain_prev` (0: first of a chain, no wait)
+    uint32_t * chain_done; uint32_t chain_serial, chain_prev;
+    unsigned * chain_ring;          // four work counters used in rotation by the frames of a chain
+    struct ChainState * chain;      // HOST: what the previous launch of this context was; null => this launch may not chain
     unsigned long long * timeline;  // diagnostic (PRTC_TIMELINE=1): per claim of k_step_pool {start ns, end ns, SM}; null otherwise
     uint32_t * work_flip;           // HOST: which one the next launch uses (toggled by the launcher); null => memset + work_counter
     unsigned * work_next;           // device: the counter this launch zeroes (set by the launcher)
@@ -131,6 +136,13 @@ bool launch_slot_refresh(StepParams const & p, int mode, cudaStream_t stream);
 //   flags[k]     (IPC exchange only) one word per destination -- this rank's slot in that device's arrival table; the LAST
 //                block of the kernel writes `flag_value` (the frame number) into all of them behind a system-wide fence, and
 //                the consumer's k_dyn_wait spins on its own table until every rank's word has reached the frame number
+// host-side memory of chained launches (one per context)
+struct ChainState {
+    bool armed = false;             // the last step launched on the context was a chained frame with the signature below
+    uint32_t serial = 0, ring = 0;
+    unsigned long long sig[6] = {0, 0, 0, 0, 0, 0};
+};
+
 struct DynPeers {
     float4 * records[15]; uint32_t n;
     uint32_t * flags[16]; uint32_t n_flags; uint32_t flag_value; unsigned * block_count;

@@ -21,6 +21,7 @@ int fail(int code, const std::string & msg) {
 int build_tree_on_device(prtc_ctx * c, cudaStream_t s);
 
 int commit_impl(prtc_ctx * c) {
+    c->chain.armed = false;
     cudaStream_t s = c->stream;
     const uint32_t n_meshes = uint32_t(c->meshes.size());
     const uint32_t n_vertices = uint32_t(c->raw.size() / 3);
@@ -367,6 +368,7 @@ int build_tree_on_device(prtc_ctx * c, cudaStream_t s) {
 
 int fill_params(prtc_ctx * c, float dt, uint32_t n, prtc_transform * d_tf, prtc_char_physics * d_ph, StepParams & p) {
     std::memset(&p, 0, sizeof(p));
+    c->chain.armed = false;                                       // (prtc_step_characters_device re-arms it for its own launches)
     p.nodes = c->d_nodes.ptr;
     p.n_nodes = uint32_t(c->flat.nodes.size());
     p.tris = c->d_tris.ptr;
@@ -529,6 +531,7 @@ int prtc_create(const prtc_config * cfg, prtc_ctx ** out) {
     if (const char * e = std::getenv("PRTC_TOP_STAGING")) ctx->top_staging = std::atoi(e);
     if (const char * e = std::getenv("PRTC_POOL_KERNEL")) ctx->pool_kernel = std::atoi(e);
     if (const char * e = std::getenv("PRTC_TIGHT_REJECT")) ctx->tight_reject = std::atoi(e);
+    if (const char * e = std::getenv("PRTC_CHAIN_FRAMES")) ctx->chain_frames = std::atoi(e) != 0;
     if (const char * e = std::getenv("PRTC_STAGED")) ctx->staged = std::atoi(e);
     if (const char * e = std::getenv("PRTC_XC_MARGIN")) ctx->xc_margin = float(std::atof(e));
     if (const char * e = std::getenv("PRTC_TUNE")) ctx->tune_hi = uint32_t(std::strtoul(e, nullptr, 0)) & 0xFFFFFF00u;
@@ -565,7 +568,7 @@ void prtc_destroy(prtc_ctx * c) {
     c->d_cap2char.release(); c->d_seg_start.release(); c->d_seg_prev.release(); c->d_last_box.release();
     for (void * q : c->dyn_ipc.opened) cudaIpcCloseMemHandle(q);
     c->dyn_ipc.opened.clear(); c->dyn_ipc.flags.release();
-    c->d_dyn_records.release(); c->d_dyn_count.release(); c->d_dyn_start.release(); c->d_dyn_items.release(); c->d_dyn_reach.release(); c->d_dyn_cursor.release(); c->d_dyn_scan.release(); c->d_timeline.release();
+    c->d_dyn_records.release(); c->d_dyn_count.release(); c->d_dyn_start.release(); c->d_dyn_items.release(); c->d_dyn_reach.release(); c->d_dyn_cursor.release(); c->d_dyn_scan.release(); c->d_timeline.release(); c->d_chain_done.release();
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
     for (int k = 0; k < prtc_ctx::PIPE_STREAMS; ++k) if (c->pipe[k]) cudaStreamDestroy(c->pipe[k]);
     if (c->dyn_ipc.push_stream) cudaStreamDestroy(c->dyn_ipc.push_stream);
@@ -740,6 +743,7 @@ int prtc_set_option(prtc_ctx * c, int option, int value) {
         case PRTC_OPT_TOP_STAGING: c->top_staging = value != 0; return PRTC_OK;
         case PRTC_OPT_POOL_KERNEL: c->pool_kernel = value != 0; return PRTC_OK;
         case PRTC_OPT_TIGHT_REJECT: c->tight_reject = value != 0; return PRTC_OK;
+        case PRTC_OPT_CHAIN_FRAMES: c->chain_frames = value != 0; c->chain.armed = false; return PRTC_OK;
         default: return fail(PRTC_ERR_INVALID, "prtc_set_option: unknown option");
     }
 }

@@ -152,6 +152,9 @@ struct prtc_ctx {
     int warp_kernel = 1;                    // small batches: one warp per character (k_step_warp); 0 = thinned lock-step kernel
     float xc_margin = 0.5f;
     prt::host::DevBuf<unsigned> d_work;                // work counters of the persistent kernel, one per concurrently running launch ([8], [9]: the pooled kernel's alternating pair)
+    prt::ChainState chain;                             // chained frames (PRTC_OPT_CHAIN_FRAMES)
+    int chain_frames = 0;
+    prt::host::DevBuf<uint32_t> d_chain_done;
     uint32_t work_flip = 0;                            // which of the pair the next pooled launch uses
     prt::host::HostStage stage;                        // small host-buffer batches: records staged in mapped pinned memory
     int staged = 1;                         // PRTC_STAGED=0: small batches take the copy path too (A/B)

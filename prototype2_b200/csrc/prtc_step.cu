@@ -406,9 +406,21 @@ int prtc_step_characters_device(prtc_ctx * c, float dt, uint32_t n, prtc_transfo
     if (c->geometry_dirty || c->tree_dirty || c->capsules_dirty) { rc = commit_impl(c); if (rc) return rc; }
     if (c->capsules.empty() && n) return fail(PRTC_ERR_INVALID, "prtc_step_characters: no capsule collider registered");
     StepParams p;
-    rc = fill_params(c, dt, n, d_tf, d_ph, p);
+    const bool chain_was_armed = c->chain.armed;
+    rc = fill_params(c, dt, n, d_tf, d_ph, p);                   // (disarms the chain: every other kind of step breaks it)
     if (rc) return rc;
     int mode = STEP_STATIC;
+    if (c->chain_frames && !c->jacobi() && n) {
+        // PRTC_OPT_CHAIN_FRAMES: this frame may start on the device while the previous one (same batch) is draining
+        if (c->d_chain_done.cap < size_t(n) + 1) {
+            PRTC_CUDA(c->d_chain_done.reserve(size_t(n) + 1));
+            PRTC_CUDA(cudaMemsetAsync(c->d_chain_done.ptr, 0, c->d_chain_done.cap * sizeof(uint32_t), c->stream));
+            c->chain.armed = false;
+        } else c->chain.armed = chain_was_armed;
+        p.chain = &c->chain;
+        p.chain_done = c->d_chain_done.ptr;
+        p.chain_ring = c->d_work.ptr + 12;
+    }
     if (c->jacobi()) {
         if (!c->dyn_prepared) { rc = dyn_prepare(c, dt, n, d_tf, d_ph); if (rc) return rc; }
         // (the records are on their way to the peers: bring the per-slot leaf lists up to date meanwhile, they do not depend on them)
