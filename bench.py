@@ -576,7 +576,8 @@ def run_ours(args):
         except Exception:
             traffic = None
     kernel = ("k_step_warp<MODE_STATIC>" if n_caps <= 2368 and not w.dynamic else
-              "k_step_pool<false, %s>" % ("MODE_JACOBI" if w.dynamic else "MODE_STATIC"))          # what launch_step picks
+              "k_step_pool<false, %s, %s>" % ("MODE_JACOBI" if w.dynamic else "MODE_STATIC",
+                                               "true" if (args.chain and not w.dynamic and int(cnt["launches"]) == args.steps) else "false"))   # what launch_step picks
     avg_ms = float(np.mean(kernel_ms))
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "kernel": kernel, "peak_source": peak_src,
