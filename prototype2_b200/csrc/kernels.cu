@@ -377,8 +377,7 @@ static int launch_step_inner(StepParams const & p_in, bool traced, int mode, cud
             if (p.chain) p.chain->armed = false;
             p.chain_done = nullptr;
         }
-        if (p.xc_version != nullptr && !(p.tune & 1u)) { static const bool keep_refresh = std::getenv("PRTC_CHAIN_KEEP_REFRESH") != nullptr;   // experiments
-            if (!p.xc_fresh && (!chained || keep_refresh)) { launch_k_xc_refresh(p, stream); ++launches; } }
+        if (p.xc_version != nullptr && !(p.tune & 1u)) { if (!p.xc_fresh && !chained) { launch_k_xc_refresh(p, stream); ++launches; } }
         else p.xc_version = nullptr;
         launch_k_step_pool(p, want < p.pool_blocks ? want : p.pool_blocks, false, mode, stream);
         return launches;
