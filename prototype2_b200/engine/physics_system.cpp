@@ -13,9 +13,23 @@
 static_assert(sizeof(Transform) == sizeof(prtc_transform), "prtc_transform must stay bit-compatible with the engine's Transform");
 
 // Error behaviour of the reference: asserts (compiled out in its release build) and a bool from raycast.  A CUDA
-// failure has no counterpart there, so it is reported and the process stops instead of silently doing nothing.
-void PhysicsSystem::check(int status, char const * what) const {
-    if (status == PRTC_OK) return;
+// failure has no counterpart there: by default it is reported and the process stops instead of silently doing nothing;
+// with PhysicsSystem::setErrorHandler the failing call is skipped and the engine is told (physics_system.h).
+static PhysicsSystem::ErrorHandler g_errorHandler = nullptr;
+static void * g_errorUser = nullptr;
+
+void PhysicsSystem::setErrorHandler(ErrorHandler handler, void * user) {
+    g_errorHandler = handler;
+    g_errorUser = user;
+}
+
+bool PhysicsSystem::check(int status, char const * what) const {
+    if (status == PRTC_OK) return true;
+    m_lastStatus = status;
+    if (g_errorHandler) {
+        g_errorHandler(status, what, prtc_last_error(), g_errorUser);
+        return false;
+    }
     std::fprintf(stderr, "PhysicsSystem::%s: %s\n", what, prtc_last_error());
     assert(false && "prtc call failed");
     std::abort();
@@ -179,7 +193,8 @@ void PhysicsSystem::updateCharacters(float deltaTime, Scene & scene, Transform *
         q.grounded = p.isGrounded ? 1u : 0u;
     }
 
-    check(m_multi ? prtc_multi_step_characters(m_multi, deltaTime, uint32_t(n), m_tf.data(), m_ph.data()) : prtc_step_characters(m_ctx, deltaTime, uint32_t(n), m_tf.data(), m_ph.data()), "updateCharacters");
+    if (!check(m_multi ? prtc_multi_step_characters(m_multi, deltaTime, uint32_t(n), m_tf.data(), m_ph.data()) : prtc_step_characters(m_ctx, deltaTime, uint32_t(n), m_tf.data(), m_ph.data()), "updateCharacters"))
+        return;                                                   // (error handler installed: the frame is skipped, nothing is written)
 
     // scatter: position is the only Transform field the reference writes (collision_system.cpp:242, physics_system.cpp:350,437)
     for (size_t i = 0; i < n; ++i) {

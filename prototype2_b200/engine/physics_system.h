@@ -60,7 +60,19 @@ private:
     std::vector<prtc_char_physics> m_ph;
     float m_gravity = 1.0f;                       // physics_system.h:122
 
-    void check(int status, char const * what) const;
+    bool check(int status, char const * what) const;
+    mutable int m_lastStatus = 0;
+
+public:
+    // Not in the reference (it has no failure to report): what happens when the device side fails -- no GPU, out of memory, a
+    // lost device.  Default: the message goes to stderr and the process stops, as before.  With a handler installed the
+    // failing call becomes a no-op instead (outputs untouched, raycast answers "no hit", tags come back as 0), the handler is
+    // told which call failed with which prtc_status and message, and the engine can carry on without physics, fall back to the
+    // reference's CPU PhysicsSystem or shut down in an orderly way.  Process-wide, so it can be installed before the first
+    // PhysicsSystem is constructed.
+    typedef void (*ErrorHandler)(int status, char const * what, char const * message, void * user);
+    static void setErrorHandler(ErrorHandler handler, void * user);
+    int lastStatus() const { return m_lastStatus; }      // prtc_status of the last failed call of this object (0: none failed)
 };
 
 #endif

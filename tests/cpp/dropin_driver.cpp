@@ -30,7 +30,34 @@ static void put(std::vector<uint8_t> & out, void const * p, size_t n) {
     out.insert(out.end(), b, b + n);
 }
 
+#ifdef PRTC_DROPIN
+// "errors": the drop-in with an error handler installed on a machine where the device side cannot come up (no GPU): every
+// call must come back, the handler must be told, nothing may abort
+static int g_handled = 0;
+static void onError(int status, char const * what, char const * message, void *) {
+    ++g_handled;
+    std::printf("handler: %s status %d: %s\n", what, status, message);
+}
+static int errorsMode() {
+    PhysicsSystem::setErrorHandler(onError, nullptr);
+    PhysicsSystem physics;
+    int const afterCreate = g_handled;
+    ColliderTag tag = physics.addCapsuleCollider(0.5f, 0.5f, glm::vec3(0.0f, 0.5f, 0.0f));
+    glm::vec3 hit(0.0f);
+    bool const any = physics.raycast(glm::vec3(0.0f, 5.0f, 0.0f), glm::vec3(0.0f, -1.0f, 0.0f), 10.0f, hit);
+    Scene scene;
+    Transform tf[1];
+    physics.updateCharacters(1.0f / 30.0f, scene, tf);
+    std::printf("errors mode: create failed %d, handled %d, last status %d, tag %u, hit %d\n", afterCreate, g_handled, physics.lastStatus(),
+                unsigned(tag.index), int(any));
+    return 0;
+}
+#endif
+
 int main(int argc, char ** argv) {
+#ifdef PRTC_DROPIN
+    if (argc > 1 && std::strcmp(argv[1], "errors") == 0) return errorsMode();
+#endif
     int const N = argc > 1 ? std::atoi(argv[1]) : 24;          // terrain cells per side
     int const nChars = argc > 2 ? std::atoi(argv[2]) : 12;
     int const frames = argc > 3 ? std::atoi(argv[3]) : 40;

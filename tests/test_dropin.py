@@ -37,6 +37,23 @@ def test_drop_in_keeps_the_reference_class_surface():
         assert " ".join(w.split()) in text, w
 
 
+def test_drop_in_error_handler_instead_of_abort():
+    """No GPU here: prtc_create fails.  Without a handler the drop-in reports and aborts; with PhysicsSystem::setErrorHandler
+    every call comes back as a no-op and the handler is told (physics_system.h)."""
+    from prototype2_b200 import capi
+    if capi.device_count() > 0:
+        pytest.skip("needs a machine without a CUDA device")
+    _build()
+    r = subprocess.run([os.path.join(BIN, "driver_dropin"), "errors"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert r.returncode == 0, r.stdout
+    last = r.stdout.strip().splitlines()[-1]
+    assert last.startswith("errors mode: create failed 1, handled ") and "hit 0" in last, r.stdout
+    assert int(last.split("handled ")[1].split(",")[0]) >= 3, r.stdout            # create, raycast, updateCharacters at least
+    # ... and without the handler the same situation stops the process (the documented default)
+    r2 = subprocess.run([os.path.join(BIN, "driver_dropin"), "8", "2", "1", os.devnull], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert r2.returncode != 0 and "PhysicsSystem::PhysicsSystem" in r2.stdout, r2.stdout
+
+
 @pytest.mark.gpu
 # the long runs matter: the map is moved at frame 20 and a wrong ORDER of tree operations (mesh leaves re-inserted after
 # instead of before the capsule leaves of that frame) only showed as a different candidate order at frame 63 and as a
