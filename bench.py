@@ -705,7 +705,7 @@ def run_ours(args):
             "ms_per_step_by_rank": rank_ms,
             "frames": ("chained: consecutive frames overlap on the device (PRTC_OPT_CHAIN_FRAMES; per-claim ordering, same bytes)"
                        if (args.chain and unchained is not None and int(cnt["launches"]) == args.steps) else
-                       "one launch after the other (the library chains batches of up to 6 rounds of claims; this one has more)"
+                       "one launch after the other (the library chains batches of up to 8 rounds of claims; this one has more)"
                        if (args.chain and unchained is not None) else "one launch after the other"),
             "unchained": unchained,
             "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None,

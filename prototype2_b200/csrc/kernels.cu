@@ -352,9 +352,10 @@ static int launch_step_inner(StepParams const & p_in, bool traced, int mode, cud
         const uint32_t want = (p.n + opw - 1) / opw;
         // chained frames: the static pass of a batch that fills the machine, nothing of the resident I/O in it
         bool chained = false;
-        // ... and of few rounds of claims: the chained kernel is ~4 % slower per claim (slot refresh and claim words inside it), which
-        // pays when the tail it fills is a larger share of the frame than that (a 125 k shard: 2 rounds; the full 1 M batch: 13)
-        static const uint32_t chain_max_rounds = [] { const char * e = std::getenv("PRTC_CHAIN_MAX_ROUNDS"); return e ? uint32_t(std::atoi(e)) : 6u; }();
+        // ... and of few rounds of claims: the chained kernel costs 6 - 7 % per claim when frames overlap (slot refresh, claim words and
+        // the acquire inside it), which pays when the tail it fills is a larger share of the frame than that -- measured: 2 rounds
+        // (a 125 k shard) -10 %, 3.3 rounds -2.5 %, 6.6 rounds (500 k) -1.7 %, 13 rounds (the full 1 M batch) +1.5 %
+        static const uint32_t chain_max_rounds = [] { const char * e = std::getenv("PRTC_CHAIN_MAX_ROUNDS"); return e ? uint32_t(std::atoi(e)) : 8u; }();
         if (p.chain && p.chain_done && p.chain_ring && mode == MODE_STATIC && want >= p.pool_blocks && want <= chain_max_rounds * p.pool_blocks && p.xc_version != nullptr &&
             !(p.tune & 1u) && !p.io_move && !p.io_result && !p.done_flag && !p.host_flags) {
             ChainState & cs = *p.chain;
