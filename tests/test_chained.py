@@ -71,3 +71,40 @@ def test_chain_broken_by_another_call_and_resumed():
     plain, _ = _device_run(scene, 5, chain=False)
     chained, _ = _device_run(scene, 5, chain=True, interrupt_at=2)
     assert H.state_diff(plain, chained) == []
+
+
+def test_chained_soak_long_run_equals_unchained():
+    """150 frames of a walking crowd of 300 000 (four rounds of claims: every frame overlaps its neighbours), one shared capsule
+    shape; chained and unchained runs must leave the same bytes, and so must a chained run that is synchronised every 7th frame"""
+    import torch
+    from prototype2_b200 import capi
+    n = 300000
+    scene = H.make_scene(330, 2, 2, n, seed=78)
+    ang = np.random.RandomState(4).uniform(-np.pi, np.pi, n)
+    move = np.stack([0.06 * np.cos(ang), np.zeros(n), 0.06 * np.sin(ang)], axis=1).astype(np.float32)
+
+    def run(chain, sync_every=0):
+        ctx = capi.PhysicsContext()
+        ctx.add_model_collider(scene["xyz"], scene["mesh_first"], scene["mesh_count"])
+        cid = ctx.add_capsule_collider()
+        ctx.set_option(capi.OPT_CHAIN_FRAMES, 1 if chain else 0)
+        tf = capi.make_transforms(scene["pos"])
+        ph = capi.make_physics(scene["vel"], movement=move, collider=np.full(n, cid, np.uint32))
+        d_tf = torch.from_numpy(tf.view(np.uint8).reshape(-1).copy()).cuda()
+        d_ph = torch.from_numpy(ph.view(np.uint8).reshape(-1).copy()).cuda()
+        torch.cuda.synchronize()
+        for f in range(150):
+            ctx.update_characters_device(DT, n, d_tf.data_ptr(), d_ph.data_ptr())
+            if sync_every and f % sync_every == 0:
+                ctx.synchronize()
+        ctx.synchronize()
+        return d_tf.cpu().numpy().tobytes(), d_ph.cpu().numpy().tobytes(), ctx.counters()
+
+    a = run(False)
+    b = run(True)
+    c = run(True, sync_every=7)
+    assert a[0] == b[0] and a[1] == b[1]
+    assert a[0] == c[0] and a[1] == c[1]
+    for k in ("substeps", "tri_tests", "contacts", "exact_tests"):
+        assert a[2][k] == b[2][k] == c[2][k], k
+    assert b[2]["launches"] == 150 and a[2]["launches"] == 300
