@@ -301,7 +301,7 @@ int prtc_get_counters(prtc_ctx * ctx, prtc_counters * out, int reset);
  *                          test, speculative ordered commit); 0: the lane-per-character kernel of round 1.
  *   PRTC_OPT_TIGHT_REJECT  (default 1) pooled kernel only: a second conservative cull (plane and edge-plane distances of
  *                          the capsule segment) behind the box cull.
- *   PRTC_OPT_CHAIN_FRAMES  (default 0) prtc_step_characters_device, static pass, batches that fill the GPU: consecutive
+ *   PRTC_OPT_CHAIN_FRAMES  (default 0) prtc_step_characters_device, static pass, batches of ~20 000 characters and more: consecutive
  *                          calls with the same arguments may OVERLAP on the device -- the next frame's thread blocks are
  *                          scheduled as the current frame's finish (programmatic dependent launch) and a character's next
  *                          frame starts when its own current frame has been stored, so the idle tail of one frame is filled

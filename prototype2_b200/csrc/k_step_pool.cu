@@ -70,9 +70,10 @@ struct PoolShared {
 __device__ __forceinline__ V3 ld3(const float (*a)[32], int f, uint32_t o) { return v3(a[f][o], a[f + 1][o], a[f + 2][o]); }
 __device__ __forceinline__ void st3(float (*a)[32], int f, uint32_t o, V3 v) { a[f][o] = v.x; a[f + 1][o] = v.y; a[f + 2][o] = v.z; }
 
-// CHAINED (static pass, a batch that fills the machine, PRTC_OPT_CHAIN_FRAMES): consecutive frames of the same batch overlap on
-// the device.  The launch carries the programmatic-stream-serialization attribute and every block lets the next launch in
-// as soon as it runs, so the next frame's blocks take the warp slots this frame's tail leaves empty; what orders the
+// CHAINED (static pass, PRTC_OPT_CHAIN_FRAMES): consecutive frames of the same batch overlap on the device.  The launch
+// carries the programmatic-stream-serialization attribute and every block lets the next launch in as soon as it runs (a
+// launch starts when every block of the one before it HAS STARTED -- not finished), so later frames' blocks take the warp
+// slots that earlier frames leave empty or never needed; several frames can be on the machine at once.  What orders the
 // frames is a word per claim: claim g of frame f+1 starts when claim g of frame f (the same characters) has stored its
 // results (StepParams::chain_done).  Nothing may sit between the two step kernels, so this variant brings the per-slot leaf
 // lists up to date itself at LOAD (the check and, rarely, the walk of k_xc_refresh).  What another frame wrote -- the records,

@@ -350,24 +350,25 @@ static int launch_step_inner(StepParams const & p_in, bool traced, int mode, cud
         if (force_opw >= 1u && force_opw <= 32u) opw = force_opw;   // experiments
         p.lanes_per_warp = opw;
         const uint32_t want = (p.n + opw - 1) / opw;
-        // chained frames: the static pass of a batch that fills the machine, nothing of the resident I/O in it
+        // chained frames: the static pass of a batch of at least a quarter of the machine's warp slots (below that, frames pile up as
+        // spinning blocks faster than they retire), nothing of the resident I/O in it
         bool chained = false;
         // ... and of few rounds of claims: the chained kernel costs 6 - 7 % per claim when frames overlap (slot refresh, claim words and
         // the acquire inside it), which pays when the tail it fills is a larger share of the frame than that -- measured: 2 rounds
         // (a 125 k shard) -10 %, 3.3 rounds -2.5 %, 6.6 rounds (500 k) -1.7 %, 13 rounds (the full 1 M batch) +1.5 %
         static const uint32_t chain_max_rounds = [] { const char * e = std::getenv("PRTC_CHAIN_MAX_ROUNDS"); return e ? uint32_t(std::atoi(e)) : 8u; }();
-        if (p.chain && p.chain_done && p.chain_ring && mode == MODE_STATIC && want >= p.pool_blocks && want <= chain_max_rounds * p.pool_blocks && p.xc_version != nullptr &&
+        if (p.chain && p.chain_done && p.chain_ring && mode == MODE_STATIC && 4u * want >= p.pool_blocks && want <= chain_max_rounds * p.pool_blocks && p.xc_version != nullptr &&
             !(p.tune & 1u) && !p.io_move && !p.io_result && !p.done_flag && !p.host_flags) {
             ChainState & cs = *p.chain;
             const unsigned long long sig[6] = {p.n, opw, (unsigned long long)(uintptr_t)p.transforms, (unsigned long long)(uintptr_t)p.physics,
                                                (unsigned long long)(uintptr_t)stream, p.tree_version};
             static const bool no_follow = std::getenv("PRTC_CHAIN_NOFOLLOW") != nullptr;     // experiments: the chained kernel, launch after launch
             const bool follow = cs.armed && std::memcmp(sig, cs.sig, sizeof(sig)) == 0 && !no_follow;
-            if (!follow) { cudaMemsetAsync(p.chain_ring, 0, 4 * sizeof(unsigned), stream); cs.ring = 0; }
-            const uint32_t k = cs.ring & 3u;
+            if (!follow) { cudaMemsetAsync(p.chain_ring, 0, CHAIN_RING * sizeof(unsigned), stream); cs.ring = 0; }
+            const uint32_t k = cs.ring % CHAIN_RING;
             ++cs.ring;
             p.work_counter = p.chain_ring + k;
-            p.work_next = p.chain_ring + ((k + 1u) & 3u);
+            p.work_next = p.chain_ring + ((k + 1u) % CHAIN_RING);
             p.chain_prev = follow ? cs.serial : 0u;
             if (++cs.serial == 0u) cs.serial = 1u;
             p.chain_serial = cs.serial;

@@ -80,7 +80,7 @@ struct StepParams {
     // chained frames (k_step_pool<CHAINED>, PRTC_OPT_CHAIN_FRAMES): a word per claim; this launch writes `chain_serial` into the
     // word of every claim it finishes and starts a claim only when its word holds `chain_prev` (0: first of a chain, no wait)
     uint32_t * chain_done; uint32_t chain_serial, chain_prev;
-    unsigned * chain_ring;          // four work counters used in rotation by the frames of a chain
+    unsigned * chain_ring;          // CHAIN_RING work counters used in rotation by the frames of a chain (see CHAIN_RING)
     struct ChainState * chain;      // HOST: what the previous launch of this context was; null => this launch may not chain
     unsigned long long * timeline;  // diagnostic (PRTC_TIMELINE=1): per claim of k_step_pool {start ns, end ns, SM}; null otherwise
     uint32_t * work_flip;           // HOST: which one the next launch uses (toggled by the launcher); null => memset + work_counter
@@ -136,6 +136,13 @@ bool launch_slot_refresh(StepParams const & p, int mode, cudaStream_t stream);
 //   flags[k]     (IPC exchange only) one word per destination -- this rank's slot in that device's arrival table; the LAST
 //                block of the kernel writes `flag_value` (the frame number) into all of them behind a system-wide fence, and
 //                the consumer's k_dyn_wait spins on its own table until every rank's word has reached the frame number
+// Work counters of chained frames: frame f claims from counter f % CHAIN_RING and zeroes counter (f + 1) % CHAIN_RING before it lets
+// frame f + 1 in.  That counter was last used by frame f + 1 - CHAIN_RING, which must be gone: a frame with an unfinished claim
+// keeps every later frame unfinished too (their claim of the same characters waits), every unfinished frame holds at least one
+// resident block, and the machine has room for 148 x 16 = 2368 one-warp blocks -- so no more than 2368 consecutive frames can be
+// unfinished at the same time, however long a single claim takes.
+constexpr uint32_t CHAIN_RING = 4096;
+
 // host-side memory of chained launches (one per context)
 struct ChainState {
     bool armed = false;             // the last step launched on the context was a chained frame with the signature below

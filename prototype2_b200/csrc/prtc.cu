@@ -568,7 +568,7 @@ void prtc_destroy(prtc_ctx * c) {
     c->d_cap2char.release(); c->d_seg_start.release(); c->d_seg_prev.release(); c->d_last_box.release();
     for (void * q : c->dyn_ipc.opened) cudaIpcCloseMemHandle(q);
     c->dyn_ipc.opened.clear(); c->dyn_ipc.flags.release();
-    c->d_dyn_records.release(); c->d_dyn_count.release(); c->d_dyn_start.release(); c->d_dyn_items.release(); c->d_dyn_reach.release(); c->d_dyn_cursor.release(); c->d_dyn_scan.release(); c->d_timeline.release(); c->d_chain_done.release();
+    c->d_dyn_records.release(); c->d_dyn_count.release(); c->d_dyn_start.release(); c->d_dyn_items.release(); c->d_dyn_reach.release(); c->d_dyn_cursor.release(); c->d_dyn_scan.release(); c->d_timeline.release(); c->d_chain_done.release(); c->d_chain_ring.release();
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
     for (int k = 0; k < prtc_ctx::PIPE_STREAMS; ++k) if (c->pipe[k]) cudaStreamDestroy(c->pipe[k]);
     if (c->dyn_ipc.push_stream) cudaStreamDestroy(c->dyn_ipc.push_stream);

@@ -155,6 +155,7 @@ struct prtc_ctx {
     prt::ChainState chain;                             // chained frames (PRTC_OPT_CHAIN_FRAMES)
     int chain_frames = 0;
     prt::host::DevBuf<uint32_t> d_chain_done;
+    prt::host::DevBuf<unsigned> d_chain_ring;          // CHAIN_RING work counters
     uint32_t work_flip = 0;                            // which of the pair the next pooled launch uses
     prt::host::HostStage stage;                        // small host-buffer batches: records staged in mapped pinned memory
     int staged = 1;                         // PRTC_STAGED=0: small batches take the copy path too (A/B)

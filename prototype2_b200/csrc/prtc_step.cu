@@ -419,7 +419,8 @@ int prtc_step_characters_device(prtc_ctx * c, float dt, uint32_t n, prtc_transfo
         } else c->chain.armed = chain_was_armed;
         p.chain = &c->chain;
         p.chain_done = c->d_chain_done.ptr;
-        p.chain_ring = c->d_work.ptr + 12;
+        if (!c->d_chain_ring.ptr) { PRTC_CUDA(c->d_chain_ring.reserve(CHAIN_RING)); c->chain.armed = false; }
+        p.chain_ring = c->d_chain_ring.ptr;
     }
     if (c->jacobi()) {
         if (!c->dyn_prepared) { rc = dyn_prepare(c, dt, n, d_tf, d_ph); if (rc) return rc; }

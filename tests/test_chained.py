@@ -66,6 +66,26 @@ def test_chained_frames_equal_unchained_and_the_oracle(moving):
     assert c_chain["launches"] == frames and c_plain["launches"] == 2 * frames
 
 
+@pytest.mark.parametrize("n", [30000, 64000])
+def test_chained_frames_of_a_batch_that_does_not_fill_the_machine(n):
+    """fewer claims than warp slots (one claim per block): every queued frame is on the machine at once, each block waiting
+    for the same characters' claim of the frame before it"""
+    import os
+    scene = H.make_scene(200, 2, 2, n, seed=79)
+    ang = np.random.RandomState(6).uniform(-np.pi, np.pi, n)
+    scene["move"] = np.stack([0.1 * np.cos(ang), np.zeros(n), 0.1 * np.sin(ang)], axis=1).astype(np.float32)
+    frames = 12
+    orc = H.build_oracle(scene, "l1", order="canonical", threads=os.cpu_count() or 1)
+    for _ in range(frames):
+        orc.step(DT)
+    chained, c_chain = _device_run(scene, frames, chain=True)
+    assert H.state_diff(orc.get_state(), chained) == []
+    assert c_chain["launches"] == frames
+    co = orc.counters()
+    for k in ("substeps", "tri_tests", "contacts"):
+        assert co[k] == c_chain[k], k
+
+
 def test_chain_broken_by_another_call_and_resumed():
     scene = _scene(True)
     plain, _ = _device_run(scene, 5, chain=False)
